@@ -1,0 +1,162 @@
+/*
+ * qlb200.h -- C ABI of libqlb200.so: the B200 (sm_100a) Householder-QL hot path behind
+ * MatrixFactorizations.jl's own plugin surface.
+ *
+ * Every entry point is what a Julia `ccall` from the reference's layout-dispatch hooks would
+ * bind (see INTEGRATION.md for the Julia stub of each).  Plain C types only: int64_t
+ * dimensions (Julia BlasInt on 64-bit), column-major arrays, by-value scalars, no torch types,
+ * no exceptions across the boundary.
+ *
+ * Return value (`info`, LAPACK convention extended):
+ *      0           success
+ *     -i           argument i (1-based, counting the handle as argument 1) is illegal; the Julia
+ *                  shim maps it to ArgumentError / DimensionMismatch exactly where the reference
+ *                  throws (src/ql.jl:326-328,356-358,494,508)
+ *     >0, <1000    numerical status (index of a zero pivot in a triangular solve / UL: the
+ *                  reference's SingularException / `info` field, src/ul.jl:54,102-107)
+ *     1000+e       CUDA runtime error e (cudaError_t); text via qlb200_last_error()
+ *
+ * Pointer kinds: functions ending in `_dev` take DEVICE pointers and run asynchronously on the
+ * handle's stream (no hidden copies, caller owns all buffers, results valid after
+ * qlb200_sync()).  Functions without the suffix take HOST pointers, stage through the handle's
+ * device workspace (H2D, compute, D2H) and return after the results are in host memory.
+ *
+ * There is NO CPU fallback anywhere in this library: without a CUDA device every call fails
+ * with 1000+cudaErrorNoDevice (or similar).
+ *
+ * Packed layout (bit-compatible with the reference's `QL.factors` / `QL.tau`, src/ql.jl:37-45):
+ * for column k (1-based, k >= n-min(m,n)+1) with mu = m-n+k: factors[1:mu-1,k] = v_k tail
+ * (v_k[mu] = 1 implicit), factors[mu,k] = L diagonal, factors[mu+1:m,k] = L below the diagonal;
+ * tau index k-n+min(m,n).  Q = H_n ... H_1 ("backward", LAPACK ?geqlf).
+ */
+#ifndef QLB200_H
+#define QLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef struct qlb200_ctx *qlb200_handle;
+
+/* ---- handle ------------------------------------------------------------------------------- */
+/* Library ABI version (major*1000+minor). */
+int qlb200_version(void);
+/* Create a handle bound to CUDA device `device` (its own non-blocking stream + workspace).
+ * Calls on one handle are serialized by the caller; different handles are thread-safe. */
+int qlb200_create(qlb200_handle *h, int device);
+int qlb200_destroy(qlb200_handle h);
+/* Run subsequent calls on the caller's cudaStream_t (NULL = the CUDA default stream). */
+int qlb200_set_stream(qlb200_handle h, void *cuda_stream);
+/* Go back to the handle's own non-blocking stream. */
+int qlb200_reset_stream(qlb200_handle h);
+/* Block until everything queued on the handle's stream has finished. */
+int qlb200_sync(qlb200_handle h);
+/* Text of the last error recorded on this handle ("" if none).  Valid until the next call. */
+const char *qlb200_last_error(qlb200_handle h);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t qlb200_launch_count(qlb200_handle h);
+/* Tunables: "nb" (panel width, multiple of 16 in [16,128]), "lookahead" (0/1), "gemm_cfg" (-1 auto,
+ * 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V). */
+int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
+
+/* ---- single matrix: ql! -------------------------------------------------------------------
+ * Replaces qlfactUnblocked!(A::StridedMatrix{<:BlasFloat}) = QL(LAPACK.geqlf!(A)...)
+ * (reference src/ql.jl:72, reached from ql!/ql_layout! src/ql.jl:114-117).
+ * A (m x n, leading dimension lda >= m) is overwritten with the packed factors; tau gets
+ * min(m,n) entries.
+ * Float64 only for the single-matrix path (Float32 single matrices are listed as "next" in DESIGN.md);
+ * m <= 16384 (row capacity of the cluster-resident panel kernel), any n. */
+int qlb200_dgeqlf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb200_dgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau);
+
+/* ---- single matrix: lmul!(Q,B), lmul!(Q',B), rmul!(C,Q), rmul!(C,Q') ------------------------
+ * Replaces materialize!(::Lmul{<:QLPackedQLayout}) / {<:AdjQLPackedQLayout}
+ * (reference src/ql.jl:321-347 / 350-377) and materialize!(::Rmul...) (src/ql.jl:381-406 /
+ * 409-435).  LAPACK ?ormql argument order.  side 'L': C (m x n) <- op(Q) C, Q is m x m built
+ * from the k = min(m, nA) reflectors stored in the LAST k columns of the m x nA factors; pass
+ * A = pointer to the first of those k columns.  side 'R': C (m x n) <- C op(Q), Q is n x n.
+ * trans 'N' or 'T'.  Returns -i on a dimension mismatch (reference: DimensionMismatch). */
+int qlb200_dormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k,
+                  const double *A, int64_t lda, const double *tau, double *C, int64_t ldc);
+int qlb200_dormql_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k,
+                      const double *dA, int64_t lda, const double *dtau, double *dC, int64_t ldc);
+
+/* ---- single matrix: ldiv!(F::QL, B), square ------------------------------------------------
+ * Replaces materialize!(::Ldiv{<:QLPackedLayout}) square branch (reference src/ql.jl:440-447,
+ * 467): B (n x nrhs) <- L^{-1} (Q' B) with L = tril(factors).  The reference's tall/wide
+ * branches are @test_broken (test/test_ql.jl:148) and are not offered.  The host-pointer form
+ * returns i > 0 if L[i,i] == 0 (SingularException); the asynchronous _dev form cannot and
+ * produces Inf/NaN like ?trsm. */
+int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                    const double *tau, double *B, int64_t ldb);
+int qlb200_dqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
+                        const double *dtau, double *dB, int64_t ldb);
+
+/* ---- RQ through index reversal -------------------------------------------------------------
+ * Replaces rq!(A::StridedMatrix{<:BlasFloat}) = RQ(LAPACK.gerqf!(A)...) (reference
+ * src/rq.jl:401): gerqf(A) = geqlf(A^T)^T with identical tau. */
+int qlb200_dgerqf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb200_dgerqf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau);
+
+/* ---- the FP64 tensor-core GEMM of the trailing update, exposed for tests and benchmarks -------
+ * C = alpha*op(A)*op(B) + beta*C, column-major device pointers, op 'N' or 'T' (BLAS dgemm order). */
+int qlb200_dgemm_dev(qlb200_handle h, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
+                     const double *dA, int64_t lda, const double *dB, int64_t ldb, double beta, double *dC,
+                     int64_t ldc);
+
+/* ---- batched small square QL (new surface; per-matrix semantics = src/ql.jl:72) ------------
+ * `batch` independent n x n matrices, n in {8, 16, 32}; matrix b starts at A + b*strideA,
+ * column-major with leading dimension lda; tau of matrix b at tau + b*strideTau (n entries).
+ * Reference-equivalent workload: `for i: ql!(view(A,:,:,i))`. */
+int qlb200_dgeqlf_batched(qlb200_handle h, int64_t n, double *A, int64_t lda, int64_t strideA,
+                          double *tau, int64_t strideTau, int64_t batch);
+int qlb200_sgeqlf_batched(qlb200_handle h, int64_t n, float *A, int64_t lda, int64_t strideA,
+                          float *tau, int64_t strideTau, int64_t batch);
+int qlb200_dgeqlf_batched_dev(qlb200_handle h, int64_t n, double *dA, int64_t lda, int64_t strideA,
+                              double *dtau, int64_t strideTau, int64_t batch);
+int qlb200_sgeqlf_batched_dev(qlb200_handle h, int64_t n, float *dA, int64_t lda, int64_t strideA,
+                              float *dtau, int64_t strideTau, int64_t batch);
+
+/* Batched lmul!(Q,B) (trans 'N', src/ql.jl:321-347) / lmul!(Q',B) (trans 'T', src/ql.jl:350-377):
+ * B_b (n x nrhs, leading dimension ldb, matrix stride strideB) <- op(Q_b) B_b. */
+int qlb200_dormql_batched(qlb200_handle h, char trans, int64_t n, int64_t nrhs, const double *A,
+                          int64_t lda, int64_t strideA, const double *tau, int64_t strideTau,
+                          double *B, int64_t ldb, int64_t strideB, int64_t batch);
+int qlb200_sormql_batched(qlb200_handle h, char trans, int64_t n, int64_t nrhs, const float *A,
+                          int64_t lda, int64_t strideA, const float *tau, int64_t strideTau,
+                          float *B, int64_t ldb, int64_t strideB, int64_t batch);
+int qlb200_dormql_batched_dev(qlb200_handle h, char trans, int64_t n, int64_t nrhs, const double *dA,
+                              int64_t lda, int64_t strideA, const double *dtau, int64_t strideTau,
+                              double *dB, int64_t ldb, int64_t strideB, int64_t batch);
+int qlb200_sormql_batched_dev(qlb200_handle h, char trans, int64_t n, int64_t nrhs, const float *dA,
+                              int64_t lda, int64_t strideA, const float *dtau, int64_t strideTau,
+                              float *dB, int64_t ldb, int64_t strideB, int64_t batch);
+
+/* Batched ldiv!(F::QL, B), square (src/ql.jl:440-447,467): B_b <- L_b^{-1} (Q_b' B_b).
+ * `info_out` (may be NULL; `batch` int32 entries, device memory for _dev) receives per matrix
+ * 0 or the 1-based index of a zero diagonal entry of L. */
+int qlb200_dqlsolve_batched(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                            int64_t strideA, const double *tau, int64_t strideTau, double *B,
+                            int64_t ldb, int64_t strideB, int64_t batch, int32_t *info_out);
+int qlb200_sqlsolve_batched(qlb200_handle h, int64_t n, int64_t nrhs, const float *A, int64_t lda,
+                            int64_t strideA, const float *tau, int64_t strideTau, float *B,
+                            int64_t ldb, int64_t strideB, int64_t batch, int32_t *info_out);
+int qlb200_dqlsolve_batched_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
+                                int64_t strideA, const double *dtau, int64_t strideTau, double *dB,
+                                int64_t ldb, int64_t strideB, int64_t batch, int32_t *dinfo_out);
+int qlb200_sqlsolve_batched_dev(qlb200_handle h, int64_t n, int64_t nrhs, const float *dA, int64_t lda,
+                                int64_t strideA, const float *dtau, int64_t strideTau, float *dB,
+                                int64_t ldb, int64_t strideB, int64_t batch, int32_t *dinfo_out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLB200_H */

@@ -1,0 +1,10 @@
+"""qlb200: B200-native (sm_100a) Householder QL hot path behind MatrixFactorizations.jl's API.
+
+The directory name carries a dot, so it is not importable by name; load it with
+`__graft_entry__.load_package()` (imports it as module `qlb200`).
+"""
+from ._lib import (ArgumentError, DimensionMismatch, Handle, QLB200Error, SingularException,  # noqa: F401
+                   LIB_PATH, SIGNATURES, HANDLE_FUNCS, default_handle, lib)
+from .ql import (QL, QLPackedQ, ql, ql_, rq_, lmul_, rmul_, ldiv_, ql_batched_, lmul_batched_,  # noqa: F401
+                 ldiv_batched_)
+from . import shard  # noqa: F401

@@ -1,0 +1,168 @@
+"""ctypes binding of libqlb200.so -- the C-ABI declared in include/qlb200.h.
+
+This is the same binding a Julia `ccall` makes: plain pointers and int64 sizes.
+There is no CPU fallback: if the shared library is missing or no sm_100 device is present every
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char, c_char_p, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqlb200.so")
+_LIB = None
+
+
+class QLB200Error(RuntimeError):
+    """CUDA/runtime failure reported by libqlb200 (info >= 1000)."""
+
+
+class ArgumentError(ValueError):
+    """info == -i for a non-dimension argument (Julia: ArgumentError)."""
+
+
+class DimensionMismatch(ValueError):
+    """Dimension check failed (reference: DimensionMismatch, src/ql.jl:326-328,356-358)."""
+
+
+class SingularException(ArithmeticError):
+    """Zero diagonal entry met in a triangular solve / UL (reference: SingularException)."""
+
+    def __init__(self, info):
+        super().__init__(f"SingularException({info})")
+        self.info = info
+
+
+_I, _P = c_int64, c_void_p
+
+# name -> argtypes (after the handle).  Mirrors include/qlb200.h one to one.
+_FACT = [_I, _I, _P, _I, _P]
+_ORM = [c_char, c_char, _I, _I, _I, _P, _I, _P, _P, _I]
+_SOLVE = [_I, _I, _P, _I, _P, _P, _I]
+_FACT_B = [_I, _P, _I, _I, _P, _I, _I]
+_ORM_B = [c_char, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I]
+_SOLVE_B = [_I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P]
+_UL = [_I, _I, _P, _I, _P, c_int, _P]
+_ULS = [_I, _I, _P, _I, _P, _P, _I]
+SIGNATURES = {}
+for _sfx in ("", "_dev"):
+    SIGNATURES[f"qlb200_dgeqlf{_sfx}"] = _FACT
+    SIGNATURES[f"qlb200_dgerqf{_sfx}"] = _FACT
+    SIGNATURES[f"qlb200_dormql{_sfx}"] = _ORM
+    SIGNATURES[f"qlb200_dqlsolve{_sfx}"] = _SOLVE
+    for _t in "ds":
+        SIGNATURES[f"qlb200_{_t}geqlf_batched{_sfx}"] = _FACT_B
+        SIGNATURES[f"qlb200_{_t}ormql_batched{_sfx}"] = _ORM_B
+        SIGNATURES[f"qlb200_{_t}qlsolve_batched{_sfx}"] = _SOLVE_B
+SIGNATURES["qlb200_dgemm_dev"] = [c_char, c_char, _I, _I, _I, ctypes.c_double, _P, _I, _P, _I, ctypes.c_double, _P, _I]
+HANDLE_FUNCS = ["qlb200_version", "qlb200_create", "qlb200_destroy", "qlb200_set_stream", "qlb200_sync",
+                "qlb200_last_error", "qlb200_launch_count", "qlb200_set_option", "qlb200_reset_stream"]
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise QLB200Error(f"{LIB_PATH} is missing: build it with `make -C {_HERE}/csrc` "
+                              "(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.qlb200_version.restype = c_int
+        L.qlb200_create.argtypes = [POINTER(c_void_p), c_int]
+        L.qlb200_destroy.argtypes = [c_void_p]
+        L.qlb200_set_stream.argtypes = [c_void_p, c_void_p]
+        L.qlb200_reset_stream.argtypes = [c_void_p]
+        L.qlb200_sync.argtypes = [c_void_p]
+        L.qlb200_last_error.argtypes = [c_void_p]
+        L.qlb200_last_error.restype = c_char_p
+        L.qlb200_launch_count.argtypes = [c_void_p]
+        L.qlb200_launch_count.restype = c_int64
+        L.qlb200_set_option.argtypes = [c_void_p, c_char_p, c_int64]
+        _LIB = L
+    return _LIB
+
+
+_BOUND = {}
+
+
+def fn(name: str):
+    """The C entry point `name` with its argtypes set (bound on first use)."""
+    f = _BOUND.get(name)
+    if f is None:
+        f = getattr(lib(), name)          # AttributeError if the library does not export it
+        f.argtypes = [c_void_p] + SIGNATURES[name]
+        f.restype = c_int
+        _BOUND[name] = f
+    return f
+
+
+class Handle:
+    """qlb200_handle: one CUDA device, its stream and workspaces."""
+
+    def __init__(self, device: int = 0):
+        self._h = c_void_p()
+        rc = lib().qlb200_create(ctypes.byref(self._h), int(device))
+        if rc != 0:
+            self._h = c_void_p()
+            raise QLB200Error(f"qlb200_create(device={device}) failed: info={rc}"
+                              + (" (CUDA error %d)" % (rc - 1000) if rc >= 1000 else ""))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            lib().qlb200_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self.check(lib().qlb200_sync(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(lib().qlb200_set_stream(self._h, c_void_p(cuda_stream_ptr or 0)))
+
+    def set_option(self, name: str, value: int):
+        self.check(lib().qlb200_set_option(self._h, name.encode(), int(value)))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().qlb200_launch_count(self._h))
+
+    def last_error(self) -> str:
+        return lib().qlb200_last_error(self._h).decode(errors="replace")
+
+    def check(self, info: int, dim_args=()):
+        """Map the LAPACK-style info to the exception types the reference throws."""
+        if info == 0:
+            return
+        msg = self.last_error()
+        if info >= 1000:
+            raise QLB200Error(f"CUDA error {info - 1000}: {msg}")
+        if info > 0:
+            raise SingularException(info)
+        if (-info) in dim_args or "DimensionMismatch" in msg:
+            raise DimensionMismatch(f"argument {-info}: {msg}")
+        raise ArgumentError(f"argument {-info}: {msg}")
+
+    def call(self, name: str, *args, dim_args=()):
+        info = fn(name)(self._h, *args)
+        self.check(info, dim_args)
+        return info
+
+    def call_raw(self, name: str, *args) -> int:
+        return fn(name)(self._h, *args)
+
+
+_DEFAULT = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    h = _DEFAULT.get(device)
+    if h is None:
+        h = _DEFAULT[device] = Handle(device)
+    return h

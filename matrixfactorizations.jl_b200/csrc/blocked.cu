@@ -1,0 +1,324 @@
+// blocked.cu -- device-side drivers of the single-matrix hot path (all pointers are DEVICE pointers,
+// everything is queued on h->stream and returns without synchronizing):
+//
+//   qlb_dgeqlf_dev    ql!(A): blocked Householder QL, packed output identical in layout to LAPACK
+//                     ?geqlf / the reference's QL.factors + QL.tau (reference src/ql.jl:72, 37-45).
+//                     Panels of nb columns from the right; each panel = strips of 16 columns factored
+//                     by the cluster kernel (panel.cu) + in-panel compact-WY updates; then T from the
+//                     Gram matrix (larft) and the trailing update C -= V (T' (V' C))' as three DMMA
+//                     GEMMs (gemm.cu).  SURVEY.md A.2 spells out the backward/columnwise conventions.
+//   qlb_dormql_dev    lmul!/rmul! with Q or Q' (reference src/ql.jl:321-435) as blocked ?ormql
+//                     (SURVEY.md A.3): T rebuilt per block from V and tau, same GEMMs.
+//   qlb_dqlsolve_dev  ldiv!(F,B), square (reference src/ql.jl:440-447,467): Q'B then a blocked
+//                     forward substitution with L = tril(factors).
+//   qlb_dgerqf_dev    rq!(A) (reference src/rq.jl:401) through gerqf(A) = geqlf(A')' (SURVEY.md A.4).
+#include "common.cuh"
+#include "internal.h"
+
+namespace qlb {
+
+static inline int64_t even_up(int64_t x) { return (x + 1) & ~(int64_t)1; }
+
+// Split-K factor for a GEMM with `tiles` output tiles and reduction length K: fill the SMs, keep
+// chunks >= minchunk, never more than maxS partials.
+static int choose_splits(int sm, int64_t tiles, int K, int minchunk, int maxS) {
+    if (tiles <= 0) return 1;
+    int smax = K / minchunk;
+    if (smax > maxS) smax = maxS;
+    if (smax < 1) smax = 1;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= smax; ++s) {
+        const double work = (double)tiles * s;
+        const double waves = (double)((int64_t)((work + sm - 1) / sm));
+        double eff = work / (waves * sm);
+        eff -= 0.01 * (s - 1);                 // partial-sum traffic penalty
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+struct Workspace {
+    double *Vw;  int64_t ldv;      // clean reflector block, p x nb
+    double *T;   int64_t ldt;      // nb x nb
+    double *Ts;                    // 16 x 16 strip T
+    double *G;                     // nb x nb Gram matrix
+    double *Wsum, *W2; int64_t ldw; // (other dimension) x nb
+    double *part; int64_t part_elems;
+};
+
+// carve the handle's workspace: rows = reflector length bound, other = max #columns/rows of the operand
+static int get_workspace(qlb200_ctx *h, int64_t rows, int64_t other, int nb, int max_splits, Workspace *w) {
+    const int64_t ldv = even_up(rows), ldw = even_up(other);
+    int64_t part = (int64_t)max_splits * ldw * nb;
+    const int64_t gram_part = (int64_t)160 * nb * nb;
+    const int64_t strip_part = (int64_t)128 * even_up(nb) * 16;
+    if (gram_part > part) part = gram_part;
+    if (strip_part > part) part = strip_part;
+    const int64_t total = ldv * nb + 2 * (int64_t)nb * nb + 256 + 2 * ldw * nb + part + 64;
+    int rc = qlb_reserve(h, &h->ws, &h->ws_bytes, (size_t)total * sizeof(double));
+    if (rc) return rc;
+    double *q = (double *)h->ws;
+    w->Vw = q;  w->ldv = ldv;  q += ldv * nb;
+    w->T = q;   w->ldt = nb;   q += (int64_t)nb * nb;
+    w->G = q;                  q += (int64_t)nb * nb;
+    w->Ts = q;                 q += 256;
+    w->Wsum = q; w->ldw = ldw; q += ldw * nb;
+    w->W2 = q;                 q += ldw * nb;
+    w->part = q; w->part_elems = part;
+    return 0;
+}
+
+// T (ib x ib) of the block reflector stored in ws.Vw[0:p, 0:ib] with scalars tau: Gram (split-K DMMA
+// GEMM) -> reduce -> ?larft recurrence.
+static int build_T(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, int p, int ib, const double *tau) {
+    int S = (p + 127) / 128;
+    if (S > 148) S = 148;
+    S = qlb_gemm_splits(p, S, 16);
+    const int64_t stride = (int64_t)ib * ib;
+    int rc = qlb_gemm(h, st, ib <= 16 ? 2 : -1, true, true, ib, ib, p, 1.0, ws.Vw, ws.ldv, ws.Vw, ws.ldv, 0.0,
+                      S > 1 ? ws.part : ws.G, ib, S, stride);
+    if (rc) return rc;
+    if (S > 1) {
+        rc = qlb_reduce_partials(h, st, ws.part, S, stride, ib, ib, ib, ws.G, ib);
+        if (rc) return rc;
+    }
+    return qlb_larft(h, st, ws.G, ib, tau, ib, ws.T, ws.ldt);
+}
+
+// Apply the block reflector H = I - V T V' (V = ws.Vw[0:p,0:ib] or Vptr) to C.
+//   left : C (p x nc, ldc)  <- (I - V Tm V') C      W = C' V (nc x ib)
+//   right: C (mc x p, ldc)  <- C (I - V Tm V')      W = C V  (mc x ib)
+// Tm = T (tt == false) or T' (tt == true) in W2 = W * Tm.
+static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool left, bool tt, const double *V,
+                       int64_t ldv, const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other) {
+    if (other <= 0 || p <= 0 || ib <= 0) return 0;
+    const bool small = ib <= 16;
+    const int cfg_w = small ? 2 : -1;
+    // 1. W partials: M = other, N = ib, K = p
+    const int64_t tiles = (int64_t)((other + 127) / 128) * ((ib + 127) / 128);
+    int S;
+    if (small) {
+        S = (p + 127) / 128;
+        if (S > 128) S = 128;
+    } else if (h->opt_trail_splits > 0) {
+        S = (int)h->opt_trail_splits;
+    } else {
+        S = choose_splits(h->sm_count, tiles, p, 512, 8);
+    }
+    S = qlb_gemm_splits(p, S, 16);
+    const bool to_part = (S > 1 || small);
+    const int64_t ldp = to_part ? even_up(other) : ws.ldw;      // partials are packed tightly
+    const int64_t stride = ldp * (int64_t)ib;
+    if (to_part && (int64_t)S * stride > ws.part_elems)
+        return qlb_fail(h, 1000 + (int)cudaErrorMemoryAllocation, "partial buffer too small%s");
+    double *Wdst = to_part ? ws.part : ws.Wsum;
+    int rc = qlb_gemm(h, st, cfg_w, /*akc=*/left, /*bkc=*/true, other, ib, p, 1.0, C, ldc, V, ldv, 0.0, Wdst, ldp, S, stride);
+    if (rc) return rc;
+    // 2. W2 = (sum of partials) * Tm
+    if (small && !tt) {
+        rc = qlb_reduce_mult_t(h, st, ws.part, S, stride, other, ib, ldp, T, (int)ldt, ws.W2, ws.ldw);
+        if (rc) return rc;
+    } else {
+        if (to_part) {
+            rc = qlb_reduce_partials(h, st, ws.part, S, stride, other, ib, ldp, ws.Wsum, ws.ldw);
+            if (rc) return rc;
+        }
+        rc = qlb_gemm(h, st, cfg_w, false, /*bkc=*/!tt, other, ib, ib, 1.0, ws.Wsum, ws.ldw, T, ldt, 0.0, ws.W2, ws.ldw, 1, 0);
+        if (rc) return rc;
+    }
+    // 3. C -= V W2' (left)  or  C -= W2 V' (right)
+    if (left) return qlb_gemm(h, st, -1, false, false, p, other, ib, -1.0, V, ldv, ws.W2, ws.ldw, 1.0, C, ldc, 1, 0);
+    return qlb_gemm(h, st, -1, false, false, other, p, ib, -1.0, ws.W2, ws.ldw, V, ldv, 1.0, C, ldc, 1, 0);
+}
+
+// 32x32 tiled transpose: out (cols x rows, ldo) = in (rows x cols, ldi)'
+__global__ void transpose_kernel(const double *__restrict__ in, int64_t ldi, int rows, int cols, double *__restrict__ out,
+                                 int64_t ldo) {
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + threadIdx.x, c = c0 + j;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[r + (int64_t)c * ldi];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + threadIdx.x, r = r0 + j;
+        if (r < rows && c < cols) out[c + (int64_t)r * ldo] = tile[threadIdx.x][j];
+    }
+}
+
+// Forward substitution with one tb x tb diagonal block of L (lower, non-unit): X = L^{-1} B in place.
+// One CTA of TB threads; thread r owns row r of up to 8 right-hand sides at a time.
+template <int TB>
+__global__ void __launch_bounds__(TB) trsm_diag_kernel(const double *__restrict__ L, int64_t ldl, int tb, double *__restrict__ B,
+                                                      int64_t ldb, int nrhs, int row_base, int32_t *__restrict__ info) {
+    extern __shared__ __align__(16) double sm[];
+    double *Ls = sm;                       // tb x tb, pitch TB+1
+    __shared__ double xs[8];
+    const int r = threadIdx.x;
+    for (int idx = threadIdx.x; idx < tb * tb; idx += TB) {
+        const int i = idx % tb, j = idx / tb;
+        Ls[j * (TB + 1) + i] = (i >= j) ? L[i + (int64_t)j * ldl] : 0.0;
+    }
+    __syncthreads();
+    if (info != nullptr && r < tb && Ls[r * (TB + 1) + r] == 0.0) atomicMin((int *)info, row_base + r + 1);
+    for (int c0 = 0; c0 < nrhs; c0 += 8) {
+        const int nc = (nrhs - c0) < 8 ? (nrhs - c0) : 8;
+        double b[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[q] = (r < tb && q < nc) ? B[r + (int64_t)(c0 + q) * ldb] : 0.0;
+        for (int c = 0; c < tb; ++c) {
+            if (r == c) {
+                const double inv = 1.0 / Ls[c * (TB + 1) + c];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { b[q] *= inv; xs[q] = b[q]; }
+            }
+            __syncthreads();
+            if (r > c && r < tb) {
+                const double l = Ls[c * (TB + 1) + r];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b[q] = fma(-l, xs[q], b[q]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (r < tb && q < nc) B[r + (int64_t)(c0 + q) * ldb] = b[q];
+    }
+}
+
+__global__ void set_int_kernel(int32_t *p, int32_t v) { *p = v; }
+
+}  // namespace qlb
+
+using namespace qlb;
+
+int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
+    const int m = (int)m64, n = (int)n64;
+    const int k = m < n ? m : n;
+    if (k == 0) return 0;
+    if (m > qlb_strip_max_rows()) return qlb_fail(h, -2, "geqlf: m exceeds the panel kernel's row capacity (16384)%s");
+    const int nb = (int)h->opt_nb, sb = 16;
+    cudaStream_t st = h->stream;
+    Workspace ws;
+    int rc = get_workspace(h, m, n, nb, 8, &ws);
+    if (rc) return rc;
+    int c1 = n;
+    while (c1 > n - k) {
+        const int c0 = (c1 - nb > n - k) ? c1 - nb : n - k;
+        const int ib = c1 - c0;
+        const int p = m - n + c1;
+        // ---- panel: strips from the right ----
+        int s1 = c1;
+        while (s1 > c0) {
+            const int s0 = (s1 - sb > c0) ? s1 - sb : c0;
+            const int w = s1 - s0, ps = m - n + s1;
+            rc = qlb_strip_factor(h, st, A + (int64_t)s0 * lda, lda, ps, w, tau + (s0 - (n - k)), ws.Vw + (int64_t)(s0 - c0) * ws.ldv,
+                                  ws.ldv, p, ws.Ts, 16);
+            if (rc) return rc;
+            if (s0 > c0) {
+                rc = apply_block(h, st, ws, true, false, ws.Vw + (int64_t)(s0 - c0) * ws.ldv, ws.ldv, ws.Ts, 16, ps, w,
+                                 A + (int64_t)c0 * lda, lda, s0 - c0);
+                if (rc) return rc;
+            }
+            s1 = s0;
+        }
+        // ---- trailing update of the c0 columns left of the panel ----
+        if (c0 > 0) {
+            if (ib > 16) {
+                rc = build_T(h, st, ws, p, ib, tau + (c0 - (n - k)));
+                if (rc) return rc;
+                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, ws.T, ws.ldt, p, ib, A, lda, c0);
+            } else {
+                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, ws.Ts, 16, p, ib, A, lda, c0);
+            }
+            if (rc) return rc;
+        }
+        c1 = c0;
+    }
+    return 0;
+}
+
+int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n64, int64_t k64, const double *A,
+                   int64_t lda, const double *tau, double *C, int64_t ldc) {
+    const int m = (int)m64, n = (int)n64, k = (int)k64;
+    const bool left = (side == 'L' || side == 'l');
+    const bool notran = (trans == 'N' || trans == 'n');
+    const int nq = left ? m : n, other = left ? n : m;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    const int nb = (int)h->opt_nb;
+    cudaStream_t st = h->stream;
+    Workspace ws;
+    int rc = get_workspace(h, nq, other, nb, 8, &ws);
+    if (rc) return rc;
+    const int nblk = (k + nb - 1) / nb;
+    // Q = H_k ... H_1.  Q C and C Q' apply H_1 first (ascending blocks); Q' C and C Q descending.
+    const bool ascending = (left && notran) || (!left && !notran);
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int b = ascending ? bi : nblk - 1 - bi;
+        const int i = b * nb;
+        const int ib = (k - i) < nb ? (k - i) : nb;
+        const int p = nq - k + i + ib;          // rows of V for this block
+        rc = qlb_extract_v(h, st, A + (int64_t)i * lda, lda, p, ib, nq - k + i, ws.Vw, ws.ldv);
+        if (rc) return rc;
+        rc = build_T(h, st, ws, p, ib, tau + i);
+        if (rc) return rc;
+        // left: H C = C - V T V'C -> W2 = W T' (notrans), W T (trans); right: C H = C - (C V) T V' -> W T / W T'
+        const bool tt = left ? notran : !notran;
+        rc = apply_block(h, st, ws, left, tt, ws.Vw, ws.ldv, ws.T, ws.ldt, p, ib, C, ldc, other);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A, int64_t lda, const double *tau, double *B,
+                     int64_t ldb, int32_t *dinfo) {
+    const int n = (int)n64, nrhs = (int)nrhs64;
+    if (n == 0 || nrhs == 0) return 0;
+    cudaStream_t st = h->stream;
+    int rc = qlb_dormql_dev(h, 'L', 'T', n, nrhs, n, A, lda, tau, B, ldb);      // src/ql.jl:445
+    if (rc) return rc;
+    if (dinfo) {
+        set_int_kernel<<<1, 1, 0, st>>>(dinfo, 0x7fffffff);
+        QLB_LAUNCH_CHECK(h);
+    }
+    constexpr int TB = 128;
+    static_assert(TB * (TB + 1) * 8 <= 227 * 1024, "diag block must fit in shared memory");
+    const size_t smem = (size_t)TB * (TB + 1) * sizeof(double);
+    if (!h->trsm_attr_done) {
+        QLB_CUDA(h, cudaFuncSetAttribute(trsm_diag_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->trsm_attr_done = true;
+    }
+    for (int i = 0; i < n; i += TB) {                                            // src/ql.jl:467
+        const int tb = (n - i) < TB ? (n - i) : TB;
+        trsm_diag_kernel<TB><<<1, TB, smem, st>>>(A + i + (int64_t)i * lda, lda, tb, B + i, ldb, nrhs, i, dinfo);
+        QLB_LAUNCH_CHECK(h);
+        const int rem = n - i - tb;
+        if (rem > 0) {
+            rc = qlb_gemm(h, st, nrhs <= 16 ? 2 : -1, false, true, rem, nrhs, tb, -1.0, A + (i + tb) + (int64_t)i * lda, lda,
+                          B + i, ldb, 1.0, B + i + tb, ldb, 1, 0);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
+    const int m = (int)m64, n = (int)n64;
+    if (m == 0 || n == 0) return 0;
+    cudaStream_t st = h->stream;
+    // A' (n x m) in a second buffer: gerqf(A) = geqlf(A')' with identical tau
+    const int64_t ldt = even_up(n);
+    int rc = qlb_reserve(h, &h->ws2, &h->ws2_bytes, (size_t)ldt * m * sizeof(double));
+    if (rc) return rc;
+    double *At = (double *)h->ws2;
+    dim3 blk(32, 8);
+    transpose_kernel<<<dim3((m + 31) / 32, (n + 31) / 32), blk, 0, st>>>(A, lda, m, n, At, ldt);
+    QLB_LAUNCH_CHECK(h);
+    rc = qlb_dgeqlf_dev(h, n, m, At, ldt, tau);
+    if (rc) return rc;
+    transpose_kernel<<<dim3((n + 31) / 32, (m + 31) / 32), blk, 0, st>>>(At, ldt, n, m, A, lda);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}

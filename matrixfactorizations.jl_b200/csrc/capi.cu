@@ -1,0 +1,464 @@
+// capi.cu -- extern "C" boundary of libqlb200.so (see include/qlb200.h): handle management and the
+// host-pointer / device-pointer entry points.  No torch types, no exceptions, no CPU fallback.
+#include "common.cuh"
+#include "internal.h"
+#include <new>
+
+#define QLB_REQUIRE(h, cond, argno, msg)                      \
+    do {                                                      \
+        if (!(cond)) return qlb_fail(h, -(argno), msg "%s");  \
+    } while (0)
+
+extern "C" {
+
+int qlb200_version(void) { return QLB200_VERSION; }
+
+int qlb200_create(qlb200_handle *out, int device) {
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return 1000 + (int)e;
+    if (device < 0 || device >= ndev) return -2;
+    qlb200_ctx *h = new (std::nothrow) qlb200_ctx();
+    if (!h) return 1000 + (int)cudaErrorMemoryAllocation;
+    h->device = device;
+    QLB_CUDA(h, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QLB_CUDA(h, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete h;
+        return 1000 + (int)cudaErrorInvalidDevice;      // sm_100a only -- no fallback path
+    }
+    h->sm_count = prop.multiProcessorCount;
+    QLB_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    QLB_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+    QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    QLB_CUDA(h, cudaMalloc(&h->dinfo, 64));
+    h->stream = h->own_stream;
+    *out = h;
+    return 0;
+}
+
+int qlb200_destroy(qlb200_handle h) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->ws) cudaFree(h->ws);
+    if (h->ws2) cudaFree(h->ws2);
+    if (h->stage) cudaFree(h->stage);
+    if (h->stage2) cudaFree(h->stage2);
+    if (h->dinfo) cudaFree(h->dinfo);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    delete h;
+    return 0;
+}
+
+int qlb200_set_stream(qlb200_handle h, void *cuda_stream) {
+    if (!h) return -1;
+    h->stream = (cudaStream_t)cuda_stream;        // NULL = the CUDA default stream
+    return 0;
+}
+
+int qlb200_reset_stream(qlb200_handle h) {
+    if (!h) return -1;
+    h->stream = h->own_stream;
+    return 0;
+}
+
+int qlb200_sync(qlb200_handle h) {
+    if (!h) return -1;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+const char *qlb200_last_error(qlb200_handle h) { return h ? h->err : "null handle"; }
+
+int64_t qlb200_launch_count(qlb200_handle h) { return h ? h->launches : -1; }
+
+int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
+    if (!h) return -1;
+    if (!name) return -2;
+    if (!strcmp(name, "nb")) {
+        if (value < 16 || value > 128 || value % 16) return qlb_fail(h, -3, "nb must be a multiple of 16 in [16,128]%s");
+        h->opt_nb = value;
+    } else if (!strcmp(name, "gemm_cfg")) {
+        if (value < -1 || value > 3) return qlb_fail(h, -3, "gemm_cfg must be in [-1,3]%s");
+        h->opt_gemm_cfg = value;
+    } else if (!strcmp(name, "trail_splits")) {
+        if (value < 0 || value > 8) return qlb_fail(h, -3, "trail_splits must be in [0,8]%s");
+        h->opt_trail_splits = value;
+    } else if (!strcmp(name, "lookahead")) {
+        h->opt_lookahead = value ? 1 : 0;
+    } else if (!strcmp(name, "strip")) {
+        if (value != 8 && value != 16 && value != 32) return qlb_fail(h, -3, "strip must be 8, 16 or 32%s");
+        h->opt_strip = value;
+    } else {
+        return qlb_fail(h, -2, "unknown option %s", name);
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// batched: argument checks shared by the typed entry points
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int check_batched(qlb200_ctx *h, int64_t n, const T *A, int64_t lda, int64_t strideA, const T *tau,
+                         int64_t strideTau, int64_t batch) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, n == 8 || n == 16 || n == 32, 2, "n must be 8, 16 or 32");
+    QLB_REQUIRE(h, A != nullptr || batch == 0, 3, "A is null");
+    QLB_REQUIRE(h, lda >= n, 4, "lda < n");
+    QLB_REQUIRE(h, strideA >= lda * (n - 1) + n || batch <= 1, 5, "strideA too small (matrices overlap)");
+    QLB_REQUIRE(h, tau != nullptr || batch == 0, 6, "tau is null");
+    QLB_REQUIRE(h, strideTau >= n || batch <= 1, 7, "strideTau < n");
+    QLB_REQUIRE(h, batch >= 0, 8, "batch < 0");
+    return 0;
+}
+
+template <typename T>
+static int geqlf_batched_dev(qlb200_ctx *h, int64_t n, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau,
+                             int64_t batch);
+template <>
+int geqlf_batched_dev<double>(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int64_t strideA, double *tau,
+                              int64_t strideTau, int64_t batch) {
+    return qlb_geqlf_batched_f64(h, n, A, lda, strideA, tau, strideTau, batch);
+}
+template <>
+int geqlf_batched_dev<float>(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
+                             int64_t strideTau, int64_t batch) {
+    return qlb_geqlf_batched_f32(h, n, A, lda, strideA, tau, strideTau, batch);
+}
+static int apply_batched_dev(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                             int64_t strideA, const double *tau, int64_t strideTau, double *B, int64_t ldb,
+                             int64_t strideB, int64_t batch, int32_t *info) {
+    return qlb_apply_batched_f64(h, mode, n, nrhs, A, lda, strideA, tau, strideTau, B, ldb, strideB, batch, info);
+}
+static int apply_batched_dev(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, const float *A, int64_t lda,
+                             int64_t strideA, const float *tau, int64_t strideTau, float *B, int64_t ldb,
+                             int64_t strideB, int64_t batch, int32_t *info) {
+    return qlb_apply_batched_f32(h, mode, n, nrhs, A, lda, strideA, tau, strideTau, B, ldb, strideB, batch, info);
+}
+
+template <typename T>
+static int geqlf_batched_any(qlb200_ctx *h, bool host, int64_t n, T *A, int64_t lda, int64_t strideA, T *tau,
+                             int64_t strideTau, int64_t batch) {
+    int rc = check_batched(h, n, A, lda, strideA, tau, strideTau, batch);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    if (!host) return geqlf_batched_dev<T>(h, n, A, lda, strideA, tau, strideTau, batch);
+    // host pointers: stage the whole strided slab (H2D), factor, copy back (D2H)
+    const size_t a_elems = (size_t)((batch - 1) * strideA + lda * (n - 1) + n);
+    const size_t t_elems = (size_t)((batch - 1) * strideTau + n);
+    const size_t a_bytes = (a_elems * sizeof(T) + 255) & ~(size_t)255;
+    rc = qlb_reserve(h, &h->stage, &h->stage_bytes, a_bytes + t_elems * sizeof(T));
+    if (rc) return rc;
+    T *dA = (T *)h->stage, *dT = (T *)((char *)h->stage + a_bytes);
+    QLB_CUDA(h, cudaMemcpyAsync(dA, A, a_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    rc = geqlf_batched_dev<T>(h, n, dA, lda, strideA, dT, strideTau, batch);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaMemcpyAsync(A, dA, a_elems * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(tau, dT, t_elems * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// mode 0: lmul!(Q,B); 1: lmul!(Q',B); 2: ldiv!(F,B)
+template <typename T>
+static int apply_batched_any(qlb200_ctx *h, bool host, int mode, int64_t n, int64_t nrhs, const T *A, int64_t lda,
+                             int64_t strideA, const T *tau, int64_t strideTau, T *B, int64_t ldb, int64_t strideB,
+                             int64_t batch, int32_t *info_out, int argbase) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, n == 8 || n == 16 || n == 32, argbase, "n must be 8, 16 or 32");
+    QLB_REQUIRE(h, nrhs >= 0, argbase + 1, "nrhs < 0");
+    QLB_REQUIRE(h, A != nullptr || batch == 0, argbase + 2, "A is null");
+    QLB_REQUIRE(h, lda >= n, argbase + 3, "lda < n");
+    QLB_REQUIRE(h, strideA >= lda * (n - 1) + n || batch <= 1, argbase + 4, "strideA too small");
+    QLB_REQUIRE(h, tau != nullptr || batch == 0, argbase + 5, "tau is null");
+    QLB_REQUIRE(h, strideTau >= n || batch <= 1, argbase + 6, "strideTau < n");
+    QLB_REQUIRE(h, B != nullptr || batch == 0 || nrhs == 0, argbase + 7, "B is null");
+    QLB_REQUIRE(h, ldb >= n, argbase + 8, "ldb < n (reference: DimensionMismatch)");
+    QLB_REQUIRE(h, nrhs == 0 || strideB >= ldb * (nrhs - 1) + n || batch <= 1, argbase + 9, "strideB too small");
+    QLB_REQUIRE(h, batch >= 0, argbase + 10, "batch < 0");
+    if (batch == 0 || nrhs == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    if (!host) return apply_batched_dev(h, mode, n, nrhs, A, lda, strideA, tau, strideTau, B, ldb, strideB, batch, info_out);
+    const size_t a_elems = (size_t)((batch - 1) * strideA + lda * (n - 1) + n);
+    const size_t t_elems = (size_t)((batch - 1) * strideTau + n);
+    const size_t b_elems = (size_t)((batch - 1) * strideB + ldb * (nrhs - 1) + n);
+    const size_t a_bytes = (a_elems * sizeof(T) + 255) & ~(size_t)255;
+    const size_t t_bytes = (t_elems * sizeof(T) + 255) & ~(size_t)255;
+    const size_t b_bytes = (b_elems * sizeof(T) + 255) & ~(size_t)255;
+    int rc = qlb_reserve(h, &h->stage, &h->stage_bytes, a_bytes + t_bytes + b_bytes + (size_t)batch * 4);
+    if (rc) return rc;
+    T *dA = (T *)h->stage, *dT = (T *)((char *)h->stage + a_bytes), *dB = (T *)((char *)h->stage + a_bytes + t_bytes);
+    int32_t *dI = (int32_t *)((char *)h->stage + a_bytes + t_bytes + b_bytes);
+    QLB_CUDA(h, cudaMemcpyAsync(dA, A, a_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dT, tau, t_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dB, B, b_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    rc = apply_batched_dev(h, mode, n, nrhs, dA, lda, strideA, dT, strideTau, dB, ldb, strideB, batch, (mode == 2) ? dI : nullptr);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaMemcpyAsync(B, dB, b_elems * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    if (mode == 2 && info_out)
+        QLB_CUDA(h, cudaMemcpyAsync(info_out, dI, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int trans_mode(qlb200_ctx *h, char trans, int *mode) {
+    if (trans == 'N' || trans == 'n') { *mode = 0; return 0; }
+    if (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c') { *mode = 1; return 0; }
+    return qlb_fail(h, -2, "trans must be 'N' or 'T'%s");
+}
+
+extern "C" {
+
+int qlb200_dgeqlf_batched(qlb200_handle h, int64_t n, double *A, int64_t lda, int64_t strideA, double *tau,
+                          int64_t strideTau, int64_t batch) {
+    return geqlf_batched_any<double>(h, true, n, A, lda, strideA, tau, strideTau, batch);
+}
+int qlb200_sgeqlf_batched(qlb200_handle h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
+                          int64_t strideTau, int64_t batch) {
+    return geqlf_batched_any<float>(h, true, n, A, lda, strideA, tau, strideTau, batch);
+}
+int qlb200_dgeqlf_batched_dev(qlb200_handle h, int64_t n, double *A, int64_t lda, int64_t strideA, double *tau,
+                              int64_t strideTau, int64_t batch) {
+    return geqlf_batched_any<double>(h, false, n, A, lda, strideA, tau, strideTau, batch);
+}
+int qlb200_sgeqlf_batched_dev(qlb200_handle h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
+                              int64_t strideTau, int64_t batch) {
+    return geqlf_batched_any<float>(h, false, n, A, lda, strideA, tau, strideTau, batch);
+}
+
+#define QLB_ORMQL_BATCHED(NAME, T, HOST)                                                                           \
+    int NAME(qlb200_handle h, char trans, int64_t n, int64_t nrhs, const T *A, int64_t lda, int64_t strideA,       \
+             const T *tau, int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int64_t batch) {                 \
+        if (!h) return -1;                                                                                         \
+        int mode;                                                                                                  \
+        int rc = trans_mode(h, trans, &mode);                                                                      \
+        if (rc) return rc;                                                                                         \
+        return apply_batched_any<T>(h, HOST, mode, n, nrhs, A, lda, strideA, tau, strideTau, B, ldb, strideB,      \
+                                    batch, nullptr, 3);                                                            \
+    }
+QLB_ORMQL_BATCHED(qlb200_dormql_batched, double, true)
+QLB_ORMQL_BATCHED(qlb200_sormql_batched, float, true)
+QLB_ORMQL_BATCHED(qlb200_dormql_batched_dev, double, false)
+QLB_ORMQL_BATCHED(qlb200_sormql_batched_dev, float, false)
+
+#define QLB_QLSOLVE_BATCHED(NAME, T, HOST)                                                                         \
+    int NAME(qlb200_handle h, int64_t n, int64_t nrhs, const T *A, int64_t lda, int64_t strideA, const T *tau,     \
+             int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int64_t batch, int32_t *info_out) {            \
+        return apply_batched_any<T>(h, HOST, 2, n, nrhs, A, lda, strideA, tau, strideTau, B, ldb, strideB, batch,  \
+                                    info_out, 2);                                                                  \
+    }
+QLB_QLSOLVE_BATCHED(qlb200_dqlsolve_batched, double, true)
+QLB_QLSOLVE_BATCHED(qlb200_sqlsolve_batched, float, true)
+QLB_QLSOLVE_BATCHED(qlb200_dqlsolve_batched_dev, double, false)
+QLB_QLSOLVE_BATCHED(qlb200_sqlsolve_batched_dev, float, false)
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// single matrix: argument checks (LAPACK order: the handle is argument 1)
+// ---------------------------------------------------------------------------------------------
+static int check_fact(qlb200_ctx *h, int64_t m, int64_t n, const double *A, int64_t lda, const double *tau) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, m >= 0 && m < (1 << 30), 2, "m out of range");
+    QLB_REQUIRE(h, n >= 0 && n < (1 << 30), 3, "n out of range");
+    QLB_REQUIRE(h, A != nullptr || m * n == 0, 4, "A is null");
+    QLB_REQUIRE(h, lda >= (m > 1 ? m : 1), 5, "lda < max(1,m)");
+    QLB_REQUIRE(h, tau != nullptr || m * n == 0, 6, "tau is null");
+    return 0;
+}
+
+// stage a column-major host matrix into a device buffer with an even leading dimension
+static int stage_in(qlb200_ctx *h, void **buf, size_t *have, const double *A, int64_t m, int64_t n, int64_t lda,
+                    double **dA, int64_t *ldd) {
+    *ldd = (m + 1) & ~(int64_t)1;
+    if (*ldd < 2) *ldd = 2;
+    int rc = qlb_reserve(h, buf, have, (size_t)(*ldd) * (n > 0 ? n : 1) * sizeof(double));
+    if (rc) return rc;
+    *dA = (double *)*buf;
+    if (m > 0 && n > 0)
+        QLB_CUDA(h, cudaMemcpy2DAsync(*dA, (size_t)(*ldd) * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
+                                      cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+static int stage_out(qlb200_ctx *h, double *A, int64_t m, int64_t n, int64_t lda, const double *dA, int64_t ldd) {
+    if (m > 0 && n > 0)
+        QLB_CUDA(h, cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, (size_t)ldd * 8, (size_t)m * 8, (size_t)n,
+                                      cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+typedef int (*fact_fn)(qlb200_ctx *, int64_t, int64_t, double *, int64_t, double *);
+
+static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
+    int rc = check_fact(h, m, n, A, lda, tau);
+    if (rc) return rc;
+    const int64_t k = m < n ? m : n;
+    if (k == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA;
+    int64_t ldd;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, &dA, &ldd);
+    if (rc) return rc;
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * sizeof(double));
+    if (rc) return rc;
+    double *dtau = (double *)h->stage2;
+    rc = f(h, m, n, dA, ldd, dtau);
+    if (rc) return rc;
+    rc = stage_out(h, A, m, n, lda, dA, ldd);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int check_ormql(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                       const double *tau, const double *C, int64_t ldc) {
+    if (!h) return -1;
+    const bool left = side == 'L' || side == 'l', right = side == 'R' || side == 'r';
+    QLB_REQUIRE(h, left || right, 2, "side must be 'L' or 'R'");
+    QLB_REQUIRE(h, trans == 'N' || trans == 'n' || trans == 'T' || trans == 't' || trans == 'C' || trans == 'c', 3,
+                "trans must be 'N' or 'T'");
+    QLB_REQUIRE(h, m >= 0 && m < (1 << 30), 4, "m out of range");
+    QLB_REQUIRE(h, n >= 0 && n < (1 << 30), 5, "n out of range");
+    const int64_t nq = left ? m : n;
+    QLB_REQUIRE(h, k >= 0 && k <= nq, 6, "k must satisfy 0 <= k <= order of Q (DimensionMismatch)");
+    QLB_REQUIRE(h, A != nullptr || k == 0, 7, "A is null");
+    QLB_REQUIRE(h, lda >= (nq > 1 ? nq : 1), 8, "lda < order of Q (DimensionMismatch)");
+    QLB_REQUIRE(h, tau != nullptr || k == 0, 9, "tau is null");
+    QLB_REQUIRE(h, C != nullptr || m * n == 0, 10, "C is null");
+    QLB_REQUIRE(h, ldc >= (m > 1 ? m : 1), 11, "ldc < max(1,m)");
+    return 0;
+}
+
+extern "C" {
+
+int qlb200_dgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
+    int rc = check_fact(h, m, n, dA, lda, dtau);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dgeqlf_dev(h, m, n, dA, lda, dtau);
+}
+int qlb200_dgeqlf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
+    return fact_host(h, qlb_dgeqlf_dev, m, n, A, lda, tau);
+}
+int qlb200_dgerqf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
+    int rc = check_fact(h, m, n, dA, lda, dtau);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dgerqf_dev(h, m, n, dA, lda, dtau);
+}
+int qlb200_dgerqf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
+    return fact_host(h, qlb_dgerqf_dev, m, n, A, lda, tau);
+}
+
+int qlb200_dormql_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *dA,
+                      int64_t lda, const double *dtau, double *dC, int64_t ldc) {
+    int rc = check_ormql(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dormql_dev(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+}
+int qlb200_dormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                  const double *tau, double *C, int64_t ldc) {
+    int rc = check_ormql(h, side, trans, m, n, k, A, lda, tau, C, ldc);
+    if (rc) return rc;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t nq = (side == 'L' || side == 'l') ? m : n;
+    double *dA, *dC;
+    int64_t ldda, lddc;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, nq, k, lda, &dA, &ldda);
+    if (rc) return rc;
+    // C and tau share the second staging buffer
+    const int64_t ldc2 = ((m + 1) & ~(int64_t)1) < 2 ? 2 : ((m + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)ldc2 * n + (size_t)k + 2) * sizeof(double));
+    if (rc) return rc;
+    dC = (double *)h->stage2;
+    lddc = ldc2;
+    double *dtau = dC + (size_t)ldc2 * n;
+    QLB_CUDA(h, cudaMemcpy2DAsync(dC, (size_t)lddc * 8, C, (size_t)ldc * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice,
+                                  h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb_dormql_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc);
+    if (rc) return rc;
+    rc = stage_out(h, C, m, n, ldc, dC, lddc);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int check_solve(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau,
+                       const double *B, int64_t ldb) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, n >= 0 && n < (1 << 30), 2, "n out of range");
+    QLB_REQUIRE(h, nrhs >= 0 && nrhs < (1 << 30), 3, "nrhs out of range");
+    QLB_REQUIRE(h, A != nullptr || n == 0, 4, "A is null");
+    QLB_REQUIRE(h, lda >= (n > 1 ? n : 1), 5, "lda < max(1,n)");
+    QLB_REQUIRE(h, tau != nullptr || n == 0, 6, "tau is null");
+    QLB_REQUIRE(h, B != nullptr || n * nrhs == 0, 7, "B is null");
+    QLB_REQUIRE(h, ldb >= (n > 1 ? n : 1), 8, "ldb < max(1,n) (DimensionMismatch)");
+    return 0;
+}
+
+int qlb200_dqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const double *dtau,
+                        double *dB, int64_t ldb) {
+    int rc = check_solve(h, n, nrhs, dA, lda, dtau, dB, ldb);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dqlsolve_dev(h, n, nrhs, dA, lda, dtau, dB, ldb, nullptr);
+}
+int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
+                    int64_t ldb) {
+    int rc = check_solve(h, n, nrhs, A, lda, tau, B, ldb);
+    if (rc) return rc;
+    if (n == 0 || nrhs == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA, *dB;
+    int64_t ldda;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, n, n, lda, &dA, &ldda);
+    if (rc) return rc;
+    const int64_t lddb = ((n + 1) & ~(int64_t)1) < 2 ? 2 : ((n + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)lddb * nrhs + (size_t)n + 2) * sizeof(double));
+    if (rc) return rc;
+    dB = (double *)h->stage2;
+    double *dtau = dB + (size_t)lddb * nrhs;
+    QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)n * 8, (size_t)nrhs, cudaMemcpyHostToDevice,
+                                  h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb_dqlsolve_dev(h, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo);
+    if (rc) return rc;
+    rc = stage_out(h, B, n, nrhs, ldb, dB, lddb);
+    if (rc) return rc;
+    int32_t info = 0;
+    QLB_CUDA(h, cudaMemcpyAsync(&info, h->dinfo, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return info == 0x7fffffff ? 0 : (int)info;       // i > 0: L[i,i] == 0 (SingularException)
+}
+
+// BLAS-style test/benchmark hook for the DMMA GEMM (column-major, device pointers):
+// C = alpha*op(A)*op(B) + beta*C, op = 'N' or 'T'.
+int qlb200_dgemm_dev(qlb200_handle h, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
+                     const double *dA, int64_t lda, const double *dB, int64_t ldb, double beta, double *dC, int64_t ldc) {
+    if (!h) return -1;
+    const bool ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
+    QLB_REQUIRE(h, ta || transa == 'N' || transa == 'n', 2, "transa must be 'N' or 'T'");
+    QLB_REQUIRE(h, tb || transb == 'N' || transb == 'n', 3, "transb must be 'N' or 'T'");
+    QLB_REQUIRE(h, m >= 0 && n >= 0 && k >= 0, 4, "negative dimension");
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_gemm(h, h->stream, -1, /*akc=*/ta, /*bkc=*/!tb, (int)m, (int)n, (int)k, alpha, dA, lda, dB, ldb, beta, dC, ldc,
+                    1, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+// common.cuh -- handle, error plumbing and sm_100a PTX helpers (mbarrier, TMA bulk copies, DMMA).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/qlb200.h"
+
+#define QLB200_VERSION 1000
+
+struct qlb200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;     // created with the handle
+    cudaStream_t stream = nullptr;         // stream `_dev` calls run on
+    cudaStream_t side_stream = nullptr;    // look-ahead panel stream
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    void *ws = nullptr;                    // device workspace (grown on demand)
+    size_t ws_bytes = 0;
+    void *ws2 = nullptr;                   // second workspace (transposed copy for RQ)
+    size_t ws2_bytes = 0;
+    void *stage = nullptr;                 // device staging for host-pointer entry points
+    size_t stage_bytes = 0;
+    void *stage2 = nullptr;                // second staging buffer (C / B operands)
+    size_t stage2_bytes = 0;
+    int32_t *dinfo = nullptr;              // device-side status word
+    int64_t launches = 0;
+    int64_t opt_nb = 128, opt_strip = 16, opt_lookahead = 0;
+    int64_t opt_gemm_cfg = -1;             // -1 auto, else forces a tile configuration (benchmarking)
+    int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM
+    bool strip_attr_done[8] = {false};
+    bool larft_attr_done = false, trsm_attr_done = false;
+    bool gemm_attr_done[64] = {false};
+    char err[512] = {0};
+};
+
+static inline int qlb_fail(qlb200_ctx *h, int code, const char *fmt, const char *detail = "") {
+    if (h) snprintf(h->err, sizeof(h->err), fmt, detail);
+    return code;
+}
+
+#define QLB_CUDA(h, call)                                                                     \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            if (h) snprintf((h)->err, sizeof((h)->err), "%s:%d %s -> %s", __FILE__, __LINE__, \
+                            #call, cudaGetErrorString(e__));                                  \
+            return 1000 + (int)e__;                                                           \
+        }                                                                                     \
+    } while (0)
+
+#define QLB_LAUNCH_CHECK(h)            \
+    do {                               \
+        (h)->launches++;               \
+        QLB_CUDA(h, cudaGetLastError()); \
+    } while (0)
+
+// Grow-only device buffers owned by the handle.
+static inline int qlb_reserve(qlb200_ctx *h, void **buf, size_t *have, size_t need) {
+    if (need <= *have) return 0;
+    if (*buf) {
+        QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+        QLB_CUDA(h, cudaFree(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    size_t sz = (need + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    QLB_CUDA(h, cudaMalloc(buf, sz));
+    *have = sz;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace qlb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// TMA 1-D bulk copy shared -> global (bulk async-group completion).
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Ampere-style 16-byte async copy global -> shared (SASS: LDGSTS), zero-fill when !pred.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool pred) {
+    int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src, bool pred) {
+    int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4, row) * B(4x8, col).
+// Fragment layout (g = lane>>2, t = lane&3): a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+// m16n8k8 (sm_90+): a0=A[g][t] a1=A[g+8][t] a2=A[g][t+4] a3=A[g+8][t+4]; b0=B[t][g] b1=B[t+4][g];
+// c0,c1 = C[g][2t,2t+1]; c2,c3 = C[g+8][2t,2t+1].
+__device__ __forceinline__ void dmma1688(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+__device__ __forceinline__ void dmma1684(double (&c)[4], const double (&a)[2], double b) {
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(b));
+}
+__device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+        "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]),
+          "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+}  // namespace qlb
+#endif

@@ -1,0 +1,275 @@
+// gemm.cu -- K3: the FP64 tensor-core (DMMA, mma.sync.m16n8k8.f64) GEMM behind every Level-3 step of
+// the blocked QL: the compact-WY trailing update ?larfb('L','T','B','C') that LAPACK ?geqlf runs
+// inside the reference's ql! (reference src/ql.jl:72), the Gram matrix V'V for the
+// T-factor (?larft), the blocked Q-apply (reference src/ql.jl:321-377 done as ?ormql)
+// and the trsm updates of ldiv! (src/ql.jl:467).
+//
+//   D (M x N, column-major, ldd) = alpha * op(A) * op(B) + beta * D
+//
+// Operand layouts are template flags, so no operand is ever transposed in memory:
+//   AKC: A(m,k) at A[k + m*lda] ("K-contiguous", BLAS transa='T')   else A[m + k*lda] (transa='N')
+//   BKC: B(k,n) at B[k + n*ldb] ("K-contiguous", BLAS transb='N')   else B[n + k*ldb] (transb='T')
+// Tiles are staged global -> shared with 16-byte cp.async (LDGSTS) through a STAGES-deep ring; the
+// pitch of every shared tile is == 4 (mod 16) doubles so the 8-byte fragment loads of a half-warp
+// hit 16 distinct bank pairs.  There is no FP64 tcgen05/wgmma kind on sm_100a: warp-level DMMA fed
+// from registers is the FP64 tensor path of this architecture.
+// Split-K (gridDim.z > 1) writes partial products to `D + z*split_stride`; partials are summed in
+// a fixed order by reduce_partials_kernel, so results are bitwise reproducible.
+#include "common.cuh"
+#include "internal.h"
+
+namespace qlb {
+
+struct GemmParams {
+    int M, N, K;
+    const double *A;
+    int64_t lda;
+    const double *B;
+    int64_t ldb;
+    double *D;
+    int64_t ldd;
+    double alpha, beta;
+    int kchunk;               // K range handled by one blockIdx.z (multiple of BK unless splits == 1)
+    int64_t split_stride;     // elements between the partial outputs of consecutive z
+};
+
+template <int BM_, int BN_, int BK_, int WM_, int WN_, int STAGES_, int MINB_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN, WARPS = WARPS_M * WARPS_N, THREADS = WARPS * 32;
+    static constexpr int MT = WM / 16, NT = WN / 8;
+    static constexpr int PK = BK + 4;                     // pitch of a K-contiguous tile row
+    static constexpr int PA_MC = BM + 4, PB_NC = BN + 4;  // pitch of an M/N-contiguous tile row
+    static constexpr int A_ELEMS = (BM * PK > BK * PA_MC) ? BM * PK : BK * PA_MC;
+    static constexpr int B_ELEMS = (BN * PK > BK * PB_NC) ? BN * PK : BK * PB_NC;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+};
+
+// Stage one operand tile.  KC: tile is [ROWS][BK] (K contiguous), else [BK][ROWS] (row index contiguous).
+// VEC = 2: 16-byte cp.async (needs 16-byte aligned base and even ld), VEC = 1: 8-byte.
+template <int ROWS, int BK, bool KC, int VEC, int THREADS>
+__device__ __forceinline__ void load_tile(double *s, const double *__restrict__ g, int64_t ld, int row0, int k0,
+                                          int rows_total, int k_end, int tid) {
+    constexpr int PITCH = KC ? (BK + 4) : (ROWS + 4);
+    constexpr int INNER = KC ? BK : ROWS;                // contiguous extent of the tile
+    constexpr int OUTER = KC ? ROWS : BK;
+    constexpr int CHUNKS = INNER / VEC * OUTER;
+    static_assert(CHUNKS % THREADS == 0 || CHUNKS < THREADS, "tile/threads mismatch");
+#pragma unroll
+    for (int it = 0; it < (CHUNKS + THREADS - 1) / THREADS; ++it) {
+        const int idx = tid + it * THREADS;
+        if (CHUNKS % THREADS != 0 && idx >= CHUNKS) break;
+        const int o = idx / (INNER / VEC), i = (idx % (INNER / VEC)) * VEC;
+        const int r = KC ? (row0 + o) : (row0 + i);      // operand row (m or n) index
+        const int k = KC ? (k0 + i) : (k0 + o);
+        const int inner_left = KC ? (k_end - k) : (rows_total - r);      // valid elements along the chunk
+        const bool outer_ok = KC ? (r < rows_total) : (k < k_end);
+        int valid = outer_ok ? inner_left : 0;
+        valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
+        const double *src = valid > 0 ? (KC ? g + (int64_t)r * ld + k : g + (int64_t)k * ld + r) : g;
+        double *dst = s + o * PITCH + i;
+        if constexpr (VEC == 2) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid * 8)
+                         : "memory");
+        } else {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid * 8)
+                         : "memory");
+        }
+    }
+}
+
+template <class Cfg, bool AKC, bool BKC, int VEC>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const GemmParams p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
+    constexpr int PA = AKC ? Cfg::PK : Cfg::PA_MC, PB = BKC ? Cfg::PK : Cfg::PB_NC;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM, wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kbeg = blockIdx.z * p.kchunk;
+    const int kend = (kbeg + p.kchunk < p.K) ? kbeg + p.kchunk : p.K;
+    const int KT = (kend - kbeg + BK - 1) / BK;
+
+    double acc[MT][NT][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.0;
+
+    auto stage_a = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS; };
+    auto stage_b = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS + Cfg::A_ELEMS; };
+    auto issue = [&](int kt) {
+        if (kt < KT) {
+            const int s = kt % STAGES, k0 = kbeg + kt * BK;
+            load_tile<BM, BK, AKC, VEC, Cfg::THREADS>(stage_a(s), p.A, p.lda, m0, k0, p.M, kend, tid);
+            load_tile<BN, BK, BKC, VEC, Cfg::THREADS>(stage_b(s), p.B, p.ldb, n0, k0, p.N, kend, tid);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(kt + STAGES - 1);
+        const double *As = stage_a(kt % STAGES), *Bs = stage_b(kt % STAGES);
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+            double a[MT][4], b[NT][2];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int m = wm0 + i * 16 + g, k = ks * 8 + t;
+                if constexpr (AKC) {
+                    a[i][0] = As[m * PA + k];
+                    a[i][1] = As[(m + 8) * PA + k];
+                    a[i][2] = As[m * PA + k + 4];
+                    a[i][3] = As[(m + 8) * PA + k + 4];
+                } else {
+                    a[i][0] = As[k * PA + m];
+                    a[i][1] = As[k * PA + m + 8];
+                    a[i][2] = As[(k + 4) * PA + m];
+                    a[i][3] = As[(k + 4) * PA + m + 8];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int n = wn0 + j * 8 + g, k = ks * 8 + t;
+                if constexpr (BKC) {
+                    b[j][0] = Bs[n * PB + k];
+                    b[j][1] = Bs[n * PB + k + 4];
+                } else {
+                    b[j][0] = Bs[k * PB + n];
+                    b[j][1] = Bs[(k + 4) * PB + n];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma1688(acc[i][j], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: D = alpha*acc + beta*D (beta == 0 never reads D)
+    double *D = p.D + (int64_t)blockIdx.z * p.split_stride;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int m = m0 + wm0 + i * 16 + g + (r >> 1) * 8;
+                const int n = n0 + wn0 + j * 8 + 2 * t + (r & 1);
+                if (m < p.M && n < p.N) {
+                    double *d = D + m + (int64_t)n * p.ldd;
+                    double v = alpha * acc[i][j][r];
+                    if (beta != 0.0) v = fma(beta, *d, v);
+                    *d = v;
+                }
+            }
+}
+
+// out(M x N, ldo) = sum_{s < S} part[s*stride + m + n*ldp]   (fixed summation order)
+__global__ void reduce_partials_kernel(const double *__restrict__ part, int S, int64_t stride, int M, int N, int64_t ldp,
+                                       double *__restrict__ out, int64_t ldo) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(idx % M), n = (int)(idx / M);
+        const double *src = part + m + (int64_t)n * ldp;
+        double s = 0.0;
+        for (int z = 0; z < S; ++z) s += src[(int64_t)z * stride];
+        out[m + (int64_t)n * ldo] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+using CfgBig = GemmCfg<128, 128, 16, 64, 32, 4, 1>;     // 8 warps, 64x32 warp tiles, 1 CTA/SM
+using CfgMid = GemmCfg<128, 64, 16, 32, 32, 3, 2>;      // 8 warps, 32x32 warp tiles, 2 CTAs/SM
+using CfgSkinny = GemmCfg<128, 16, 16, 16, 16, 4, 2>;   // N <= 16 (strip updates): 8 warps of 16x16
+using CfgBig32 = GemmCfg<128, 128, 32, 64, 32, 3, 1>;   // BK = 32 variant
+
+template <class Cfg, bool AKC, bool BKC, int VEC>
+static int launch_cfg(qlb200_ctx *h, int slot, const GemmParams &p, int splits, cudaStream_t st) {
+    auto kern = gemm_kernel<Cfg, AKC, BKC, VEC>;
+    if (!h->gemm_attr_done[slot]) {          // once per handle (= per device) and instantiation
+        QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        h->gemm_attr_done[slot] = true;
+    }
+    dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, splits);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+template <class Cfg>
+static int launch_layout(qlb200_ctx *h, int cfg, bool akc, bool bkc, bool vec2, const GemmParams &p, int splits,
+                         cudaStream_t st) {
+#define QLB_GEMM_CASE(A_, B_)                                                                          \
+    if (akc == A_ && bkc == B_) {                                                                      \
+        const int slot = cfg * 8 + (A_ ? 4 : 0) + (B_ ? 2 : 0);                                        \
+        return vec2 ? launch_cfg<Cfg, A_, B_, 2>(h, slot + 1, p, splits, st)                           \
+                    : launch_cfg<Cfg, A_, B_, 1>(h, slot, p, splits, st);                              \
+    }
+    QLB_GEMM_CASE(true, true)
+    QLB_GEMM_CASE(false, true)
+    QLB_GEMM_CASE(false, false)
+    QLB_GEMM_CASE(true, false)
+#undef QLB_GEMM_CASE
+    return -1;
+}
+
+}  // namespace qlb
+
+// D = alpha*op(A)*op(B) + beta*D on stream `st`.  cfg: 0 big, 1 mid, 2 skinny, 3 big/BK32, -1 auto.
+// splits > 1: partial products to D + z*split_stride (alpha = 1, beta = 0 enforced by the caller).
+int qlb_gemm(qlb200_ctx *h, cudaStream_t st, int cfg, bool akc, bool bkc, int M, int N, int K, double alpha,
+             const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *D, int64_t ldd, int splits,
+             int64_t split_stride) {
+    using namespace qlb;
+    if (M <= 0 || N <= 0) return 0;
+    if (cfg < 0) cfg = (N <= 16) ? 2 : (h->opt_gemm_cfg >= 0 ? (int)h->opt_gemm_cfg : 0);
+    int bk = (cfg == 3) ? 32 : 16;
+    if (splits < 1) splits = 1;
+    int kchunk = K;
+    if (splits > 1) {
+        kchunk = ((K + splits - 1) / splits + bk - 1) / bk * bk;
+        if (kchunk < bk) kchunk = bk;
+        splits = (K + kchunk - 1) / kchunk;
+        if (splits < 1) splits = 1;
+    }
+    GemmParams p{M, N, K, A, lda, B, ldb, D, ldd, alpha, beta, kchunk, split_stride};
+    const bool vec2 = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
+    switch (cfg) {
+        case 0: return launch_layout<CfgBig>(h, 0, akc, bkc, vec2, p, splits, st);
+        case 1: return launch_layout<CfgMid>(h, 1, akc, bkc, vec2, p, splits, st);
+        case 2: return launch_layout<CfgSkinny>(h, 2, akc, bkc, vec2, p, splits, st);
+        case 3: return launch_layout<CfgBig32>(h, 3, akc, bkc, vec2, p, splits, st);
+    }
+    return qlb_fail(h, -2, "unknown gemm config%s");
+}
+
+// number of K-splits the split-K launch above will really use (callers size the partial buffer with it)
+int qlb_gemm_splits(int K, int splits, int bk) {
+    if (splits <= 1) return 1;
+    int kchunk = ((K + splits - 1) / splits + bk - 1) / bk * bk;
+    if (kchunk < bk) kchunk = bk;
+    int s = (K + kchunk - 1) / kchunk;
+    return s < 1 ? 1 : s;
+}
+
+int qlb_reduce_partials(qlb200_ctx *h, cudaStream_t st, const double *part, int S, int64_t stride, int M, int N,
+                        int64_t ldp, double *out, int64_t ldo) {
+    if (M <= 0 || N <= 0) return 0;
+    const int64_t total = (int64_t)M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > h->sm_count * 8) blocks = h->sm_count * 8;
+    qlb::reduce_partials_kernel<<<blocks, 256, 0, st>>>(part, S, stride, M, N, ldp, out, ldo);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}

@@ -1,0 +1,44 @@
+// internal.h -- typed entry points shared between the translation units of libqlb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+struct qlb200_ctx;
+
+// batched.cu
+int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int64_t strideA, double *tau,
+                          int64_t strideTau, int64_t batch);
+int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
+                          int64_t strideTau, int64_t batch);
+int qlb_apply_batched_f64(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                          int64_t strideA, const double *tau, int64_t strideTau, double *B, int64_t ldb,
+                          int64_t strideB, int64_t batch, int32_t *info_out);
+int qlb_apply_batched_f32(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, const float *A, int64_t lda,
+                          int64_t strideA, const float *tau, int64_t strideTau, float *B, int64_t ldb,
+                          int64_t strideB, int64_t batch, int32_t *info_out);
+
+// gemm.cu: D = alpha*op(A)*op(B) + beta*D (DMMA).  akc/bkc: operand is K-contiguous (see gemm.cu).
+int qlb_gemm(qlb200_ctx *h, cudaStream_t st, int cfg, bool akc, bool bkc, int M, int N, int K, double alpha,
+             const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *D, int64_t ldd, int splits,
+             int64_t split_stride);
+int qlb_gemm_splits(int K, int splits, int bk);
+int qlb_reduce_partials(qlb200_ctx *h, cudaStream_t st, const double *part, int S, int64_t stride, int M, int N,
+                        int64_t ldp, double *out, int64_t ldo);
+
+// panel.cu
+int qlb_strip_max_rows();
+int qlb_strip_factor(qlb200_ctx *h, cudaStream_t st, double *A, int64_t lda, int ps, int w, double *tau, double *Vw,
+                     int64_t ldv, int p, double *T, int ldt);
+int qlb_reduce_mult_t(qlb200_ctx *h, cudaStream_t st, const double *part, int S, int64_t stride, int rows, int w,
+                      int64_t ldp, const double *T, int ldt, double *W2, int64_t ldw);
+int qlb_larft(qlb200_ctx *h, cudaStream_t st, const double *G, int64_t ldg, const double *tau, int ib, double *T,
+              int64_t ldt);
+int qlb_extract_v(qlb200_ctx *h, cudaStream_t st, const double *F, int64_t ldf, int p, int ib, int mu0, double *Vw,
+                  int64_t ldv);
+
+// blocked.cu (device pointers, asynchronous on h->stream)
+int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                   const double *tau, double *C, int64_t ldc);
+int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
+                     int64_t ldb, int32_t *dinfo);
+int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);

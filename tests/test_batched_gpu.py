@@ -1,0 +1,185 @@
+"""GPU parity tests of the batched small-matrix kernels (K6) through the C-ABI vs the CPU oracle.
+
+Tolerances are BASELINE.json's: L and tau elementwise within 50*n*eps*||A||; solves within the
+reference's own 5000*eps-class tolerance (test/test_ql.jl:69) scaled by the solution size.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cport, lapack
+from __graft_entry__ import load_package
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ql_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def q():
+    return load_package()
+
+
+@pytest.fixture(scope="module")
+def h(q):
+    hd = q.Handle(0)
+    yield hd
+    hd.close()
+
+
+def _eps(dt):
+    return np.finfo(dt).eps
+
+
+def _check_factors(F, tau, Fo, tauo, A, n, dt):
+    nrm = np.linalg.norm(A.reshape(A.shape[0], -1), axis=1).max()
+    t = 50 * n * _eps(dt) * max(nrm, 1.0)
+    assert np.isfinite(F).all() and np.isfinite(tau).all()
+    assert np.abs(F - Fo).max() <= t, f"factors differ by {np.abs(F - Fo).max():.3e} > {t:.3e}"
+    assert np.abs(tau - tauo).max() <= 50 * n * _eps(dt), f"tau differs by {np.abs(tau - tauo).max():.3e}"
+
+
+@pytest.mark.parametrize("n", [8, 16, 32])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("batch", [1, 3, 17, 1000, 4099])
+def test_batched_geqlf_vs_oracle(q, h, n, dt, batch):
+    rng = np.random.default_rng(n * 1000 + batch)
+    A = rng.standard_normal((batch, n, n)).astype(dt)
+    F, tau = q.ql_batched_(A.copy(), handle=h)
+    Fo, tauo = cport.geql2_batched(A)
+    _check_factors(F, tau, Fo, tauo, A, n, dt)
+
+
+@pytest.mark.parametrize("name,dt,n", [("b32_f64", np.float64, 32), ("b16_f32", np.float32, 16), ("b8_f64", np.float64, 8)])
+def test_batched_vs_golden_lapack(q, h, name, dt, n):
+    """Golden fixtures were produced by LAPACK ?geqlf (the routine behind ql!, src/ql.jl:72)."""
+    A = GOLD[f"{name}_A"]
+    F, tau = q.ql_batched_(A.copy(), handle=h)
+    _check_factors(F, tau, GOLD[f"{name}_F"], GOLD[f"{name}_tau"], A, n, dt)
+    B = GOLD[f"{name}_B"]
+    tolb = 50 * n * _eps(dt) * np.abs(B).max() * n
+    QtB = q.lmul_batched_(F, tau, B.copy(), adjoint=True, handle=h)
+    assert np.abs(QtB - GOLD[f"{name}_QtB"]).max() <= tolb
+    X = q.ldiv_batched_(F, tau, B.copy(), handle=h)
+    Xo = GOLD[f"{name}_X"]
+    # per-matrix tolerance scaled with the size of the solution (ill-conditioned draws happen)
+    err = np.abs(X - Xo).reshape(X.shape[0], -1).max(axis=1)
+    scale = np.abs(Xo).reshape(X.shape[0], -1).max(axis=1)
+    cond = np.array([np.linalg.cond(A[i]) for i in range(A.shape[0])])
+    assert (err <= 50 * n * _eps(dt) * cond * np.maximum(scale, 1.0)).all()
+
+
+@pytest.mark.parametrize("n,dt", [(32, np.float64), (16, np.float32), (8, np.float64), (16, np.float64), (32, np.float32)])
+@pytest.mark.parametrize("nrhs", [1, 2, 3, 8, 11])
+def test_batched_lmul_and_solve_vs_oracle(q, h, n, dt, nrhs):
+    rng = np.random.default_rng(7 * n + nrhs)
+    batch = 37
+    A = rng.standard_normal((batch, n, n)).astype(dt)
+    Fo, tauo = cport.geql2_batched(A)
+    B = rng.standard_normal((batch, nrhs, n)).astype(dt)
+    tolb = 50 * n * _eps(dt) * np.abs(B).max() * np.sqrt(n)
+    for adj in (False, True):
+        got = q.lmul_batched_(Fo, tauo, B.copy(), adjoint=adj, handle=h)
+        ref = np.stack([cport.lmul(Fo[i].T, tauo[i], B[i].T, adjoint=adj).T for i in range(batch)])
+        assert np.abs(got - ref).max() <= tolb
+    info = np.full(batch, -1, dtype=np.int32)
+    X = q.ldiv_batched_(Fo, tauo, B.copy(), info=info, handle=h)
+    assert (info == 0).all()
+    Xo = np.stack([cport.ldiv(Fo[i].T, tauo[i], B[i].T).T for i in range(batch)])
+    cond = np.array([np.linalg.cond(A[i].astype(np.float64)) for i in range(batch)])
+    err = np.abs(X - Xo).reshape(batch, -1).max(axis=1)
+    scale = np.maximum(np.abs(Xo).reshape(batch, -1).max(axis=1), 1.0)
+    assert (err <= 50 * n * _eps(dt) * cond * scale).all()
+    # residual: A x = b within the reference's solve tolerance class
+    for i in range(batch):
+        r = A[i].T.astype(np.float64) @ X[i].T.astype(np.float64) - B[i].T
+        assert np.abs(r).max() <= 5000 * _eps(dt) * cond[i]
+
+
+def test_batched_roundtrip_properties_full_size(q, h):
+    """Size-independent properties at a large batch: ||Q'Q - I||, ||QL - A|| within 20*n*eps."""
+    import torch
+
+    n, batch = 32, 65536
+    g = torch.Generator(device="cuda").manual_seed(1234321)
+    A = torch.randn((batch, n, n), dtype=torch.float64, device="cuda", generator=g)
+    F = A.clone()
+    tau = torch.empty((batch, n), dtype=torch.float64, device="cuda")
+    q.ql_batched_(F, tau, handle=h)
+    E = torch.eye(n, dtype=torch.float64, device="cuda").expand(batch, n, n).contiguous()
+    q.lmul_batched_(F, tau, E, adjoint=False, handle=h)          # E_i = Q_i (stored column-major -> E[i] = Q_i^T)
+    h.sync()
+    Q = E.transpose(1, 2)
+    L = torch.tril(F.transpose(1, 2))
+    eye = torch.eye(n, dtype=torch.float64, device="cuda")
+    orth = (Q.transpose(1, 2) @ Q - eye).flatten(1).norm(dim=1).max().item()
+    Am = A.transpose(1, 2)
+    rec = ((Q @ L - Am).flatten(1).norm(dim=1) / Am.flatten(1).norm(dim=1)).max().item()
+    bound = 20 * n * np.finfo(np.float64).eps
+    assert orth <= bound and rec <= bound, (orth, rec, bound)
+    # run-to-run bitwise determinism (test/test_ql.jl:76 uses ==)
+    F2 = A.clone()
+    tau2 = torch.empty_like(tau)
+    q.ql_batched_(F2, tau2, handle=h)
+    h.sync()
+    assert torch.equal(F, F2) and torch.equal(tau, tau2)
+
+
+def test_batched_edge_conventions(q, h):
+    """LAPACK ?larfg exits: zero tail -> tau = 0, beta = alpha; tiny/huge columns rescaled."""
+    n = 32
+    A = np.zeros((6, n, n))
+    A[0] = np.eye(n)                                  # identity: all tails zero -> tau = 0, F = I
+    A[1] = np.diag(np.arange(1, n + 1) * -1.0)        # negative diagonal stays negative (no sign flip)
+    rng = np.random.default_rng(5)
+    A[2] = rng.standard_normal((n, n)) * 1e-160       # squares underflow
+    A[3] = rng.standard_normal((n, n)) * 1e160        # squares overflow
+    A[4] = rng.standard_normal((n, n))
+    A[4][:, 0] = 0.0                                  # a zero row of the (column-major) matrix
+    A[5] = rng.standard_normal((n, n))
+    A[5][3, :] = 0.0                                  # column 3 of the matrix entirely zero
+    F, tau = q.ql_batched_(A.copy(), handle=h)
+    Fo, tauo = cport.geql2_batched(A)
+    assert np.array_equal(tau[0], np.zeros(n)) and np.array_equal(F[0], np.eye(n))
+    assert np.array_equal(tau[1], np.zeros(n)) and np.array_equal(F[1], A[1])
+    for i in (2, 3, 4, 5):
+        sc = np.abs(A[i]).max()
+        assert np.isfinite(F[i]).all()
+        assert np.abs(F[i] - Fo[i]).max() <= 50 * n * _eps(np.float64) * sc * n, i
+        assert np.abs(tau[i] - tauo[i]).max() <= 50 * n * _eps(np.float64), i
+
+
+def test_batched_strided_layout_and_bitwise_lda_independence(q, h):
+    """test/test_ql.jl:76: the result must not depend on the leading dimension (bitwise)."""
+    n, batch, lda = 16, 50, 18
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((batch, n, n))
+    F, tau = q.ql_batched_(A.copy(), handle=h)
+    P = np.zeros((batch, n + 1, lda))
+    P[:, :n, :n] = A
+    taup = np.zeros((batch, n + 3))
+    rc = h.call("qlb200_dgeqlf_batched", n, P.ctypes.data, lda, (n + 1) * lda, taup.ctypes.data, n + 3, batch)
+    assert rc == 0
+    assert np.array_equal(P[:, :n, :n], F) and np.array_equal(taup[:, :n], tau)
+    assert (P[:, n, :] == 0).all() and (P[:, :, n:] == 0).all()      # padding untouched
+
+
+def test_batched_argument_errors(q, h):
+    A = np.zeros((2, 12, 12))
+    with pytest.raises(q.ArgumentError):
+        q.ql_batched_(A, handle=h)                         # n = 12 unsupported
+    A = np.zeros((0, 32, 32))
+    F, tau = q.ql_batched_(A, handle=h)                    # empty batch is a no-op
+    assert tau.shape == (0, 32)
+    with pytest.raises(q.DimensionMismatch):
+        q.lmul_batched_(np.zeros((2, 32, 32)), np.zeros((2, 32)), np.zeros((2, 4, 16)), handle=h)
+
+
+def test_batched_singular_info(q, h):
+    n = 8
+    A = np.random.default_rng(3).standard_normal((4, n, n))
+    Fo, tauo = cport.geql2_batched(A)
+    Fo[2, 4, 4] = 0.0                                      # L[5,5] = 0 in matrix 2
+    info = np.zeros(4, dtype=np.int32)
+    q.ldiv_batched_(Fo, tauo, np.ones((4, 1, n)), info=info, handle=h)
+    assert list(info) == [0, 0, 5, 0]

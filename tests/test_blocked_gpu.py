@@ -1,0 +1,229 @@
+"""GPU parity tests of the single-matrix path (blocked ql!, lmul!/rmul!, ldiv!, rq!) through the
+C-ABI vs the oracle: LAPACK ?geqlf/?gerqf (the routines behind the reference's ql!/rq!,
+src/ql.jl:72, src/rq.jl:401) and the C restatement of the reference's scalar loops.
+
+Tolerances (BASELINE.json north_star): L and tau elementwise within 50*n*eps*||A||;
+||QL - A||/||A|| and ||Q'Q - I|| within 20*n*eps; solves like the reference's own test
+(test/test_ql.jl:69: 5000*eps class, scaled by cond).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cport, lapack
+from __graft_entry__ import load_package
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ql_golden.npz"))
+EPS = np.finfo(np.float64).eps
+
+
+@pytest.fixture(scope="module")
+def q():
+    return load_package()
+
+
+@pytest.fixture(scope="module")
+def h(q):
+    hd = q.Handle(0)
+    yield hd
+    hd.close()
+
+
+def _tol(shape, A):
+    return 50 * max(shape) * EPS * np.linalg.norm(A)
+
+
+@pytest.mark.parametrize("transa,transb", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")])
+@pytest.mark.parametrize("mnk", [(128, 128, 128), (300, 200, 100), (257, 129, 77), (1000, 16, 500), (64, 9, 1000), (5, 3, 2)])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 3])
+def test_dmma_gemm_vs_torch(q, h, transa, transb, mnk, cfg):
+    import torch
+
+    m, n, k = mnk
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    cm = lambda r, c: torch.randn((c, r), dtype=torch.float64, device="cuda", generator=g).T   # column-major r x c
+    A = cm(k, m) if transa == "T" else cm(m, k)
+    B = cm(n, k) if transb == "T" else cm(k, n)
+    C = cm(m, n)
+    ref = 1.5 * (A.T if transa == "T" else A) @ (B.T if transb == "T" else B) - 0.5 * C
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    h.set_option("gemm_cfg", cfg)
+    try:
+        h.call("qlb200_dgemm_dev", transa.encode(), transb.encode(), m, n, k, 1.5, A.data_ptr(), A.stride(1),
+               B.data_ptr(), B.stride(1), -0.5, C.data_ptr(), C.stride(1))
+    finally:
+        h.set_option("gemm_cfg", -1)
+    torch.cuda.synchronize()
+    assert (C - ref).abs().max().item() <= 20 * k * EPS * 10
+
+
+SHAPES = [(10, 10), (10, 12), (12, 10), (3, 5), (1, 1), (5, 1), (1, 5), (16, 16), (17, 17), (100, 100), (100, 103),
+          (129, 129), (200, 150), (150, 420), (300, 300), (513, 257), (1024, 1024), (1500, 700), (2100, 2100)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_geqlf_matches_lapack(q, h, shape):
+    """test/test_ql.jl:5-33 at the LAPACK boundary: same packed factors and tau."""
+    A = np.asfortranarray(np.random.default_rng(shape[0] * 31 + shape[1]).standard_normal(shape) / 2)
+    F = q.ql(A, handle=h)
+    Fo, tauo = lapack.geqlf(A)
+    t = _tol(shape, A)
+    assert np.isfinite(F.factors).all()
+    assert np.abs(F.factors - Fo).max() <= t, np.abs(F.factors - Fo).max()
+    assert np.abs(F.tau - tauo).max() <= t
+
+
+@pytest.mark.parametrize("nb", [16, 32, 64, 96, 128])
+def test_geqlf_panel_widths(q, h, nb):
+    A = np.asfortranarray(np.random.default_rng(nb).standard_normal((700, 450)))
+    h.set_option("nb", nb)
+    try:
+        F = q.ql(A, handle=h)
+    finally:
+        h.set_option("nb", 128)
+    Fo, tauo = lapack.geqlf(A)
+    assert np.abs(F.factors - Fo).max() <= _tol(A.shape, A) and np.abs(F.tau - tauo).max() <= _tol(A.shape, A)
+
+
+def test_geqlf_golden_fixtures(q, h):
+    for name in ["sq10", "wide10x12", "tall12x10", "wide3x5", "sq100", "wide100x103", "sq200", "tall300x130"]:
+        A = GOLD[f"{name}_A"]
+        F = q.ql(A, handle=h)
+        t = _tol(A.shape, A)
+        assert np.abs(F.factors - GOLD[f"{name}_F"]).max() <= t, name
+        assert np.abs(F.tau - GOLD[f"{name}_tau"]).max() <= t, name
+
+
+def test_issue_7304_sign(q, h):
+    """test/test_ql.jl:120-124: A = [-s -s; -s s] => Q == -A."""
+    A = GOLD["i7304_A"]
+    F = q.ql(A, handle=h)
+    Q = F.Q.matrix()
+    assert np.linalg.norm(A + Q) < 4 * EPS
+
+
+def test_lda_padding_and_bitwise_lda_independence(q, h):
+    """test/test_ql.jl:76: results must not depend on the leading dimension (==), padding untouched."""
+    rng = np.random.default_rng(9)
+    A = np.asfortranarray(rng.standard_normal((200, 90)))
+    F1 = q.ql(A, handle=h)
+    big = np.full((211, 95), 7.0, order="F")
+    big[:200, :90] = A
+    view = big[:200, :90]
+    F2 = q.ql_(view, handle=h)
+    assert np.array_equal(F1.factors, F2.factors) and np.array_equal(F1.tau, F2.tau)
+    assert (big[200:, :] == 7.0).all() and (big[:, 90:] == 7.0).all()
+    F3 = q.ql(A, handle=h)
+    assert np.array_equal(F1.factors, F3.factors)          # run-to-run determinism
+
+
+def test_zero_columns_follow_lapack(q, h):
+    """LAPACK ?larfg: an exactly-zero tail gives tau = 0 and keeps the sign."""
+    A = np.asfortranarray(np.eye(40))
+    F = q.ql(A, handle=h)
+    assert np.array_equal(F.tau, np.zeros(40)) and np.array_equal(F.factors, np.eye(40))
+    A = np.asfortranarray(np.random.default_rng(2).standard_normal((60, 60)))
+    A[:, 17] = 0.0
+    F = q.ql(A, handle=h)
+    Fo, tauo = lapack.geqlf(A)
+    assert np.abs(F.factors - Fo).max() <= _tol(A.shape, A) and np.abs(F.tau - tauo).max() <= _tol(A.shape, A)
+
+
+@pytest.mark.parametrize("shape", [(100, 100), (100, 103), (300, 300), (500, 200)])
+@pytest.mark.parametrize("nrhs", [1, 2, 33])
+def test_lmul_rmul_vs_reference_loops(q, h, shape, nrhs):
+    """test/test_ql.jl:157-181: lmul!/rmul! with Q and Q' vs the reference's scalar loops."""
+    rng = np.random.default_rng(5)
+    A = np.asfortranarray(rng.standard_normal(shape))
+    Fo, tauo = lapack.geqlf(A)
+    F = q.QL(Fo, tauo, handle=h)
+    m = shape[0]
+    B = np.asfortranarray(rng.standard_normal((m, nrhs)))
+    C = np.asfortranarray(rng.standard_normal((nrhs, m)))
+    t = 50 * m * EPS * 10
+    for adj in (False, True):
+        Qx = F.Q.T if adj else F.Q
+        assert np.abs(q.lmul_(Qx, B.copy(order="F")) - cport.lmul(Fo, tauo, B, adjoint=adj)).max() <= t
+        assert np.abs(q.rmul_(C.copy(order="F"), Qx) - cport.rmul(C, Fo, tauo, adjoint=adj)).max() <= t
+    with pytest.raises(q.DimensionMismatch):
+        q.lmul_(F.Q, np.zeros((m + 1, 2), order="F"))          # src/ql.jl:326-328
+    with pytest.raises(q.DimensionMismatch):
+        q.rmul_(np.zeros((2, m + 1), order="F"), F.Q)          # src/ql.jl:385-387
+
+
+@pytest.mark.parametrize("n", [10, 100, 257, 1024])
+def test_orthogonality_reconstruction_and_solve(q, h, n):
+    """test/test_ql.jl:63-70: Q'Q = I, Q L = A, a*(F\\b) = b."""
+    rng = np.random.default_rng(n)
+    A = np.asfortranarray(rng.standard_normal((n, n)) / 2)
+    F = q.ql(A, handle=h)
+    Q = F.Q.matrix()
+    L = F.L
+    bound = 20 * n * EPS
+    assert np.linalg.norm(Q.T @ Q - np.eye(n)) <= bound * np.sqrt(n)
+    assert np.linalg.norm(Q @ L - A) / np.linalg.norm(A) <= bound
+    b = np.asfortranarray(rng.standard_normal((n, 3)))
+    x = F.solve(b)
+    Fo, tauo = lapack.geqlf(A)
+    xo = cport.ldiv(Fo, tauo, b)
+    cond = np.linalg.cond(A)
+    assert np.abs(x - xo).max() <= 50 * n * EPS * cond * max(1.0, np.abs(xo).max())
+    assert np.abs(A @ x - b).max() <= 5000 * EPS * cond
+    xv = F.solve(b[:, 0].copy())
+    assert xv.shape == (n,) and np.abs(xv - x[:, 0]).max() <= 50 * n * EPS * cond * max(1.0, np.abs(xo).max())
+
+
+def test_solve_singular_and_dimension_errors(q, h):
+    A = np.asfortranarray(np.random.default_rng(1).standard_normal((20, 20)))
+    Fo, tauo = lapack.geqlf(A)
+    Fo[7, 7] = 0.0
+    with pytest.raises(q.SingularException) as e:
+        q.ldiv_(q.QL(Fo, tauo, handle=h), np.ones((20, 1), order="F"))
+    assert e.value.info == 8
+    with pytest.raises(q.DimensionMismatch):
+        q.ldiv_(q.QL(Fo, tauo, handle=h), np.ones((19, 1), order="F"))
+
+
+@pytest.mark.parametrize("shape", [(10, 10), (8, 13), (40, 12), (300, 300), (130, 700), (900, 64)])
+def test_rq_matches_gerqf(q, h, shape):
+    """test/test_rq.jl:29-67: rq! vs LAPACK gerqf directly."""
+    A = np.asfortranarray(np.random.default_rng(sum(shape)).standard_normal(shape) / 2)
+    F, tau = q.rq_(A.copy(order="F"), handle=h)
+    Fo, tauo = lapack.gerqf(A)
+    t = _tol(shape, A)
+    assert np.abs(F - Fo).max() <= t and np.abs(tau - tauo).max() <= t
+    for name in ("rq_sq10", "rq_wide8x13", "rq_tall40x12"):
+        G, gt = q.rq_(np.asfortranarray(GOLD[f"{name}_A"]).copy(order="F"), handle=h)
+        assert np.abs(G - GOLD[f"{name}_F"]).max() <= 1e-12 and np.abs(gt - GOLD[f"{name}_tau"]).max() <= 1e-12
+
+
+def test_device_pointer_path_large_properties(q, h):
+    """Full-size style check through the _dev entry points on torch tensors: n = 4096,
+    ||Q'Q - I|| and ||QL - A||/||A|| within 20*n*eps, run-to-run bitwise determinism."""
+    import torch
+
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(1234321)
+    A = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g).T      # column-major
+    Fm = A.T.contiguous().T.clone()
+    Fm = (A.T.clone()).T
+    F = q.ql_(Fm, handle=h)
+    torch.cuda.synchronize()
+    Fm2 = (A.T.clone()).T
+    F2 = q.ql_(Fm2, handle=h)
+    torch.cuda.synchronize()
+    assert torch.equal(F.factors, F2.factors) and torch.equal(F.tau, F2.tau)
+    Q = F.Q.matrix()
+    torch.cuda.synchronize()
+    L = F.L
+    bound = 20 * n * EPS
+    eye = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert torch.linalg.norm(Q.T @ Q - eye).item() <= bound * np.sqrt(n)
+    assert (torch.linalg.norm(Q @ L - A) / torch.linalg.norm(A)).item() <= bound
+    # flip identity (test/test_ql.jl:7-13): R of QR of the doubly flipped matrix is L flipped
+    R = torch.linalg.qr(torch.flip(A, dims=(0, 1)), mode="r").R
+    Lf = torch.flip(L, dims=(0, 1))
+    sgn = torch.sign(torch.diagonal(R)) * torch.sign(torch.diagonal(Lf))
+    assert (torch.abs(R * sgn[:, None] - Lf).max() / torch.abs(L).max()).item() <= 50 * n * EPS * 10
