@@ -47,25 +47,35 @@ struct Workspace {
     double *part; int64_t part_elems;
 };
 
-// carve the handle's workspace: rows = reflector length bound, other = max #columns/rows of the operand
-static int get_workspace(qlb200_ctx *h, int64_t rows, int64_t other, int nb, int max_splits, Workspace *w) {
-    const int64_t ldv = even_up(rows), ldw = even_up(other);
-    int64_t part = (int64_t)max_splits * ldw * nb;
+// Carve the handle's workspace.  rows = reflector length bound, other = largest number of operand
+// columns (rows for side 'R') a block reflector is applied to.  With `two` a second, independent set is
+// carved for the look-ahead panel stream (its operands are at most nb wide).
+static int get_workspace(qlb200_ctx *h, int64_t rows, int64_t other, int nb, int max_splits, Workspace *w,
+                         Workspace *w2 = nullptr) {
+    const int64_t ldv = even_up(rows), ldw = even_up(other), ldw2 = even_up(nb);
     const int64_t gram_part = (int64_t)160 * nb * nb;
     const int64_t strip_part = (int64_t)128 * even_up(nb) * 16;
+    int64_t part = (int64_t)max_splits * ldw * nb;
     if (gram_part > part) part = gram_part;
     if (strip_part > part) part = strip_part;
-    const int64_t total = ldv * nb + 2 * (int64_t)nb * nb + 256 + 2 * ldw * nb + part + 64;
+    const int64_t part2 = gram_part > strip_part ? gram_part : strip_part;
+    const int64_t fixed = ldv * nb + 2 * (int64_t)nb * nb + 256 + 64;
+    int64_t total = fixed + 2 * ldw * nb + part;
+    if (w2) total += fixed + 2 * ldw2 * nb + part2;
     int rc = qlb_reserve(h, &h->ws, &h->ws_bytes, (size_t)total * sizeof(double));
     if (rc) return rc;
     double *q = (double *)h->ws;
-    w->Vw = q;  w->ldv = ldv;  q += ldv * nb;
-    w->T = q;   w->ldt = nb;   q += (int64_t)nb * nb;
-    w->G = q;                  q += (int64_t)nb * nb;
-    w->Ts = q;                 q += 256;
-    w->Wsum = q; w->ldw = ldw; q += ldw * nb;
-    w->W2 = q;                 q += ldw * nb;
-    w->part = q; w->part_elems = part;
+    auto carve = [&](Workspace *x, int64_t ldwx, int64_t partx) {
+        x->Vw = q;  x->ldv = ldv;  q += ldv * nb;
+        x->T = q;   x->ldt = nb;   q += (int64_t)nb * nb;
+        x->G = q;                  q += (int64_t)nb * nb;
+        x->Ts = q;                 q += 256 + 64;
+        x->Wsum = q; x->ldw = ldwx; q += ldwx * nb;
+        x->W2 = q;                 q += ldwx * nb;
+        x->part = q; x->part_elems = partx; q += partx;
+    };
+    carve(w, ldw, part);
+    if (w2) carve(w2, ldw2, part2);
     return 0;
 }
 
@@ -93,8 +103,8 @@ static int build_T(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, int p, i
 static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool left, bool tt, const double *V,
                        int64_t ldv, const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other) {
     if (other <= 0 || p <= 0 || ib <= 0) return 0;
-    const bool small = ib <= 16;
-    const int cfg_w = small ? 2 : -1;
+    const bool small = ib <= 16 && other <= 128;      // in-panel strip update: many thin partials, fused reduce*T
+    const int cfg_w = ib <= 16 ? 2 : -1;
     // 1. W partials: M = other, N = ib, K = p
     const int64_t tiles = (int64_t)((other + 127) / 128) * ((ib + 127) / 128);
     int S;
@@ -194,48 +204,93 @@ __global__ void set_int_kernel(int32_t *p, int32_t v) { *p = v; }
 
 using namespace qlb;
 
+// Factor one panel (columns [c0, c1) of A, rows [0, p)) on stream st: strips from the right, each
+// followed by its compact-WY update of the panel columns left of it; then the panel's T.
+// Reflectors (clean copy) -> V (ldv), T -> Tp (ldt = nb).  `scr` provides Ts/G/W/partial scratch.
+static int factor_panel(qlb200_ctx *h, cudaStream_t st, const Workspace &scr, double *A, int64_t lda, int m, int n, int k,
+                        int c0, int c1, double *tau, double *V, int64_t ldv, double *Tp, int ldt, bool need_T) {
+    const int sb = 16, ib = c1 - c0, p = m - n + c1;
+    int rc;
+    int s1 = c1;
+    while (s1 > c0) {
+        const int s0 = (s1 - sb > c0) ? s1 - sb : c0;
+        const int w = s1 - s0, ps = m - n + s1;
+        // a single-strip panel writes its T straight into the panel's T
+        double *Tdst = (ib <= sb) ? Tp : scr.Ts;
+        const int ldtd = (ib <= sb) ? ldt : 16;
+        rc = qlb_strip_factor(h, st, A + (int64_t)s0 * lda, lda, ps, w, tau + (s0 - (n - k)), V + (int64_t)(s0 - c0) * ldv, ldv, p,
+                              Tdst, ldtd);
+        if (rc) return rc;
+        if (s0 > c0) {
+            rc = apply_block(h, st, scr, true, false, V + (int64_t)(s0 - c0) * ldv, ldv, Tdst, ldtd, ps, w, A + (int64_t)c0 * lda,
+                             lda, s0 - c0);
+            if (rc) return rc;
+        }
+        s1 = s0;
+    }
+    if (need_T && ib > sb) {
+        Workspace tmp = scr;
+        tmp.Vw = V; tmp.ldv = ldv; tmp.T = Tp; tmp.ldt = ldt;
+        rc = build_T(h, st, tmp, p, ib, tau + (c0 - (n - k)));
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
     const int m = (int)m64, n = (int)n64;
     const int k = m < n ? m : n;
     if (k == 0) return 0;
     if (m > qlb_strip_max_rows()) return qlb_fail(h, -2, "geqlf: m exceeds the panel kernel's row capacity (16384)%s");
-    const int nb = (int)h->opt_nb, sb = 16;
+    const int nb = (int)h->opt_nb;
     cudaStream_t st = h->stream;
-    Workspace ws;
-    int rc = get_workspace(h, m, n, nb, 8, &ws);
+    const int npanels = (k + nb - 1) / nb;
+    const bool la = h->opt_lookahead && npanels > 1;
+    Workspace ws, ws2;
+    int rc = get_workspace(h, m, n, nb, 8, &ws, la ? &ws2 : nullptr);
     if (rc) return rc;
-    int c1 = n;
-    while (c1 > n - k) {
-        const int c0 = (c1 - nb > n - k) ? c1 - nb : n - k;
-        const int ib = c1 - c0;
-        const int p = m - n + c1;
-        // ---- panel: strips from the right ----
-        int s1 = c1;
-        while (s1 > c0) {
-            const int s0 = (s1 - sb > c0) ? s1 - sb : c0;
-            const int w = s1 - s0, ps = m - n + s1;
-            rc = qlb_strip_factor(h, st, A + (int64_t)s0 * lda, lda, ps, w, tau + (s0 - (n - k)), ws.Vw + (int64_t)(s0 - c0) * ws.ldv,
-                                  ws.ldv, p, ws.Ts, 16);
+    auto panel_c1 = [&](int j) { return n - j * nb; };
+    auto panel_c0 = [&](int j) { int c = n - (j + 1) * nb; return c > n - k ? c : n - k; };
+    if (!la) {
+        for (int j = 0; j < npanels; ++j) {
+            const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
+            rc = factor_panel(h, st, ws, A, lda, m, n, k, c0, c1, tau, ws.Vw, ws.ldv, ws.T, (int)ws.ldt, c0 > 0);
             if (rc) return rc;
-            if (s0 > c0) {
-                rc = apply_block(h, st, ws, true, false, ws.Vw + (int64_t)(s0 - c0) * ws.ldv, ws.ldv, ws.Ts, 16, ps, w,
-                                 A + (int64_t)c0 * lda, lda, s0 - c0);
-                if (rc) return rc;
-            }
-            s1 = s0;
-        }
-        // ---- trailing update of the c0 columns left of the panel ----
-        if (c0 > 0) {
-            if (ib > 16) {
-                rc = build_T(h, st, ws, p, ib, tau + (c0 - (n - k)));
-                if (rc) return rc;
+            if (c0 > 0) {
                 rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, ws.T, ws.ldt, p, ib, A, lda, c0);
-            } else {
-                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, ws.Ts, 16, p, ib, A, lda, c0);
+                if (rc) return rc;
             }
+        }
+        return 0;
+    }
+    // ---- look-ahead: panel j+1 is factored on the (high-priority) side stream while the main stream
+    // applies panel j to the columns left of panel j+1.  Vw/T alternate between the two workspaces; the
+    // main stream's GEMM scratch is ws, the side stream's is ws2.
+    cudaStream_t side = h->side_stream;
+    double *Vb[2] = {ws.Vw, ws2.Vw}, *Tb[2] = {ws.T, ws2.T};
+    rc = factor_panel(h, st, ws2, A, lda, m, n, k, panel_c0(0), panel_c1(0), tau, Vb[0], ws.ldv, Tb[0], nb, panel_c0(0) > 0);
+    if (rc) return rc;
+    for (int j = 0; j < npanels; ++j) {
+        const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
+        double *V = Vb[j & 1], *T = Tb[j & 1];
+        if (j + 1 < npanels) {
+            const int d0 = panel_c0(j + 1);          // next panel = columns [d0, c0)
+            rc = apply_block(h, st, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)d0 * lda, lda, c0 - d0);
+            if (rc) return rc;
+            QLB_CUDA(h, cudaEventRecord(h->ev_a, st));
+            QLB_CUDA(h, cudaStreamWaitEvent(side, h->ev_a, 0));
+            rc = factor_panel(h, side, ws2, A, lda, m, n, k, d0, c0, tau, Vb[(j + 1) & 1], ws.ldv, Tb[(j + 1) & 1], nb, d0 > 0);
+            if (rc) return rc;
+            QLB_CUDA(h, cudaEventRecord(h->ev_b, side));
+            if (d0 > 0) {
+                rc = apply_block(h, st, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, d0);
+                if (rc) return rc;
+            }
+            QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_b, 0));
+        } else if (c0 > 0) {
+            rc = apply_block(h, st, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, c0);
             if (rc) return rc;
         }
-        c1 = c0;
     }
     return 0;
 }

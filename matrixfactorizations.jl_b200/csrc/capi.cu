@@ -32,7 +32,11 @@ int qlb200_create(qlb200_handle *out, int device) {
     }
     h->sm_count = prop.multiProcessorCount;
     QLB_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    QLB_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;      // side stream (look-ahead panel) gets the highest priority
+        QLB_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        QLB_CUDA(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, hi));
+    }
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     QLB_CUDA(h, cudaMalloc(&h->dinfo, 64));
@@ -90,6 +94,9 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "gemm_cfg")) {
         if (value < -1 || value > 3) return qlb_fail(h, -3, "gemm_cfg must be in [-1,3]%s");
         h->opt_gemm_cfg = value;
+    } else if (!strcmp(name, "strip_rpt")) {
+        if (value != 1 && value != 2 && value != 4) return qlb_fail(h, -3, "strip_rpt must be 1, 2 or 4%s");
+        h->opt_strip_rpt = value;
     } else if (!strcmp(name, "trail_splits")) {
         if (value < 0 || value > 8) return qlb_fail(h, -3, "trail_splits must be in [0,8]%s");
         h->opt_trail_splits = value;

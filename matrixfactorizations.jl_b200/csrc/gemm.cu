@@ -92,13 +92,23 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     const int kend = (kbeg + p.kchunk < p.K) ? kbeg + p.kchunk : p.K;
     const int KT = (kend - kbeg + BK - 1) / BK;
 
+    // Accumulators start from (beta/alpha)*D, loaded BEFORE the operand pipeline is primed, so the
+    // latency of reading D overlaps the prologue instead of being exposed in the epilogue (the
+    // rank-nb trailing update has only K = nb: every exposed round trip counts).
+    double *D = p.D + (int64_t)blockIdx.z * p.split_stride;
+    const bool preload = (p.beta != 0.0) && (p.alpha != 0.0);
+    const double pre = preload ? p.beta / p.alpha : 0.0;
     double acc[MT][NT][4];
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.0;
+            for (int r = 0; r < 4; ++r) {
+                const int m = m0 + wm0 + i * 16 + g + (r >> 1) * 8;
+                const int n = n0 + wn0 + j * 8 + 2 * t + (r & 1);
+                acc[i][j][r] = (preload && m < p.M && n < p.N) ? pre * D[m + (int64_t)n * p.ldd] : 0.0;
+            }
 
     auto stage_a = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS; };
     auto stage_b = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS + Cfg::A_ELEMS; };
@@ -155,9 +165,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     }
     cp_async_wait<0>();
 
-    // epilogue: D = alpha*acc + beta*D (beta == 0 never reads D)
-    double *D = p.D + (int64_t)blockIdx.z * p.split_stride;
-    const double alpha = p.alpha, beta = p.beta;
+    // epilogue: D = alpha*acc (the beta*D term is already inside acc)
+    const double alpha = p.alpha;
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
                 if (m < p.M && n < p.N) {
                     double *d = D + m + (int64_t)n * p.ldd;
                     double v = alpha * acc[i][j][r];
-                    if (beta != 0.0) v = fma(beta, *d, v);
+                    if (!preload && p.beta != 0.0) v = fma(p.beta, *d, v);      // alpha == 0
                     *d = v;
                 }
             }
@@ -233,7 +242,11 @@ int qlb_gemm(qlb200_ctx *h, cudaStream_t st, int cfg, bool akc, bool bkc, int M,
              int64_t split_stride) {
     using namespace qlb;
     if (M <= 0 || N <= 0) return 0;
-    if (cfg < 0) cfg = (N <= 16) ? 2 : (h->opt_gemm_cfg >= 0 ? (int)h->opt_gemm_cfg : 0);
+    if (cfg < 0) {
+        if (N <= 16) cfg = 2;
+        else if (h->opt_gemm_cfg >= 0) cfg = (int)h->opt_gemm_cfg;
+        else cfg = (K <= 256 && N > 64) ? 1 : 0;      // short-K updates: 2 CTAs/SM hide the tile prologue
+    }
     int bk = (cfg == 3) ? 32 : 16;
     if (splits < 1) splits = 1;
     int kchunk = K;

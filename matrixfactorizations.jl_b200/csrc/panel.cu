@@ -33,10 +33,26 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void st_cluster_f64(const void *local_smem_ptr, uint32_t cta, double v) {
-    uint32_t ra;
+// Asynchronous 8-byte store into the shared memory of CTA `cta` of the cluster; completion is
+// signalled as 8 transaction bytes on that CTA's mbarrier (st.async + mbarrier::complete_tx).
+__device__ __forceinline__ void st_async_f64(const void *local_smem_ptr, const uint64_t *local_mbar, uint32_t cta, double v) {
+    uint32_t ra, rb;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem_ptr)), "r"(cta));
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_mbar)), "r"(cta));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(ra), "d"(v), "r"(rb)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
 }
 
 struct StripParams {
@@ -56,19 +72,152 @@ struct StripParams {
 constexpr int STRIP_THREADS = 256;
 constexpr int STRIP_MAXC = 16;      // largest cluster
 
+// Shared-memory working set of one strip CTA.
+template <int SB>
+struct StripSmem {
+    static constexpr int NW = STRIP_THREADS / 32;
+    double wpart[2][NW][SB];              // per-warp partial dots (double-buffered by step parity)
+    double rowv_local[2][SB];             // row of the pivot (owner CTA only)
+    double red[2][STRIP_MAXC][SB];        // partial dots of every CTA of the cluster (st.async target)
+    double rowv[2][SB];                   // pivot row, sent by the owner CTA (st.async target)
+    double totw[NW][SB];                  // cluster-wide totals, one private copy per warp
+    uint64_t mbar[2];                     // transaction barriers guarding red[par]/rowv[par]
+    double Gs[SB][SB + 1];                // v_j . v_c for the T recurrence (CTA 0)
+    double Ts[SB][SB + 1];
+    double taus[SB];
+};
+
+// One Householder step.  The register tile is kept ROTATED so that the pivot column always sits in
+// register column SB-1 (static register indices, one loop body for every step: the fully unrolled
+// variant was instruction-cache bound).  At step s (0-based) register column q holds
+//   q <  s : the finished reflector of local column SB-s+q,
+//   q >= s : the still-to-be-updated local column q-s      (q == SB-1: the pivot, local column SB-1-s).
 template <int SB, int RPT>
-__global__ void __launch_bounds__(STRIP_THREADS, 1) strip_kernel(const StripParams p) {
+__device__ __forceinline__ void strip_step(double (&a)[RPT][SB], const int (&rr)[RPT], StripSmem<SB> &sm, const int ps,
+                                           const int rpc, const int tid, const uint32_t cta, const uint32_t nc, const int s) {
     constexpr int NW = STRIP_THREADS / 32;
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ double wpart[NW][SB];                 // per-warp partial dots
-    __shared__ double rowv_local[SB];                // row of the pivot (owner CTA only)
-    __shared__ double red[2][STRIP_MAXC][SB];        // partial dots of every CTA of the cluster (DSMEM target)
-    __shared__ double rowv[2][SB];                   // pivot row, broadcast by the owner CTA (DSMEM target)
-    __shared__ double tot[SB];                       // cluster-wide totals
-    __shared__ double Gs[SB][SB + 1];                // v_j . v_c for the T recurrence (CTA 0)
-    __shared__ double Ts[SB][SB + 1];
-    __shared__ double taus[SB];
+    constexpr int P = SB - 1;                        // register column of the pivot
+    const int par = s & 1;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int C = SB - 1 - s;                        // local column being eliminated
+    const int mu = ps - 1 - s;                       // its pivot row
+    // ---- 1. this thread's part of d_q = sum_{r < mu} x_r a_q[r], and the pivot row -----------------
+    double x[RPT], d[SB];
+#pragma unroll
+    for (int j = 0; j < SB; ++j) d[j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        if (rr[i] == mu) {
+#pragma unroll
+            for (int j = 0; j < SB; ++j) sm.rowv_local[par][j] = a[i][j];
+        }
+        x[i] = (rr[i] < mu) ? a[i][P] : 0.0;
+#pragma unroll
+        for (int j = 0; j < SB; ++j) d[j] = fma(x[i], a[i][j], d[j]);
+    }
+    // ---- 2. warp reduction of SB values (recursive halving, fixed order) ----------------------------
+    {
+        int n = SB;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            if (n > 1) {
+                const bool up = (lane & o) != 0;
+                n >>= 1;
+#pragma unroll
+                for (int q = 0; q < SB / 2; ++q) {
+                    if (q < n) {
+                        const double keep = up ? d[q + n] : d[q];
+                        const double send = up ? d[q] : d[q + n];
+                        d[q] = keep + __shfl_xor_sync(FULL, send, o);
+                    }
+                }
+            } else {
+                d[0] += __shfl_xor_sync(FULL, d[0], o);
+            }
+        }
+    }
+    // index of the value this lane ended up with: every halving round added (up ? n_round : 0)
+    int vidx = 0;
+    {
+        int n = SB;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            if (n > 1) {
+                n >>= 1;
+                if (lane & o) vidx += n;
+            }
+        }
+    }
+    constexpr int LANES_PER_VAL = 32 / SB;           // lanes holding the same total (SB <= 32)
+    if ((lane & (LANES_PER_VAL - 1)) == 0) sm.wpart[par][warp][vidx] = d[0];
+    __syncthreads();
+    // ---- 3. CTA partials -> every CTA of the cluster: st.async into their shared memory, completion
+    //         counted on their transaction barrier (no cluster-wide hardware barrier on the critical path)
+    const int owner = mu / rpc;
+    if (tid < SB * (int)nc) {
+        const int j = tid % SB;
+        const uint32_t dst = tid / SB;
+        double v = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < NW; ++w8) v += sm.wpart[par][w8][j];
+        st_async_f64(&sm.red[par][cta][j], &sm.mbar[par], dst, v);
+        if ((int)cta == owner) st_async_f64(&sm.rowv[par][j], &sm.mbar[par], dst, sm.rowv_local[par][j]);
+    }
+    mbar_wait_cluster(&sm.mbar[par], (uint32_t)((s >> 1) & 1));
+    if (tid == 0) mbar_arrive_expect_tx(&sm.mbar[par], (uint32_t)((nc + 1) * SB * sizeof(double)));   // arm the next use
+    // ---- 4. totals: every warp sums the cluster's partials itself (fixed pairwise order) ---------------
+    double *tot = sm.totw[warp];
+    if (lane < SB) {
+        double v[STRIP_MAXC];
+#pragma unroll
+        for (int k = 0; k < STRIP_MAXC; ++k) v[k] = (k < (int)nc) ? sm.red[par][k][lane] : 0.0;
+#pragma unroll
+        for (int o = STRIP_MAXC / 2; o >= 1; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < o; ++k) v[k] += v[k + o];
+        tot[lane] = v[0];
+    }
+    __syncwarp();
+    const double ssq = tot[P], alpha = sm.rowv[par][P];
+    // ---- 5. ?larfg scalars ----------------------------------------------------------------------------
+    double beta = alpha, tauc = 0.0, scale = 0.0;
+    if (ssq != 0.0) {
+        const double nrm = sqrt(fma(alpha, alpha, ssq));
+        beta = -copysign(nrm, alpha);
+        tauc = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+    }
+    // ---- 6. rank-1 update of the unfinished columns (q >= s); the pivot becomes v (tail) and beta, and
+    //         the tile rotates by one register column ----------------------------------------------------
+    double vi[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) vi[i] = (rr[i] < mu) ? x[i] * scale : ((rr[i] == mu) ? 1.0 : 0.0);
+    double newp[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) newp[i] = (rr[i] < mu) ? vi[i] : ((rr[i] == mu) ? beta : a[i][P]);
+#pragma unroll
+    for (int j = P - 1; j >= 0; --j) {
+        const double coef = (j >= s) ? -tauc * fma(tot[j], scale, sm.rowv[par][j]) : 0.0;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) a[i][j + 1] = fma(coef, vi[i], a[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) a[i][0] = newp[i];
+    if (cta == 0) {
+        // v_f . v_C for every finished column f = SB-s+q (register column q < s); warp 0 only
+        if (tid < s) sm.Gs[SB - s + tid][C] = fma(scale, tot[tid], sm.rowv[par][tid]);
+        if (tid == 0) sm.taus[C] = tauc;
+    }
+    __syncwarp();      // this warp's totals are rewritten in the next step
+}
 
+template <int SB, int RPT>
+__global__ void __launch_bounds__(STRIP_THREADS, 1) strip_kernel(const StripParams p) {
+    __shared__ StripSmem<SB> sm;
+    double(&Gs)[SB][SB + 1] = sm.Gs;
+    double(&Ts)[SB][SB + 1] = sm.Ts;
+    double(&taus)[SB] = sm.taus;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta = cluster_ctarank(), nc = cluster_nctarank();
     const int off = SB - p.w;                        // local columns [off, SB) are active
@@ -90,115 +239,18 @@ __global__ void __launch_bounds__(STRIP_THREADS, 1) strip_kernel(const StripPara
         }
     }
     if (tid < SB) taus[tid] = 0.0;
-    cluster_sync_all();          // every CTA of the cluster is resident before any remote store
-
-    int par = 0;
-    for (int c = SB - 1; c >= off; --c, par ^= 1) {
-        const int mu = p.ps - (SB - c);              // pivot row of local column c
-        // ---- 1. this thread's part of d_j = sum_{r < mu} x_r a_j[r], and the pivot row -------------
-        double x[RPT], d[SB];
-#pragma unroll
-        for (int j = 0; j < SB; ++j) d[j] = 0.0;
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int r = rr[i];
-            double xi = 0.0;
-#pragma unroll
-            for (int j = 0; j < SB; ++j) xi = (j == c) ? a[i][j] : xi;
-            if (r == mu) {
-#pragma unroll
-                for (int j = 0; j < SB; ++j) rowv_local[j] = a[i][j];
-            }
-            x[i] = (r < mu) ? xi : 0.0;
-#pragma unroll
-            for (int j = 0; j < SB; ++j) d[j] = fma(x[i], a[i][j], d[j]);
-        }
-        // ---- 2. warp reduction of SB values (recursive halving, fixed order) ------------------------
-        // after the loop lane L holds the warp total of value index vidx(L)
-        {
-            int n = SB;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                if (n > 1) {
-                    const bool up = (lane & o) != 0;
-                    n >>= 1;
-#pragma unroll
-                    for (int q = 0; q < SB / 2; ++q) {
-                        if (q < n) {
-                            const double keep = up ? d[q + n] : d[q];
-                            const double send = up ? d[q] : d[q + n];
-                            d[q] = keep + __shfl_xor_sync(FULL, send, o);
-                        }
-                    }
-                } else {
-                    d[0] += __shfl_xor_sync(FULL, d[0], o);
-                }
-            }
-        }
-        // index of the value this lane ended up with: every halving round added (up ? n_round : 0)
-        int vidx;
-        {
-            int n = SB, v = 0;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                if (n > 1) {
-                    n >>= 1;
-                    if (lane & o) v += n;
-                }
-            }
-            vidx = v;
-        }
-        constexpr int LANES_PER_VAL = 32 / SB;       // lanes holding the same total (SB <= 32)
-        if ((lane & (LANES_PER_VAL - 1)) == 0) wpart[warp][vidx] = d[0];
-        __syncthreads();
-        // ---- 3. CTA partials -> every CTA of the cluster (distributed shared memory) ----------------
-        const int owner = mu / p.rpc;
-        if (tid < SB * (int)nc) {
-            const int j = tid % SB;
-            const uint32_t dst = tid / SB;
-            double v = 0.0;
-#pragma unroll
-            for (int w8 = 0; w8 < NW; ++w8) v += wpart[w8][j];
-            st_cluster_f64(&red[par][cta][j], dst, v);
-            if ((int)cta == owner) st_cluster_f64(&rowv[par][j], dst, rowv_local[j]);
-        }
-        cluster_sync_all();
-        // ---- 4. totals --------------------------------------------------------------------------------
-        if (tid < SB) {
-            double v = 0.0;
-            for (uint32_t k = 0; k < nc; ++k) v += red[par][k][tid];
-            tot[tid] = v;
-        }
-        __syncthreads();
-        const double ssq = tot[c], alpha = rowv[par][c];
-        // ---- 5. ?larfg scalars -------------------------------------------------------------------------
-        double beta = alpha, tauc = 0.0, scale = 0.0;
-        if (ssq != 0.0) {
-            const double nrm = sqrt(fma(alpha, alpha, ssq));
-            beta = -copysign(nrm, alpha);
-            tauc = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        // ---- 6. rank-1 update of the columns left of c; column c becomes v (tail) and beta ------------
-        double vi[RPT];
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) vi[i] = (rr[i] < mu) ? x[i] * scale : ((rr[i] == mu) ? 1.0 : 0.0);
-#pragma unroll
-        for (int j = 0; j < SB; ++j) {
-            const double coef = (j < c) ? -tauc * fma(tot[j], scale, rowv[par][j]) : 0.0;
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                const double upd = fma(coef, vi[i], a[i][j]);
-                const double colc = (rr[i] < mu) ? vi[i] : ((rr[i] == mu) ? beta : a[i][j]);
-                a[i][j] = (j == c) ? colc : upd;
-            }
-        }
-        if (cta == 0) {
-            if (tid < SB && tid > c) Gs[tid][c] = fma(scale, tot[tid], rowv[par][tid]);      // v_tid . v_c
-            if (tid == 0) taus[c] = tauc;
-        }
-        // tot / wpart / rowv_local are rewritten only after the next __syncthreads / cluster barrier
+    if (tid == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(&sm.mbar[0], (uint32_t)((nc + 1) * SB * sizeof(double)));
+        mbar_arrive_expect_tx(&sm.mbar[1], (uint32_t)((nc + 1) * SB * sizeof(double)));
     }
+    cluster_sync_all();          // every CTA is resident and its barriers are armed before any remote store
+
+#pragma unroll 1
+    for (int s = 0; s < p.w; ++s) strip_step<SB, RPT>(a, rr, sm, p.ps, p.rpc, tid, cta, nc, s);
+    // after w rotations register column q holds local column (q - w) mod SB
 
     // ---- write back the factors and the clean reflectors ----------------------------------------------
 #pragma unroll
@@ -206,11 +258,12 @@ __global__ void __launch_bounds__(STRIP_THREADS, 1) strip_kernel(const StripPara
         const int r = rr[i];
         if (r != NOROW) {
 #pragma unroll
-            for (int j = 0; j < SB; ++j) {
+            for (int q = 0; q < SB; ++q) {
+                const int j = (q - p.w) & (SB - 1);          // local column held by register column q
                 if (j >= off) {
                     const int mu = p.ps - (SB - j);
-                    p.A[r + (int64_t)(j - off) * p.lda] = a[i][j];
-                    p.Vw[r + (int64_t)(j - off) * p.ldv] = (r < mu) ? a[i][j] : ((r == mu) ? 1.0 : 0.0);
+                    p.A[r + (int64_t)(j - off) * p.lda] = a[i][q];
+                    p.Vw[r + (int64_t)(j - off) * p.ldv] = (r < mu) ? a[i][q] : ((r == mu) ? 1.0 : 0.0);
                 }
             }
         }
@@ -251,7 +304,16 @@ __global__ void reduce_mult_t_kernel(const double *__restrict__ part, int S, int
     double s = 0.0;
     if (i < rows && l < w) {
         const double *src = part + i + (int64_t)l * ldp;
-        for (int z = 0; z < S; ++z) s += src[(int64_t)z * stride];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains, fixed order
+        int z = 0;
+        for (; z + 4 <= S; z += 4) {
+            s0 += src[(int64_t)z * stride];
+            s1 += src[(int64_t)(z + 1) * stride];
+            s2 += src[(int64_t)(z + 2) * stride];
+            s3 += src[(int64_t)(z + 3) * stride];
+        }
+        for (; z < S; ++z) s0 += src[(int64_t)z * stride];
+        s = (s0 + s1) + (s2 + s3);
     }
     sums[ri][l] = s;
     __syncthreads();
@@ -264,38 +326,68 @@ __global__ void reduce_mult_t_kernel(const double *__restrict__ part, int S, int
 }
 
 // T (ib x ib, lower triangular, zero above) from G = V'V (ib x ib, only the strict lower part is read)
-// and tau; T(j,j) = tau_j, T(j+1:,j) = -tau_j * T(j+1:,j+1:) * G(j+1:,j), j = ib-1 ... 0.
-// One CTA; the recurrence runs in place in shared memory (pitch ib).
+// and tau; T(j,j) = tau_j, T(j+1:,j) = -tau_j * T(j+1:,j+1:) * G(j+1:,j), j = ib-1 ... 0 (?larft
+// backward/columnwise).  One CTA, in place in shared memory, blocked by 16:
+//   phase 1: the 16x16 diagonal blocks by the column recurrence, one warp per block, all in parallel;
+//   phase 2: block columns right to left, T(below,b) = -(T(below,below) * G(below,b)) * T(b,b).
 __global__ void __launch_bounds__(256, 1) larft_kernel(const double *__restrict__ G, int64_t ldg, const double *__restrict__ tau,
                                                       int ib, double *__restrict__ T, int64_t ldt) {
     extern __shared__ __align__(16) double sm[];
-    double *W = sm;                     // ib x ib, column-major pitch ib
-    double *ts = sm + (size_t)ib * ib;
-    const int tid = threadIdx.x;
+    double *W = sm;                                   // ib x ib, column-major pitch ib
+    double *ts = sm + (size_t)ib * ib;                // tau
+    double *Ys = ts + 128;                            // (<=112) x 17 scratch
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int idx = tid; idx < ib * ib; idx += blockDim.x) {
         const int i = idx % ib, j = idx / ib;
         W[idx] = (i > j) ? G[i + (int64_t)j * ldg] : 0.0;
     }
     if (tid < ib) ts[tid] = tau[tid];
     __syncthreads();
-    // two threads per row: thread (i, h) sums l = j+1+h, j+3+h, ... ; combined through a shuffle
-    const int i = tid >> 1, hh = tid & 1;
-    for (int j = ib - 1; j >= 0; --j) {
-        double s0 = 0.0, s1 = 0.0;
-        if (i < ib && i > j) {
-            int l = j + 1 + hh;
-            for (; l + 2 <= i; l += 4) {
-                s0 = fma(W[l * ib + i], W[j * ib + l], s0);
-                s1 = fma(W[(l + 2) * ib + i], W[j * ib + l + 2], s1);
+    const int nblk = (ib + 15) / 16;
+    // ---- phase 1: diagonal blocks ----
+    for (int b = warp; b < nblk; b += 8) {
+        const int r0 = b * 16, r1 = (r0 + 16 < ib) ? r0 + 16 : ib;
+        const int i = r0 + lane;
+        for (int j = r1 - 1; j >= r0; --j) {
+            double s = 0.0;
+            if (lane < 16 && i < r1 && i > j)
+                for (int l = j + 1; l <= i; ++l) s = fma(W[l * ib + i], W[j * ib + l], s);
+            __syncwarp();
+            if (lane < 16 && i < r1) {
+                if (i > j) W[j * ib + i] = -ts[j] * s;
+                else if (i == j) W[j * ib + i] = ts[j];
             }
-            if (l <= i) s0 = fma(W[l * ib + i], W[j * ib + l], s0);
+            __syncwarp();
         }
-        double s = s0 + s1;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
+    }
+    __syncthreads();
+    // ---- phase 2: off-diagonal blocks, block column b from the right ----
+    const int ri = tid >> 1, cg = (tid & 1) * 8;      // thread = (row below, group of 8 columns)
+    for (int b = nblk - 2; b >= 0; --b) {
+        const int c0 = b * 16, R0 = c0 + 16, R = ib - R0;
+        double y[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[q] = 0.0;
+        if (ri < R) {
+            const int i = R0 + ri;
+            for (int l = R0; l <= i; ++l) {          // T(i,l) * G(l, c0+cg+q)
+                const double t = W[l * ib + i];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) y[q] = fma(t, W[(c0 + cg + q) * ib + l], y[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) Ys[ri * 17 + cg + q] = y[q];
+        }
         __syncthreads();
-        if (hh == 0 && i < ib) {
-            if (i > j) W[j * ib + i] = -ts[j] * s;
-            else if (i == j) W[j * ib + i] = ts[j];
+        if (ri < R) {
+            const int i = R0 + ri;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = cg + q;               // Z(i,col) = -sum_{c >= col} Y(i,c) T_bb(c,col)
+                double z = 0.0;
+                for (int c = col; c < 16; ++c) z = fma(Ys[ri * 17 + c], W[(c0 + col) * ib + c0 + c], z);
+                W[(c0 + col) * ib + i] = -z;
+            }
         }
         __syncthreads();
     }
@@ -348,9 +440,11 @@ int qlb_strip_factor(qlb200_ctx *h, cudaStream_t st, double *A, int64_t lda, int
     using namespace qlb;
     if (w < 1 || w > 16) return qlb_fail(h, -2, "strip width must be in [1,16]%s");
     if (ps > qlb_strip_max_rows()) return qlb_fail(h, -2, "strip taller than the cluster kernel supports%s");
-    // rows per thread, then CTAs per cluster (power of two <= 16)
-    int rpt = (ps + STRIP_THREADS - 1) / STRIP_THREADS;
+    // rows per thread (smallest of 1/2/4 that fits 16 CTAs, or the "strip_rpt" option), then CTAs per
+    // cluster (power of two <= 16)
+    int rpt = (ps + STRIP_THREADS * STRIP_MAXC - 1) / (STRIP_THREADS * STRIP_MAXC);
     rpt = rpt <= 1 ? 1 : (rpt <= 2 ? 2 : 4);
+    if (h->opt_strip_rpt > rpt) rpt = (int)h->opt_strip_rpt;
     int nc = (ps + STRIP_THREADS * rpt - 1) / (STRIP_THREADS * rpt);
     int ncp = 1;
     while (ncp < nc) ncp <<= 1;
@@ -380,9 +474,10 @@ int qlb_larft(qlb200_ctx *h, cudaStream_t st, const double *G, int64_t ldg, cons
               int64_t ldt) {
     if (ib <= 0) return 0;
     if (ib > 128) return qlb_fail(h, -2, "larft: block wider than 128%s");
-    const size_t smem = ((size_t)ib * ib + ib) * sizeof(double);
+    const size_t smem = ((size_t)ib * ib + 128 + 112 * 17) * sizeof(double);
     if (!h->larft_attr_done) {
-        QLB_CUDA(h, cudaFuncSetAttribute(qlb::larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 128 + 128) * 8));
+        QLB_CUDA(h, cudaFuncSetAttribute(qlb::larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (128 * 128 + 128 + 112 * 17) * 8));
         h->larft_attr_done = true;
     }
     qlb::larft_kernel<<<1, 256, smem, st>>>(G, ldg, tau, ib, T, ldt);

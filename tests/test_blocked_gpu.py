@@ -64,10 +64,15 @@ SHAPES = [(10, 10), (10, 12), (12, 10), (3, 5), (1, 1), (5, 1), (1, 5), (16, 16)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_geqlf_matches_lapack(q, h, shape):
+@pytest.mark.parametrize("lookahead", [0, 1])
+def test_geqlf_matches_lapack(q, h, shape, lookahead):
     """test/test_ql.jl:5-33 at the LAPACK boundary: same packed factors and tau."""
     A = np.asfortranarray(np.random.default_rng(shape[0] * 31 + shape[1]).standard_normal(shape) / 2)
-    F = q.ql(A, handle=h)
+    h.set_option("lookahead", lookahead)
+    try:
+        F = q.ql(A, handle=h)
+    finally:
+        h.set_option("lookahead", 0)
     Fo, tauo = lapack.geqlf(A)
     t = _tol(shape, A)
     assert np.isfinite(F.factors).all()
@@ -76,13 +81,18 @@ def test_geqlf_matches_lapack(q, h, shape):
 
 
 @pytest.mark.parametrize("nb", [16, 32, 64, 96, 128])
-def test_geqlf_panel_widths(q, h, nb):
+@pytest.mark.parametrize("lookahead,rpt", [(0, 4), (1, 4), (1, 1), (0, 2)])
+def test_geqlf_panel_widths(q, h, nb, lookahead, rpt):
     A = np.asfortranarray(np.random.default_rng(nb).standard_normal((700, 450)))
     h.set_option("nb", nb)
+    h.set_option("lookahead", lookahead)
+    h.set_option("strip_rpt", rpt)
     try:
         F = q.ql(A, handle=h)
     finally:
         h.set_option("nb", 128)
+        h.set_option("lookahead", 0)
+        h.set_option("strip_rpt", 4)
     Fo, tauo = lapack.geqlf(A)
     assert np.abs(F.factors - Fo).max() <= _tol(A.shape, A) and np.abs(F.tau - tauo).max() <= _tol(A.shape, A)
 

@@ -1,0 +1,40 @@
+"""Small fixed workloads for ncu (run under gpurun).  usage: prof_case.py <case> [n]
+ cases: geqlf (one blocked ql! of n x n), gemms (one C'V and one rank-128 update at n), batched (32x32 f64)"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+case = sys.argv[1]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+q = load_package()
+h = q.Handle(0)
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)
+h.set_stream(st.cuda_stream)
+for kv in sys.argv[3:]:
+    k, v = kv.split("=")
+    h.set_option(k, int(v))
+cm = lambda r, c: torch.randn((c, r), dtype=torch.float64, device="cuda").T
+if case == "geqlf":
+    A = cm(n, n)
+    tau = torch.empty(n, dtype=torch.float64, device="cuda")
+    h.call("qlb200_dgeqlf_dev", n, n, A.data_ptr(), A.stride(1), tau.data_ptr())
+elif case == "gemms":
+    C, V, W = cm(n, n), cm(n, 128), cm(n, 128)
+    h.call("qlb200_dgemm_dev", b"T", b"N", n, 128, n, 1.0, C.data_ptr(), C.stride(1), V.data_ptr(), V.stride(1), 0.0,
+           W.data_ptr(), W.stride(1))
+    h.call("qlb200_dgemm_dev", b"N", b"T", n, n, 128, -1.0, V.data_ptr(), V.stride(1), W.data_ptr(), W.stride(1), 1.0,
+           C.data_ptr(), C.stride(1))
+elif case == "batched":
+    A = torch.randn(n, 32, 32, dtype=torch.float64, device="cuda")
+    tau = torch.empty(n, 32, dtype=torch.float64, device="cuda")
+    B = torch.randn(n, 8, 32, dtype=torch.float64, device="cuda")
+    q.ql_batched_(A, tau, handle=h)
+    q.lmul_batched_(A, tau, B, adjoint=True, handle=h)
+torch.cuda.synchronize()
+print("done", case, n, "launches", h.launches)
