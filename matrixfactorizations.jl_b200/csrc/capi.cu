@@ -39,7 +39,8 @@ int qlb200_create(qlb200_handle *out, int device) {
     }
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
-    QLB_CUDA(h, cudaMalloc(&h->dinfo, 64));
+    QLB_CUDA(h, cudaMalloc(&h->dinfo, 64 + 256 * sizeof(unsigned)));      // status word + per-SM tickets
+    QLB_CUDA(h, cudaMemset(h->dinfo, 0, 64 + 256 * sizeof(unsigned)));
     h->stream = h->own_stream;
     *out = h;
     return 0;
@@ -94,6 +95,10 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "gemm_cfg")) {
         if (value < -1 || value > 3) return qlb_fail(h, -3, "gemm_cfg must be in [-1,3]%s");
         h->opt_gemm_cfg = value;
+    } else if (!strcmp(name, "stagger")) {
+        h->opt_stagger = value;
+    } else if (!strcmp(name, "rankk")) {
+        h->opt_rankk = value ? 1 : 0;
     } else if (!strcmp(name, "strip_rpt")) {
         if (value != 1 && value != 2 && value != 4) return qlb_fail(h, -3, "strip_rpt must be 1, 2 or 4%s");
         h->opt_strip_rpt = value;

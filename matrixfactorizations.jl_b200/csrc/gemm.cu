@@ -46,38 +46,76 @@ struct GemmCfg {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
 };
 
-// Stage one operand tile.  KC: tile is [ROWS][BK] (K contiguous), else [BK][ROWS] (row index contiguous).
-// VEC = 2: 16-byte cp.async (needs 16-byte aligned base and even ld), VEC = 1: 8-byte.
+// Stages one operand tile per k-step.  KC: tile is [ROWS][BK] (K contiguous), else [BK][ROWS] (row index
+// contiguous).  VEC = 2: 16-byte cp.async (16-byte aligned base, even ld), VEC = 1: 8-byte.
+// Every thread owns N fixed chunks of the tile; their shared-memory offsets and global pointers are
+// computed once per tile and the pointers just advance by one k-step, so the steady-state cost is one
+// cp.async + one 64-bit add per chunk (the predicated path is taken only by edge tiles / the K tail).
 template <int ROWS, int BK, bool KC, int VEC, int THREADS>
-__device__ __forceinline__ void load_tile(double *s, const double *__restrict__ g, int64_t ld, int row0, int k0,
-                                          int rows_total, int k_end, int tid) {
-    constexpr int PITCH = KC ? (BK + 4) : (ROWS + 4);
-    constexpr int INNER = KC ? BK : ROWS;                // contiguous extent of the tile
-    constexpr int OUTER = KC ? ROWS : BK;
-    constexpr int CHUNKS = INNER / VEC * OUTER;
-    static_assert(CHUNKS % THREADS == 0 || CHUNKS < THREADS, "tile/threads mismatch");
+struct TileLoader {
+    static constexpr int PITCH = KC ? (BK + 4) : (ROWS + 4);
+    static constexpr int INNER = KC ? BK : ROWS;         // contiguous extent of the tile
+    static constexpr int OUTER = KC ? ROWS : BK;
+    static constexpr int CPR = INNER / VEC;              // chunks per outer index
+    static constexpr int CHUNKS = CPR * OUTER;
+    static constexpr int N = (CHUNKS + THREADS - 1) / THREADS;
+    static constexpr bool EXACT = (CHUNKS % THREADS) == 0;
+    const double *gp[N];
+    int so[N];
+    int64_t kstep;
+    int row0, k0;                                        // tile origin of the NEXT load
+    bool rows_full;
+
+    __device__ __forceinline__ void init(const double *g, int64_t ld, int row0_, int k0_, int rows_total, int tid) {
+        row0 = row0_;
+        k0 = k0_;
+        rows_full = row0_ + ROWS <= rows_total;
+        kstep = KC ? (int64_t)BK : (int64_t)BK * ld;
 #pragma unroll
-    for (int it = 0; it < (CHUNKS + THREADS - 1) / THREADS; ++it) {
-        const int idx = tid + it * THREADS;
-        if (CHUNKS % THREADS != 0 && idx >= CHUNKS) break;
-        const int o = idx / (INNER / VEC), i = (idx % (INNER / VEC)) * VEC;
-        const int r = KC ? (row0 + o) : (row0 + i);      // operand row (m or n) index
-        const int k = KC ? (k0 + i) : (k0 + o);
-        const int inner_left = KC ? (k_end - k) : (rows_total - r);      // valid elements along the chunk
-        const bool outer_ok = KC ? (r < rows_total) : (k < k_end);
-        int valid = outer_ok ? inner_left : 0;
-        valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
-        const double *src = valid > 0 ? (KC ? g + (int64_t)r * ld + k : g + (int64_t)k * ld + r) : g;
-        double *dst = s + o * PITCH + i;
-        if constexpr (VEC == 2) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid * 8)
-                         : "memory");
-        } else {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid * 8)
-                         : "memory");
+        for (int q = 0; q < N; ++q) {
+            const int idx = tid + q * THREADS;
+            const int o = idx / CPR, i = (idx % CPR) * VEC;
+            so[q] = o * PITCH + i;
+            gp[q] = KC ? g + (int64_t)(row0_ + o) * ld + (k0_ + i) : g + (int64_t)(k0_ + o) * ld + (row0_ + i);
         }
     }
-}
+    __device__ __forceinline__ void load(double *s, const double *g, int64_t ld, int rows_total, int k_end, int tid) {
+        if (rows_full && k0 + BK <= k_end) {
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                if (EXACT || tid + q * THREADS < CHUNKS) {
+                    if constexpr (VEC == 2)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s + so[q])), "l"(gp[q]) : "memory");
+                    else
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(s + so[q])), "l"(gp[q]) : "memory");
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                const int idx = tid + q * THREADS;
+                if (!EXACT && idx >= CHUNKS) break;
+                const int o = idx / CPR, i = (idx % CPR) * VEC;
+                const int r = KC ? (row0 + o) : (row0 + i);      // operand row (m or n) index
+                const int k = KC ? (k0 + i) : (k0 + o);
+                const int inner_left = KC ? (k_end - k) : (rows_total - r);
+                const bool outer_ok = KC ? (r < rows_total) : (k < k_end);
+                int valid = outer_ok ? inner_left : 0;
+                valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
+                const double *src = valid > 0 ? gp[q] : g;
+                if constexpr (VEC == 2)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(s + so[q])), "l"(src), "r"(valid * 8)
+                                 : "memory");
+                else
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(s + so[q])), "l"(src), "r"(valid * 8)
+                                 : "memory");
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) gp[q] += kstep;
+        k0 += BK;
+    }
+};
 
 template <class Cfg, bool AKC, bool BKC, int VEC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const GemmParams p) {
@@ -112,11 +150,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
 
     auto stage_a = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS; };
     auto stage_b = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS + Cfg::A_ELEMS; };
+    TileLoader<BM, BK, AKC, VEC, Cfg::THREADS> la;
+    TileLoader<BN, BK, BKC, VEC, Cfg::THREADS> lb;
+    la.init(p.A, p.lda, m0, kbeg, p.M, tid);
+    lb.init(p.B, p.ldb, n0, kbeg, p.N, tid);
     auto issue = [&](int kt) {
         if (kt < KT) {
-            const int s = kt % STAGES, k0 = kbeg + kt * BK;
-            load_tile<BM, BK, AKC, VEC, Cfg::THREADS>(stage_a(s), p.A, p.lda, m0, k0, p.M, kend, tid);
-            load_tile<BN, BK, BKC, VEC, Cfg::THREADS>(stage_b(s), p.B, p.ldb, n0, k0, p.N, kend, tid);
+            const int s = kt % STAGES;
+            la.load(stage_a(s), p.A, p.lda, p.M, kend, tid);
+            lb.load(stage_b(s), p.B, p.ldb, p.N, kend, tid);
         }
         cp_async_commit();
     };
@@ -182,6 +224,139 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
                     *d = v;
                 }
             }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent rank-K update  D = alpha * A * B' + beta * D  for SHORT K (the trailing update of the
+// blocked QL: K = nb).  A is M x K (M-contiguous), B is N x K (N-contiguous).  With only K/16 k-steps
+// per tile the pipeline fill and the read of D dominate a tile-per-CTA kernel, so here two CTAs per SM
+// each walk a list of tiles and (1) the cp.async operand ring runs continuously across tile
+// boundaries, (2) the D tile of the NEXT tile is pulled into L2 (prefetch.global.L2) while the current
+// tile is multiplied, so the accumulator preload at the next tile start is an L2 hit.
+// ---------------------------------------------------------------------------------------------
+struct RankKCfg {
+    static constexpr int BM = 128, BN = 64, BK = 16, WM = 32, WN = 32, STAGES = 3, THREADS = 256;
+    static constexpr int WARPS_M = BM / WM, MT = WM / 16, NT = WN / 8;
+    static constexpr int PA = BM + 4, PB = BN + 4;          // pitches (doubles)
+    static constexpr int A_ELEMS = BK * PA, B_ELEMS = BK * PB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+};
+
+__global__ void __launch_bounds__(RankKCfg::THREADS, 2) rankk_persistent_kernel(const GemmParams p, const int tiles_m,
+                                                                               const int ntiles) {
+    using Cfg = RankKCfg;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
+    constexpr int PA = Cfg::PA, PB = Cfg::PB;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM, wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
+    const int KT = (p.K + BK - 1) / BK;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_steps = my_tiles * KT;
+    const double pre = p.beta / p.alpha;
+
+    auto tile_origin = [&](int i, int &m0, int &n0) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        m0 = (tile % tiles_m) * BM;
+        n0 = (tile / tiles_m) * BN;
+    };
+    TileLoader<BM, BK, false, 2, Cfg::THREADS> la;
+    TileLoader<BN, BK, false, 2, Cfg::THREADS> lb;
+    int iss_tile = 0, iss_kt = 0;          // issue-side position: runs STAGES-1 k-steps ahead, across tiles
+    auto issue = [&](int step) {
+        if (step < total_steps) {
+            if (iss_kt == 0) {
+                int m0, n0;
+                tile_origin(iss_tile, m0, n0);
+                la.init(p.A, p.lda, m0, 0, p.M, tid);
+                lb.init(p.B, p.ldb, n0, 0, p.N, tid);
+            }
+            const int s = step % STAGES;
+            double *As = smem + (size_t)s * Cfg::STAGE_ELEMS, *Bs = As + Cfg::A_ELEMS;
+            la.load(As, p.A, p.lda, p.M, p.K, tid);
+            lb.load(Bs, p.B, p.ldb, p.N, p.K, tid);
+            if (++iss_kt == KT) {
+                iss_kt = 0;
+                ++iss_tile;
+            }
+        }
+        cp_async_commit();
+    };
+    // pull the D tile of tile i into L2: 64 columns x 1 KiB = 512 lines of 128 bytes, two per thread
+    auto prefetch_d = [&](int i) {
+        if (i < my_tiles) {
+            int m0, n0;
+            tile_origin(i, m0, n0);
+#pragma unroll
+            for (int q = 0; q < (BN * BM / 16) / Cfg::THREADS; ++q) {
+                const int line = tid + q * Cfg::THREADS;
+                const int c = line / (BM / 16), r = (line % (BM / 16)) * 16;
+                if (m0 + r < p.M && n0 + c < p.N) {
+                    const double *ptr = p.D + m0 + r + (int64_t)(n0 + c) * p.ldd;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                }
+            }
+        }
+    };
+    prefetch_d(0);
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    int step = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+        int m0, n0;
+        tile_origin(i, m0, n0);
+        prefetch_d(i + 1);
+        double acc[MT][NT][4];
+#pragma unroll
+        for (int a = 0; a < MT; ++a)
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int m = m0 + wm0 + a * 16 + g + (r >> 1) * 8, n = n0 + wn0 + b * 8 + 2 * t + (r & 1);
+                    acc[a][b][r] = (m < p.M && n < p.N) ? pre * p.D[m + (int64_t)n * p.ldd] : 0.0;
+                }
+        for (int kt = 0; kt < KT; ++kt, ++step) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            issue(step + STAGES - 1);
+            const double *As = smem + (size_t)(step % STAGES) * Cfg::STAGE_ELEMS, *Bs = As + Cfg::A_ELEMS;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                double a[MT][4], b[NT][2];
+#pragma unroll
+                for (int x = 0; x < MT; ++x) {
+                    const int m = wm0 + x * 16 + g, k = ks * 8 + t;
+                    a[x][0] = As[k * PA + m];
+                    a[x][1] = As[k * PA + m + 8];
+                    a[x][2] = As[(k + 4) * PA + m];
+                    a[x][3] = As[(k + 4) * PA + m + 8];
+                }
+#pragma unroll
+                for (int y = 0; y < NT; ++y) {
+                    const int n = wn0 + y * 8 + g, k = ks * 8 + t;
+                    b[y][0] = Bs[k * PB + n];
+                    b[y][1] = Bs[(k + 4) * PB + n];
+                }
+#pragma unroll
+                for (int x = 0; x < MT; ++x)
+#pragma unroll
+                    for (int y = 0; y < NT; ++y) dmma1688(acc[x][y], a[x], b[y]);
+            }
+        }
+        // epilogue: plain stores (D's beta term is already in the accumulators)
+#pragma unroll
+        for (int a = 0; a < MT; ++a)
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int m = m0 + wm0 + a * 16 + g + (r >> 1) * 8, n = n0 + wn0 + b * 8 + 2 * t + (r & 1);
+                    if (m < p.M && n < p.N) p.D[m + (int64_t)n * p.ldd] = p.alpha * acc[a][b][r];
+                }
+    }
+    cp_async_wait<0>();
 }
 
 // out(M x N, ldo) = sum_{s < S} part[s*stride + m + n*ldp]   (fixed summation order)
@@ -258,6 +433,21 @@ int qlb_gemm(qlb200_ctx *h, cudaStream_t st, int cfg, bool akc, bool bkc, int M,
     }
     GemmParams p{M, N, K, A, lda, B, ldb, D, ldd, alpha, beta, kchunk, split_stride};
     const bool vec2 = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
+    // short-K rank update with enough tiles to keep every SM busy: persistent pipelined kernel
+    if (!akc && !bkc && splits == 1 && K <= 512 && alpha != 0.0 && beta != 0.0 && vec2 && h->opt_rankk && h->opt_gemm_cfg < 0) {
+        const int tiles_m = (M + RankKCfg::BM - 1) / RankKCfg::BM, tiles_n = (N + RankKCfg::BN - 1) / RankKCfg::BN;
+        const int64_t ntiles = (int64_t)tiles_m * tiles_n;
+        if (ntiles >= 4 * (int64_t)h->sm_count && ntiles < (1 << 30)) {
+            if (!h->gemm_attr_done[63]) {
+                QLB_CUDA(h, cudaFuncSetAttribute(rankk_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)RankKCfg::SMEM));
+                h->gemm_attr_done[63] = true;
+            }
+            rankk_persistent_kernel<<<2 * h->sm_count, RankKCfg::THREADS, RankKCfg::SMEM, st>>>(p, tiles_m, (int)ntiles);
+            QLB_LAUNCH_CHECK(h);
+            return 0;
+        }
+    }
     switch (cfg) {
         case 0: return launch_layout<CfgBig>(h, 0, akc, bkc, vec2, p, splits, st);
         case 1: return launch_layout<CfgMid>(h, 1, akc, bkc, vec2, p, splits, st);

@@ -293,34 +293,40 @@ __global__ void __launch_bounds__(STRIP_THREADS, 1) strip_kernel(const StripPara
 }
 
 // W2 (rows x w, ldw) = (sum_{s<S} part[s*stride + i + l*ldp]) * T (w x w, lower, ldt), w <= 16.
-// blockDim = (16, 16): threadIdx.x = local row (coalesced loads), threadIdx.y = column l.
-__global__ void reduce_mult_t_kernel(const double *__restrict__ part, int S, int64_t stride, int rows, int w, int64_t ldp,
-                                     const double *__restrict__ T, int ldt, double *__restrict__ W2, int64_t ldw) {
-    __shared__ double sums[16][17];
+// blockDim = (16, 16, 4): x = local row (coalesced loads), y = column l, z = slice of the S partials
+// (each slice sums a fixed quarter in a fixed order, the quarters are added pairwise).
+__global__ void __launch_bounds__(1024) reduce_mult_t_kernel(const double *__restrict__ part, int S, int64_t stride, int rows, int w,
+                                                            int64_t ldp, const double *__restrict__ T, int ldt,
+                                                            double *__restrict__ W2, int64_t ldw) {
+    __shared__ double slice[4][16][17];
     __shared__ double Tsm[16][17];
-    const int ri = threadIdx.x, l = threadIdx.y;
+    const int ri = threadIdx.x, l = threadIdx.y, zs = threadIdx.z;
     const int i = blockIdx.x * 16 + ri;
-    Tsm[ri][l] = (ri < w && l < w && ri >= l) ? T[ri + l * ldt] : 0.0;      // Tsm[row][col]
+    if (zs == 0) Tsm[ri][l] = (ri < w && l < w && ri >= l) ? T[ri + l * ldt] : 0.0;      // Tsm[row][col]
     double s = 0.0;
     if (i < rows && l < w) {
+        const int per = (S + 3) / 4;
+        const int z0 = zs * per, z1 = (z0 + per < S) ? z0 + per : S;
         const double *src = part + i + (int64_t)l * ldp;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains, fixed order
-        int z = 0;
-        for (; z + 4 <= S; z += 4) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int z = z0;
+        for (; z + 4 <= z1; z += 4) {
             s0 += src[(int64_t)z * stride];
             s1 += src[(int64_t)(z + 1) * stride];
             s2 += src[(int64_t)(z + 2) * stride];
             s3 += src[(int64_t)(z + 3) * stride];
         }
-        for (; z < S; ++z) s0 += src[(int64_t)z * stride];
+        for (; z < z1; ++z) s0 += src[(int64_t)z * stride];
         s = (s0 + s1) + (s2 + s3);
     }
-    sums[ri][l] = s;
+    slice[zs][ri][l] = s;
     __syncthreads();
-    if (i < rows && l < w) {
+    if (zs == 0) slice[0][ri][l] = (slice[0][ri][l] + slice[1][ri][l]) + (slice[2][ri][l] + slice[3][ri][l]);
+    __syncthreads();
+    if (zs == 0 && i < rows && l < w) {
         double o = 0.0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) o = fma(sums[ri][q], Tsm[q][l], o);
+        for (int q = 0; q < 16; ++q) o = fma(slice[0][ri][q], Tsm[q][l], o);
         W2[i + (int64_t)l * ldw] = o;
     }
 }
@@ -464,7 +470,7 @@ int qlb_strip_factor(qlb200_ctx *h, cudaStream_t st, double *A, int64_t lda, int
 int qlb_reduce_mult_t(qlb200_ctx *h, cudaStream_t st, const double *part, int S, int64_t stride, int rows, int w,
                       int64_t ldp, const double *T, int ldt, double *W2, int64_t ldw) {
     if (rows <= 0 || w <= 0) return 0;
-    dim3 block(16, 16);
+    dim3 block(16, 16, 4);
     qlb::reduce_mult_t_kernel<<<(rows + 15) / 16, block, 0, st>>>(part, S, stride, rows, w, ldp, T, ldt, W2, ldw);
     QLB_LAUNCH_CHECK(h);
     return 0;

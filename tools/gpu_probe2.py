@@ -63,7 +63,7 @@ def main():
         A0 = cm(n, n)
         A = torch.empty_like(A0.T).T
         tau = torch.empty(n, dtype=torch.float64, device="cuda")
-        for (nbv, la, rpt) in ((128, 0, 4), (128, 0, 2), (128, 0, 1), (64, 0, 4), (96, 0, 4)):
+        for (nbv, la, rpt) in ((128, 0, 4), (128, 0, 1), (96, 0, 4)):
             h.set_option("nb", nbv)
             h.set_option("lookahead", la)
             h.set_option("strip_rpt", rpt)
