@@ -106,7 +106,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     const bool small = ib <= 16 && other <= 128;      // in-panel strip update: many thin partials, fused reduce*T
     const int cfg_w = ib <= 16 ? 2 : -1;
     // 1. W partials: M = other, N = ib, K = p
-    const int64_t tiles = (int64_t)((other + 127) / 128) * ((ib + 127) / 128);
+    const int64_t tiles = (int64_t)((other + 127) / 128) * ((ib + 63) / 64);      // 128x64 tiles, 2 CTAs per SM
     int S;
     if (small) {
         S = (p + 127) / 128;
@@ -114,7 +114,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     } else if (h->opt_trail_splits > 0) {
         S = (int)h->opt_trail_splits;
     } else {
-        S = choose_splits(h->sm_count, tiles, p, 512, 8);
+        S = choose_splits(2 * h->sm_count, tiles, p, 512, 8);
     }
     S = qlb_gemm_splits(p, S, 16);
     const bool to_part = (S > 1 || small);

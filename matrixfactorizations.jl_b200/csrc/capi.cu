@@ -95,10 +95,6 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "gemm_cfg")) {
         if (value < -1 || value > 3) return qlb_fail(h, -3, "gemm_cfg must be in [-1,3]%s");
         h->opt_gemm_cfg = value;
-    } else if (!strcmp(name, "stagger")) {
-        h->opt_stagger = value;
-    } else if (!strcmp(name, "rankk")) {
-        h->opt_rankk = value ? 1 : 0;
     } else if (!strcmp(name, "strip_rpt")) {
         if (value != 1 && value != 2 && value != 4) return qlb_fail(h, -3, "strip_rpt must be 1, 2 or 4%s");
         h->opt_strip_rpt = value;

@@ -10,8 +10,8 @@
 //   AKC: A(m,k) at A[k + m*lda] ("K-contiguous", BLAS transa='T')   else A[m + k*lda] (transa='N')
 //   BKC: B(k,n) at B[k + n*ldb] ("K-contiguous", BLAS transb='N')   else B[n + k*ldb] (transb='T')
 // Tiles are staged global -> shared with 16-byte cp.async (LDGSTS) through a STAGES-deep ring; the
-// pitch of every shared tile is == 4 (mod 16) doubles so the 8-byte fragment loads of a half-warp
-// hit 16 distinct bank pairs.  There is no FP64 tcgen05/wgmma kind on sm_100a: warp-level DMMA fed
+// fragments are read with 16-byte LDS; tile pitches (== 4 mod 8 doubles for K-contiguous tiles, == 2
+// mod 8 for M/N-contiguous ones) make the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups.  There is no FP64 tcgen05/wgmma kind on sm_100a: warp-level DMMA fed
 // from registers is the FP64 tensor path of this architecture.
 // Split-K (gridDim.z > 1) writes partial products to `D + z*split_stride`; partials are summed in
 // a fixed order by reduce_partials_kernel, so results are bitwise reproducible.
@@ -38,8 +38,8 @@ struct GemmCfg {
     static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
     static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN, WARPS = WARPS_M * WARPS_N, THREADS = WARPS * 32;
     static constexpr int MT = WM / 16, NT = WN / 8;
-    static constexpr int PK = BK + 4;                     // pitch of a K-contiguous tile row
-    static constexpr int PA_MC = BM + 4, PB_NC = BN + 4;  // pitch of an M/N-contiguous tile row
+    static constexpr int PK = BK + 4;                     // pitch of a K-contiguous tile row (== 4 mod 8)
+    static constexpr int PA_MC = BM + 2, PB_NC = BN + 2;  // pitch of an M/N-contiguous tile row (== 2 mod 8)
     static constexpr int A_ELEMS = (BM * PK > BK * PA_MC) ? BM * PK : BK * PA_MC;
     static constexpr int B_ELEMS = (BN * PK > BK * PB_NC) ? BN * PK : BK * PB_NC;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
@@ -53,7 +53,7 @@ struct GemmCfg {
 // cp.async + one 64-bit add per chunk (the predicated path is taken only by edge tiles / the K tail).
 template <int ROWS, int BK, bool KC, int VEC, int THREADS>
 struct TileLoader {
-    static constexpr int PITCH = KC ? (BK + 4) : (ROWS + 4);
+    static constexpr int PITCH = KC ? (BK + 4) : (ROWS + 2);
     static constexpr int INNER = KC ? BK : ROWS;         // contiguous extent of the tile
     static constexpr int OUTER = KC ? ROWS : BK;
     static constexpr int CPR = INNER / VEC;              // chunks per outer index
@@ -117,6 +117,108 @@ struct TileLoader {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Fragment addressing.  The m16n8k8 DMMA fixes which (row, k) / (k, col) slot each lane feeds, but
+// which MATRIX row / column / k index sits in a slot is free as long as A, B and the accumulators
+// agree.  The maps below put the two values a lane needs next to each other in shared memory, so
+// every fragment load is one 16-byte LDS and the accumulator pairs (c0,c2) / (c1,c3) are 16 contiguous
+// bytes of a column of D:
+//   MMA row g   -> tile row 2g,   MMA row g+8 -> tile row 2g+1         (within a 16-row m-tile)
+//   MMA k   t   -> k 2t,          MMA k t+4   -> k 2t+1                (within a k8 group)
+//   MMA col g of n-tile j -> tile column (j/2)*16 + 2g + (j&1)         (n-tiles paired)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lds128(const double *p, double &x, double &y) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(smem_u32(p)));
+}
+
+// a[i][0..3] for m-tiles i < MT of the warp tile at row wm0; As = stage tile, ks = k8 group
+template <int MT, bool KC, int PITCH>
+__device__ __forceinline__ void load_a_frags(double (&a)[MT][4], const double *As, int wm0, int ks, int g, int t) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int m = wm0 + i * 16 + 2 * g, k = ks * 8 + 2 * t;
+        if constexpr (KC) {
+            lds128(As + m * PITCH + k, a[i][0], a[i][2]);
+            lds128(As + (m + 1) * PITCH + k, a[i][1], a[i][3]);
+        } else {
+            lds128(As + k * PITCH + m, a[i][0], a[i][1]);
+            lds128(As + (k + 1) * PITCH + m, a[i][2], a[i][3]);
+        }
+    }
+}
+template <int NT, bool KC, int PITCH>
+__device__ __forceinline__ void load_b_frags(double (&b)[NT][2], const double *Bs, int wn0, int ks, int g, int t) {
+    static_assert(NT % 2 == 0, "n-tiles are paired");
+#pragma unroll
+    for (int jp = 0; jp < NT / 2; ++jp) {
+        const int n = wn0 + jp * 16 + 2 * g, k = ks * 8 + 2 * t;
+        if constexpr (KC) {
+            lds128(Bs + n * PITCH + k, b[2 * jp][0], b[2 * jp][1]);
+            lds128(Bs + (n + 1) * PITCH + k, b[2 * jp + 1][0], b[2 * jp + 1][1]);
+        } else {
+            lds128(Bs + k * PITCH + n, b[2 * jp][0], b[2 * jp + 1][0]);
+            lds128(Bs + (k + 1) * PITCH + n, b[2 * jp][1], b[2 * jp + 1][1]);
+        }
+    }
+}
+// tile-relative row of accumulator registers (r = 0,1 -> row 2g; r = 2,3 -> row 2g+1) and column
+__device__ __forceinline__ int acc_row(int wm0, int i, int g, int r) { return wm0 + i * 16 + 2 * g + (r >> 1); }
+__device__ __forceinline__ int acc_col(int wn0, int j, int t, int r) { return wn0 + (j >> 1) * 16 + 2 * (2 * t + (r & 1)) + (j & 1); }
+
+// acc = pre * D (tile origin m0,n0), D = alpha*acc: (c0,c2) and (c1,c3) are 16-byte pairs of a column.
+template <int MT, int NT>
+__device__ __forceinline__ void acc_preload(double (&acc)[MT][NT][4], const double *D, int64_t ldd, int M, int N, int m0, int n0,
+                                            int wm0, int wn0, int g, int t, double pre, bool vec_ok) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = m0 + acc_row(wm0, i, g, 0), n = n0 + acc_col(wn0, j, t, e);
+                double x = 0.0, y = 0.0;
+                if (n < N) {
+                    const double *d = D + m + (int64_t)n * ldd;
+                    if (vec_ok && m + 1 < M) {
+                        const double2 v = *reinterpret_cast<const double2 *>(d);
+                        x = v.x;
+                        y = v.y;
+                    } else {
+                        if (m < M) x = d[0];
+                        if (m + 1 < M) y = d[1];
+                    }
+                }
+                acc[i][j][e] = pre * x;
+                acc[i][j][2 + e] = pre * y;
+            }
+}
+template <int MT, int NT>
+__device__ __forceinline__ void acc_store(const double (&acc)[MT][NT][4], double *D, int64_t ldd, int M, int N, int m0, int n0,
+                                          int wm0, int wn0, int g, int t, double alpha, double beta_late, bool vec_ok) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = m0 + acc_row(wm0, i, g, 0), n = n0 + acc_col(wn0, j, t, e);
+                if (n < N) {
+                    double *d = D + m + (int64_t)n * ldd;
+                    double x = alpha * acc[i][j][e], y = alpha * acc[i][j][2 + e];
+                    if (beta_late != 0.0) {          // alpha == 0: D = beta*D
+                        if (m < M) x = fma(beta_late, d[0], x);
+                        if (m + 1 < M) y = fma(beta_late, d[1], y);
+                    }
+                    if (vec_ok && m + 1 < M) {
+                        *reinterpret_cast<double2 *>(d) = make_double2(x, y);
+                    } else {
+                        if (m < M) d[0] = x;
+                        if (m + 1 < M) d[1] = y;
+                    }
+                }
+            }
+}
+
 template <class Cfg, bool AKC, bool BKC, int VEC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const GemmParams p) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
@@ -137,16 +239,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     const bool preload = (p.beta != 0.0) && (p.alpha != 0.0);
     const double pre = preload ? p.beta / p.alpha : 0.0;
     double acc[MT][NT][4];
+    const bool vec_ok = ((uintptr_t)D % 16 == 0) && (p.ldd % 2 == 0);
+    if (preload) {
+        acc_preload<MT, NT>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, pre, vec_ok);
+    } else {
 #pragma unroll
-    for (int i = 0; i < MT; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+            for (int j = 0; j < NT; ++j)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int m = m0 + wm0 + i * 16 + g + (r >> 1) * 8;
-                const int n = n0 + wn0 + j * 8 + 2 * t + (r & 1);
-                acc[i][j][r] = (preload && m < p.M && n < p.N) ? pre * D[m + (int64_t)n * p.ldd] : 0.0;
-            }
+                for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.0;
+    }
 
     auto stage_a = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS; };
     auto stage_b = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS + Cfg::A_ELEMS; };
@@ -173,32 +276,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
             double a[MT][4], b[NT][2];
-#pragma unroll
-            for (int i = 0; i < MT; ++i) {
-                const int m = wm0 + i * 16 + g, k = ks * 8 + t;
-                if constexpr (AKC) {
-                    a[i][0] = As[m * PA + k];
-                    a[i][1] = As[(m + 8) * PA + k];
-                    a[i][2] = As[m * PA + k + 4];
-                    a[i][3] = As[(m + 8) * PA + k + 4];
-                } else {
-                    a[i][0] = As[k * PA + m];
-                    a[i][1] = As[k * PA + m + 8];
-                    a[i][2] = As[(k + 4) * PA + m];
-                    a[i][3] = As[(k + 4) * PA + m + 8];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int n = wn0 + j * 8 + g, k = ks * 8 + t;
-                if constexpr (BKC) {
-                    b[j][0] = Bs[n * PB + k];
-                    b[j][1] = Bs[n * PB + k + 4];
-                } else {
-                    b[j][0] = Bs[k * PB + n];
-                    b[j][1] = Bs[(k + 4) * PB + n];
-                }
-            }
+            load_a_frags<MT, AKC, PA>(a, As, wm0, ks, g, t);
+            load_b_frags<NT, BKC, PB>(b, Bs, wn0, ks, g, t);
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -207,156 +286,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     }
     cp_async_wait<0>();
 
-    // epilogue: D = alpha*acc (the beta*D term is already inside acc)
-    const double alpha = p.alpha;
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int m = m0 + wm0 + i * 16 + g + (r >> 1) * 8;
-                const int n = n0 + wn0 + j * 8 + 2 * t + (r & 1);
-                if (m < p.M && n < p.N) {
-                    double *d = D + m + (int64_t)n * p.ldd;
-                    double v = alpha * acc[i][j][r];
-                    if (!preload && p.beta != 0.0) v = fma(p.beta, *d, v);      // alpha == 0
-                    *d = v;
-                }
-            }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent rank-K update  D = alpha * A * B' + beta * D  for SHORT K (the trailing update of the
-// blocked QL: K = nb).  A is M x K (M-contiguous), B is N x K (N-contiguous).  With only K/16 k-steps
-// per tile the pipeline fill and the read of D dominate a tile-per-CTA kernel, so here two CTAs per SM
-// each walk a list of tiles and (1) the cp.async operand ring runs continuously across tile
-// boundaries, (2) the D tile of the NEXT tile is pulled into L2 (prefetch.global.L2) while the current
-// tile is multiplied, so the accumulator preload at the next tile start is an L2 hit.
-// ---------------------------------------------------------------------------------------------
-struct RankKCfg {
-    static constexpr int BM = 128, BN = 64, BK = 16, WM = 32, WN = 32, STAGES = 3, THREADS = 256;
-    static constexpr int WARPS_M = BM / WM, MT = WM / 16, NT = WN / 8;
-    static constexpr int PA = BM + 4, PB = BN + 4;          // pitches (doubles)
-    static constexpr int A_ELEMS = BK * PA, B_ELEMS = BK * PB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
-};
-
-__global__ void __launch_bounds__(RankKCfg::THREADS, 2) rankk_persistent_kernel(const GemmParams p, const int tiles_m,
-                                                                               const int ntiles) {
-    using Cfg = RankKCfg;
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
-    constexpr int PA = Cfg::PA, PB = Cfg::PB;
-    extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM, wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
-    const int KT = (p.K + BK - 1) / BK;
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_steps = my_tiles * KT;
-    const double pre = p.beta / p.alpha;
-
-    auto tile_origin = [&](int i, int &m0, int &n0) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        m0 = (tile % tiles_m) * BM;
-        n0 = (tile / tiles_m) * BN;
-    };
-    TileLoader<BM, BK, false, 2, Cfg::THREADS> la;
-    TileLoader<BN, BK, false, 2, Cfg::THREADS> lb;
-    int iss_tile = 0, iss_kt = 0;          // issue-side position: runs STAGES-1 k-steps ahead, across tiles
-    auto issue = [&](int step) {
-        if (step < total_steps) {
-            if (iss_kt == 0) {
-                int m0, n0;
-                tile_origin(iss_tile, m0, n0);
-                la.init(p.A, p.lda, m0, 0, p.M, tid);
-                lb.init(p.B, p.ldb, n0, 0, p.N, tid);
-            }
-            const int s = step % STAGES;
-            double *As = smem + (size_t)s * Cfg::STAGE_ELEMS, *Bs = As + Cfg::A_ELEMS;
-            la.load(As, p.A, p.lda, p.M, p.K, tid);
-            lb.load(Bs, p.B, p.ldb, p.N, p.K, tid);
-            if (++iss_kt == KT) {
-                iss_kt = 0;
-                ++iss_tile;
-            }
-        }
-        cp_async_commit();
-    };
-    // pull the D tile of tile i into L2: 64 columns x 1 KiB = 512 lines of 128 bytes, two per thread
-    auto prefetch_d = [&](int i) {
-        if (i < my_tiles) {
-            int m0, n0;
-            tile_origin(i, m0, n0);
-#pragma unroll
-            for (int q = 0; q < (BN * BM / 16) / Cfg::THREADS; ++q) {
-                const int line = tid + q * Cfg::THREADS;
-                const int c = line / (BM / 16), r = (line % (BM / 16)) * 16;
-                if (m0 + r < p.M && n0 + c < p.N) {
-                    const double *ptr = p.D + m0 + r + (int64_t)(n0 + c) * p.ldd;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-                }
-            }
-        }
-    };
-    prefetch_d(0);
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(s);
-    int step = 0;
-    for (int i = 0; i < my_tiles; ++i) {
-        int m0, n0;
-        tile_origin(i, m0, n0);
-        prefetch_d(i + 1);
-        double acc[MT][NT][4];
-#pragma unroll
-        for (int a = 0; a < MT; ++a)
-#pragma unroll
-            for (int b = 0; b < NT; ++b)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int m = m0 + wm0 + a * 16 + g + (r >> 1) * 8, n = n0 + wn0 + b * 8 + 2 * t + (r & 1);
-                    acc[a][b][r] = (m < p.M && n < p.N) ? pre * p.D[m + (int64_t)n * p.ldd] : 0.0;
-                }
-        for (int kt = 0; kt < KT; ++kt, ++step) {
-            cp_async_wait<STAGES - 2>();
-            __syncthreads();
-            issue(step + STAGES - 1);
-            const double *As = smem + (size_t)(step % STAGES) * Cfg::STAGE_ELEMS, *Bs = As + Cfg::A_ELEMS;
-#pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-                double a[MT][4], b[NT][2];
-#pragma unroll
-                for (int x = 0; x < MT; ++x) {
-                    const int m = wm0 + x * 16 + g, k = ks * 8 + t;
-                    a[x][0] = As[k * PA + m];
-                    a[x][1] = As[k * PA + m + 8];
-                    a[x][2] = As[(k + 4) * PA + m];
-                    a[x][3] = As[(k + 4) * PA + m + 8];
-                }
-#pragma unroll
-                for (int y = 0; y < NT; ++y) {
-                    const int n = wn0 + y * 8 + g, k = ks * 8 + t;
-                    b[y][0] = Bs[k * PB + n];
-                    b[y][1] = Bs[(k + 4) * PB + n];
-                }
-#pragma unroll
-                for (int x = 0; x < MT; ++x)
-#pragma unroll
-                    for (int y = 0; y < NT; ++y) dmma1688(acc[x][y], a[x], b[y]);
-            }
-        }
-        // epilogue: plain stores (D's beta term is already in the accumulators)
-#pragma unroll
-        for (int a = 0; a < MT; ++a)
-#pragma unroll
-            for (int b = 0; b < NT; ++b)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int m = m0 + wm0 + a * 16 + g + (r >> 1) * 8, n = n0 + wn0 + b * 8 + 2 * t + (r & 1);
-                    if (m < p.M && n < p.N) p.D[m + (int64_t)n * p.ldd] = p.alpha * acc[a][b][r];
-                }
-    }
-    cp_async_wait<0>();
+    // epilogue: D = alpha*acc (the beta*D term is already inside acc unless alpha == 0)
+    acc_store<MT, NT>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, p.alpha, preload ? 0.0 : p.beta, vec_ok);
 }
 
 // out(M x N, ldo) = sum_{s < S} part[s*stride + m + n*ldp]   (fixed summation order)
@@ -420,7 +351,7 @@ int qlb_gemm(qlb200_ctx *h, cudaStream_t st, int cfg, bool akc, bool bkc, int M,
     if (cfg < 0) {
         if (N <= 16) cfg = 2;
         else if (h->opt_gemm_cfg >= 0) cfg = (int)h->opt_gemm_cfg;
-        else cfg = (K <= 256 && N > 64) ? 1 : 0;      // short-K updates: 2 CTAs/SM hide the tile prologue
+        else cfg = 1;      // 128x64 tiles, 2 CTAs/SM: measured best for the skinny-K update and for long K
     }
     int bk = (cfg == 3) ? 32 : 16;
     if (splits < 1) splits = 1;
@@ -433,21 +364,6 @@ int qlb_gemm(qlb200_ctx *h, cudaStream_t st, int cfg, bool akc, bool bkc, int M,
     }
     GemmParams p{M, N, K, A, lda, B, ldb, D, ldd, alpha, beta, kchunk, split_stride};
     const bool vec2 = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
-    // short-K rank update with enough tiles to keep every SM busy: persistent pipelined kernel
-    if (!akc && !bkc && splits == 1 && K <= 512 && alpha != 0.0 && beta != 0.0 && vec2 && h->opt_rankk && h->opt_gemm_cfg < 0) {
-        const int tiles_m = (M + RankKCfg::BM - 1) / RankKCfg::BM, tiles_n = (N + RankKCfg::BN - 1) / RankKCfg::BN;
-        const int64_t ntiles = (int64_t)tiles_m * tiles_n;
-        if (ntiles >= 4 * (int64_t)h->sm_count && ntiles < (1 << 30)) {
-            if (!h->gemm_attr_done[63]) {
-                QLB_CUDA(h, cudaFuncSetAttribute(rankk_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)RankKCfg::SMEM));
-                h->gemm_attr_done[63] = true;
-            }
-            rankk_persistent_kernel<<<2 * h->sm_count, RankKCfg::THREADS, RankKCfg::SMEM, st>>>(p, tiles_m, (int)ntiles);
-            QLB_LAUNCH_CHECK(h);
-            return 0;
-        }
-    }
     switch (cfg) {
         case 0: return launch_layout<CfgBig>(h, 0, akc, bkc, vec2, p, splits, st);
         case 1: return launch_layout<CfgMid>(h, 1, akc, bkc, vec2, p, splits, st);

@@ -41,7 +41,7 @@ def main():
     C = cm(p, qd)
     V = cm(p, nb)
     W = cm(qd, nb)
-    for cfg in (-1, 0, 1):
+    for cfg in (-1, 0, 1, 3):
         h.set_option("gemm_cfg", cfg)
         # W = C' V : M = q, N = nb, K = p  (TN)
         t = ev_time(lambda: h.call("qlb200_dgemm_dev", b"T", b"N", qd, nb, p, 1.0, C.data_ptr(), C.stride(1), V.data_ptr(),
