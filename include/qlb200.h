@@ -60,8 +60,13 @@ int qlb200_sync(qlb200_handle h);
 const char *qlb200_last_error(qlb200_handle h);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t qlb200_launch_count(qlb200_handle h);
+/* With option "profile" = 1 the trailing-update / Q-apply DMMA GEMM launches are bracketed by CUDA
+ * event pairs on the launching stream.  This call synchronizes, returns the summed device time (ms),
+ * the summed algorithmic flops and the number of launches since the last collect, and resets. */
+int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_total, int64_t *launches);
 /* Tunables: "nb" (panel width, multiple of 16 in [16,128]), "lookahead" (0/1), "gemm_cfg" (-1 auto,
- * 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V). */
+ * 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V),
+ * "strip_rpt" (1/2/4 minimum rows per thread in the panel kernel), "profile" (0/1, see above). */
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
 
 /* ---- single matrix: ql! -------------------------------------------------------------------

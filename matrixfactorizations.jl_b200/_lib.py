@@ -58,7 +58,8 @@ for _sfx in ("", "_dev"):
         SIGNATURES[f"qlb200_{_t}qlsolve_batched{_sfx}"] = _SOLVE_B
 SIGNATURES["qlb200_dgemm_dev"] = [c_char, c_char, _I, _I, _I, ctypes.c_double, _P, _I, _P, _I, ctypes.c_double, _P, _I]
 HANDLE_FUNCS = ["qlb200_version", "qlb200_create", "qlb200_destroy", "qlb200_set_stream", "qlb200_sync",
-                "qlb200_last_error", "qlb200_launch_count", "qlb200_set_option", "qlb200_reset_stream"]
+                "qlb200_last_error", "qlb200_launch_count", "qlb200_set_option", "qlb200_reset_stream",
+                "qlb200_profile_collect"]
 
 
 def lib() -> ctypes.CDLL:
@@ -73,6 +74,7 @@ def lib() -> ctypes.CDLL:
         L.qlb200_destroy.argtypes = [c_void_p]
         L.qlb200_set_stream.argtypes = [c_void_p, c_void_p]
         L.qlb200_reset_stream.argtypes = [c_void_p]
+        L.qlb200_profile_collect.argtypes = [c_void_p, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]
         L.qlb200_sync.argtypes = [c_void_p]
         L.qlb200_last_error.argtypes = [c_void_p]
         L.qlb200_last_error.restype = c_char_p
@@ -126,8 +128,17 @@ class Handle:
     def set_stream(self, cuda_stream_ptr):
         self.check(lib().qlb200_set_stream(self._h, c_void_p(cuda_stream_ptr or 0)))
 
+    def reset_stream(self):
+        self.check(lib().qlb200_reset_stream(self._h))
+
     def set_option(self, name: str, value: int):
         self.check(lib().qlb200_set_option(self._h, name.encode(), int(value)))
+
+    def profile_collect(self):
+        """(device ms, algorithmic flops, launches) of the bracketed GEMM launches since the last call."""
+        ms, fl, n = ctypes.c_double(0), ctypes.c_double(0), c_int64(0)
+        self.check(lib().qlb200_profile_collect(self._h, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)))
+        return ms.value, fl.value, n.value
 
     @property
     def launches(self) -> int:

@@ -123,7 +123,11 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     if (to_part && (int64_t)S * stride > ws.part_elems)
         return qlb_fail(h, 1000 + (int)cudaErrorMemoryAllocation, "partial buffer too small%s");
     double *Wdst = to_part ? ws.part : ws.Wsum;
-    int rc = qlb_gemm(h, st, cfg_w, /*akc=*/left, /*bkc=*/true, other, ib, p, 1.0, C, ldc, V, ldv, 0.0, Wdst, ldp, S, stride);
+    int rc;
+    {
+        QlbProfScope prof(h, st, ib > 16 ? 2.0 * other * ib * p : 0.0);
+        rc = qlb_gemm(h, st, cfg_w, /*akc=*/left, /*bkc=*/true, other, ib, p, 1.0, C, ldc, V, ldv, 0.0, Wdst, ldp, S, stride);
+    }
     if (rc) return rc;
     // 2. W2 = (sum of partials) * Tm
     if (small && !tt) {
@@ -138,6 +142,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
         if (rc) return rc;
     }
     // 3. C -= V W2' (left)  or  C -= W2 V' (right)
+    QlbProfScope prof(h, st, ib > 16 ? 2.0 * other * ib * p : 0.0);
     if (left) return qlb_gemm(h, st, -1, false, false, p, other, ib, -1.0, V, ldv, ws.W2, ws.ldw, 1.0, C, ldc, 1, 0);
     return qlb_gemm(h, st, -1, false, false, other, p, ib, -1.0, ws.W2, ws.ldw, V, ldv, 1.0, C, ldc, 1, 0);
 }

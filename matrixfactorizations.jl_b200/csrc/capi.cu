@@ -55,6 +55,11 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->stage) cudaFree(h->stage);
     if (h->stage2) cudaFree(h->stage2);
     if (h->dinfo) cudaFree(h->dinfo);
+    if (h->prof_ev) {
+        for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+        delete[] h->prof_ev;
+        delete[] h->prof_flops;
+    }
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -84,6 +89,27 @@ int qlb200_sync(qlb200_handle h) {
 
 const char *qlb200_last_error(qlb200_handle h) { return h ? h->err : "null handle"; }
 
+int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_total, int64_t *launches) {
+    if (!h) return -1;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    double ms = 0.0, fl = 0.0;
+    int64_t cnt = 0;
+    for (int i = 0; i < h->prof_n; ++i) {
+        if (h->prof_flops[i] <= 0.0) continue;
+        float t = 0.f;
+        QLB_CUDA(h, cudaEventElapsedTime(&t, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+        ms += t;
+        fl += h->prof_flops[i];
+        ++cnt;
+    }
+    h->prof_n = 0;
+    if (ms_total) *ms_total = ms;
+    if (flops_total) *flops_total = fl;
+    if (launches) *launches = cnt;
+    return 0;
+}
+
 int64_t qlb200_launch_count(qlb200_handle h) { return h ? h->launches : -1; }
 
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
@@ -95,6 +121,16 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "gemm_cfg")) {
         if (value < -1 || value > 3) return qlb_fail(h, -3, "gemm_cfg must be in [-1,3]%s");
         h->opt_gemm_cfg = value;
+    } else if (!strcmp(name, "profile")) {
+        if (value && !h->prof_ev) {
+            h->prof_cap = 8192;
+            h->prof_ev = new (std::nothrow) cudaEvent_t[2 * h->prof_cap];
+            h->prof_flops = new (std::nothrow) double[h->prof_cap];
+            if (!h->prof_ev || !h->prof_flops) return qlb_fail(h, 1000 + (int)cudaErrorMemoryAllocation, "profile buffers%s");
+            for (int i = 0; i < 2 * h->prof_cap; ++i) QLB_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
+        }
+        h->opt_profile = value ? 1 : 0;
+        h->prof_n = 0;
     } else if (!strcmp(name, "strip_rpt")) {
         if (value != 1 && value != 2 && value != 4) return qlb_fail(h, -3, "strip_rpt must be 1, 2 or 4%s");
         h->opt_strip_rpt = value;

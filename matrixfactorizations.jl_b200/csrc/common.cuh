@@ -33,7 +33,30 @@ struct qlb200_ctx {
     bool strip_attr_done[8] = {false};
     bool larft_attr_done = false, trsm_attr_done = false;
     bool gemm_attr_done[64] = {false};
+    // optional device-side timing of the dominant kernels (trailing-update GEMMs): event pairs around
+    // each launch, summed by qlb200_profile_collect (bench.py's roofline leg)
+    int64_t opt_profile = 0;
+    cudaEvent_t *prof_ev = nullptr;        // 2 * prof_cap events
+    double *prof_flops = nullptr;
+    int prof_cap = 0, prof_n = 0;
     char err[512] = {0};
+};
+
+// Brackets one launch with an event pair when profiling is on.
+struct QlbProfScope {
+    qlb200_ctx *h;
+    cudaStream_t st;
+    int slot;
+    QlbProfScope(qlb200_ctx *h_, cudaStream_t st_, double flops) : h(h_), st(st_), slot(-1) {
+        if (h->opt_profile && h->prof_n < h->prof_cap) {
+            slot = h->prof_n++;
+            h->prof_flops[slot] = flops;
+            cudaEventRecord(h->prof_ev[2 * slot], st);
+        }
+    }
+    ~QlbProfScope() {
+        if (slot >= 0) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
+    }
 };
 
 static inline int qlb_fail(qlb200_ctx *h, int code, const char *fmt, const char *detail = "") {
