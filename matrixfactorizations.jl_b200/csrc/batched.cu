@@ -65,34 +65,16 @@ struct BatchedCfg {
     static constexpr int WARP_BYTES = BUF_BYTES + X_BYTES + 16;   // + mbarrier slot
 };
 
-// Rare, warp-uniform repair step shared by all pivots (kept out of line and un-unrolled so that it
-// costs no code in the hot loop).  Mirrors ?larfg's two special exits: a tail that is EXACTLY zero
-// gives tau = 0 / H = I (*zero_tail), and a tail whose squares under/overflow is rescaled by an
-// exact power of two (LAPACK's safmin loop): the group's pivot column in `xg` is rescaled in place,
-// the factor is returned and *ssq receives the sum of squares of the rescaled tail.  Groups that
-// were safe are left untouched (factor 1), so a matrix's result never depends on its neighbours.
+// Rare, warp-uniform check shared by all pivots (kept out of line so that it costs no code in the hot
+// loop).  ?larfg has two special exits.  A tail that is EXACTLY zero gives tau = 0 / H = I: handled
+// in line by the caller (returns true).  A tail whose squares under/overflow needs LAPACK's scaled
+// norm and safmin rescaling loop: such matrices are flagged, left untouched by the fast kernel and
+// re-factored by geql2_generic_kernel, which follows ?larfg literally.
 template <typename T>
-__device__ __noinline__ T ql_rare_fixup(T *xg, int R, int jl, int lpm, T alpha, bool safe, bool *zero_tail, T *ssq, T *sc_inv) {
+__device__ __noinline__ bool ql_rare_zero_tail(const T *xg, int R) {
     T amax = T(0);
     for (int i = 0; i < R; ++i) amax = fmax(amax, t_abs(xg[i]));
-    *zero_tail = (amax == T(0));
-    T sc = T(1);
-    *sc_inv = T(1);
-    if (!safe && amax != T(0)) {
-        int ex = t_ilogb(fmax(amax, t_abs(alpha)));
-        const int lim = (sizeof(T) == 8) ? 1020 : 124;
-        ex = ex < -lim ? -lim : (ex > lim ? lim : ex);
-        sc = t_scalbn(T(1), -ex);
-        *sc_inv = t_scalbn(T(1), ex);
-    }
-    __syncwarp();
-    for (int i = jl; i < R; i += lpm) xg[i] *= sc;
-    __syncwarp();
-    T s0 = T(0), s1 = T(0);
-    for (int i = 0; i + 1 < R; i += 2) { s0 = t_fma(xg[i], xg[i], s0); s1 = t_fma(xg[i + 1], xg[i + 1], s1); }
-    if (R & 1) s0 = t_fma(xg[R - 1], xg[R - 1], s0);
-    *ssq = s0 + s1;
-    return sc;
+    return amax == T(0);
 }
 
 // 1/sqrt(x) and 1/x for x in the normal range: hardware approximation (MUFU.RSQ64H / RCP64H) plus
@@ -123,7 +105,7 @@ __device__ __forceinline__ float nr_rcp(float x) { return __frcp_rn(x); }
 
 // One Householder QL step at compile-time pivot row/column R (0-based), LAPACK ?larfg conventions.
 template <typename T, int N, int CPL, int R>
-__device__ __forceinline__ void ql_step(T (&a)[CPL][N], T (&mytau)[CPL], T (&myscale)[CPL], T *xg, int jl) {
+__device__ __forceinline__ void ql_step(T (&a)[CPL][N], T (&mytau)[CPL], T (&myscale)[CPL], T *xg, int jl, bool &bad) {
     using V = typename Vec16<T>::type;
     constexpr int E = Vec16<T>::E;
     constexpr int LPM = N / CPL;
@@ -176,19 +158,16 @@ __device__ __forceinline__ void ql_step(T (&a)[CPL][N], T (&mytau)[CPL], T (&mys
         T ssq = __shfl_sync(FULL, d[OWN_SLOT], OWN_LANE, LPM);
         T alpha = __shfl_sync(FULL, a[OWN_SLOT][R], OWN_LANE, LPM);
         T tot = t_fma(alpha, alpha, ssq);
-        T sc = T(1), sc_inv = T(1);
         bool zero_tail = false;
         const bool safe = (ssq >= Lim<T>::LO) && (tot <= Lim<T>::HI);
         if (__any_sync(FULL, !safe)) {
-            T ssq2;
-            sc = ql_rare_fixup<T>(xg, R, jl, LPM, alpha, safe, &zero_tail, &ssq2, &sc_inv);
-            if (sc != T(1)) {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) d[c] *= sc;
-                alpha *= sc;
-                tot = t_fma(alpha, alpha, ssq2);
+            zero_tail = ql_rare_zero_tail<T>(xg, R);
+            if (!safe) {
+                if (!zero_tail) bad = true;      // needs ?larfg's scaled path: redo in the generic kernel
+                tot = T(1);
+            } else {
+                zero_tail = false;
             }
-            if (zero_tail) tot = T(1);
         }
         // 3. scalars: beta = -sign(alpha) ||[alpha;x]||, tau = (beta-alpha)/beta = 1 + |alpha|/||.||,
         //    scale = 1/(alpha-beta) = -1/(tau*beta)
@@ -202,8 +181,8 @@ __device__ __forceinline__ void ql_step(T (&a)[CPL][N], T (&mytau)[CPL], T (&mys
         // 4. owner bookkeeping (scaling of v deferred to the end of the factorization)
         if (jl == OWN_LANE) {
             mytau[OWN_SLOT] = tauk;
-            myscale[OWN_SLOT] = scale * sc;            // v_i = x_i * sc / (alpha~ - beta~)
-            if (!zero_tail) a[OWN_SLOT][R] = beta * sc_inv;
+            myscale[OWN_SLOT] = scale;                 // v_i = x_i / (alpha - beta)
+            if (!zero_tail) a[OWN_SLOT][R] = beta;
         }
         // 5. rank-1 update of the live columns left of the pivot: a_j -= tau (v^T a_j) v
 #pragma unroll
@@ -236,16 +215,16 @@ __device__ __forceinline__ void ql_step(T (&a)[CPL][N], T (&mytau)[CPL], T (&mys
 
 template <typename T, int N, int CPL, int R>
 struct StepLoop {
-    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&mytau)[CPL], T (&myscale)[CPL], T *xg, int jl) {
-        ql_step<T, N, CPL, R>(a, mytau, myscale, xg, jl);
-        if constexpr (R > 0) StepLoop<T, N, CPL, R - 1>::run(a, mytau, myscale, xg, jl);
+    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&mytau)[CPL], T (&myscale)[CPL], T *xg, int jl, bool &bad) {
+        ql_step<T, N, CPL, R>(a, mytau, myscale, xg, jl, bad);
+        if constexpr (R > 0) StepLoop<T, N, CPL, R - 1>::run(a, mytau, myscale, xg, jl, bad);
     }
 };
 
 template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restrict__ tau, int64_t strideTau,
-                     int64_t batch) {
+                     int64_t batch, int *__restrict__ redo_count, int *__restrict__ redo_list) {
     using Cfg = BatchedCfg<T, N, CPL>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, PITCH = Cfg::PITCH;
@@ -319,7 +298,8 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
 #pragma unroll
         for (int c = 0; c < CPL; ++c) { mytau[c] = T(0); myscale[c] = T(0); }
 
-        StepLoop<T, N, CPL, N - 1>::run(a, mytau, myscale, xg, jl);
+        bool bad = false;
+        StepLoop<T, N, CPL, N - 1>::run(a, mytau, myscale, xg, jl, bad);
 
         // deferred scaling of the reflector tails: v_i = x_i / (alpha - beta), rows above the pivot only
 #pragma unroll
@@ -328,7 +308,8 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
 #pragma unroll
             for (int i = 0; i < N - 1; ++i) a[c][i] *= (i < col) ? myscale[c] : T(1);
         }
-        if (valid) {
+        if (valid && bad && jl == 0) redo_list[atomicAdd(redo_count, 1)] = (int)mi;      // untouched; redone generically
+        if (valid && !bad) {
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const int col = jl + c * LPM;
@@ -350,6 +331,122 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic robust QL: one warp per matrix, matrix resident in shared memory, any 1 <= n <= 64.
+// Follows LAPACK ?geql2 / ?larfg literally (scaled 2-norm, ?lapy2, the safmin rescaling loop), so it
+// is the path for (a) matrices the register kernels flagged (squares under/overflow), and (b) sizes
+// without a specialised kernel.  Matrices come from `list` (count = *count_ptr) or, when list is
+// null, are simply 0 .. count_val-1.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct LarfgConst;
+template <> struct LarfgConst<double> { static __device__ double safmin() { return 2.2250738585072014e-308 / 1.1102230246251565e-16; } };
+template <> struct LarfgConst<float>  { static __device__ float  safmin() { return 1.17549435e-38f / 5.96046448e-08f; } };
+
+template <typename T>
+__device__ __forceinline__ T warp_nrm2(const T *x, int len, int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    T amax = T(0);
+    for (int i = lane; i < len; i += 32) amax = fmax(amax, t_abs(x[i]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) amax = fmax(amax, __shfl_xor_sync(FULL, amax, o));
+    if (amax == T(0)) return T(0);
+    T s = T(0);
+    for (int i = lane; i < len; i += 32) {
+        const T q = x[i] / amax;
+        s = t_fma(q, q, s);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    return amax * sqrt(s);
+}
+template <typename T>
+__device__ __forceinline__ T t_lapy2(T x, T y) {
+    const T xa = t_abs(x), ya = t_abs(y);
+    const T w = fmax(xa, ya), z = fmin(xa, ya);
+    if (z == T(0)) return w;
+    const T q = z / w;
+    return w * sqrt(T(1) + q * q);
+}
+
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) geql2_generic_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restrict__ tau,
+                                                                  int64_t strideTau, int n, const int *__restrict__ count_ptr,
+                                                                  int64_t count_val, const int *__restrict__ list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = n + 1;                                     // column pitch
+    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)warp * (P * n + n);
+    T *taus = S + P * n;
+    const int64_t count = list ? (int64_t)*count_ptr : count_val;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+    const T safmin = LarfgConst<T>::safmin(), rsafmn = T(1) / safmin;
+    for (int64_t it = gw; it < count; it += nw) {
+        const int64_t mi = list ? (int64_t)list[it] : it;
+        T *Am = A + mi * strideA;
+        for (int idx = lane; idx < n * n; idx += 32) S[(idx / n) * P + (idx % n)] = Am[(int64_t)(idx / n) * lda + (idx % n)];
+        __syncwarp();
+        for (int k = n - 1; k >= 0; --k) {
+            T *x = S + k * P;                                // column k: tail rows 0..k-1, pivot row k
+            T tk = T(0);
+            T xnorm = (k > 0) ? warp_nrm2<T>(x, k, lane) : T(0);
+            if (xnorm != T(0)) {
+                T alpha = x[k];
+                T beta = -t_copysign(t_lapy2(alpha, xnorm), alpha);
+                int knt = 0;
+                if (t_abs(beta) < safmin) {
+                    do {
+                        ++knt;
+                        __syncwarp();
+                        for (int i = lane; i < k; i += 32) x[i] *= rsafmn;
+                        beta *= rsafmn;
+                        alpha *= rsafmn;
+                    } while (t_abs(beta) < safmin && knt < 20);
+                    __syncwarp();
+                    xnorm = warp_nrm2<T>(x, k, lane);
+                    beta = -t_copysign(t_lapy2(alpha, xnorm), alpha);
+                }
+                tk = (beta - alpha) / beta;
+                const T sc = T(1) / (alpha - beta);
+                __syncwarp();
+                for (int i = lane; i < k; i += 32) x[i] *= sc;
+                for (int j = 0; j < knt; ++j) beta *= safmin;
+                __syncwarp();
+                if (lane == 0) x[k] = beta;
+                // apply H = I - tau v v' (v = [x(0:k-1); 1]) to columns j < k, one column per lane
+                for (int j = lane; j < k; j += 32) {
+                    T *c = S + j * P;
+                    T w = c[k];
+                    for (int i = 0; i < k; ++i) w = t_fma(x[i], c[i], w);
+                    w *= tk;
+                    c[k] -= w;
+                    for (int i = 0; i < k; ++i) c[i] = t_fma(-w, x[i], c[i]);
+                }
+            }
+            if (lane == 0) taus[k] = tk;
+            __syncwarp();
+        }
+        for (int idx = lane; idx < n * n; idx += 32) Am[(int64_t)(idx / n) * lda + (idx % n)] = S[(idx / n) * P + (idx % n)];
+        for (int i = lane; i < n; i += 32) tau[mi * strideTau + i] = taus[i];
+        __syncwarp();
+    }
+}
+
+template <typename T>
+static int launch_geql2_generic(qlb200_ctx *h, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau, int n,
+                                const int *count_ptr, int64_t count_val, const int *list) {
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * ((size_t)(n + 1) * n + n) * sizeof(T);
+    auto kern = geql2_generic_kernel<T, WARPS>;
+    QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = list ? (int64_t)h->sm_count : (count_val + WARPS - 1) / WARPS;
+    const int64_t cap = (int64_t)h->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, n, count_ptr, count_val, list);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,9 +584,15 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     const int64_t cap = (int64_t)h->sm_count * occ;        // persistent: one resident wave
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, batch);
+    // flagged matrices (under/overflowing squares) are collected here and redone by the generic kernel
+    if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
+    int rc = qlb_reserve(h, &h->redo, &h->redo_bytes, ((size_t)batch + 4) * sizeof(int));
+    if (rc) return rc;
+    int *redo_count = (int *)h->redo, *redo_list = redo_count + 4;
+    QLB_CUDA(h, cudaMemsetAsync(redo_count, 0, sizeof(int), h->stream));
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, batch, redo_count, redo_list);
     QLB_LAUNCH_CHECK(h);
-    return 0;
+    return launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, N, redo_count, 0, redo_list);
 }
 
 template <typename T, int N, int NR, int MODE>
@@ -550,7 +653,8 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
         case 32: return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
-    return qlb_fail(h, -2, "batched QL: n must be 8, 16 or 32%s");
+    if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
+    return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }
 int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
                           int64_t strideTau, int64_t batch) {
@@ -559,7 +663,8 @@ int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64
         case 16: return qlb::launch_geqlf_batched<float, 16, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
         case 32: return qlb::launch_geqlf_batched<float, 32, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
     }
-    return qlb_fail(h, -2, "batched QL: n must be 8, 16 or 32%s");
+    if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
+    return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }
 // mode 0: Q*B, 1: Q'*B, 2: L^{-1} Q' B
 int qlb_apply_batched_f64(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, const double *A, int64_t lda,

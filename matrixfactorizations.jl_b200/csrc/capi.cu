@@ -55,6 +55,7 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->stage) cudaFree(h->stage);
     if (h->stage2) cudaFree(h->stage2);
     if (h->dinfo) cudaFree(h->dinfo);
+    if (h->redo) cudaFree(h->redo);
     if (h->prof_ev) {
         for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
         delete[] h->prof_ev;
@@ -157,7 +158,7 @@ template <typename T>
 static int check_batched(qlb200_ctx *h, int64_t n, const T *A, int64_t lda, int64_t strideA, const T *tau,
                          int64_t strideTau, int64_t batch) {
     if (!h) return -1;
-    QLB_REQUIRE(h, n == 8 || n == 16 || n == 32, 2, "n must be 8, 16 or 32");
+    QLB_REQUIRE(h, n >= 1 && n <= 64, 2, "n must be in [1,64]");
     QLB_REQUIRE(h, A != nullptr || batch == 0, 3, "A is null");
     QLB_REQUIRE(h, lda >= n, 4, "lda < n");
     QLB_REQUIRE(h, strideA >= lda * (n - 1) + n || batch <= 1, 5, "strideA too small (matrices overlap)");

@@ -25,6 +25,8 @@ struct qlb200_ctx {
     void *stage2 = nullptr;                // second staging buffer (C / B operands)
     size_t stage2_bytes = 0;
     int32_t *dinfo = nullptr;              // device-side status word
+    void *redo = nullptr;                  // batched: counter + list of matrices for the generic kernel
+    size_t redo_bytes = 0;
     int64_t launches = 0;
     int64_t opt_nb = 128, opt_strip = 16, opt_lookahead = 0;
     int64_t opt_gemm_cfg = -1;             // -1 auto, else forces a tile configuration (benchmarking)

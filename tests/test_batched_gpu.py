@@ -50,6 +50,18 @@ def test_batched_geqlf_vs_oracle(q, h, n, dt, batch):
     _check_factors(F, tau, Fo, tauo, A, n, dt)
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 12, 31, 33, 48, 64])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_batched_generic_sizes_vs_lapack(q, h, n, dt):
+    """Sizes without a register kernel go through the generic ?geql2/?larfg kernel (any n <= 64)."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((70, n, n)).astype(dt)
+    F, tau = q.ql_batched_(A.copy(), handle=h)
+    Fo = A.copy()
+    tauo = lapack.geqlf_loop(Fo)
+    _check_factors(F, tau, Fo, tauo, A, n, dt)
+
+
 @pytest.mark.parametrize("name,dt,n", [("b32_f64", np.float64, 32), ("b16_f32", np.float32, 16), ("b8_f64", np.float64, 8)])
 def test_batched_vs_golden_lapack(q, h, name, dt, n):
     """Golden fixtures were produced by LAPACK ?geqlf (the routine behind ql!, src/ql.jl:72)."""
@@ -145,7 +157,11 @@ def test_batched_edge_conventions(q, h):
     for i in (2, 3, 4, 5):
         sc = np.abs(A[i]).max()
         assert np.isfinite(F[i]).all()
-        assert np.abs(F[i] - Fo[i]).max() <= 50 * n * _eps(np.float64) * sc * n, i
+        # column-major storage: F[i][col][row]; L lives at row >= col and scales with the data, the
+        # reflector tails v (row < col) are scale free
+        Lg, Lo = np.triu(F[i]), np.triu(Fo[i])
+        assert np.abs(Lg - Lo).max() <= 50 * n * _eps(np.float64) * sc * n, i
+        assert np.abs((F[i] - Lg) - (Fo[i] - Lo)).max() <= 50 * n * _eps(np.float64), i
         assert np.abs(tau[i] - tauo[i]).max() <= 50 * n * _eps(np.float64), i
 
 
@@ -165,9 +181,11 @@ def test_batched_strided_layout_and_bitwise_lda_independence(q, h):
 
 
 def test_batched_argument_errors(q, h):
-    A = np.zeros((2, 12, 12))
+    A = np.zeros((2, 65, 65))
     with pytest.raises(q.ArgumentError):
-        q.ql_batched_(A, handle=h)                         # n = 12 unsupported
+        q.ql_batched_(A, handle=h)                         # n > 64 unsupported
+    with pytest.raises(q.ArgumentError):
+        q.lmul_batched_(np.zeros((2, 12, 12)), np.zeros((2, 12)), np.zeros((2, 1, 12)), handle=h)   # apply: 8/16/32 only
     A = np.zeros((0, 32, 32))
     F, tau = q.ql_batched_(A, handle=h)                    # empty batch is a no-op
     assert tau.shape == (0, 32)
