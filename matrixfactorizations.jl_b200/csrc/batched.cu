@@ -61,166 +61,193 @@ struct BatchedCfg {
     static constexpr int NCOLS = G * N;              // columns staged per warp-batch
     static constexpr int XPITCH = N + E;             // per-group pivot-column broadcast buffer
     static constexpr int BUF_BYTES = NCOLS * PITCH * (int)sizeof(T);
-    static constexpr int X_BYTES = G * XPITCH * (int)sizeof(T);
+    static constexpr int X_BYTES = 2 * G * XPITCH * (int)sizeof(T);      // double-buffered
     static constexpr int WARP_BYTES = BUF_BYTES + X_BYTES + 16;   // + mbarrier slot
 };
 
-// Rare, warp-uniform check shared by all pivots (kept out of line so that it costs no code in the hot
-// loop).  ?larfg has two special exits.  A tail that is EXACTLY zero gives tau = 0 / H = I: handled
-// in line by the caller (returns true).  A tail whose squares under/overflow needs LAPACK's scaled
-// norm and safmin rescaling loop: such matrices are flagged, left untouched by the fast kernel and
-// re-factored by geql2_generic_kernel, which follows ?larfg literally.
-template <typename T>
-__device__ __noinline__ bool ql_rare_zero_tail(const T *xg, int R) {
-    T amax = T(0);
-    for (int i = 0; i < R; ++i) amax = fmax(amax, t_abs(xg[i]));
-    return amax == T(0);
-}
-
-// 1/sqrt(x) and 1/x for x in the normal range: hardware approximation (MUFU.RSQ64H / RCP64H) plus
-// Newton steps in FMA arithmetic -- no special-case branches (callers guarantee the range).
+// 1/sqrt(x) and 1/x for x in the normal range: hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) plus ONE
+// third-order correction in FMA arithmetic (error ~ seed^3, i.e. below half an ulp before the final
+// rounding) -- no special-case branches (callers guarantee the range).
 __device__ __forceinline__ double nr_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double hx = 0.5 * x;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double e = fma(-hx * y, y, 0.5);      // 0.5 - 0.5 x y^2
-        y = fma(y, e, y);
-    }
-    return y;
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);               // 1 - x y^2
+    const double p = fma(0.375, e, 0.5);
+    const double q = y * e;
+    return fma(q, p, y);                            // y (1 + e/2 + 3 e^2/8)
 }
-__device__ __forceinline__ float nr_rsqrt(float x) { return rsqrtf(x) ; }
+__device__ __forceinline__ float nr_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double nr_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double e = fma(-x, y, 1.0);
-        y = fma(y, e, y);
-    }
-    return y;
+    const double e = fma(-x, y, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y, p, y);                            // y (1 + e + e^2)
 }
 __device__ __forceinline__ float nr_rcp(float x) { return __frcp_rn(x); }
 
-// One Householder QL step at compile-time pivot row/column R (0-based), LAPACK ?larfg conventions.
-template <typename T, int N, int CPL, int R>
-__device__ __forceinline__ void ql_step(T (&a)[CPL][N], T (&mytau)[CPL], T (&myscale)[CPL], T *xg, int jl, bool &bad) {
+// ---------------------------------------------------------------------------------------------
+// Register-tile factorization, organised as LOOPS so that the hot code stays inside the 32 KB
+// instruction cache (tools/ubench/icache.cu: straight-line code beyond ~32 KB is fetch-bound at
+// ~0.3 instructions/cycle per SM sub-partition -- the fully unrolled variant of this kernel ran at
+// exactly that rate no matter how many warps were resident).
+//
+// The tile is kept SHIFTED: after s steps register index i holds matrix row i-s, so the pivot row of
+// step s (R = N-1-s) always sits at index N-1 and every register index is a compile-time constant.
+// The shift is free -- the rank-1 update writes a[i+1] = fma(coef, x_i, a[i]).  The finished row R
+// leaves the tile each step (straight into the shared-memory image of the output, reflector entries
+// already scaled) and a zero is shifted in at the bottom, so finished positions contribute exact
+// zeros to the dot products and need no masks.  Steps are grouped by GS = 4: group g has a static
+// lower index LO = 4g (indices below hold only zeros) and a static number of live column slots.
+// ---------------------------------------------------------------------------------------------
+constexpr int QL_GS = 4;
+
+// GS (or GS-1) Householder steps of group LO/GS.  NS = column slots still in registers (slot c holds
+// column jl + c*LPM); the pivot columns of this group all live in slot NS-1.
+template <typename T, int N, int CPL, int LO, int NS>
+__device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, T *taup,
+                                         bool wr, int nsteps) {
     using V = typename Vec16<T>::type;
-    constexpr int E = Vec16<T>::E;
-    constexpr int LPM = N / CPL;
-    constexpr int OWN_LANE = R % LPM, OWN_SLOT = R / LPM;
+    using Cfg = BatchedCfg<T, N, CPL>;
+    constexpr int E = Cfg::E, LPM = Cfg::LPM, PITCH = Cfg::PITCH, XP = Cfg::XPITCH;
+    constexpr int OWN_SLOT = NS - 1;
+    constexpr int V0 = LO / E, V1 = N / E;           // 16-byte vectors covering indices [LO, N)
+    constexpr int NCH = (NS >= 2) ? 2 : 4;           // accumulation chains per slot (fixed summation order)
+    constexpr int P = N - 1;                         // register index of the pivot row
     constexpr unsigned FULL = 0xffffffffu;
-    if constexpr (R == 0) {
-        // length-1 reflector: tau = 0, beta = alpha (H = I)
-        if (jl == 0) { mytau[0] = T(0); myscale[0] = T(0); }
-        return;
-    } else {
-        constexpr int NV = (R + E - 1) / E;      // 16-byte vectors covering the tail x[0..R-1]
-        // 1. owner publishes the pivot column's tail
-        if (jl == OWN_LANE) {
+    static_assert(LO % E == 0 && N % E == 0, "vector alignment");
+#pragma unroll 1
+    for (int t = 0; t < nsteps; ++t) {
+        const int s = LO + t, R = N - 1 - s;
+        const int own_lane = R - OWN_SLOT * LPM;
+        T *xa = xg + (s & 1) * XP;
+        // 1. the owner publishes its column (indices [LO, N): zeros, then the tail x, then the pivot)
+        if (jl == own_lane) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
+            for (int v = V0; v < V1; ++v) {
                 V q;
                 T *qp = reinterpret_cast<T *>(&q);
 #pragma unroll
                 for (int e = 0; e < E; ++e) qp[e] = a[OWN_SLOT][v * E + e];
-                reinterpret_cast<V *>(xg)[v] = q;
+                reinterpret_cast<V *>(xa)[v] = q;
             }
         }
         __syncwarp();
-        // 2. tail dot products d_c = sum_{i<R} x_i a[c][i] for every slot that still has live columns
-        //    (four fixed accumulation chains: the summation order never depends on the data)
-        T d[CPL], d1[CPL], d2[CPL], d3[CPL];
+        // 2. d_c = sum_{i < P} x_i a[c][i]  (the owner's own column gives the tail's sum of squares)
+        T d[NS][NCH];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) { d[c] = T(0); d1[c] = T(0); d2[c] = T(0); d3[c] = T(0); }
+        for (int c = 0; c < NS; ++c)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            V q = lds16(xg + v * E);
+            for (int k = 0; k < NCH; ++k) d[c][k] = T(0);
+#pragma unroll
+        for (int v = V0; v < V1; ++v) {
+            V q = lds16(xa + v * E);
             const T *qp = reinterpret_cast<const T *>(&q);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int i = v * E + e;
-                if (i < R) {
+                if (i < P) {
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c)
-                        if (c * LPM <= R) {
-                            if ((i & 3) == 0) d[c] = t_fma(qp[e], a[c][i], d[c]);
-                            else if ((i & 3) == 1) d1[c] = t_fma(qp[e], a[c][i], d1[c]);
-                            else if ((i & 3) == 2) d2[c] = t_fma(qp[e], a[c][i], d2[c]);
-                            else d3[c] = t_fma(qp[e], a[c][i], d3[c]);
-                        }
+                    for (int c = 0; c < NS; ++c) d[c][i % NCH] = t_fma(qp[e], a[c][i], d[c][i % NCH]);
                 }
             }
         }
+        T ds[NS];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) d[c] = (d[c] + d1[c]) + (d2[c] + d3[c]);
-        T ssq = __shfl_sync(FULL, d[OWN_SLOT], OWN_LANE, LPM);
-        T alpha = __shfl_sync(FULL, a[OWN_SLOT][R], OWN_LANE, LPM);
-        T tot = t_fma(alpha, alpha, ssq);
-        bool zero_tail = false;
-        const bool safe = (ssq >= Lim<T>::LO) && (tot <= Lim<T>::HI);
-        if (__any_sync(FULL, !safe)) {
-            zero_tail = ql_rare_zero_tail<T>(xg, R);
-            if (!safe) {
-                if (!zero_tail) bad = true;      // needs ?larfg's scaled path: redo in the generic kernel
-                tot = T(1);
-            } else {
-                zero_tail = false;
-            }
+        for (int c = 0; c < NS; ++c) {
+            if constexpr (NCH == 2) ds[c] = d[c][0] + d[c][1];
+            else ds[c] = (d[c][0] + d[c][1]) + (d[c][2] + d[c][3]);
         }
-        // 3. scalars: beta = -sign(alpha) ||[alpha;x]||, tau = (beta-alpha)/beta = 1 + |alpha|/||.||,
-        //    scale = 1/(alpha-beta) = -1/(tau*beta)
-        const T rinv = nr_rsqrt(tot);                    // 1/||.||
-        T nrm = tot * rinv;
-        nrm = t_fma(t_fma(-nrm, nrm, tot), T(0.5) * rinv, nrm);   // one Newton correction of the norm
+        const T ssq = __shfl_sync(FULL, ds[OWN_SLOT], own_lane, LPM);
+        const T alpha = __shfl_sync(FULL, a[OWN_SLOT][P], own_lane, LPM);
+        const T tot = t_fma(alpha, alpha, ssq);
+        // ?larfg's special exits (zero tail -> tau = 0; under/overflowing squares -> scaled norm and the
+        // safmin loop) are not taken here: the matrix is flagged and redone by geql2_generic_kernel
+        bad = bad || !((ssq >= Lim<T>::LO) && (tot <= Lim<T>::HI));
+        // 3. beta = -sign(alpha) ||[alpha;x]||, tau = (beta-alpha)/beta = 1 + |alpha|/||.||, scale = 1/(alpha-beta)
+        const T rinv = nr_rsqrt(tot);
+        const T nrm = tot * rinv;
         const T beta = -t_copysign(nrm, alpha);
-        T tauk = t_fma(t_abs(alpha), rinv, T(1));
-        T scale = -nr_rcp(tauk * beta);
-        if (zero_tail) { tauk = T(0); scale = T(0); }
-        // 4. owner bookkeeping (scaling of v deferred to the end of the factorization)
-        if (jl == OWN_LANE) {
-            mytau[OWN_SLOT] = tauk;
-            myscale[OWN_SLOT] = scale;                 // v_i = x_i / (alpha - beta)
-            if (!zero_tail) a[OWN_SLOT][R] = beta;
-        }
-        // 5. rank-1 update of the live columns left of the pivot: a_j -= tau (v^T a_j) v
+        const T tauk = t_fma(t_abs(alpha), rinv, T(1));
+        const T scale = nr_rcp(alpha - beta);
+        const T g = -tauk * scale;
+        if (jl == own_lane) myscale[OWN_SLOT] = scale;       // v_i = x_i / (alpha - beta), applied when row i leaves
+        if (wr) taup[R] = tauk;
+        // 4. pivot row: finish it, send it to the output image, and the multipliers of the rank-1 update
+        T dc[NS];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            if (c * LPM < R) {
-                const bool live = (jl + c * LPM) < R;
-                const T s = t_fma(d[c], scale, a[c][R]);
-                const T t = live ? tauk * s : T(0);
-                a[c][R] -= t;
-                d[c] = -t * scale;                      // multiplier on raw x
-            }
+        for (int c = 0; c < NS; ++c) {
+            const int col = jl + c * LPM;
+            const T aR = a[c][P];
+            T sc = t_fma(ds[c], scale, aR);
+            sc = (col < R) ? sc : T(0);                       // only columns left of the pivot are updated
+            const T newR = t_fma(-tauk, sc, aR);
+            dc[c] = g * sc;                                   // multiplier on the raw tail x
+            const T val = (col > R) ? aR * myscale[c] : ((col == R) ? beta : newR);
+            obuf[col * PITCH + R] = val;
         }
+        // 5. a_j -= tau (v^T a_j) v on the tail rows, shifting the tile up by one index
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            V q = lds16(xg + v * E);
+        for (int v = V1 - 1; v >= V0; --v) {
+            V q = lds16(xa + v * E);
             const T *qp = reinterpret_cast<const T *>(&q);
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
+            for (int e = E - 1; e >= 0; --e) {
                 const int i = v * E + e;
-                if (i < R) {
+                if (i < P) {
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c)
-                        if (c * LPM < R) a[c][i] = t_fma(d[c], qp[e], a[c][i]);
+                    for (int c = 0; c < NS; ++c) a[c][i + 1] = t_fma(dc[c], qp[e], a[c][i]);
                 }
             }
         }
-        __syncwarp();     // xg is rewritten by the next step's owner
+#pragma unroll
+        for (int c = 0; c < NS; ++c) a[c][LO] = T(0);
     }
 }
 
-template <typename T, int N, int CPL, int R>
-struct StepLoop {
-    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&mytau)[CPL], T (&myscale)[CPL], T *xg, int jl, bool &bad) {
-        ql_step<T, N, CPL, R>(a, mytau, myscale, xg, jl, bad);
-        if constexpr (R > 0) StepLoop<T, N, CPL, R - 1>::run(a, mytau, myscale, xg, jl, bad);
+// Slot C has no live column any more (all of them are right of every remaining pivot): its registers
+// hold reflector entries of rows [0, C*LPM) at indices [N - C*LPM, N); scale them and send them out.
+template <typename T, int N, int CPL, int C>
+__device__ __forceinline__ void ql_flush_slot(T (&a)[CPL][N], T (&myscale)[CPL], T *obuf, int jl) {
+    using V = typename Vec16<T>::type;
+    using Cfg = BatchedCfg<T, N, CPL>;
+    constexpr int E = Cfg::E, LPM = Cfg::LPM, PITCH = Cfg::PITCH;
+    constexpr int S = N - C * LPM;
+    T *dst = obuf + (jl + C * LPM) * PITCH;
+#pragma unroll
+    for (int i = S; i < N; i += E) {
+        V q;
+        T *qp = reinterpret_cast<T *>(&q);
+#pragma unroll
+        for (int e = 0; e < E; ++e) qp[e] = a[C][i + e] * myscale[C];
+        *reinterpret_cast<V *>(dst + (i - S)) = q;
+    }
+}
+
+template <typename T, int N, int CPL, int GI>
+struct GroupLoop {
+    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, T *taup,
+                                               bool wr) {
+        constexpr int LPM = N / CPL, LO = GI * QL_GS;
+        constexpr int NS = (N - 1 - LO) / LPM + 1;
+        constexpr bool LAST = (LO + QL_GS == N);
+        ql_group<T, N, CPL, LO, NS>(a, myscale, xg, obuf, jl, bad, taup, wr, LAST ? QL_GS - 1 : QL_GS);
+        if constexpr (!LAST) {
+            constexpr int NS_NEXT = (N - 1 - LO - QL_GS) / LPM + 1;
+            if constexpr (NS_NEXT < NS) ql_flush_slot<T, N, CPL, NS - 1>(a, myscale, obuf, jl);
+            GroupLoop<T, N, CPL, GI + 1>::run(a, myscale, xg, obuf, jl, bad, taup, wr);
+        } else {
+            // R = 0: a length-1 reflector is the identity (tau = 0, beta = alpha); row 0 leaves the tile
+            if (wr) taup[0] = T(0);
+            const T aR = a[0][N - 1];
+            obuf[jl * BatchedCfg<T, N, CPL>::PITCH] = (jl > 0) ? aR * myscale[0] : aR;
+        }
     }
 };
 
+// One warp factors G = 32/LPM matrices at a time: TMA (or plain loads) -> shared-memory image ->
+// registers -> factor (finished rows go back into the image) -> TMA bulk stores (or plain stores).
 template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restrict__ tau, int64_t strideTau,
@@ -233,7 +260,8 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
     const int g = lane / LPM, jl = lane % LPM;
     unsigned char *wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
     T *buf = reinterpret_cast<T *>(wbase);
-    T *xg = reinterpret_cast<T *>(wbase + Cfg::BUF_BYTES) + g * Cfg::XPITCH;
+    T *obuf = buf + g * N * PITCH;                           // this matrix's image (input, then output)
+    T *xg = reinterpret_cast<T *>(wbase + Cfg::BUF_BYTES) + g * 2 * Cfg::XPITCH;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + Cfg::BUF_BYTES + Cfg::X_BYTES);
 
     const int64_t nwb = (batch + G - 1) / G;                 // warp-batches of G matrices
@@ -243,94 +271,75 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
         if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
         __syncwarp();
     }
-    auto issue = [&](int64_t wb) {
-        const int64_t m0 = wb * G;
-        const int64_t nvalid = (batch - m0) < G ? (batch - m0) : G;
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * N * N * sizeof(T)));
-        const int64_t mi = m0 + g;
-        if (mi < batch) {
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int col = jl + c * LPM;
-                tma_load_1d(buf + (g * N + col) * PITCH, A + mi * strideA + (int64_t)col * lda, N * sizeof(T), bar);
-            }
-        }
-    };
     uint32_t phase = 0;
-    if constexpr (USE_TMA) {
-        if (gw < nwb) issue(gw);
-    }
     for (int64_t wb = gw; wb < nwb; wb += nw) {
-        const int64_t mi = wb * G + g;
+        const int64_t m0 = wb * G, mi = m0 + g;
         const bool valid = mi < batch;
-        T a[CPL][N];
+        T *Am = A + (valid ? mi : 0) * strideA;
+        // ---- stage the matrices of this warp-batch ----
         if constexpr (USE_TMA) {
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            const int64_t nvalid = (batch - m0) < G ? (batch - m0) : G;
+            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * N * N * sizeof(T)));
+            __syncwarp();
+            if (valid) {
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const V *src = reinterpret_cast<const V *>(buf + (g * N + jl + c * LPM) * PITCH);
-#pragma unroll
-                for (int v = 0; v < N / E; ++v) {
-                    V q = src[v];
-                    const T *qp = reinterpret_cast<const T *>(&q);
-#pragma unroll
-                    for (int e = 0; e < E; ++e) a[c][v * E + e] = qp[e];
+                for (int c = 0; c < CPL; ++c) {
+                    const int col = jl + c * LPM;
+                    tma_load_1d(obuf + col * PITCH, Am + (int64_t)col * lda, N * sizeof(T), bar);
                 }
             }
-            __syncwarp();
-            if (wb + nw < nwb) issue(wb + nw);            // prefetch the next warp-batch into the same buffer
+            mbar_wait(bar, phase);
+            phase ^= 1;
         } else {
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const T *src = A + (valid ? mi : 0) * strideA + (int64_t)(jl + c * LPM) * lda;
-#pragma unroll
-                for (int i = 0; i < N; ++i) a[c][i] = src[i];
+            if (valid) {
+                for (int idx = jl; idx < N * N; idx += LPM) obuf[(idx / N) * PITCH + (idx % N)] = Am[(int64_t)(idx / N) * lda + (idx % N)];
             }
+            __syncwarp();
         }
-        if (!valid) {
-#pragma unroll
-            for (int c = 0; c < CPL; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i) a[c][i] = (i == jl + c * LPM) ? T(1) : T(0);
-        }
-        T mytau[CPL], myscale[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) { mytau[c] = T(0); myscale[c] = T(0); }
-
-        bool bad = false;
-        StepLoop<T, N, CPL, N - 1>::run(a, mytau, myscale, xg, jl, bad);
-
-        // deferred scaling of the reflector tails: v_i = x_i / (alpha - beta), rows above the pivot only
+        T a[CPL][N];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const int col = jl + c * LPM;
+            const V *src = reinterpret_cast<const V *>(obuf + col * PITCH);
 #pragma unroll
-            for (int i = 0; i < N - 1; ++i) a[c][i] *= (i < col) ? myscale[c] : T(1);
-        }
-        if (valid && bad && jl == 0) redo_list[atomicAdd(redo_count, 1)] = (int)mi;      // untouched; redone generically
-        if (valid && !bad) {
+            for (int v = 0; v < N / E; ++v) {
+                V q = src[v];
+                const T *qp = reinterpret_cast<const T *>(&q);
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int col = jl + c * LPM;
-                T *dst = A + mi * strideA + (int64_t)col * lda;
-                if constexpr (USE_TMA) {
-#pragma unroll
-                    for (int v = 0; v < N / E; ++v) {
-                        V q;
-                        T *qp = reinterpret_cast<T *>(&q);
-#pragma unroll
-                        for (int e = 0; e < E; ++e) qp[e] = a[c][v * E + e];
-                        reinterpret_cast<V *>(dst)[v] = q;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) dst[i] = a[c][i];
-                }
-                tau[mi * strideTau + col] = mytau[c];
+                for (int e = 0; e < E; ++e) a[c][v * E + e] = valid ? qp[e] : ((v * E + e == col) ? T(1) : T(0));
             }
         }
+        T myscale[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) myscale[c] = T(0);
+
+        bool bad = false;
+        GroupLoop<T, N, CPL, 0>::run(a, myscale, xg, obuf, jl, bad, tau + (valid ? mi : 0) * strideTau, valid && jl == 0);
+
+        // flagged matrices stay untouched in global memory and are redone by the generic kernel
+        if (valid && bad && jl == 0) redo_list[atomicAdd(redo_count, 1)] = (int)mi;
+        __syncwarp();
+        if constexpr (USE_TMA) {
+            fence_proxy_async();                                  // generic-proxy writes -> visible to the bulk copies
+            __syncwarp();
+            if (valid && !bad) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const int col = jl + c * LPM;
+                    tma_store_1d(Am + (int64_t)col * lda, obuf + col * PITCH, N * sizeof(T));
+                }
+            }
+            tma_store_commit();
+            tma_store_wait_read();                                // the image may be overwritten by the next load
+            __syncwarp();
+        } else {
+            if (valid && !bad) {
+                for (int idx = jl; idx < N * N; idx += LPM) Am[(int64_t)(idx / N) * lda + (idx % N)] = obuf[(idx / N) * PITCH + (idx % N)];
+            }
+            __syncwarp();
+        }
     }
+    if constexpr (USE_TMA) tma_store_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -651,7 +660,12 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
     switch (n) {
         case 8: return qlb::launch_geqlf_batched<double, 8, 1, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
-        case 32: return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
+        case 32:
+            if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<double, 32, 1, 4, 4>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 3) return qlb::launch_geqlf_batched<double, 32, 1, 4, 5>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 4) return qlb::launch_geqlf_batched<double, 32, 1, 4, 6>(h, A, lda, strideA, tau, strideTau, batch);
+            return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
