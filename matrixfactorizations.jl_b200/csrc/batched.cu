@@ -13,6 +13,7 @@
 // tau = (2 n^2 + n) * sizeof(T) bytes per matrix, the compulsory minimum.
 #include "common.cuh"
 #include "internal.h"
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace qlb {
 
@@ -52,6 +53,24 @@ __device__ __forceinline__ float4 lds16(const float *p) {
     return r;
 }
 
+
+// ---- TMA tensor copies (SASS: UTMALDG / UTMASTG) ----------------------------------------------------
+// The batch is described to the TMA unit as a 3-D tensor {rows = N, cols = N, matrix}; the box is
+// {N + E, N, 1}: the E rows past the end of each column are out of bounds, so loads fill them with zeros
+// and stores skip them -- one copy per matrix produces / consumes the PADDED shared-memory image
+// (column pitch N + E, conflict-free for "one column per lane" accesses).
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, int c0, int c1, int c2, const void *smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
 template <typename T, int N, int CPL>
 struct BatchedCfg {
     static constexpr int E = Vec16<T>::E;            // elements per 16-byte vector
@@ -62,7 +81,8 @@ struct BatchedCfg {
     static constexpr int XPITCH = N + E;             // per-group pivot-column broadcast buffer
     static constexpr int BUF_BYTES = NCOLS * PITCH * (int)sizeof(T);
     static constexpr int X_BYTES = 2 * G * XPITCH * (int)sizeof(T);      // double-buffered
-    static constexpr int WARP_BYTES = BUF_BYTES + X_BYTES + 16;   // + mbarrier slot
+    static constexpr int IMG_BYTES = N * PITCH * (int)sizeof(T);   // one matrix image (multiple of 128 bytes)
+    static constexpr int WARP_BYTES = (BUF_BYTES + X_BYTES + 16 + 127) / 128 * 128;   // + mbarrier slot, 128-byte granular
 };
 
 // 1/sqrt(x) and 1/x for x in the normal range: hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) plus ONE
@@ -98,12 +118,11 @@ __device__ __forceinline__ float nr_rcp(float x) { return __frcp_rn(x); }
 // The shift is free -- the rank-1 update writes a[i+1] = fma(coef, x_i, a[i]).  The finished row R
 // leaves the tile each step (straight into the shared-memory image of the output, reflector entries
 // already scaled) and a zero is shifted in at the bottom, so finished positions contribute exact
-// zeros to the dot products and need no masks.  Steps are grouped by GS = 4: group g has a static
-// lower index LO = 4g (indices below hold only zeros) and a static number of live column slots.
+// zeros to the dot products and need no masks.  Steps are grouped (4 or 8 at a time): a group has a
+// static lower index LO (indices below hold only zeros) and a static number of live column slots.
 // ---------------------------------------------------------------------------------------------
-constexpr int QL_GS = 4;
 
-// GS (or GS-1) Householder steps of group LO/GS.  NS = column slots still in registers (slot c holds
+// The Householder steps of the group that starts after LO steps.  NS = column slots still in registers (slot c holds
 // column jl + c*LPM); the pivot columns of this group all live in slot NS-1.
 template <typename T, int N, int CPL, int LO, int NS>
 __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, T *taup,
@@ -225,18 +244,24 @@ __device__ __forceinline__ void ql_flush_slot(T (&a)[CPL][N], T (&myscale)[CPL],
     }
 }
 
-template <typename T, int N, int CPL, int GI>
+// Group sizes: 4 steps while more than 16 rows are live, 8 afterwards (short tiles: the zero rows cost
+// little, and fewer loop bodies keep the code small).  LO is the number of steps already done.
+template <int N, int LO>
+struct GroupSize { static constexpr int value = (N - LO > 16) ? 4 : 8; };
+
+template <typename T, int N, int CPL, int LO>
 struct GroupLoop {
     static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, T *taup,
                                                bool wr) {
-        constexpr int LPM = N / CPL, LO = GI * QL_GS;
+        constexpr int LPM = N / CPL, GS = GroupSize<N, LO>::value;
         constexpr int NS = (N - 1 - LO) / LPM + 1;
-        constexpr bool LAST = (LO + QL_GS == N);
-        ql_group<T, N, CPL, LO, NS>(a, myscale, xg, obuf, jl, bad, taup, wr, LAST ? QL_GS - 1 : QL_GS);
+        constexpr bool LAST = (LO + GS == N);
+        static_assert((N - 1 - LO) / LPM == (N - LO - GS) / LPM, "a group's pivot columns live in one slot");
+        ql_group<T, N, CPL, LO, NS>(a, myscale, xg, obuf, jl, bad, taup, wr, LAST ? GS - 1 : GS);
         if constexpr (!LAST) {
-            constexpr int NS_NEXT = (N - 1 - LO - QL_GS) / LPM + 1;
+            constexpr int NS_NEXT = (N - 1 - LO - GS) / LPM + 1;
             if constexpr (NS_NEXT < NS) ql_flush_slot<T, N, CPL, NS - 1>(a, myscale, obuf, jl);
-            GroupLoop<T, N, CPL, GI + 1>::run(a, myscale, xg, obuf, jl, bad, taup, wr);
+            GroupLoop<T, N, CPL, LO + GS>::run(a, myscale, xg, obuf, jl, bad, taup, wr);
         } else {
             // R = 0: a length-1 reflector is the identity (tau = 0, beta = alpha); row 0 leaves the tile
             if (wr) taup[0] = T(0);
@@ -250,12 +275,13 @@ struct GroupLoop {
 // registers -> factor (finished rows go back into the image) -> TMA bulk stores (or plain stores).
 template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restrict__ tau, int64_t strideTau,
-                     int64_t batch, int *__restrict__ redo_count, int *__restrict__ redo_list) {
+geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A, int64_t lda, int64_t strideA,
+                     T *__restrict__ tau, int64_t strideTau, int64_t batch, int *__restrict__ redo_count,
+                     int *__restrict__ redo_list) {
     using Cfg = BatchedCfg<T, N, CPL>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, PITCH = Cfg::PITCH;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / LPM, jl = lane % LPM;
     unsigned char *wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
@@ -278,22 +304,20 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
         T *Am = A + (valid ? mi : 0) * strideA;
         // ---- stage the matrices of this warp-batch ----
         if constexpr (USE_TMA) {
-            const int64_t nvalid = (batch - m0) < G ? (batch - m0) : G;
-            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * N * N * sizeof(T)));
-            __syncwarp();
-            if (valid) {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const int col = jl + c * LPM;
-                    tma_load_1d(obuf + col * PITCH, Am + (int64_t)col * lda, N * sizeof(T), bar);
-                }
+            const int nvalid = (int)((batch - m0) < G ? (batch - m0) : G);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * Cfg::IMG_BYTES));
+                for (int q = 0; q < nvalid; ++q) tma_load_3d(buf + q * N * PITCH, &tmap, 0, 0, (int)(m0 + q), bar);
+            }
+            if (!valid) {      // tail of the batch: an identity keeps the arithmetic finite (results are discarded)
+                for (int idx = jl; idx < N * N; idx += LPM) obuf[(idx / N) * PITCH + (idx % N)] = (idx / N == idx % N) ? T(1) : T(0);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
+            __syncwarp();
         } else {
-            if (valid) {
-                for (int idx = jl; idx < N * N; idx += LPM) obuf[(idx / N) * PITCH + (idx % N)] = Am[(int64_t)(idx / N) * lda + (idx % N)];
-            }
+            for (int idx = jl; idx < N * N; idx += LPM)
+                obuf[(idx / N) * PITCH + (idx % N)] = valid ? Am[(int64_t)(idx / N) * lda + (idx % N)] : ((idx / N == idx % N) ? T(1) : T(0));
             __syncwarp();
         }
         T a[CPL][N];
@@ -306,7 +330,7 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
                 V q = src[v];
                 const T *qp = reinterpret_cast<const T *>(&q);
 #pragma unroll
-                for (int e = 0; e < E; ++e) a[c][v * E + e] = valid ? qp[e] : ((v * E + e == col) ? T(1) : T(0));
+                for (int e = 0; e < E; ++e) a[c][v * E + e] = qp[e];
             }
         }
         T myscale[CPL];
@@ -322,13 +346,7 @@ geqlf_batched_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restr
         if constexpr (USE_TMA) {
             fence_proxy_async();                                  // generic-proxy writes -> visible to the bulk copies
             __syncwarp();
-            if (valid && !bad) {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const int col = jl + c * LPM;
-                    tma_store_1d(Am + (int64_t)col * lda, obuf + col * PITCH, N * sizeof(T));
-                }
-            }
+            if (valid && !bad && jl == 0) tma_store_3d(&tmap, 0, 0, (int)mi, obuf);
             tma_store_commit();
             tma_store_wait_read();                                // the image may be overwritten by the next load
             __syncwarp();
@@ -572,6 +590,38 @@ apply_batched_kernel(const T *__restrict__ A, int64_t lda, int64_t strideA, cons
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
+// 3-D tensor map {rows N, cols N, matrix} over the strided batch, box {pitch, N, 1} (see tma_load_3d).
+// The encoder lives in the driver library; it is fetched through the runtime so that libqlb200.so has no
+// link-time dependency on libcuda (the library must load on a box without a GPU driver).
+typedef CUresult (*qlb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+template <typename T>
+static bool make_batch_tensor_map(CUtensorMap *tm, const T *A, int n, int64_t lda, int64_t strideA, int64_t batch, int pitch) {
+    static qlb_encode_tiled_fn enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            enc = (qlb_encode_tiled_fn)fn;
+        else
+            (void)cudaGetLastError();
+    }
+    if (!enc || pitch > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch};
+    // a single matrix may come with any stride: use a harmless consistent one
+    const int64_t sA = batch > 1 ? strideA : (int64_t)lda * n;
+    const cuuint64_t strides[2] = {(cuuint64_t)lda * sizeof(T), (cuuint64_t)sA * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)pitch, (cuuint32_t)n, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(tm, dt, 3, (void *)A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T>
 static bool tma_ok(const T *A, int64_t lda, int64_t strideA) {
     return ((uintptr_t)A % 16 == 0) && ((lda * sizeof(T)) % 16 == 0) && ((strideA * sizeof(T)) % 16 == 0);
@@ -582,7 +632,9 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
                                 int64_t batch) {
     using Cfg = BatchedCfg<T, N, CPL>;
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES;
-    const bool tma = tma_ok(A, lda, strideA);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<T>(&tmap, A, N, lda, strideA, batch, Cfg::PITCH);
     auto kern = tma ? geqlf_batched_kernel<T, N, CPL, WARPS, MINB, true> : geqlf_batched_kernel<T, N, CPL, WARPS, MINB, false>;
     QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -599,7 +651,7 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     if (rc) return rc;
     int *redo_count = (int *)h->redo, *redo_list = redo_count + 4;
     QLB_CUDA(h, cudaMemsetAsync(redo_count, 0, sizeof(int), h->stream));
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, batch, redo_count, redo_list);
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, redo_count, redo_list);
     QLB_LAUNCH_CHECK(h);
     return launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, N, redo_count, 0, redo_list);
 }
