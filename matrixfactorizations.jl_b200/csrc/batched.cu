@@ -125,8 +125,7 @@ __device__ __forceinline__ float nr_rcp(float x) { return __frcp_rn(x); }
 // The Householder steps of the group that starts after LO steps.  NS = column slots still in registers (slot c holds
 // column jl + c*LPM); the pivot columns of this group all live in slot NS-1.
 template <typename T, int N, int CPL, int LO, int NS>
-__device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, T *taup,
-                                         bool wr, int nsteps) {
+__device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, int nsteps) {
     using V = typename Vec16<T>::type;
     using Cfg = BatchedCfg<T, N, CPL>;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, PITCH = Cfg::PITCH, XP = Cfg::XPITCH;
@@ -191,8 +190,10 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         const T tauk = t_fma(t_abs(alpha), rinv, T(1));
         const T scale = nr_rcp(alpha - beta);
         const T g = -tauk * scale;
-        if (jl == own_lane) myscale[OWN_SLOT] = scale;       // v_i = x_i / (alpha - beta), applied when row i leaves
-        if (wr) taup[R] = tauk;
+        if (jl == own_lane) {
+            myscale[OWN_SLOT] = scale;                        // v_i = x_i / (alpha - beta), applied when row i leaves
+            obuf[(jl + OWN_SLOT * LPM) * PITCH + N] = tauk;   // tau_R waits in the padding row of its column
+        }
         // 4. pivot row: finish it, send it to the output image, and the multipliers of the rank-1 update
         T dc[NS];
 #pragma unroll
@@ -251,22 +252,21 @@ struct GroupSize { static constexpr int value = (N - LO > 16) ? 4 : 8; };
 
 template <typename T, int N, int CPL, int LO>
 struct GroupLoop {
-    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, T *taup,
-                                               bool wr) {
+    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad) {
         constexpr int LPM = N / CPL, GS = GroupSize<N, LO>::value;
         constexpr int NS = (N - 1 - LO) / LPM + 1;
         constexpr bool LAST = (LO + GS == N);
         static_assert((N - 1 - LO) / LPM == (N - LO - GS) / LPM, "a group's pivot columns live in one slot");
-        ql_group<T, N, CPL, LO, NS>(a, myscale, xg, obuf, jl, bad, taup, wr, LAST ? GS - 1 : GS);
+        ql_group<T, N, CPL, LO, NS>(a, myscale, xg, obuf, jl, bad, LAST ? GS - 1 : GS);
         if constexpr (!LAST) {
             constexpr int NS_NEXT = (N - 1 - LO - GS) / LPM + 1;
             if constexpr (NS_NEXT < NS) ql_flush_slot<T, N, CPL, NS - 1>(a, myscale, obuf, jl);
-            GroupLoop<T, N, CPL, LO + GS>::run(a, myscale, xg, obuf, jl, bad, taup, wr);
+            GroupLoop<T, N, CPL, LO + GS>::run(a, myscale, xg, obuf, jl, bad);
         } else {
             // R = 0: a length-1 reflector is the identity (tau = 0, beta = alpha); row 0 leaves the tile
-            if (wr) taup[0] = T(0);
             const T aR = a[0][N - 1];
             obuf[jl * BatchedCfg<T, N, CPL>::PITCH] = (jl > 0) ? aR * myscale[0] : aR;
+            if (jl == 0) obuf[N] = T(0);
         }
     }
 };
@@ -290,24 +290,24 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
     T *xg = reinterpret_cast<T *>(wbase + Cfg::BUF_BYTES) + g * 2 * Cfg::XPITCH;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + Cfg::BUF_BYTES + Cfg::X_BYTES);
 
-    const int64_t nwb = (batch + G - 1) / G;                 // warp-batches of G matrices
-    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+    const int nbatch = (int)batch;                           // < 2^31 (checked by the launcher)
+    const int nwb = (nbatch + G - 1) / G;                    // warp-batches of G matrices
+    const int gw = (int)blockIdx.x * WARPS + warp, nw = (int)gridDim.x * WARPS;
 
     if constexpr (USE_TMA) {
         if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
         __syncwarp();
     }
     uint32_t phase = 0;
-    for (int64_t wb = gw; wb < nwb; wb += nw) {
-        const int64_t m0 = wb * G, mi = m0 + g;
-        const bool valid = mi < batch;
-        T *Am = A + (valid ? mi : 0) * strideA;
+    for (int wb = gw; wb < nwb; wb += nw) {
+        const int m0 = wb * G, mi = m0 + g;
+        const bool valid = mi < nbatch;
         // ---- stage the matrices of this warp-batch ----
         if constexpr (USE_TMA) {
-            const int nvalid = (int)((batch - m0) < G ? (batch - m0) : G);
+            const int nvalid = (nbatch - m0) < G ? (nbatch - m0) : G;
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * Cfg::IMG_BYTES));
-                for (int q = 0; q < nvalid; ++q) tma_load_3d(buf + q * N * PITCH, &tmap, 0, 0, (int)(m0 + q), bar);
+                for (int q = 0; q < nvalid; ++q) tma_load_3d(buf + q * N * PITCH, &tmap, 0, 0, m0 + q, bar);
             }
             if (!valid) {      // tail of the batch: an identity keeps the arithmetic finite (results are discarded)
                 for (int idx = jl; idx < N * N; idx += LPM) obuf[(idx / N) * PITCH + (idx % N)] = (idx / N == idx % N) ? T(1) : T(0);
@@ -316,6 +316,7 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
             phase ^= 1;
             __syncwarp();
         } else {
+            const T *Am = A + (int64_t)(valid ? mi : 0) * strideA;
             for (int idx = jl; idx < N * N; idx += LPM)
                 obuf[(idx / N) * PITCH + (idx % N)] = valid ? Am[(int64_t)(idx / N) * lda + (idx % N)] : ((idx / N == idx % N) ? T(1) : T(0));
             __syncwarp();
@@ -338,20 +339,28 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
         for (int c = 0; c < CPL; ++c) myscale[c] = T(0);
 
         bool bad = false;
-        GroupLoop<T, N, CPL, 0>::run(a, myscale, xg, obuf, jl, bad, tau + (valid ? mi : 0) * strideTau, valid && jl == 0);
+        GroupLoop<T, N, CPL, 0>::run(a, myscale, xg, obuf, jl, bad);
 
         // flagged matrices stay untouched in global memory and are redone by the generic kernel
-        if (valid && bad && jl == 0) redo_list[atomicAdd(redo_count, 1)] = (int)mi;
+        if (valid && bad && jl == 0) redo_list[atomicAdd(redo_count, 1)] = mi;
         __syncwarp();
+        if (valid && !bad) {                                      // tau: one coalesced row per matrix
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int col = jl + c * LPM;
+                tau[(int64_t)mi * strideTau + col] = obuf[col * PITCH + N];
+            }
+        }
         if constexpr (USE_TMA) {
             fence_proxy_async();                                  // generic-proxy writes -> visible to the bulk copies
             __syncwarp();
-            if (valid && !bad && jl == 0) tma_store_3d(&tmap, 0, 0, (int)mi, obuf);
+            if (valid && !bad && jl == 0) tma_store_3d(&tmap, 0, 0, mi, obuf);
             tma_store_commit();
             tma_store_wait_read();                                // the image may be overwritten by the next load
             __syncwarp();
         } else {
             if (valid && !bad) {
+                T *Am = A + (int64_t)mi * strideA;
                 for (int idx = jl; idx < N * N; idx += LPM) Am[(int64_t)(idx / N) * lda + (idx % N)] = obuf[(idx / N) * PITCH + (idx % N)];
             }
             __syncwarp();
@@ -714,9 +723,9 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
             if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<double, 32, 1, 4, 4>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 3) return qlb::launch_geqlf_batched<double, 32, 1, 4, 5>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 4) return qlb::launch_geqlf_batched<double, 32, 1, 4, 6>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 5) return qlb::launch_geqlf_batched<double, 32, 2, 5, 2>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 6) return qlb::launch_geqlf_batched<double, 32, 2, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 7) return qlb::launch_geqlf_batched<double, 32, 2, 11, 1>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
