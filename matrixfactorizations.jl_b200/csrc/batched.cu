@@ -131,6 +131,8 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
     constexpr int E = Cfg::E, LPM = Cfg::LPM, PITCH = Cfg::PITCH, XP = Cfg::XPITCH;
     constexpr int OWN_SLOT = NS - 1;
     constexpr int V0 = LO / E, V1 = N / E;           // 16-byte vectors covering indices [LO, N)
+    constexpr int NVEC = V1 - V0;
+    constexpr int PD = 5;                            // x vectors in flight
     constexpr int NCH = (NS >= 2) ? 2 : 4;           // accumulation chains per slot (fixed summation order)
     constexpr int P = N - 1;                         // register index of the pivot row
     constexpr unsigned FULL = 0xffffffffu;
@@ -158,19 +160,28 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         for (int c = 0; c < NS; ++c)
 #pragma unroll
             for (int k = 0; k < NCH; ++k) d[c][k] = T(0);
+        // (x is read through an explicit queue of PD vectors: shared-memory latency under load is ~60-80
+        //  cycles, one vector feeds only ~9 cycles of FP64 issue, and ptxas by itself keeps just 2 in flight)
+        V qa[NVEC];
 #pragma unroll
-        for (int v = V0; v < V1; ++v) {
-            V q = lds16(xa + v * E);
-            const T *qp = reinterpret_cast<const T *>(&q);
+        for (int w = 0; w < PD && w < NVEC; ++w) qa[w] = lds16(xa + (V0 + w) * E);
+#pragma unroll
+        for (int w = 0; w < NVEC; ++w) {
+            if (w + PD < NVEC) qa[w + PD] = lds16(xa + (V0 + w + PD) * E);
+            const T *qp = reinterpret_cast<const T *>(&qa[w]);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int i = v * E + e;
+                const int i = (V0 + w) * E + e;
                 if (i < P) {
 #pragma unroll
                     for (int c = 0; c < NS; ++c) d[c][i % NCH] = t_fma(qp[e], a[c][i], d[c][i % NCH]);
                 }
             }
         }
+        // the update pass walks x downwards; its first PD vectors are requested now, ahead of the scalar chain
+        V qb[NVEC];
+#pragma unroll
+        for (int w = 0; w < PD && w < NVEC; ++w) qb[w] = lds16(xa + (V1 - 1 - w) * E);
         T ds[NS];
 #pragma unroll
         for (int c = 0; c < NS; ++c) {
@@ -209,12 +220,12 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         }
         // 5. a_j -= tau (v^T a_j) v on the tail rows, shifting the tile up by one index
 #pragma unroll
-        for (int v = V1 - 1; v >= V0; --v) {
-            V q = lds16(xa + v * E);
-            const T *qp = reinterpret_cast<const T *>(&q);
+        for (int w = 0; w < NVEC; ++w) {
+            if (w + PD < NVEC) qb[w + PD] = lds16(xa + (V1 - 1 - w - PD) * E);
+            const T *qp = reinterpret_cast<const T *>(&qb[w]);
 #pragma unroll
             for (int e = E - 1; e >= 0; --e) {
-                const int i = v * E + e;
+                const int i = (V1 - 1 - w) * E + e;
                 if (i < P) {
 #pragma unroll
                     for (int c = 0; c < NS; ++c) a[c][i + 1] = t_fma(dc[c], qp[e], a[c][i]);
@@ -719,8 +730,8 @@ static int dispatch_apply_n(qlb200_ctx *h, int64_t n, const T *A, int64_t lda, i
 int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int64_t strideA, double *tau,
                           int64_t strideTau, int64_t batch) {
     switch (n) {
-        case 8: return qlb::launch_geqlf_batched<double, 8, 1, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
-        case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
+        case 8: return qlb::launch_geqlf_batched<double, 8, 1, 4, 6>(h, A, lda, strideA, tau, strideTau, batch);
+        case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
             if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
             if (h->opt_bvar == 5) return qlb::launch_geqlf_batched<double, 32, 2, 5, 2>(h, A, lda, strideA, tau, strideTau, batch);
@@ -734,9 +745,9 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
 int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
                           int64_t strideTau, int64_t batch) {
     switch (n) {
-        case 8: return qlb::launch_geqlf_batched<float, 8, 1, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
-        case 16: return qlb::launch_geqlf_batched<float, 16, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
-        case 32: return qlb::launch_geqlf_batched<float, 32, 2, 4, 1>(h, A, lda, strideA, tau, strideTau, batch);
+        case 8: return qlb::launch_geqlf_batched<float, 8, 1, 4, 8>(h, A, lda, strideA, tau, strideTau, batch);
+        case 16: return qlb::launch_geqlf_batched<float, 16, 2, 4, 5>(h, A, lda, strideA, tau, strideTau, batch);
+        case 32: return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");

@@ -59,7 +59,7 @@ for bv in bvars:
     err = float(np.abs(A[:sub].cpu().numpy() - Fo).max())
     terr = float(np.abs(tau[:sub].cpu().numpy() - tauo).max())
     r = {"geqlf_ms": med * 1e3, "best_ms": best * 1e3, "matrices_per_s": batch / med, "gbs": batch * (2 * n * n + n) * es / med / 1e9,
-         "max_err_factors": err, "max_err_tau": terr, "tol": 50 * n * eps * n}
+         "max_err_factors": err, "max_err_tau": terr, "tol": float(50 * n * eps * n)}
     # the factors are in A now: time the apply kernels on them
     F = A.clone()
     med, best = timed(lambda: q.lmul_batched_(F, tau, B, adjoint=True, handle=h))
