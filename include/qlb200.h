@@ -108,6 +108,33 @@ int qlb200_dqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *
 int qlb200_dgerqf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
 int qlb200_dgerqf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau);
 
+/* RQ's packed Q (reference src/rq.jl:118-137 lmul!(Q::RQPackedQ,B) = LAPACK.ormrq!('L','N',...), :183-202
+ * adjoint, :234-291 rmul!): LAPACK ?ormrq argument order.  A is k x nq (lda >= k): row i holds the vector
+ * of H(i) as returned by gerqf in the LAST k rows of its factors (pass a pointer to the first of them).
+ * Implemented as ?ormql on the transposed reflectors (Q_rq = Q_ql'). */
+int qlb200_dormrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k,
+                  const double *A, int64_t lda, const double *tau, double *C, int64_t ldc);
+int qlb200_dormrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k,
+                      const double *dA, int64_t lda, const double *dtau, double *dC, int64_t ldc);
+
+/* ---- UL: reverse-order partially pivoted LU -------------------------------------------------------
+ * Replaces ul!(A, pivot; check) = generic_ulfact!(A, pivot) (reference src/ul.jl:146-196): A[p,:] = U*L,
+ * U unit upper / L lower packed in A, ipiv[k] (1-based, min(m,n) entries, Julia BlasInt = int64) the row
+ * interchanged with row k, first maximum wins ties (src/ul.jl:162).  Only rows/columns 1..min(m,n) are
+ * eliminated (src/ul.jl:155-191); interchanges run over all n columns.  pivot = 0 is Val(false).
+ * *info_singular (device int32 for _dev) receives the reference's `info` field: 0, or the largest k with
+ * a zero pivot (the Julia shim raises SingularException when check = true, src/ul.jl:193). */
+int qlb200_dulfact(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, int64_t *ipiv,
+                   int pivot, int32_t *info_singular);
+int qlb200_dulfact_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, int64_t *dipiv,
+                       int pivot, int32_t *dinfo_singular);
+/* ldiv!(F::UL, B), square (reference src/ul.jl:363-393): rows of B permuted by ipiv in reverse order,
+ * then U^{-1} (unit upper), then L^{-1}.  Host form returns i > 0 if L[i,i] == 0. */
+int qlb200_dulsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                    const int64_t *ipiv, double *B, int64_t ldb);
+int qlb200_dulsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
+                        const int64_t *dipiv, double *dB, int64_t ldb);
+
 /* ---- the FP64 tensor-core GEMM of the trailing update, exposed for tests and benchmarks -------
  * C = alpha*op(A)*op(B) + beta*C, column-major device pointers, op 'N' or 'T' (BLAS dgemm order). */
 int qlb200_dgemm_dev(qlb200_handle h, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
@@ -115,7 +142,7 @@ int qlb200_dgemm_dev(qlb200_handle h, char transa, char transb, int64_t m, int64
                      int64_t ldc);
 
 /* ---- batched small square QL (new surface; per-matrix semantics = src/ql.jl:72) ------------
- * `batch` independent n x n matrices, n in {8, 16, 32}; matrix b starts at A + b*strideA,
+ * `batch` independent n x n matrices, 1 <= n <= 64 (register kernels for n in {8, 16, 32}); matrix b starts at A + b*strideA,
  * column-major with leading dimension lda; tau of matrix b at tau + b*strideTau (n entries).
  * Reference-equivalent workload: `for i: ql!(view(A,:,:,i))`. */
 int qlb200_dgeqlf_batched(qlb200_handle h, int64_t n, double *A, int64_t lda, int64_t strideA,
@@ -157,6 +184,27 @@ int qlb200_dqlsolve_batched_dev(qlb200_handle h, int64_t n, int64_t nrhs, const 
 int qlb200_sqlsolve_batched_dev(qlb200_handle h, int64_t n, int64_t nrhs, const float *dA, int64_t lda,
                                 int64_t strideA, const float *dtau, int64_t strideTau, float *dB,
                                 int64_t ldb, int64_t strideB, int64_t batch, int32_t *dinfo_out);
+
+/* ---- batched work sharded over several GPUs of one box (host pointers) ----------------------------
+ * `hs[0..nh)` are handles created on the devices to use; handle g gets the contiguous matrix-index range
+ * [g*batch/nh, (g+1)*batch/nh) (+ remainder on the first handles) and runs it on its own device from its
+ * own host thread.  No cross-GPU communication; results land in the caller's arrays. */
+int qlb200_dgeqlf_batched_mg(qlb200_handle *hs, int nh, int64_t n, double *A, int64_t lda, int64_t strideA,
+                             double *tau, int64_t strideTau, int64_t batch);
+int qlb200_sgeqlf_batched_mg(qlb200_handle *hs, int nh, int64_t n, float *A, int64_t lda, int64_t strideA,
+                             float *tau, int64_t strideTau, int64_t batch);
+int qlb200_dormql_batched_mg(qlb200_handle *hs, int nh, char trans, int64_t n, int64_t nrhs, const double *A,
+                             int64_t lda, int64_t strideA, const double *tau, int64_t strideTau, double *B,
+                             int64_t ldb, int64_t strideB, int64_t batch);
+int qlb200_sormql_batched_mg(qlb200_handle *hs, int nh, char trans, int64_t n, int64_t nrhs, const float *A,
+                             int64_t lda, int64_t strideA, const float *tau, int64_t strideTau, float *B,
+                             int64_t ldb, int64_t strideB, int64_t batch);
+int qlb200_dqlsolve_batched_mg(qlb200_handle *hs, int nh, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                               int64_t strideA, const double *tau, int64_t strideTau, double *B, int64_t ldb,
+                               int64_t strideB, int64_t batch, int32_t *info_out);
+int qlb200_sqlsolve_batched_mg(qlb200_handle *hs, int nh, int64_t n, int64_t nrhs, const float *A, int64_t lda,
+                               int64_t strideA, const float *tau, int64_t strideTau, float *B, int64_t ldb,
+                               int64_t strideB, int64_t batch, int32_t *info_out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -52,10 +52,19 @@ for _sfx in ("", "_dev"):
     SIGNATURES[f"qlb200_dgerqf{_sfx}"] = _FACT
     SIGNATURES[f"qlb200_dormql{_sfx}"] = _ORM
     SIGNATURES[f"qlb200_dqlsolve{_sfx}"] = _SOLVE
+    SIGNATURES[f"qlb200_dormrq{_sfx}"] = _ORM
+    SIGNATURES[f"qlb200_dulfact{_sfx}"] = _UL
+    SIGNATURES[f"qlb200_dulsolve{_sfx}"] = _ULS
     for _t in "ds":
         SIGNATURES[f"qlb200_{_t}geqlf_batched{_sfx}"] = _FACT_B
         SIGNATURES[f"qlb200_{_t}ormql_batched{_sfx}"] = _ORM_B
         SIGNATURES[f"qlb200_{_t}qlsolve_batched{_sfx}"] = _SOLVE_B
+# multi-GPU forms: the first argument is an array of handles + its length instead of one handle
+MG_SIGNATURES = {}
+for _t in "ds":
+    MG_SIGNATURES[f"qlb200_{_t}geqlf_batched_mg"] = _FACT_B
+    MG_SIGNATURES[f"qlb200_{_t}ormql_batched_mg"] = _ORM_B
+    MG_SIGNATURES[f"qlb200_{_t}qlsolve_batched_mg"] = _SOLVE_B
 SIGNATURES["qlb200_dgemm_dev"] = [c_char, c_char, _I, _I, _I, ctypes.c_double, _P, _I, _P, _I, ctypes.c_double, _P, _I]
 HANDLE_FUNCS = ["qlb200_version", "qlb200_create", "qlb200_destroy", "qlb200_set_stream", "qlb200_sync",
                 "qlb200_last_error", "qlb200_launch_count", "qlb200_set_option", "qlb200_reset_stream",
@@ -97,6 +106,24 @@ def fn(name: str):
         f.restype = c_int
         _BOUND[name] = f
     return f
+
+
+def fn_mg(name: str):
+    f = _BOUND.get(name)
+    if f is None:
+        f = getattr(lib(), name)
+        f.argtypes = [POINTER(c_void_p), c_int] + MG_SIGNATURES[name]
+        f.restype = c_int
+        _BOUND[name] = f
+    return f
+
+
+def call_mg(handles, name: str, *args):
+    """Call a `_mg` entry point with a list of Handle objects (one per device)."""
+    arr = (c_void_p * len(handles))(*[h._h for h in handles])
+    info = fn_mg(name)(arr, len(handles), *args)
+    handles[0].check(info)
+    return info
 
 
 class Handle:

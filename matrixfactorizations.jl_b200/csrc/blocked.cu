@@ -332,13 +332,11 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     return 0;
 }
 
-int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A, int64_t lda, const double *tau, double *B,
-                     int64_t ldb, int32_t *dinfo) {
-    const int n = (int)n64, nrhs = (int)nrhs64;
-    if (n == 0 || nrhs == 0) return 0;
+// Forward substitution with L = tril(A) (n x n, non-unit): B (n x nrhs) <- L^{-1} B, blocked by 128 rows
+// (diagonal-block kernel + DMMA GEMM).  dinfo (may be null): receives the 1-based index of the first zero
+// diagonal entry, or 0x7fffffff if there is none.
+int qlb_trsm_lower_dev(qlb200_ctx *h, int n, int nrhs, const double *A, int64_t lda, double *B, int64_t ldb, int32_t *dinfo) {
     cudaStream_t st = h->stream;
-    int rc = qlb_dormql_dev(h, 'L', 'T', n, nrhs, n, A, lda, tau, B, ldb);      // src/ql.jl:445
-    if (rc) return rc;
     if (dinfo) {
         set_int_kernel<<<1, 1, 0, st>>>(dinfo, 0x7fffffff);
         QLB_LAUNCH_CHECK(h);
@@ -356,12 +354,41 @@ int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A
         QLB_LAUNCH_CHECK(h);
         const int rem = n - i - tb;
         if (rem > 0) {
-            rc = qlb_gemm(h, st, nrhs <= 16 ? 2 : -1, false, true, rem, nrhs, tb, -1.0, A + (i + tb) + (int64_t)i * lda, lda,
-                          B + i, ldb, 1.0, B + i + tb, ldb, 1, 0);
+            int rc = qlb_gemm(h, st, nrhs <= 16 ? 2 : -1, false, true, rem, nrhs, tb, -1.0, A + (i + tb) + (int64_t)i * lda, lda,
+                              B + i, ldb, 1.0, B + i + tb, ldb, 1, 0);
             if (rc) return rc;
         }
     }
     return 0;
+}
+
+int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A, int64_t lda, const double *tau, double *B,
+                     int64_t ldb, int32_t *dinfo) {
+    const int n = (int)n64, nrhs = (int)nrhs64;
+    if (n == 0 || nrhs == 0) return 0;
+    int rc = qlb_dormql_dev(h, 'L', 'T', n, nrhs, n, A, lda, tau, B, ldb);      // src/ql.jl:445
+    if (rc) return rc;
+    return qlb_trsm_lower_dev(h, n, nrhs, A, lda, B, ldb, dinfo);
+}
+
+// ormrq through index reversal: gerqf(A) = geqlf(A')' (SURVEY.md A.4), so the RQ reflectors (rows of the k x nq
+// array A, LAPACK ?ormrq layout, reference src/rq.jl:130-137,183-202,234-242,272-291) are the QL reflectors of A'
+// and Q_rq = Q_ql': op(Q_rq) = op'(Q_ql) with the transposition flipped.
+int qlb_dormrq_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n64, int64_t k64, const double *A, int64_t lda,
+                   const double *tau, double *C, int64_t ldc) {
+    const int m = (int)m64, n = (int)n64, k = (int)k64;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    const bool left = (side == 'L' || side == 'l');
+    const bool notran = (trans == 'N' || trans == 'n');
+    const int nq = left ? m : n;
+    const int64_t ldt = even_up(nq);
+    int rc = qlb_reserve(h, &h->ws2, &h->ws2_bytes, (size_t)ldt * k * sizeof(double));
+    if (rc) return rc;
+    double *At = (double *)h->ws2;                  // nq x k: column i = reflector row i
+    dim3 blk(32, 8);
+    transpose_kernel<<<dim3((k + 31) / 32, (nq + 31) / 32), blk, 0, h->stream>>>(A, lda, k, nq, At, ldt);
+    QLB_LAUNCH_CHECK(h);
+    return qlb_dormql_dev(h, side, notran ? 'T' : 'N', m, n, k, At, ldt, tau, C, ldc);
 }
 
 int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "internal.h"
 #include <new>
+#include <thread>
+#include <vector>
 
 #define QLB_REQUIRE(h, cond, argno, msg)                      \
     do {                                                      \
@@ -493,6 +495,210 @@ int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, i
     QLB_CUDA(h, cudaStreamSynchronize(h->stream));
     return info == 0x7fffffff ? 0 : (int)info;       // i > 0: L[i,i] == 0 (SingularException)
 }
+
+
+int qlb200_dormrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *dA, int64_t lda,
+                      const double *dtau, double *dC, int64_t ldc) {
+    if (!h) return -1;
+    const bool left = side == 'L' || side == 'l', right = side == 'R' || side == 'r';
+    QLB_REQUIRE(h, left || right, 2, "side must be 'L' or 'R'");
+    QLB_REQUIRE(h, trans == 'N' || trans == 'n' || trans == 'T' || trans == 't' || trans == 'C' || trans == 'c', 3,
+                "trans must be 'N' or 'T'");
+    QLB_REQUIRE(h, m >= 0 && m < (1 << 30), 4, "m out of range");
+    QLB_REQUIRE(h, n >= 0 && n < (1 << 30), 5, "n out of range");
+    const int64_t nq = left ? m : n;
+    QLB_REQUIRE(h, k >= 0 && k <= nq, 6, "k must satisfy 0 <= k <= order of Q (DimensionMismatch)");
+    QLB_REQUIRE(h, dA != nullptr || k == 0, 7, "A is null");
+    QLB_REQUIRE(h, lda >= (k > 1 ? k : 1), 8, "lda < max(1,k)");
+    QLB_REQUIRE(h, dtau != nullptr || k == 0, 9, "tau is null");
+    QLB_REQUIRE(h, dC != nullptr || m * n == 0, 10, "C is null");
+    QLB_REQUIRE(h, ldc >= (m > 1 ? m : 1), 11, "ldc < max(1,m)");
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dormrq_dev(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+}
+int qlb200_dormrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                  const double *tau, double *C, int64_t ldc) {
+    if (!h) return -1;
+    if (m == 0 || n == 0 || k == 0) return qlb200_dormrq_dev(h, side, trans, m, n, k, A, lda, tau, C, ldc);   // checks only
+    const bool left = side == 'L' || side == 'l';
+    const int64_t nq = left ? m : n;
+    QLB_REQUIRE(h, (left || side == 'R' || side == 'r'), 2, "side must be 'L' or 'R'");
+    QLB_REQUIRE(h, k >= 0 && k <= nq, 6, "k must satisfy 0 <= k <= order of Q (DimensionMismatch)");
+    QLB_REQUIRE(h, lda >= (k > 1 ? k : 1), 8, "lda < max(1,k)");
+    QLB_REQUIRE(h, ldc >= (m > 1 ? m : 1), 11, "ldc < max(1,m)");
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA, *dC;
+    int64_t ldda;
+    int rc = stage_in(h, &h->stage, &h->stage_bytes, A, k, nq, lda, &dA, &ldda);
+    if (rc) return rc;
+    const int64_t lddc = ((m + 1) & ~(int64_t)1) < 2 ? 2 : ((m + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)lddc * n + (size_t)k + 2) * sizeof(double));
+    if (rc) return rc;
+    dC = (double *)h->stage2;
+    double *dtau = dC + (size_t)lddc * n;
+    QLB_CUDA(h, cudaMemcpy2DAsync(dC, (size_t)lddc * 8, C, (size_t)ldc * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice,
+                                  h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb200_dormrq_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc);
+    if (rc) return rc;
+    rc = stage_out(h, C, m, n, ldc, dC, lddc);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* ---- UL ------------------------------------------------------------------------------------------- */
+static int check_ul(qlb200_ctx *h, int64_t m, int64_t n, const double *A, int64_t lda, const int64_t *ipiv) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, m >= 0 && m < (1 << 30), 2, "m out of range");
+    QLB_REQUIRE(h, n >= 0 && n < (1 << 30), 3, "n out of range");
+    QLB_REQUIRE(h, A != nullptr || m * n == 0, 4, "A is null");
+    QLB_REQUIRE(h, lda >= (m > 1 ? m : 1), 5, "lda < max(1,m)");
+    QLB_REQUIRE(h, ipiv != nullptr || m * n == 0, 6, "ipiv is null");
+    return 0;
+}
+int qlb200_dulfact_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, int64_t *dipiv, int pivot,
+                       int32_t *dinfo_singular) {
+    int rc = check_ul(h, m, n, dA, lda, dipiv);
+    if (rc) return rc;
+    QLB_REQUIRE(h, dinfo_singular != nullptr, 8, "info_singular is null");
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dulfact_dev(h, m, n, dA, lda, dipiv, pivot, dinfo_singular);
+}
+int qlb200_dulfact(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, int64_t *ipiv, int pivot,
+                   int32_t *info_singular) {
+    int rc = check_ul(h, m, n, A, lda, ipiv);
+    if (rc) return rc;
+    if (info_singular) *info_singular = 0;
+    const int64_t k = m < n ? m : n;
+    if (k == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA;
+    int64_t ldd;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, &dA, &ldd);
+    if (rc) return rc;
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * sizeof(int64_t));
+    if (rc) return rc;
+    int64_t *dipiv = (int64_t *)h->stage2;
+    rc = qlb_dulfact_dev(h, m, n, dA, ldd, dipiv, pivot, h->dinfo);
+    if (rc) return rc;
+    rc = stage_out(h, A, m, n, lda, dA, ldd);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaMemcpyAsync(ipiv, dipiv, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    int32_t info = 0;
+    QLB_CUDA(h, cudaMemcpyAsync(&info, h->dinfo, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (info_singular) *info_singular = info;
+    return 0;
+}
+static int check_ulsolve(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const int64_t *ipiv, const double *B,
+                         int64_t ldb) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, n >= 0 && n < (1 << 30), 2, "n out of range");
+    QLB_REQUIRE(h, nrhs >= 0 && nrhs < (1 << 30), 3, "nrhs out of range");
+    QLB_REQUIRE(h, A != nullptr || n == 0, 4, "A is null");
+    QLB_REQUIRE(h, lda >= (n > 1 ? n : 1), 5, "lda < max(1,n)");
+    QLB_REQUIRE(h, ipiv != nullptr || n == 0, 6, "ipiv is null");
+    QLB_REQUIRE(h, B != nullptr || n * nrhs == 0, 7, "B is null");
+    QLB_REQUIRE(h, ldb >= (n > 1 ? n : 1), 8, "ldb < max(1,n) (DimensionMismatch)");
+    return 0;
+}
+int qlb200_dulsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const int64_t *dipiv, double *dB,
+                        int64_t ldb) {
+    int rc = check_ulsolve(h, n, nrhs, dA, lda, dipiv, dB, ldb);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dulsolve_dev(h, n, nrhs, dA, lda, dipiv, dB, ldb, nullptr);
+}
+int qlb200_dulsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const int64_t *ipiv, double *B,
+                    int64_t ldb) {
+    int rc = check_ulsolve(h, n, nrhs, A, lda, ipiv, B, ldb);
+    if (rc) return rc;
+    if (n == 0 || nrhs == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA, *dB;
+    int64_t ldda;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, n, n, lda, &dA, &ldda);
+    if (rc) return rc;
+    const int64_t lddb = ((n + 1) & ~(int64_t)1) < 2 ? 2 : ((n + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)lddb * nrhs + (size_t)n + 2) * sizeof(double));
+    if (rc) return rc;
+    dB = (double *)h->stage2;
+    int64_t *dipiv = (int64_t *)(dB + (size_t)lddb * nrhs);
+    QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)n * 8, (size_t)nrhs, cudaMemcpyHostToDevice,
+                                  h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dipiv, ipiv, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb_dulsolve_dev(h, n, nrhs, dA, ldda, dipiv, dB, lddb, h->dinfo);
+    if (rc) return rc;
+    rc = stage_out(h, B, n, nrhs, ldb, dB, lddb);
+    if (rc) return rc;
+    int32_t info = 0;
+    QLB_CUDA(h, cudaMemcpyAsync(&info, h->dinfo, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return info == 0x7fffffff ? 0 : (int)info;       // i > 0: L[i,i] == 0 (SingularException)
+}
+
+/* ---- batched work sharded over several devices (host pointers) --------------------------------------
+ * Matrices are independent: handle g of G (each bound to its own device) gets the contiguous index range
+ * [g*batch/G, (g+1)*batch/G) (+ remainder on the first ranks), one host thread per device, no data-path
+ * collective.  Returns the first non-zero info of any shard. */
+static void shard_range(int64_t total, int g, int G, int64_t *lo, int64_t *hi) {
+    const int64_t base = total / G, rem = total % G;
+    *lo = g * base + (g < rem ? g : rem);
+    *hi = *lo + base + (g < rem ? 1 : 0);
+}
+}  // extern "C"
+template <typename F>
+static int run_sharded(qlb200_handle *hs, int nh, int64_t batch, F fn) {
+    if (!hs || nh < 1) return -1;
+    for (int g = 0; g < nh; ++g)
+        if (!hs[g]) return -1;
+    std::vector<int> rcs((size_t)nh, 0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < nh; ++g) {
+        int64_t lo, hi;
+        shard_range(batch, g, nh, &lo, &hi);
+        th.emplace_back([&, g, lo, hi]() { rcs[(size_t)g] = (hi > lo) ? fn(hs[g], lo, hi) : 0; });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < nh; ++g)
+        if (rcs[(size_t)g]) return rcs[(size_t)g];
+    return 0;
+}
+
+extern "C" {
+#define QLB_GEQLF_MG(NAME, T, SINGLE)                                                                              \
+    int NAME(qlb200_handle *hs, int nh, int64_t n, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau,   \
+             int64_t batch) {                                                                                       \
+        return run_sharded(hs, nh, batch, [&](qlb200_handle h, int64_t lo, int64_t hi) {                            \
+            return SINGLE(h, n, A + lo * strideA, lda, strideA, tau + lo * strideTau, strideTau, hi - lo);          \
+        });                                                                                                         \
+    }
+QLB_GEQLF_MG(qlb200_dgeqlf_batched_mg, double, qlb200_dgeqlf_batched)
+QLB_GEQLF_MG(qlb200_sgeqlf_batched_mg, float, qlb200_sgeqlf_batched)
+
+#define QLB_ORMQL_MG(NAME, T, SINGLE)                                                                              \
+    int NAME(qlb200_handle *hs, int nh, char trans, int64_t n, int64_t nrhs, const T *A, int64_t lda,              \
+             int64_t strideA, const T *tau, int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int64_t batch) { \
+        return run_sharded(hs, nh, batch, [&](qlb200_handle h, int64_t lo, int64_t hi) {                            \
+            return SINGLE(h, trans, n, nrhs, A + lo * strideA, lda, strideA, tau + lo * strideTau, strideTau,       \
+                          B + lo * strideB, ldb, strideB, hi - lo);                                                 \
+        });                                                                                                         \
+    }
+QLB_ORMQL_MG(qlb200_dormql_batched_mg, double, qlb200_dormql_batched)
+QLB_ORMQL_MG(qlb200_sormql_batched_mg, float, qlb200_sormql_batched)
+
+#define QLB_QLSOLVE_MG(NAME, T, SINGLE)                                                                            \
+    int NAME(qlb200_handle *hs, int nh, int64_t n, int64_t nrhs, const T *A, int64_t lda, int64_t strideA,         \
+             const T *tau, int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int64_t batch,                    \
+             int32_t *info_out) {                                                                                   \
+        return run_sharded(hs, nh, batch, [&](qlb200_handle h, int64_t lo, int64_t hi) {                            \
+            return SINGLE(h, n, nrhs, A + lo * strideA, lda, strideA, tau + lo * strideTau, strideTau,              \
+                          B + lo * strideB, ldb, strideB, hi - lo, info_out ? info_out + lo : nullptr);             \
+        });                                                                                                         \
+    }
+QLB_QLSOLVE_MG(qlb200_dqlsolve_batched_mg, double, qlb200_dqlsolve_batched)
+QLB_QLSOLVE_MG(qlb200_sqlsolve_batched_mg, float, qlb200_sqlsolve_batched)
 
 // BLAS-style test/benchmark hook for the DMMA GEMM (column-major, device pointers):
 // C = alpha*op(A)*op(B) + beta*C, op = 'N' or 'T'.

@@ -42,3 +42,11 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, i
 int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
                      int64_t ldb, int32_t *dinfo);
 int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb_trsm_lower_dev(qlb200_ctx *h, int n, int nrhs, const double *A, int64_t lda, double *B, int64_t ldb, int32_t *dinfo);
+int qlb_dormrq_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                   const double *tau, double *C, int64_t ldc);
+
+// ul.cu (device pointers, asynchronous on h->stream)
+int qlb_dulfact_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, int64_t *ipiv, int pivot, int32_t *dinfo);
+int qlb_dulsolve_dev(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const int64_t *ipiv, double *B,
+                     int64_t ldb, int32_t *dinfo);

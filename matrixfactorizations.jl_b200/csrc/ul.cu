@@ -1,0 +1,273 @@
+// ul.cu -- A13: the reverse-order partially pivoted LU of the reference, A[p,:] = U*L with U unit upper and
+// L lower triangular (generic_ulfact!, reference src/ul.jl:148-196), and ldiv!(F::UL, B) (src/ul.jl:363-393).
+//
+// Blocked right-looking elimination that starts at the bottom-right corner, strips of SB = 16 columns:
+//   ul_panel_kernel   columns [c0,c1) x rows [0,c1): per column k = c1-1 ... c0 the pivot search over rows 0..k
+//                     (first row attaining the maximum, exactly the reference's strict '>' scan, src/ul.jl:158-166),
+//                     the row interchange inside the strip, the scaling of the column above the pivot
+//                     (src/ul.jl:177-180) and the rank-1 update of the strip's remaining columns (:185-189);
+//   ul_laswp_kernel   the same interchanges on every column outside the strip (the reference swaps whole rows, :170-175);
+//   ul_trsm_row_kernel  rows [c0,c1) of the columns left of the strip: L21 = U22^{-1} A21 (the updates :185-189 that
+//                     the strip's own columns apply to those rows, collected as one unit-upper back substitution);
+//   DMMA GEMM         A11 -= U12 * L21 (gemm.cu).
+// ipiv is 1-based like the reference's Vector{BlasInt}; info = the largest k with a zero pivot (the first one the
+// descending loop meets, src/ul.jl:181-183), 0 if none.
+// Round-1 status: parity path; one CTA per strip and K = 16 updates (HBM-bound) -- not tuned.
+#include "common.cuh"
+#include "internal.h"
+
+namespace qlb {
+
+constexpr int UL_SB = 16;
+constexpr int UL_THREADS = 1024;
+
+struct ArgMax {
+    double v;
+    int i;
+};
+__device__ __forceinline__ ArgMax argmax_combine(ArgMax a, ArgMax b) {
+    // larger value wins; on ties the lower row index (the reference keeps the first maximum)
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+
+__global__ void __launch_bounds__(UL_THREADS) ul_panel_kernel(double *__restrict__ A, int64_t lda, int c0, int c1, int pivot,
+                                                              int64_t *__restrict__ ipiv, int32_t *__restrict__ info) {
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    __shared__ double rowk[UL_SB];
+    __shared__ int s_kp;
+    __shared__ double s_piv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = c1 - 1; k >= c0; --k) {
+        double *colk = A + (int64_t)k * lda;
+        // ---- pivot search over rows 0..k of column k ----
+        if (pivot) {
+            ArgMax best{0.0, 0x7fffffff};
+            for (int r = tid; r <= k; r += UL_THREADS) {
+                const double v = fabs(colk[r]);
+                if (v > best.v) best = ArgMax{v, r};          // ascending r inside a thread: first maximum kept
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                ArgMax other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+                best = argmax_combine(best, other);
+            }
+            if (lane == 0) { red_v[warp] = best.v; red_i[warp] = best.i; }
+            __syncthreads();
+            if (warp == 0) {
+                ArgMax b{red_v[lane], red_i[lane]};
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    ArgMax other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.i, o)};
+                    b = argmax_combine(b, other);
+                }
+                if (lane == 0) s_kp = (b.i == 0x7fffffff) ? k : b.i;       // all zero (or NaN): kp = k
+            }
+        } else if (tid == 0) {
+            s_kp = k;
+        }
+        __syncthreads();
+        const int kp = s_kp;
+        if (tid == 0) {
+            ipiv[k] = (int64_t)kp + 1;
+            s_piv = colk[kp];
+        }
+        __syncthreads();
+        const double piv = s_piv;
+        if (piv != 0.0) {
+            // ---- interchange rows k and kp inside the strip; the new row k feeds the update ----
+            if (tid < c1 - c0) {
+                double *col = A + (int64_t)(c0 + tid) * lda;
+                const double a = col[k], b = col[kp];
+                col[k] = b;
+                col[kp] = a;
+                rowk[tid] = b;
+            }
+        } else {
+            if (tid == 0 && *info == 0) *info = k + 1;
+            if (tid < c1 - c0) rowk[tid] = A[(int64_t)(c0 + tid) * lda + k];
+        }
+        __syncthreads();
+        // ---- scale the column above the pivot, rank-1 update of the strip's columns left of k ----
+        const double pinv = (piv != 0.0) ? 1.0 / piv : 1.0;
+        const int nj = k - c0;
+        for (int r = tid; r < k; r += UL_THREADS) {
+            double m = colk[r];
+            if (piv != 0.0) {
+                m *= pinv;
+                colk[r] = m;
+            }
+            for (int j = 0; j < nj; ++j) {
+                double *p = A + (int64_t)(c0 + j) * lda + r;
+                *p = fma(-m, rowk[j], *p);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Row interchanges of one strip (k = c1-1 ... c0, in that order) applied to the columns [j0, j1).
+__global__ void ul_laswp_kernel(double *__restrict__ A, int64_t lda, int c0, int c1, const int64_t *__restrict__ ipiv, int j0,
+                                int j1) {
+    const int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j1) return;
+    double *col = A + (int64_t)j * lda;
+    for (int k = c1 - 1; k >= c0; --k) {
+        const int kp = (int)ipiv[k] - 1;
+        if (kp != k) {
+            const double a = col[k], b = col[kp];
+            col[k] = b;
+            col[kp] = a;
+        }
+    }
+}
+
+// X = U22^{-1} A21 in place: U22 = unit upper triangle of A[c0:c1, c0:c1], A21 = A[c0:c1, 0:ncols).
+__global__ void ul_trsm_row_kernel(double *__restrict__ A, int64_t lda, int c0, int c1, int ncols) {
+    __shared__ double U[UL_SB][UL_SB + 1];
+    const int w = c1 - c0;
+    for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+        const int i = idx % w, j = idx / w;
+        U[i][j] = A[(int64_t)(c0 + j) * lda + c0 + i];
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    double *x = A + (int64_t)j * lda + c0;
+    double v[UL_SB];
+#pragma unroll
+    for (int i = 0; i < UL_SB; ++i) v[i] = (i < w) ? x[i] : 0.0;
+#pragma unroll
+    for (int i = UL_SB - 1; i >= 0; --i) {
+        if (i < w) {
+#pragma unroll
+            for (int q = i + 1; q < UL_SB; ++q)
+                if (q < w) v[i] = fma(-U[i][q], v[q], v[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < UL_SB; ++i)
+        if (i < w) x[i] = v[i];
+}
+
+// Rows of B permuted by ipiv in REVERSE order (_apply_ipiv_rows!, src/ul.jl:363-376): thread = column of B.
+__global__ void ul_permute_rows_kernel(double *__restrict__ B, int64_t ldb, int n, int nrhs, const int64_t *__restrict__ ipiv) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nrhs) return;
+    double *col = B + (int64_t)c * ldb;
+    for (int i = n - 1; i >= 0; --i) {
+        const int p = (int)ipiv[i] - 1;
+        if (p != i) {
+            const double a = col[i], b = col[p];
+            col[i] = b;
+            col[p] = a;
+        }
+    }
+}
+
+// Back substitution with one tb x tb UNIT upper-triangular diagonal block: X = U^{-1} B in place.
+template <int TB>
+__global__ void __launch_bounds__(TB) trsm_unit_upper_diag_kernel(const double *__restrict__ U, int64_t ldu, int tb, double *__restrict__ B,
+                                                                 int64_t ldb, int nrhs) {
+    extern __shared__ __align__(16) double sm[];
+    double *Us = sm;                       // tb x tb, pitch TB+1
+    __shared__ double xs[8];
+    const int r = threadIdx.x;
+    for (int idx = threadIdx.x; idx < tb * tb; idx += TB) {
+        const int i = idx % tb, j = idx / tb;
+        Us[j * (TB + 1) + i] = (i < j) ? U[i + (int64_t)j * ldu] : 0.0;
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < nrhs; c0 += 8) {
+        const int nc = (nrhs - c0) < 8 ? (nrhs - c0) : 8;
+        double b[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[q] = (r < tb && q < nc) ? B[r + (int64_t)(c0 + q) * ldb] : 0.0;
+        for (int c = tb - 1; c >= 0; --c) {
+            if (r == c) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) xs[q] = b[q];
+            }
+            __syncthreads();
+            if (r < c) {
+                const double u = Us[c * (TB + 1) + r];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b[q] = fma(-u, xs[q], b[q]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (r < tb && q < nc) B[r + (int64_t)(c0 + q) * ldb] = b[q];
+    }
+}
+
+__global__ void ul_set_info_kernel(int32_t *p, int32_t v) { *p = v; }
+
+}  // namespace qlb
+
+using namespace qlb;
+
+// ipiv: device array of min(m,n) int64 (1-based); dinfo: device int32 (0 or the reference's `info`).
+int qlb_dulfact_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, int64_t *ipiv, int pivot, int32_t *dinfo) {
+    const int m = (int)m64, n = (int)n64;
+    const int k = m < n ? m : n;
+    cudaStream_t st = h->stream;
+    ul_set_info_kernel<<<1, 1, 0, st>>>(dinfo, 0);
+    QLB_LAUNCH_CHECK(h);
+    // The reference's loop touches rows/columns 1..k only (k = min(m,n) ... 1), except for the row
+    // interchanges which run over all n columns (src/ul.jl:155-191).
+    for (int c1 = k; c1 > 0; c1 -= UL_SB) {
+        const int c0 = (c1 - UL_SB > 0) ? c1 - UL_SB : 0;
+        ul_panel_kernel<<<1, UL_THREADS, 0, st>>>(A, lda, c0, c1, pivot, ipiv, dinfo);
+        QLB_LAUNCH_CHECK(h);
+        if (pivot) {
+            if (c0 > 0) {
+                ul_laswp_kernel<<<(c0 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, 0, c0);
+                QLB_LAUNCH_CHECK(h);
+            }
+            if (n > c1) {
+                ul_laswp_kernel<<<(n - c1 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, c1, n);
+                QLB_LAUNCH_CHECK(h);
+            }
+        }
+        if (c0 > 0) {
+            ul_trsm_row_kernel<<<(c0 + 127) / 128, 128, 0, st>>>(A, lda, c0, c1, c0);
+            QLB_LAUNCH_CHECK(h);
+            // A11 (c0 x c0) -= U12 (c0 x w, M-contiguous) * L21 (w x c0, K-contiguous)
+            int rc = qlb_gemm(h, st, -1, false, true, c0, c0, c1 - c0, -1.0, A + (int64_t)c0 * lda, lda, A + c0, lda, 1.0, A, lda, 1, 0);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+// ldiv!(F::UL, B), square: permute rows (reverse ipiv order), unit-upper back substitution, lower forward substitution.
+int qlb_dulsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A, int64_t lda, const int64_t *ipiv, double *B,
+                     int64_t ldb, int32_t *dinfo) {
+    const int n = (int)n64, nrhs = (int)nrhs64;
+    if (n == 0 || nrhs == 0) return 0;
+    cudaStream_t st = h->stream;
+    ul_permute_rows_kernel<<<(nrhs + 127) / 128, 128, 0, st>>>(B, ldb, n, nrhs, ipiv);
+    QLB_LAUNCH_CHECK(h);
+    constexpr int TB = 128;
+    const size_t smem = (size_t)TB * (TB + 1) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        QLB_CUDA(h, cudaFuncSetAttribute(trsm_unit_upper_diag_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int nblk = (n + TB - 1) / TB;
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int i = b * TB, tb = (n - i) < TB ? (n - i) : TB;
+        trsm_unit_upper_diag_kernel<TB><<<1, TB, smem, st>>>(A + i + (int64_t)i * lda, lda, tb, B + i, ldb, nrhs);
+        QLB_LAUNCH_CHECK(h);
+        if (i > 0) {      // B[0:i] -= U[0:i, i:i+tb] * X[i:i+tb]
+            int rc = qlb_gemm(h, st, nrhs <= 16 ? 2 : -1, false, true, i, nrhs, tb, -1.0, A + (int64_t)i * lda, lda, B + i, ldb, 1.0, B, ldb,
+                              1, 0);
+            if (rc) return rc;
+        }
+    }
+    return qlb_trsm_lower_dev(h, n, nrhs, A, lda, B, ldb, dinfo);
+}

@@ -241,6 +241,117 @@ def rq_(A, handle=None):
     return A, tau
 
 
+class RQPackedQ:
+    """RQ's packed orthogonal factor (reference src/rq.jl:59-72): aliases factors (m x n) and tau; the k =
+    min(m,n) reflectors are the LAST k rows of `factors`.  size(Q) = (n, n) (src/rq.jl:95)."""
+
+    def __init__(self, factors, tau, adjoint=False, handle=None):
+        self.factors, self.tau, self.adjoint, self.handle = factors, tau, adjoint, handle
+
+    @property
+    def T(self):
+        return RQPackedQ(self.factors, self.tau, not self.adjoint, self.handle)
+
+    @property
+    def shape(self):
+        n = self.factors.shape[1]
+        return (n, n)
+
+
+def _ormrq(side, Q: RQPackedQ, C):
+    """lmul!/rmul! with RQ's Q: LAPACK.ormrq! (src/rq.jl:130-137,183-202,234-242,272-291)."""
+    f, c, t = _Mat(Q.factors, "A(const)"), _Mat(C, "C"), _Mat(Q.tau, "tau")
+    _same_kind(f, c, t)
+    h = _handle(Q.handle, f)
+    mA, nA = f.m, f.n
+    k = min(mA, nA)
+    nq = c.m if side == "L" else c.n
+    if nq != nA:
+        raise DimensionMismatch(f"matrix A has dimensions ({mA},{nA}) but {'B' if side == 'L' else 'A'} has dimensions ({c.m}, {c.n})")
+    aptr = f.ptr + (mA - k) * 8           # first of the last k rows
+    h.call(f"qlb200_{f.pfx}ormrq{f.sfx}", side.encode(), (b"T" if Q.adjoint else b"N"), c.m, c.n, k, aptr, f.ld, t.ptr,
+           c.ptr, c.ld)
+    return C
+
+
+class UL:
+    """UL factorization object (reference src/ul.jl:51-60): `factors` (U unit upper above the diagonal, L on and
+    below it), `ipiv` (1-based int64) and `info`; A[p,:] = U*L."""
+
+    def __init__(self, factors, ipiv, info, handle=None):
+        self.factors, self.ipiv, self.info, self.handle = factors, ipiv, int(info), handle
+
+    @property
+    def L(self):
+        return np.tril(self.factors) if not _is_torch(self.factors) else self.factors.tril()
+
+    @property
+    def U(self):
+        if _is_torch(self.factors):
+            import torch
+
+            return self.factors.triu(1) + torch.eye(*self.factors.shape, dtype=self.factors.dtype, device=self.factors.device)
+        return np.triu(self.factors, 1) + np.eye(*self.factors.shape, dtype=self.factors.dtype)
+
+    @property
+    def p(self):
+        """Row permutation (0-based) such that A[p,:] = U*L (src/ul.jl:317-349 ipiv2perm, reverse order)."""
+        m = self.factors.shape[0]
+        perm = np.arange(m)
+        ip = np.asarray(self.ipiv.cpu() if _is_torch(self.ipiv) else self.ipiv)
+        for i in range(len(ip) - 1, -1, -1):
+            j = int(ip[i]) - 1
+            perm[i], perm[j] = perm[j], perm[i]
+        return perm
+
+    def solve(self, b):
+        r"""F \ b for square A (src/ul.jl:390-393)."""
+        X = _copy_colmajor(b)
+        f, bm = _Mat(self.factors, "A(const)"), _Mat(X, "B")
+        if f.m != f.n:
+            raise DimensionMismatch("UL solve needs a square factorization")
+        if bm.m != f.m:
+            raise DimensionMismatch(f"arguments must have the same number of rows; has {f.m} and {bm.m}")
+        h = _handle(self.handle, f)
+        ip = self.ipiv
+        iptr = ip.data_ptr() if _is_torch(ip) else ip.ctypes.data
+        h.call(f"qlb200_dulsolve{f.sfx}", f.n, bm.n, f.ptr, f.ld, iptr, bm.ptr, bm.ld)
+        return X
+
+
+def ul_(A, pivot=True, check=True, handle=None) -> UL:
+    """ul!(A, Val(pivot); check) (src/ul.jl:146-196), Float64."""
+    a = _Mat(A)
+    if a.pfx != "d":
+        raise TypeError("ul_: Float64 only")
+    h = _handle(handle, a)
+    k = min(a.m, a.n)
+    if a.dev:
+        import torch
+
+        ipiv = torch.zeros(k, dtype=torch.int64, device=A.device)
+        dinfo = torch.zeros(1, dtype=torch.int32, device=A.device)
+        h.call("qlb200_dulfact_dev", a.m, a.n, a.ptr, a.ld, ipiv.data_ptr(), int(bool(pivot)), dinfo.data_ptr())
+        info = int(dinfo.item())
+    else:
+        ipiv = np.zeros(k, dtype=np.int64)
+        cinfo = _c.c_int32(0)
+        h.call("qlb200_dulfact", a.m, a.n, a.ptr, a.ld, ipiv.ctypes.data, int(bool(pivot)), _c.addressof(cinfo))
+        info = int(cinfo.value)
+    if check and info != 0:          # _checknonsingular (src/ul.jl:193)
+        raise SingularException(info)
+    return UL(A, ipiv, info, handle)
+
+
+def ul(A, pivot=True, check=True, handle=None) -> UL:
+    """ul(A): copy (promoting integers like ultype, src/ul.jl:198-210), then ul!."""
+    if not _is_torch(A):
+        A = np.asarray(A)
+        if A.dtype != np.float64:
+            A = A.astype(np.float64)
+    return ul_(_copy_colmajor(A), pivot, check, handle)
+
+
 def _ormql(side, Q: QLPackedQ, C):
     f, c = _Mat(Q.factors, "A(const)"), _Mat(C, "C")
     t = _Mat(Q.tau, "tau")
@@ -258,14 +369,14 @@ def _ormql(side, Q: QLPackedQ, C):
     return C
 
 
-def lmul_(Q: QLPackedQ, B):
-    """lmul!(Q,B) / lmul!(Q',B): src/ql.jl:321-347 / 350-377."""
-    return _ormql("L", Q, B)
+def lmul_(Q, B):
+    """lmul!(Q,B) / lmul!(Q',B): src/ql.jl:321-347 / 350-377 (QLPackedQ), src/rq.jl:130-137,183-202 (RQPackedQ)."""
+    return _ormrq("L", Q, B) if isinstance(Q, RQPackedQ) else _ormql("L", Q, B)
 
 
-def rmul_(C, Q: QLPackedQ):
-    """rmul!(C,Q) / rmul!(C,Q'): src/ql.jl:381-406 / 409-435."""
-    return _ormql("R", Q, C)
+def rmul_(C, Q):
+    """rmul!(C,Q) / rmul!(C,Q'): src/ql.jl:381-406 / 409-435 (QLPackedQ), src/rq.jl:234-291 (RQPackedQ)."""
+    return _ormrq("R", Q, C) if isinstance(Q, RQPackedQ) else _ormql("R", Q, C)
 
 
 def ldiv_(F: QL, B):
@@ -339,3 +450,19 @@ def lmul_batched_(A3, tau, B3, adjoint=False, handle=None):
 def ldiv_batched_(A3, tau, B3, info=None, handle=None):
     """B_i <- L_i^{-1} Q_i' B_i (src/ql.jl:440-447,467 per matrix)."""
     return _apply_batched("qlsolve", None, A3, tau, B3, handle, info)
+
+
+def ql_batched_mg_(A3, tau=None, handles=None):
+    """Host arrays, several GPUs of one box: matrices are sharded by contiguous index ranges over `handles`
+    (one per device), no cross-GPU communication; qlb200_?geqlf_batched_mg."""
+    a = _Bat(A3, "A3")
+    if a.dev:
+        raise TypeError("ql_batched_mg_ takes host (NumPy) arrays")
+    if len(a.shape) != 3 or a.shape[1] != a.shape[2]:
+        raise DimensionMismatch("ql_batched_mg_: expected (batch, n, n)")
+    batch, n, _ = a.shape
+    if tau is None:
+        tau = np.empty((batch, n), dtype=A3.dtype)
+    t = _Bat(tau, "tau")
+    _lib.call_mg(list(handles), f"qlb200_{a.pfx}geqlf_batched_mg", n, a.ptr, n, n * n, t.ptr, n, batch)
+    return A3, tau

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_table_matches_header():
     q = load_package()
     names = set(_declared())
-    table = set(q.SIGNATURES) | set(q.HANDLE_FUNCS)
+    table = set(q.SIGNATURES) | set(q.MG_SIGNATURES) | set(q.HANDLE_FUNCS)
     assert table == names, (sorted(table - names), sorted(names - table))
 
 
