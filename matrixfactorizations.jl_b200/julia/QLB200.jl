@@ -1,0 +1,189 @@
+# QLB200.jl -- Julia-side shim that routes MatrixFactorizations.jl's QL hot path to libqlb200.so.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no `julia` binary (SURVEY.md 0.7), so this file is
+# the reference-side binding a maintainer would add (as a package extension or a tiny companion package); the
+# executable mirror of the same calls is ../ql.py (ctypes) and is what tests/ drive.  Every method below is a
+# single `ccall` into the C-ABI of include/qlb200.h; nothing here does arithmetic.
+#
+# Hooks overridden (all exist in the reference, precedent: ext/MatrixFactorizationsBandedMatricesExt.jl:14-16,38,66):
+#   qlfactUnblocked!(::StridedMatrix{Float64})                         src/ql.jl:72
+#   materialize!(::Lmul{<:QLPackedQLayout{<:AbstractColumnMajor}})     src/ql.jl:321
+#   materialize!(::Lmul{<:AdjQLPackedQLayout{<:AbstractColumnMajor}})  src/ql.jl:350
+#   materialize!(::Rmul{<:Any,<:QLPackedQLayout}) / Adj                src/ql.jl:381,409
+#   materialize!(::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor}})      src/ql.jl:440 (square only)
+#   rq!(::StridedMatrix{Float64})                                      src/rq.jl:401
+#   lmul!/rmul!(::RQPackedQ{Float64,<:StridedMatrix}, ...)             src/rq.jl:130,183,234,272
+#   ul!(::StridedMatrix{Float64}, pivot; check)                        src/ul.jl:146
+# plus the new batched surface ql_batched!/lmul_batched!/ldiv_batched! (SURVEY.md 0.6).
+module QLB200
+
+using LinearAlgebra, MatrixFactorizations
+using MatrixFactorizations.ArrayLayouts
+using LinearAlgebra: BlasInt
+import MatrixFactorizations: qlfactUnblocked!, rq!, ul!, QL, QLPackedQ, RQ, RQPackedQ, UL,
+                             QLPackedQLayout, AdjQLPackedQLayout, QLPackedLayout
+import ArrayLayouts: materialize!, Lmul, Rmul, Ldiv, AbstractColumnMajor
+
+const libqlb200 = get(ENV, "QLB200_LIB", joinpath(@__DIR__, "..", "libqlb200.so"))
+
+# ---- handle ---------------------------------------------------------------------------------------------
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        info = ccall((:qlb200_create, libqlb200), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
+        info == 0 || error("qlb200_create(device=$device) failed with info=$info (no CUDA device? there is no CPU fallback)")
+        h = new(r[])
+        finalizer(x -> ccall((:qlb200_destroy, libqlb200), Cint, (Ptr{Cvoid},), x.ptr), h)
+        h
+    end
+end
+const DEFAULT = Ref{Union{Nothing,Handle}}(nothing)
+handle() = (DEFAULT[] === nothing && (DEFAULT[] = Handle(0)); DEFAULT[]::Handle)
+
+lasterror(h::Handle) = unsafe_string(ccall((:qlb200_last_error, libqlb200), Cstring, (Ptr{Cvoid},), h.ptr))
+
+# info -> the exception the reference throws at the same place
+function chk(h::Handle, info::Integer; dims = ())
+    info == 0 && return nothing
+    msg = lasterror(h)
+    info >= 1000 && error("libqlb200: CUDA error $(info - 1000): $msg")
+    info > 0 && throw(SingularException(info))
+    (-info in dims || occursin("DimensionMismatch", msg)) && throw(DimensionMismatch(msg))
+    throw(ArgumentError("libqlb200: invalid argument #$(-info): $msg"))
+end
+
+# ---- ql! -------------------------------------------------------------------------------------------------
+# replaces `QL(LAPACK.geqlf!(A)...)` (src/ql.jl:72); ql!/ql/ql_layout! reach it unchanged (src/ql.jl:114-117,179-191)
+function qlfactUnblocked!(A::StridedMatrix{Float64})
+    Base.require_one_based_indexing(A)
+    LinearAlgebra.chkstride1(A)
+    m, n = size(A)
+    τ = Vector{Float64}(undef, min(m, n))
+    h = handle()
+    info = ccall((:qlb200_dgeqlf, libqlb200), Cint,
+                 (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
+                 h.ptr, m, n, A, max(1, stride(A, 2)), τ)
+    chk(h, info)
+    QL(A, τ)
+end
+
+# ---- lmul!/rmul! with the packed Q -------------------------------------------------------------------------
+function _ormql!(side::Char, trans::Char, A::QLPackedQ{Float64,<:StridedMatrix}, C::StridedVecOrMat{Float64})
+    Base.require_one_based_indexing(C)
+    mA, nA = size(A.factors)
+    k = min(mA, nA)
+    m, n = size(C, 1), size(C, 2)
+    nq = side == 'L' ? m : n
+    nq == mA || throw(DimensionMismatch("matrix A has dimensions ($mA,$nA) but $(side == 'L' ? "B" : "A") has dimensions ($m, $n)"))
+    V = view(A.factors, :, nA-k+1:nA)                  # the reflectors live in the last k columns (src/ql.jl:331)
+    h = handle()
+    info = ccall((:qlb200_dormql, libqlb200), Cint,
+                 (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+                 h.ptr, side, trans, m, n, k, V, max(1, stride(A.factors, 2)), A.τ, C, max(1, stride(C, 2)))
+    chk(h, info; dims = (6, 8))
+    C
+end
+materialize!(M::Lmul{<:QLPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QLPackedQ{Float64},<:StridedVecOrMat{Float64}}) =
+    _ormql!('L', 'N', M.A, M.B)                                                           # src/ql.jl:321-347
+materialize!(M::Lmul{<:AdjQLPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:Any,<:StridedVecOrMat{Float64}}) =
+    _ormql!('L', 'T', parent(M.A), M.B)                                                   # src/ql.jl:350-377
+materialize!(M::Rmul{<:AbstractColumnMajor,<:QLPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{Float64},<:QLPackedQ{Float64}}) =
+    _ormql!('R', 'N', M.B, M.A)                                                           # src/ql.jl:381-406
+materialize!(M::Rmul{<:AbstractColumnMajor,<:AdjQLPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{Float64}}) =
+    _ormql!('R', 'T', parent(M.B), M.A)                                                   # src/ql.jl:409-435
+
+# ---- ldiv!(F::QL, B), square --------------------------------------------------------------------------------
+function materialize!(Ldv::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QL{Float64},<:StridedVecOrMat{Float64}})
+    F, B = Ldv.A, Ldv.B
+    m, n = size(F)
+    m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # rectangular: keep the reference's own branch (src/ql.jl:448-486)
+    size(B, 1) == n || throw(DimensionMismatch("arguments must have the same number of rows; has $n and $(size(B,1))"))
+    h = handle()
+    info = ccall((:qlb200_dqlsolve, libqlb200), Cint,
+                 (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+                 h.ptr, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
+    chk(h, info; dims = (8,))
+    B
+end
+
+# ---- rq! and RQ's packed Q --------------------------------------------------------------------------------------
+function rq!(A::StridedMatrix{Float64})                                                    # src/rq.jl:401
+    m, n = size(A)
+    τ = Vector{Float64}(undef, min(m, n))
+    h = handle()
+    chk(h, ccall((:qlb200_dgerqf, libqlb200), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
+                 h.ptr, m, n, A, max(1, stride(A, 2)), τ))
+    RQ(A, τ)
+end
+function _ormrq!(side::Char, trans::Char, Q::RQPackedQ{Float64,<:StridedMatrix}, C::StridedVecOrMat{Float64})
+    mA, nA = size(Q.factors)
+    k = min(mA, nA)
+    m, n = size(C, 1), size(C, 2)
+    (side == 'L' ? m : n) == nA || throw(DimensionMismatch("matrix A has dimensions ($mA,$nA) but B has dimensions ($m, $n)"))
+    V = view(Q.factors, mA-k+1:mA, :)                  # the last k rows hold the reflectors (LAPACK ?ormrq)
+    h = handle()
+    chk(h, ccall((:qlb200_dormrq, libqlb200), Cint,
+                 (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+                 h.ptr, side, trans, m, n, k, V, max(1, stride(Q.factors, 2)), Q.τ, C, max(1, stride(C, 2))); dims = (6, 8))
+    C
+end
+LinearAlgebra.lmul!(Q::RQPackedQ{Float64,<:StridedMatrix}, B::StridedVecOrMat{Float64}) = _ormrq!('L', 'N', Q, B)          # src/rq.jl:130-137
+LinearAlgebra.lmul!(Q::Adjoint{<:Any,<:RQPackedQ{Float64,<:StridedMatrix}}, B::StridedVecOrMat{Float64}) = _ormrq!('L', 'T', parent(Q), B)   # :183-202
+LinearAlgebra.rmul!(A::StridedMatrix{Float64}, Q::RQPackedQ{Float64,<:StridedMatrix}) = _ormrq!('R', 'N', Q, A)           # :234-242
+LinearAlgebra.rmul!(A::StridedMatrix{Float64}, Q::Adjoint{<:Any,<:RQPackedQ{Float64,<:StridedMatrix}}) = _ormrq!('R', 'T', parent(Q), A)   # :272-291
+
+# ---- ul! -----------------------------------------------------------------------------------------------------------
+function ul!(A::StridedMatrix{Float64}, ::Val{Pivot} = Val(true); check::Bool = true) where Pivot        # src/ul.jl:146-196
+    m, n = size(A)
+    ipiv = Vector{BlasInt}(undef, min(m, n))          # BlasInt == Int64 on 64-bit Julia
+    info = Ref{Int32}(0)
+    h = handle()
+    chk(h, ccall((:qlb200_dulfact, libqlb200), Cint,
+                 (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Cint, Ref{Int32}),
+                 h.ptr, m, n, A, max(1, stride(A, 2)), ipiv, Pivot ? 1 : 0, info))
+    check && MatrixFactorizations._checknonsingular(info[], Val{Pivot}())                                 # src/ul.jl:193
+    UL{Float64}(A, ipiv, convert(BlasInt, info[]))
+end
+
+# ---- batched surface (new; per-matrix semantics = ql!, lmul!, ldiv!) --------------------------------------------------
+for (T, p) in ((Float64, :d), (Float32, :s))
+    geqlf = QuoteNode(Symbol(:qlb200_, p, :geqlf_batched))
+    ormql = QuoteNode(Symbol(:qlb200_, p, :ormql_batched))
+    solve = QuoteNode(Symbol(:qlb200_, p, :qlsolve_batched))
+    @eval begin
+        """`ql_batched!(A::Array{T,3})`: `[ql!(view(A,:,:,i)) for i]` in one call; returns the vector of `QL`s."""
+        function ql_batched!(A::Array{$T,3})
+            n, n2, b = size(A)
+            n == n2 || throw(DimensionMismatch("ql_batched!: square matrices only"))
+            τ = Matrix{$T}(undef, n, b)
+            h = handle()
+            chk(h, ccall(($geqlf, libqlb200), Cint, (Ptr{Cvoid}, Int64, Ptr{$T}, Int64, Int64, Ptr{$T}, Int64, Int64),
+                         h.ptr, n, A, n, n * n, τ, n, b))
+            [QL(view(A, :, :, i), view(τ, :, i)) for i in 1:b]
+        end
+        function lmul_batched!(trans::Char, A::Array{$T,3}, τ::Matrix{$T}, B::Array{$T,3})
+            n, _, b = size(A)
+            size(B, 1) == n && size(B, 3) == b || throw(DimensionMismatch("lmul_batched!"))
+            h = handle()
+            chk(h, ccall(($ormql, libqlb200), Cint,
+                         (Ptr{Cvoid}, Cchar, Int64, Int64, Ptr{$T}, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Int64),
+                         h.ptr, trans, n, size(B, 2), A, n, n * n, τ, n, B, n, n * size(B, 2), b))
+            B
+        end
+        function ldiv_batched!(A::Array{$T,3}, τ::Matrix{$T}, B::Array{$T,3})
+            n, _, b = size(A)
+            size(B, 1) == n && size(B, 3) == b || throw(DimensionMismatch("ldiv_batched!"))
+            info = Vector{Int32}(undef, b)
+            h = handle()
+            chk(h, ccall(($solve, libqlb200), Cint,
+                         (Ptr{Cvoid}, Int64, Int64, Ptr{$T}, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Int64, Ptr{Int32}),
+                         h.ptr, n, size(B, 2), A, n, n * n, τ, n, B, n, n * size(B, 2), b, info))
+            i = findfirst(!iszero, info)
+            i === nothing || throw(SingularException(info[i]))
+            B
+        end
+    end
+end
+
+end # module
