@@ -207,7 +207,7 @@ def main():
     tau = torch.empty(n, dtype=torch.float64, device="cuda")
 
     def step():
-        A.copy_(A0)
+        A.T.copy_(A0.T)                                       # contiguous 2 GiB device copy (ql = copy + ql!)
         h.call("qlb200_dgeqlf_dev", n, n, A.data_ptr(), A.stride(1), tau.data_ptr())
 
     for _ in range(args.warmup):

@@ -129,7 +129,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
         rc = qlb_gemm(h, st, cfg_w, /*akc=*/left, /*bkc=*/true, other, ib, p, 1.0, C, ldc, V, ldv, 0.0, Wdst, ldp, S, stride);
     }
     if (rc) return rc;
-    // 2. W2 = (sum of partials) * Tm
+    // 2. W2 = -(sum of partials) * Tm   (negated here, so that step 3 is a pure accumulation: alpha = beta = 1)
     if (small && !tt) {
         rc = qlb_reduce_mult_t(h, st, ws.part, S, stride, other, ib, ldp, T, (int)ldt, ws.W2, ws.ldw);
         if (rc) return rc;
@@ -138,13 +138,13 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
             rc = qlb_reduce_partials(h, st, ws.part, S, stride, other, ib, ldp, ws.Wsum, ws.ldw);
             if (rc) return rc;
         }
-        rc = qlb_gemm(h, st, cfg_w, false, /*bkc=*/!tt, other, ib, ib, 1.0, ws.Wsum, ws.ldw, T, ldt, 0.0, ws.W2, ws.ldw, 1, 0);
+        rc = qlb_gemm(h, st, cfg_w, false, /*bkc=*/!tt, other, ib, ib, -1.0, ws.Wsum, ws.ldw, T, ldt, 0.0, ws.W2, ws.ldw, 1, 0);
         if (rc) return rc;
     }
-    // 3. C -= V W2' (left)  or  C -= W2 V' (right)
+    // 3. C += V W2' (left)  or  C += W2 V' (right), W2 already negated
     QlbProfScope prof(h, st, ib > 16 ? 2.0 * other * ib * p : 0.0);
-    if (left) return qlb_gemm(h, st, -1, false, false, p, other, ib, -1.0, V, ldv, ws.W2, ws.ldw, 1.0, C, ldc, 1, 0);
-    return qlb_gemm(h, st, -1, false, false, other, p, ib, -1.0, ws.W2, ws.ldw, V, ldv, 1.0, C, ldc, 1, 0);
+    if (left) return qlb_gemm(h, st, -1, false, false, p, other, ib, 1.0, V, ldv, ws.W2, ws.ldw, 1.0, C, ldc, 1, 0);
+    return qlb_gemm(h, st, -1, false, false, other, p, ib, 1.0, ws.W2, ws.ldw, V, ldv, 1.0, C, ldc, 1, 0);
 }
 
 // 32x32 tiled transpose: out (cols x rows, ldo) = in (rows x cols, ldi)'

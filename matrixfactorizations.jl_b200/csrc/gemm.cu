@@ -17,6 +17,7 @@
 // a fixed order by reduce_partials_kernel, so results are bitwise reproducible.
 #include "common.cuh"
 #include "internal.h"
+#include <type_traits>
 
 namespace qlb {
 
@@ -166,7 +167,7 @@ __device__ __forceinline__ int acc_row(int wm0, int i, int g, int r) { return wm
 __device__ __forceinline__ int acc_col(int wn0, int j, int t, int r) { return wn0 + (j >> 1) * 16 + 2 * (2 * t + (r & 1)) + (j & 1); }
 
 // acc = pre * D (tile origin m0,n0), D = alpha*acc: (c0,c2) and (c1,c3) are 16-byte pairs of a column.
-template <int MT, int NT>
+template <int MT, int NT, bool UNIT>
 __device__ __forceinline__ void acc_preload(double (&acc)[MT][NT][4], const double *D, int64_t ldd, int M, int N, int m0, int n0,
                                             int wm0, int wn0, int g, int t, double pre, bool vec_ok) {
 #pragma unroll
@@ -188,11 +189,11 @@ __device__ __forceinline__ void acc_preload(double (&acc)[MT][NT][4], const doub
                         if (m + 1 < M) y = d[1];
                     }
                 }
-                acc[i][j][e] = pre * x;
-                acc[i][j][2 + e] = pre * y;
+                acc[i][j][e] = UNIT ? x : pre * x;
+                acc[i][j][2 + e] = UNIT ? y : pre * y;
             }
 }
-template <int MT, int NT>
+template <int MT, int NT, bool UNIT>
 __device__ __forceinline__ void acc_store(const double (&acc)[MT][NT][4], double *D, int64_t ldd, int M, int N, int m0, int n0,
                                           int wm0, int wn0, int g, int t, double alpha, double beta_late, bool vec_ok) {
 #pragma unroll
@@ -204,7 +205,7 @@ __device__ __forceinline__ void acc_store(const double (&acc)[MT][NT][4], double
                 const int m = m0 + acc_row(wm0, i, g, 0), n = n0 + acc_col(wn0, j, t, e);
                 if (n < N) {
                     double *d = D + m + (int64_t)n * ldd;
-                    double x = alpha * acc[i][j][e], y = alpha * acc[i][j][2 + e];
+                    double x = UNIT ? acc[i][j][e] : alpha * acc[i][j][e], y = UNIT ? acc[i][j][2 + e] : alpha * acc[i][j][2 + e];
                     if (beta_late != 0.0) {          // alpha == 0: D = beta*D
                         if (m < M) x = fma(beta_late, d[0], x);
                         if (m + 1 < M) y = fma(beta_late, d[1], y);
@@ -219,7 +220,8 @@ __device__ __forceinline__ void acc_store(const double (&acc)[MT][NT][4], double
             }
 }
 
-template <class Cfg, bool AKC, bool BKC, int VEC>
+// UNIT: alpha == beta == 1 known at compile time (the trailing update C += V * (-W2)'): no scaling at either end.
+template <class Cfg, bool AKC, bool BKC, int VEC, bool UNIT = false>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const GemmParams p) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
     constexpr int PA = AKC ? Cfg::PK : Cfg::PA_MC, PB = BKC ? Cfg::PK : Cfg::PB_NC;
@@ -240,8 +242,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     const double pre = preload ? p.beta / p.alpha : 0.0;
     double acc[MT][NT][4];
     const bool vec_ok = ((uintptr_t)D % 16 == 0) && (p.ldd % 2 == 0);
-    if (preload) {
-        acc_preload<MT, NT>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, pre, vec_ok);
+    if (UNIT) {
+        acc_preload<MT, NT, true>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, 1.0, vec_ok);
+    } else if (preload) {
+        acc_preload<MT, NT, false>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, pre, vec_ok);
     } else {
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -287,7 +291,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     cp_async_wait<0>();
 
     // epilogue: D = alpha*acc (the beta*D term is already inside acc unless alpha == 0)
-    acc_store<MT, NT>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, p.alpha, preload ? 0.0 : p.beta, vec_ok);
+    if (UNIT) acc_store<MT, NT, true>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, 1.0, 0.0, vec_ok);
+    else acc_store<MT, NT, false>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, p.alpha, preload ? 0.0 : p.beta, vec_ok);
 }
 
 // out(M x N, ldo) = sum_{s < S} part[s*stride + m + n*ldp]   (fixed summation order)
@@ -330,6 +335,20 @@ static int launch_layout(qlb200_ctx *h, int cfg, bool akc, bool bkc, bool vec2, 
         const int slot = cfg * 8 + (A_ ? 4 : 0) + (B_ ? 2 : 0);                                        \
         return vec2 ? launch_cfg<Cfg, A_, B_, 2>(h, slot + 1, p, splits, st)                           \
                     : launch_cfg<Cfg, A_, B_, 1>(h, slot, p, splits, st);                              \
+    }
+    if constexpr (std::is_same<Cfg, CfgMid>::value) {
+        if (h->opt_gemm_unit && !akc && !bkc && vec2 && p.alpha == 1.0 && p.beta == 1.0 && splits == 1) {
+            auto kern = gemm_kernel<Cfg, false, false, 2, true>;
+            const int slot = 40;
+            if (!h->gemm_attr_done[slot]) {
+                QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+                h->gemm_attr_done[slot] = true;
+            }
+            dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, 1);
+            kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+            QLB_LAUNCH_CHECK(h);
+            return 0;
+        }
     }
     QLB_GEMM_CASE(true, true)
     QLB_GEMM_CASE(false, true)

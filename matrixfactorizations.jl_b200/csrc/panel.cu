@@ -47,7 +47,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
     while (!ok) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(STRIP_THREADS, 1) strip_kernel(const StripPara
     }
 }
 
-// W2 (rows x w, ldw) = (sum_{s<S} part[s*stride + i + l*ldp]) * T (w x w, lower, ldt), w <= 16.
+// W2 (rows x w, ldw) = -(sum_{s<S} part[s*stride + i + l*ldp]) * T (w x w, lower, ldt), w <= 16.
 // blockDim = (16, 16, 4): x = local row (coalesced loads), y = column l, z = slice of the S partials
 // (each slice sums a fixed quarter in a fixed order, the quarters are added pairwise).
 __global__ void __launch_bounds__(1024) reduce_mult_t_kernel(const double *__restrict__ part, int S, int64_t stride, int rows, int w,
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(1024) reduce_mult_t_kernel(const double *__res
         double o = 0.0;
 #pragma unroll
         for (int q = 0; q < 16; ++q) o = fma(slice[0][ri][q], Tsm[q][l], o);
-        W2[i + (int64_t)l * ldw] = o;
+        W2[i + (int64_t)l * ldw] = -o;
     }
 }
 
@@ -438,7 +438,7 @@ static int launch_strip_t(qlb200_ctx *h, cudaStream_t st, const StripParams &p, 
 
 }  // namespace qlb
 
-// Largest strip (rows) the cluster kernel can hold: 16 CTAs x 256 threads x 4 rows.
+// Largest strip (rows) the cluster kernel can hold: 16 CTAs x STRIP_THREADS x 4 rows.
 int qlb_strip_max_rows() { return qlb::STRIP_MAXC * qlb::STRIP_THREADS * 4; }
 
 int qlb_strip_factor(qlb200_ctx *h, cudaStream_t st, double *A, int64_t lda, int ps, int w, double *tau, double *Vw,
