@@ -140,8 +140,6 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "trail_splits")) {
         if (value < 0 || value > 8) return qlb_fail(h, -3, "trail_splits must be in [0,8]%s");
         h->opt_trail_splits = value;
-    } else if (!strcmp(name, "gemm_unit")) {
-        h->opt_gemm_unit = value ? 1 : 0;
     } else if (!strcmp(name, "bvar")) {
         h->opt_bvar = value;
     } else if (!strcmp(name, "lookahead")) {

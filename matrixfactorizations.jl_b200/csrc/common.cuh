@@ -31,7 +31,6 @@ struct qlb200_ctx {
     int64_t opt_nb = 128, opt_strip = 16, opt_lookahead = 0;
     int64_t opt_gemm_cfg = -1;             // -1 auto, else forces a tile configuration (benchmarking)
     int64_t opt_strip_rpt = 4;             // minimum rows per thread in the strip kernel (1, 2 or 4)
-    int64_t opt_gemm_unit = 0;             // alpha = beta = 1 GEMM variant for the trailing update (measured 5% slower: off)
     int64_t opt_bvar = 0;                  // batched kernel variant (benchmarking)
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM
     bool strip_attr_done[8] = {false};

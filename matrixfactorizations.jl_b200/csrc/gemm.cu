@@ -17,7 +17,6 @@
 // a fixed order by reduce_partials_kernel, so results are bitwise reproducible.
 #include "common.cuh"
 #include "internal.h"
-#include <type_traits>
 
 namespace qlb {
 
@@ -220,8 +219,7 @@ __device__ __forceinline__ void acc_store(const double (&acc)[MT][NT][4], double
             }
 }
 
-// UNIT: alpha == beta == 1 known at compile time (the trailing update C += V * (-W2)'): no scaling at either end.
-template <class Cfg, bool AKC, bool BKC, int VEC, bool UNIT = false>
+template <class Cfg, bool AKC, bool BKC, int VEC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const GemmParams p) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
     constexpr int PA = AKC ? Cfg::PK : Cfg::PA_MC, PB = BKC ? Cfg::PK : Cfg::PB_NC;
@@ -242,9 +240,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     const double pre = preload ? p.beta / p.alpha : 0.0;
     double acc[MT][NT][4];
     const bool vec_ok = ((uintptr_t)D % 16 == 0) && (p.ldd % 2 == 0);
-    if (UNIT) {
-        acc_preload<MT, NT, true>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, 1.0, vec_ok);
-    } else if (preload) {
+    if (preload) {
         acc_preload<MT, NT, false>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, pre, vec_ok);
     } else {
 #pragma unroll
@@ -291,8 +287,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     cp_async_wait<0>();
 
     // epilogue: D = alpha*acc (the beta*D term is already inside acc unless alpha == 0)
-    if (UNIT) acc_store<MT, NT, true>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, 1.0, 0.0, vec_ok);
-    else acc_store<MT, NT, false>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, p.alpha, preload ? 0.0 : p.beta, vec_ok);
+    acc_store<MT, NT, false>(acc, D, p.ldd, p.M, p.N, m0, n0, wm0, wn0, g, t, p.alpha, preload ? 0.0 : p.beta, vec_ok);
 }
 
 // out(M x N, ldo) = sum_{s < S} part[s*stride + m + n*ldp]   (fixed summation order)
@@ -335,20 +330,6 @@ static int launch_layout(qlb200_ctx *h, int cfg, bool akc, bool bkc, bool vec2, 
         const int slot = cfg * 8 + (A_ ? 4 : 0) + (B_ ? 2 : 0);                                        \
         return vec2 ? launch_cfg<Cfg, A_, B_, 2>(h, slot + 1, p, splits, st)                           \
                     : launch_cfg<Cfg, A_, B_, 1>(h, slot, p, splits, st);                              \
-    }
-    if constexpr (std::is_same<Cfg, CfgMid>::value) {
-        if (h->opt_gemm_unit && !akc && !bkc && vec2 && p.alpha == 1.0 && p.beta == 1.0 && splits == 1) {
-            auto kern = gemm_kernel<Cfg, false, false, 2, true>;
-            const int slot = 40;
-            if (!h->gemm_attr_done[slot]) {
-                QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-                h->gemm_attr_done[slot] = true;
-            }
-            dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, 1);
-            kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
-            QLB_LAUNCH_CHECK(h);
-            return 0;
-        }
     }
     QLB_GEMM_CASE(true, true)
     QLB_GEMM_CASE(false, true)
