@@ -124,7 +124,7 @@ __device__ __forceinline__ float nr_rcp(float x) { return __frcp_rn(x); }
 
 // The Householder steps of the group that starts after LO steps.  NS = column slots still in registers (slot c holds
 // column jl + c*LPM); the pivot columns of this group all live in slot NS-1.
-template <typename T, int N, int CPL, int LO, int NS>
+template <typename T, int N, int CPL, int LO, int NS, int PD>
 __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, int nsteps) {
     using V = typename Vec16<T>::type;
     using Cfg = BatchedCfg<T, N, CPL>;
@@ -132,7 +132,6 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
     constexpr int OWN_SLOT = NS - 1;
     constexpr int V0 = LO / E, V1 = N / E;           // 16-byte vectors covering indices [LO, N)
     constexpr int NVEC = V1 - V0;
-    constexpr int PD = 5;                            // x vectors in flight
     constexpr int NCH = (NS >= 2) ? 2 : 4;           // accumulation chains per slot (fixed summation order)
     constexpr int P = N - 1;                         // register index of the pivot row
     constexpr unsigned FULL = 0xffffffffu;
@@ -261,18 +260,18 @@ __device__ __forceinline__ void ql_flush_slot(T (&a)[CPL][N], T (&myscale)[CPL],
 template <int N, int LO>
 struct GroupSize { static constexpr int value = (N - LO > 16) ? 4 : 8; };
 
-template <typename T, int N, int CPL, int LO>
+template <typename T, int N, int CPL, int LO, int PD>
 struct GroupLoop {
     static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad) {
         constexpr int LPM = N / CPL, GS = GroupSize<N, LO>::value;
         constexpr int NS = (N - 1 - LO) / LPM + 1;
         constexpr bool LAST = (LO + GS == N);
         static_assert((N - 1 - LO) / LPM == (N - LO - GS) / LPM, "a group's pivot columns live in one slot");
-        ql_group<T, N, CPL, LO, NS>(a, myscale, xg, obuf, jl, bad, LAST ? GS - 1 : GS);
+        ql_group<T, N, CPL, LO, NS, PD>(a, myscale, xg, obuf, jl, bad, LAST ? GS - 1 : GS);
         if constexpr (!LAST) {
             constexpr int NS_NEXT = (N - 1 - LO - GS) / LPM + 1;
             if constexpr (NS_NEXT < NS) ql_flush_slot<T, N, CPL, NS - 1>(a, myscale, obuf, jl);
-            GroupLoop<T, N, CPL, LO + GS>::run(a, myscale, xg, obuf, jl, bad);
+            GroupLoop<T, N, CPL, LO + GS, PD>::run(a, myscale, xg, obuf, jl, bad);
         } else {
             // R = 0: a length-1 reflector is the identity (tau = 0, beta = alpha); row 0 leaves the tile
             const T aR = a[0][N - 1];
@@ -284,7 +283,7 @@ struct GroupLoop {
 
 // One warp factors G = 32/LPM matrices at a time: TMA (or plain loads) -> shared-memory image ->
 // registers -> factor (finished rows go back into the image) -> TMA bulk stores (or plain stores).
-template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA>
+template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA, int PD = 4>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A, int64_t lda, int64_t strideA,
                      T *__restrict__ tau, int64_t strideTau, int64_t batch, int *__restrict__ redo_count,
@@ -350,7 +349,7 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
         for (int c = 0; c < CPL; ++c) myscale[c] = T(0);
 
         bool bad = false;
-        GroupLoop<T, N, CPL, 0>::run(a, myscale, xg, obuf, jl, bad);
+        GroupLoop<T, N, CPL, 0, PD>::run(a, myscale, xg, obuf, jl, bad);
 
         // flagged matrices stay untouched in global memory and are redone by the generic kernel
         if (valid && bad && jl == 0) redo_list[atomicAdd(redo_count, 1)] = mi;
@@ -647,7 +646,7 @@ static bool tma_ok(const T *A, int64_t lda, int64_t strideA) {
     return ((uintptr_t)A % 16 == 0) && ((lda * sizeof(T)) % 16 == 0) && ((strideA * sizeof(T)) % 16 == 0);
 }
 
-template <typename T, int N, int CPL, int WARPS, int MINB>
+template <typename T, int N, int CPL, int WARPS, int MINB, int PD = 4>
 static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau,
                                 int64_t batch) {
     using Cfg = BatchedCfg<T, N, CPL>;
@@ -655,7 +654,7 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<T>(&tmap, A, N, lda, strideA, batch, Cfg::PITCH);
-    auto kern = tma ? geqlf_batched_kernel<T, N, CPL, WARPS, MINB, true> : geqlf_batched_kernel<T, N, CPL, WARPS, MINB, false>;
+    auto kern = tma ? geqlf_batched_kernel<T, N, CPL, WARPS, MINB, true, PD> : geqlf_batched_kernel<T, N, CPL, WARPS, MINB, false, PD>;
     QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
@@ -734,9 +733,11 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
             if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 5) return qlb::launch_geqlf_batched<double, 32, 2, 5, 2>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 6) return qlb::launch_geqlf_batched<double, 32, 2, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 7) return qlb::launch_geqlf_batched<double, 32, 2, 11, 1>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 5) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 2>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 6) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 7) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 4>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 8) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 7>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 9) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 16>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
