@@ -420,7 +420,7 @@ template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) geql2_generic_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restrict__ tau,
                                                                   int64_t strideTau, int n, const int *__restrict__ count_ptr,
                                                                   int64_t count_val, const int *__restrict__ list) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int P = n + 1;                                     // column pitch
     T *S = reinterpret_cast<T *>(smem_raw) + (size_t)warp * (P * n + n);
@@ -496,80 +496,150 @@ static int launch_geql2_generic(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
 }
 
 // ---------------------------------------------------------------------------------------------
-// Q-apply and square solve: one warp per matrix.  Lane (jb, rg) = (lane % NR, lane / NR) owns
-// RPL = N*NR/32 consecutive rows of column jb of B; reflector k's vector is read from the factors
-// staged in shared memory, the dot product is finished with log2(32/NR) xor-shuffles.
+// Q-apply and square solve.  A group of LPM = N*NR/8 lanes owns one matrix (G = 32/LPM matrices per warp:
+// 1 for n = 32, 2 for n = 16, 4 for n = 8 when NR = 8 columns of B are processed at a time); lane
+// (jb, rg) = (l % NR, l / NR) of a group owns RPL = 8 consecutive rows of column jb of B in registers.
+// The factors of the G matrices are staged by one TMA tensor copy each (padded image, as in the
+// factorization kernel), double-buffered when the images are small; reflector k's vector is read from the
+// image with 16-byte loads, the dot product is finished with log2(RG) xor-shuffles.
 // MODE 0: B <- Q B (k ascending, src/ql.jl:321-347); MODE 1: B <- Q' B (k descending,
 // src/ql.jl:350-377); MODE 2: B <- L^{-1} Q' B (src/ql.jl:440-447,467).
 // ---------------------------------------------------------------------------------------------
 template <typename T, int N, int NR>
 struct ApplyCfg {
     static constexpr int E = Vec16<T>::E;
-    static constexpr int RG = 32 / NR;               // row groups
-    static constexpr int RPL = N / RG;               // rows per lane
     static constexpr int PITCH = N + E;
-    static constexpr int BUF_BYTES = N * PITCH * (int)sizeof(T);
-    static constexpr int WARP_BYTES = BUF_BYTES + N * (int)sizeof(T) + 16;
+    static constexpr int IMG_BYTES = N * PITCH * (int)sizeof(T);                 // multiple of 128
+    static constexpr int pow2_floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
+    static constexpr int LPM0 = (N * NR / 8) > 32 ? 32 : (N * NR / 8);           // lanes per matrix at 8 rows per lane
+    static constexpr int GMAX = pow2_floor((24 * 1024) / IMG_BYTES > 0 ? (24 * 1024) / IMG_BYTES : 1);   // shared-memory budget per warp
+    static constexpr int G = (32 / LPM0) < GMAX ? (32 / LPM0) : GMAX;            // matrices per warp
+    static constexpr int LPM = 32 / G;                    // lanes per matrix
+    static constexpr int RG = LPM / NR;                   // row groups per matrix
+    static constexpr int RPL = N / RG;                    // rows per lane
+    static constexpr int TAU_BYTES = (G * N * (int)sizeof(T) + 127) / 128 * 128;
+    static constexpr int STAGE_BYTES = G * IMG_BYTES + TAU_BYTES;
+    static constexpr int DBUF = (STAGE_BYTES <= 6 * 1024) ? 2 : 1;              // prefetch the next warp-batch if it is cheap
+    static constexpr int WARP_BYTES = DBUF * STAGE_BYTES + 128;                   // + mbarriers
+    static_assert(RG >= 1 && RPL % E == 0, "row blocks are whole 16-byte vectors");
 };
 
 template <typename T, int N, int NR, int MODE, int WARPS, bool USE_TMA>
 __global__ void __launch_bounds__(WARPS * 32)
-apply_batched_kernel(const T *__restrict__ A, int64_t lda, int64_t strideA, const T *__restrict__ tau,
-                     int64_t strideTau, T *__restrict__ B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch,
-                     int32_t *__restrict__ info_out) {
+apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ A, int64_t lda, int64_t strideA,
+                     const T *__restrict__ tau, int64_t strideTau, T *__restrict__ B, int64_t ldb, int64_t strideB, int nrhs,
+                     int64_t batch, int32_t *__restrict__ info_out, int vecB) {
     using Cfg = ApplyCfg<T, N, NR>;
-    constexpr int RPL = Cfg::RPL, PITCH = Cfg::PITCH;
+    using V = typename Vec16<T>::type;
+    constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, RPL = Cfg::RPL, PITCH = Cfg::PITCH, DBUF = Cfg::DBUF;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jb = lane % NR, rg = lane / NR, row0 = rg * RPL;
+    const int g = lane / LPM, l = lane % LPM;
+    const int jb = l % NR, rg = l / NR, row0 = rg * RPL;
     unsigned char *wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
-    T *buf = reinterpret_cast<T *>(wbase);
-    T *taus = reinterpret_cast<T *>(wbase + Cfg::BUF_BYTES);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + Cfg::BUF_BYTES + N * sizeof(T));
-    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + DBUF * Cfg::STAGE_BYTES);
+    const int nbatch = (int)batch;
+    const int nwb = (nbatch + G - 1) / G;
+    const int gw = (int)blockIdx.x * WARPS + warp, nw = (int)gridDim.x * WARPS;
     if constexpr (USE_TMA) {
-        if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+        if (lane == 0) {
+            for (int s = 0; s < DBUF; ++s) mbar_init(&bars[s], 1);
+            mbar_fence_init();
+        }
         __syncwarp();
     }
-    uint32_t phase = 0;
-    for (int64_t mi = gw; mi < batch; mi += nw) {
-        const T *Am = A + mi * strideA;
-        // stage the factors (and tau) of this matrix
+    // stage the factors and tau of warp-batch wb into stage s
+    auto issue = [&](int wb, int s) {
+        unsigned char *st = wbase + s * Cfg::STAGE_BYTES;
+        T *img = reinterpret_cast<T *>(st);
+        T *taus = reinterpret_cast<T *>(st + G * Cfg::IMG_BYTES);
+        const int m0 = wb * G;
+        const int nvalid = (nbatch - m0) < G ? (nbatch - m0) : G;
         if constexpr (USE_TMA) {
-            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(N * N * sizeof(T)));
-            for (int col = lane; col < N; col += 32) tma_load_1d(buf + col * PITCH, Am + (int64_t)col * lda, N * sizeof(T), bar);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars[s], (uint32_t)(nvalid * (Cfg::IMG_BYTES + N * (int)sizeof(T))));
+                for (int q = 0; q < nvalid; ++q) {
+                    tma_load_3d(img + q * N * PITCH, &tmap, 0, 0, m0 + q, &bars[s]);
+                    tma_load_1d(taus + q * N, tau + (int64_t)(m0 + q) * strideTau, N * sizeof(T), &bars[s]);
+                }
+            }
         } else {
-            for (int idx = lane; idx < N * N; idx += 32) buf[(idx / N) * PITCH + (idx % N)] = Am[(int64_t)(idx / N) * lda + (idx % N)];
+            for (int q = 0; q < nvalid; ++q) {
+                const T *Am = A + (int64_t)(m0 + q) * strideA;
+                for (int idx = lane; idx < N * N; idx += 32) img[q * N * PITCH + (idx / N) * PITCH + (idx % N)] = Am[(int64_t)(idx / N) * lda + (idx % N)];
+                for (int i = lane; i < N; i += 32) taus[q * N + i] = tau[(int64_t)(m0 + q) * strideTau + i];
+            }
         }
-        for (int i = lane; i < N; i += 32) taus[i] = tau[mi * strideTau + i];
+    };
+    uint32_t phase[DBUF];
+#pragma unroll
+    for (int s = 0; s < DBUF; ++s) phase[s] = 0;
+    if constexpr (DBUF == 2) {
+        if (gw < nwb) issue(gw, 0);
+    }
+    int it = 0;
+    for (int wb = gw; wb < nwb; wb += nw, ++it) {
+        const int cur = (DBUF == 2) ? (it & 1) : 0;
+        if constexpr (DBUF == 2) {
+            if (wb + nw < nwb) issue(wb + nw, cur ^ 1);         // that stage was released at the end of the last iteration
+        } else {
+            issue(wb, 0);
+        }
+        const int mi = wb * G + g;
+        const bool valid = mi < nbatch;
+        unsigned char *st = wbase + cur * Cfg::STAGE_BYTES;
+        const T *img = reinterpret_cast<const T *>(st) + g * N * PITCH;
+        const T *taus = reinterpret_cast<const T *>(st + G * Cfg::IMG_BYTES) + g * N;
+        bool waited = false;
         // this lane's slice of B: nrhs columns are processed NR at a time
         for (int c0 = 0; c0 < nrhs; c0 += NR) {
             const int col = c0 + jb;
-            const bool cvalid = col < nrhs;
+            const bool cvalid = valid && col < nrhs;
             T b[RPL];
-            T *Bc = B + mi * strideB + (int64_t)(cvalid ? col : 0) * ldb + row0;
+            T *Bc = B + (int64_t)(valid ? mi : 0) * strideB + (int64_t)(col < nrhs ? col : 0) * ldb + row0;
+            if (vecB) {
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) b[i] = cvalid ? Bc[i] : T(0);
-            if (c0 == 0) {
-                if constexpr (USE_TMA) { mbar_wait(bar, phase); phase ^= 1; }
+                for (int v = 0; v < RPL / E; ++v) {
+                    V q = cvalid ? reinterpret_cast<const V *>(Bc)[v] : V{};
+                    const T *qp = reinterpret_cast<const T *>(&q);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) b[v * E + e] = qp[e];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) b[i] = cvalid ? Bc[i] : T(0);
+            }
+            if (!waited) {
+                if constexpr (USE_TMA) {
+                    mbar_wait(&bars[cur], phase[cur]);
+                    phase[cur] ^= 1;
+                }
                 __syncwarp();
+                waited = true;
             }
             // reflectors: column k (0-based) has pivot row k, tail rows 0..k-1
+#pragma unroll 4
             for (int kk = 0; kk < N; ++kk) {
                 const int k = (MODE == 0) ? kk : N - 1 - kk;
-                const T *vk = buf + k * PITCH + row0;
-                const T tk = taus[k];
+                const T *vk = img + k * PITCH + row0;
+                const T tk = valid ? taus[k] : T(0);
+                const int kd = k - row0;                       // rows with local index < kd belong to the tail
                 T v[RPL];
                 T part = T(0);
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) {
-                    const int row = row0 + i;
-                    v[i] = (row < k) ? vk[i] : (row == k ? T(1) : T(0));
-                    part = t_fma(v[i], b[i], part);
+                for (int vv = 0; vv < RPL / E; ++vv) {
+                    V q = *reinterpret_cast<const V *>(vk + vv * E);
+                    const T *qp = reinterpret_cast<const T *>(&q);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int i = vv * E + e;
+                        v[i] = (i < kd) ? qp[e] : (i == kd ? T(1) : T(0));
+                        part = t_fma(v[i], b[i], part);
+                    }
                 }
 #pragma unroll
-                for (int off = NR; off < 32; off <<= 1) part += __shfl_xor_sync(FULL, part, off);
+                for (int off = NR; off < LPM; off <<= 1) part += __shfl_xor_sync(FULL, part, off);
                 const T s = tk * part;
 #pragma unroll
                 for (int i = 0; i < RPL; ++i) b[i] = t_fma(-s, v[i], b[i]);
@@ -579,30 +649,51 @@ apply_batched_kernel(const T *__restrict__ A, int64_t lda, int64_t strideA, cons
                 int bad = 0;
 #pragma unroll
                 for (int c = 0; c < N; ++c) {
-                    const int orow = c % RPL, org = c / RPL;       // owner row-group / local row of row c
-                    const T *lc = buf + c * PITCH + row0;
-                    const T lcc = buf[c * PITCH + c];
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int orow = c % RPL, org = c / RPL;       // owner row group / local row of row c
+                    const T *lc = img + c * PITCH + row0;
+                    const T lcc = img[c * PITCH + c];
                     if (lcc == T(0) && bad == 0) bad = c + 1;
-                    T xc = T(0);
+                    T xc = __shfl_sync(FULL, b[orow], jb + NR * org, LPM) / lcc;
+                    const int cd = c - row0;
 #pragma unroll
-                    for (int i = 0; i < RPL; ++i)
-                        if (i == orow) xc = b[i];
-                    xc = __shfl_sync(FULL, xc, jb + NR * org) / lcc;
+                    for (int vv = 0; vv < RPL / E; ++vv) {
+                        V q = *reinterpret_cast<const V *>(lc + vv * E);
+                        const T *qp = reinterpret_cast<const T *>(&q);
 #pragma unroll
-                    for (int i = 0; i < RPL; ++i) {
-                        const int row = row0 + i;
-                        if (row == c) b[i] = xc;
-                        else if (row > c) b[i] = t_fma(-lc[i], xc, b[i]);
+                        for (int e = 0; e < E; ++e) {
+                            const int i = vv * E + e;
+                            if (i == cd) b[i] = xc;
+                            else if (i > cd) b[i] = t_fma(-qp[e], xc, b[i]);
+                        }
                     }
                 }
-                if (info_out != nullptr && lane == 0 && c0 == 0) info_out[mi] = bad;
+                if (info_out != nullptr && valid && l == 0 && c0 == 0) info_out[mi] = bad;
             }
             if (cvalid) {
+                if (vecB) {
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) Bc[i] = b[i];
+                    for (int v = 0; v < RPL / E; ++v) {
+                        V q;
+                        T *qp = reinterpret_cast<T *>(&q);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) qp[e] = b[v * E + e];
+                        reinterpret_cast<V *>(Bc)[v] = q;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) Bc[i] = b[i];
+                }
             }
         }
-        __syncwarp();    // all lanes are done with buf/taus before the next matrix is staged
+        if (!waited) {      // nrhs == 0 cannot happen (checked by the caller); keep the barrier phases consistent anyway
+            if constexpr (USE_TMA) {
+                mbar_wait(&bars[cur], phase[cur]);
+                phase[cur] ^= 1;
+            }
+        }
+        __syncwarp();    // all lanes are done with this stage before it is refilled
     }
 }
 
@@ -682,18 +773,24 @@ static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
     constexpr int WARPS = 4;
     using Cfg = ApplyCfg<T, N, NR>;
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES;
-    const bool tma = tma_ok(A, lda, strideA);
+    if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const bool tau_ok = ((uintptr_t)tau % 16 == 0) && ((strideTau * sizeof(T)) % 16 == 0 || batch <= 1);
+    const bool tma = tma_ok(A, lda, strideA) && tau_ok && make_batch_tensor_map<T>(&tmap, A, N, lda, strideA, batch, Cfg::PITCH);
+    const int vecB = ((uintptr_t)B % 16 == 0) && ((ldb * sizeof(T)) % 16 == 0) && ((strideB * sizeof(T)) % 16 == 0 || batch <= 1);
     auto kern = tma ? apply_batched_kernel<T, N, NR, MODE, WARPS, true> : apply_batched_kernel<T, N, NR, MODE, WARPS, false>;
     QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
     if (occ < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched apply kernel does not fit on an SM%s");
-    int64_t blocks = (batch + WARPS - 1) / WARPS;
+    const int64_t nwb = (batch + Cfg::G - 1) / Cfg::G;
+    int64_t blocks = (nwb + WARPS - 1) / WARPS;
     const int64_t cap = (int64_t)h->sm_count * occ;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch,
-                                                           info_out);
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch,
+                                                           info_out, vecB);
     QLB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -701,12 +798,11 @@ static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
 template <typename T, int N, int MODE>
 static int dispatch_apply_nr(qlb200_ctx *h, const T *A, int64_t lda, int64_t strideA, const T *tau, int64_t strideTau,
                              T *B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch, int32_t *info_out) {
-    // NR = columns of B handled per pass: a power of two <= 8 with N*NR >= 32 rows*cols per warp
-    constexpr int NRMIN = (32 / N) > 1 ? (32 / N) : 1;
-    if (nrhs >= 8 || NRMIN >= 8) return launch_apply_batched<T, N, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
-    if (nrhs > 2 || NRMIN >= 4) return launch_apply_batched<T, N, 4, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
-    if (nrhs > 1 || NRMIN >= 2) return launch_apply_batched<T, N, (NRMIN > 2 ? NRMIN : 2), MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
-    return launch_apply_batched<T, N, (NRMIN > 1 ? NRMIN : 1), MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
+    // NR = columns of B handled per pass (a power of two <= 8)
+    if (nrhs > 4) return launch_apply_batched<T, N, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
+    if (nrhs > 2) return launch_apply_batched<T, N, 4, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
+    if (nrhs > 1) return launch_apply_batched<T, N, 2, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
+    return launch_apply_batched<T, N, 1, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
 }
 
 template <typename T, int MODE>
