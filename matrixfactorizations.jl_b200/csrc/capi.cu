@@ -58,6 +58,7 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->stage2) cudaFree(h->stage2);
     if (h->dinfo) cudaFree(h->dinfo);
     if (h->redo) cudaFree(h->redo);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->prof_ev) {
         for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
         delete[] h->prof_ev;
@@ -140,6 +141,8 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "trail_splits")) {
         if (value < 0 || value > 8) return qlb_fail(h, -3, "trail_splits must be in [0,8]%s");
         h->opt_trail_splits = value;
+    } else if (!strcmp(name, "graph")) {
+        h->opt_graph = value ? 1 : 0;
     } else if (!strcmp(name, "bvar")) {
         h->opt_bvar = value;
     } else if (!strcmp(name, "lookahead")) {
@@ -350,6 +353,59 @@ static int stage_out(qlb200_ctx *h, double *A, int64_t m, int64_t n, int64_t lda
 
 typedef int (*fact_fn)(qlb200_ctx *, int64_t, int64_t, double *, int64_t, double *);
 
+// ql! on device pointers, replayed as a CUDA graph when the same call comes again.  First sight of a key: plain launches
+// (workspace allocation and function attributes happen here).  Second sight: the launch sequence is captured on the
+// handle's stream and instantiated.  From then on: one cudaGraphLaunch.  Skipped while profiling, on the legacy default
+// stream and inside somebody else's capture.
+static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
+    const int64_t key[10] = {m, n, (int64_t)(uintptr_t)dA, lda, (int64_t)(uintptr_t)dtau, h->opt_nb, h->opt_strip_rpt * 16 + h->opt_lookahead,
+                             h->opt_gemm_cfg * 16 + h->opt_trail_splits, (int64_t)(uintptr_t)h->stream, 1};
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    bool usable = h->opt_graph && !h->opt_profile && !h->opt_lookahead && h->stream != nullptr && m * n >= 64 * 64;
+    if (usable && (cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)) {
+        (void)cudaGetLastError();
+        usable = false;
+    }
+    if (!usable) return qlb_dgeqlf_dev(h, m, n, dA, lda, dtau);
+    if (h->graph_exec && !memcmp(key, h->graph_key, sizeof(key))) {
+        QLB_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+        h->launches += h->graph_nodes;
+        return 0;
+    }
+    if (memcmp(key, h->graph_seen_key, sizeof(key))) {           // first sight: run it plainly
+        memcpy(h->graph_seen_key, key, sizeof(key));
+        return qlb_dgeqlf_dev(h, m, n, dA, lda, dtau);
+    }
+    if (h->graph_exec) {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+    const int64_t l0 = h->launches;
+    QLB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = qlb_dgeqlf_dev(h, m, n, dA, lda, dtau);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc || e != cudaSuccess || !graph) {
+        (void)cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        h->launches = l0;
+        if (rc) return rc;
+        return qlb_dgeqlf_dev(h, m, n, dA, lda, dtau);          // capture refused: plain launches
+    }
+    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        h->graph_exec = nullptr;
+        h->launches = l0;
+        return qlb_dgeqlf_dev(h, m, n, dA, lda, dtau);
+    }
+    h->graph_nodes = h->launches - l0;
+    memcpy(h->graph_key, key, sizeof(key));
+    QLB_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    return 0;
+}
+
 static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
     int rc = check_fact(h, m, n, A, lda, tau);
     if (rc) return rc;
@@ -397,10 +453,10 @@ int qlb200_dgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t
     int rc = check_fact(h, m, n, dA, lda, dtau);
     if (rc) return rc;
     QLB_CUDA(h, cudaSetDevice(h->device));
-    return qlb_dgeqlf_dev(h, m, n, dA, lda, dtau);
+    return geqlf_dev_graph(h, m, n, dA, lda, dtau);
 }
 int qlb200_dgeqlf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
-    return fact_host(h, qlb_dgeqlf_dev, m, n, A, lda, tau);
+    return fact_host(h, geqlf_dev_graph, m, n, A, lda, tau);
 }
 int qlb200_dgerqf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
     int rc = check_fact(h, m, n, dA, lda, dtau);

@@ -31,6 +31,13 @@ struct qlb200_ctx {
     int64_t opt_nb = 128, opt_strip = 16, opt_lookahead = 0;
     int64_t opt_gemm_cfg = -1;             // -1 auto, else forces a tile configuration (benchmarking)
     int64_t opt_strip_rpt = 4;             // minimum rows per thread in the strip kernel (1, 2 or 4)
+    // ql! replayed as a CUDA graph: the launch sequence of one (m, n, A, lda, tau, options, stream) call is captured the
+    // second time it is seen and replayed afterwards (same kernels, same order: bitwise identical results)
+    int64_t opt_graph = 1;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_key[10] = {0};
+    int64_t graph_seen_key[10] = {0};
+    int64_t graph_nodes = 0;
     int64_t opt_bvar = 0;                  // batched kernel variant (benchmarking)
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM
     bool strip_attr_done[8] = {false};
@@ -86,6 +93,12 @@ static inline int qlb_fail(qlb200_ctx *h, int code, const char *fmt, const char 
 // Grow-only device buffers owned by the handle.
 static inline int qlb_reserve(qlb200_ctx *h, void **buf, size_t *have, size_t need) {
     if (need <= *have) return 0;
+    if (h->graph_exec) {                   // a cached graph holds pointers into the buffers: drop it on any reallocation
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+    memset(h->graph_key, 0, sizeof(h->graph_key));
+    memset(h->graph_seen_key, 0, sizeof(h->graph_seen_key));
     if (*buf) {
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
         QLB_CUDA(h, cudaFree(*buf));
