@@ -32,11 +32,15 @@ static int choose_splits(int sm, int64_t tiles, int K, int minchunk, int maxS) {
         const double work = (double)tiles * s;
         const double waves = (double)((int64_t)((work + sm - 1) / sm));
         double eff = work / (waves * sm);
-        eff -= 0.01 * (s - 1);                 // partial-sum traffic penalty
+        eff *= 1.0 - 0.004 * (s - 1);          // partial-sum traffic penalty (relative: few-tile GEMMs must still split)
         if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
     }
     return best;
 }
+
+// Upper bound on the split-K factor of W = op(C) V for an operand with `other` columns (rows for side 'R'): thin
+// operands (a few right-hand sides) give only a handful of tiles and need deep splits to occupy the machine.
+static int max_w_splits(int64_t other) { return other >= 2048 ? 8 : (other >= 512 ? 32 : 128); }
 
 struct Workspace {
     double *Vw;  int64_t ldv;      // clean reflector block, p x nb
@@ -55,7 +59,16 @@ static int get_workspace(qlb200_ctx *h, int64_t rows, int64_t other, int nb, int
     const int64_t ldv = even_up(rows), ldw = even_up(other), ldw2 = even_up(nb);
     const int64_t gram_part = (int64_t)160 * nb * nb;
     const int64_t strip_part = (int64_t)128 * even_up(nb) * 16;
-    int64_t part = (int64_t)max_splits * ldw * nb;
+    // split-K partials of W: the deepest split allowed for each operand width (max_w_splits)
+    (void)max_splits;
+    int64_t part = 0;
+    {
+        const int64_t widths[3] = {other, other < 2047 ? other : 2047, other < 511 ? other : 511};
+        for (int i = 0; i < 3; ++i) {
+            const int64_t cand = (int64_t)max_w_splits(widths[i]) * even_up(widths[i]) * nb;
+            if (cand > part) part = cand;
+        }
+    }
     if (gram_part > part) part = gram_part;
     if (strip_part > part) part = strip_part;
     const int64_t part2 = gram_part > strip_part ? gram_part : strip_part;
@@ -114,7 +127,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     } else if (h->opt_trail_splits > 0) {
         S = (int)h->opt_trail_splits;
     } else {
-        S = choose_splits(2 * h->sm_count, tiles, p, 512, 8);
+        S = choose_splits(2 * h->sm_count, tiles, p, other >= 2048 ? 512 : 128, max_w_splits(other));
     }
     S = qlb_gemm_splits(p, S, 16);
     const bool to_part = (S > 1 || small);
@@ -177,8 +190,8 @@ __global__ void __launch_bounds__(TB) trsm_diag_kernel(const double *__restrict_
         Ls[j * (TB + 1) + i] = (i >= j) ? L[i + (int64_t)j * ldl] : 0.0;
     }
     __syncthreads();
-    if (info != nullptr && r < tb && Ls[r * (TB + 1) + r] == 0.0) atomicMin((int *)info, row_base + r + 1);
-    for (int c0 = 0; c0 < nrhs; c0 += 8) {
+    if (info != nullptr && blockIdx.x == 0 && r < tb && Ls[r * (TB + 1) + r] == 0.0) atomicMin((int *)info, row_base + r + 1);
+    for (int c0 = blockIdx.x * 8; c0 < nrhs; c0 += gridDim.x * 8) {       // CTAs share the right-hand sides
         const int nc = (nrhs - c0) < 8 ? (nrhs - c0) : 8;
         double b[8];
 #pragma unroll
@@ -252,19 +265,38 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     const int npanels = (k + nb - 1) / nb;
     const bool la = h->opt_lookahead && npanels > 1;
     Workspace ws, ws2;
-    int rc = get_workspace(h, m, n, nb, 8, &ws, la ? &ws2 : nullptr);
+    int rc = get_workspace(h, m, n, nb, max_w_splits(0), &ws, la ? &ws2 : nullptr);
     if (rc) return rc;
     auto panel_c1 = [&](int j) { return n - j * nb; };
     auto panel_c0 = [&](int j) { int c = n - (j + 1) * nb; return c > n - k ? c : n - k; };
+    // T-factor cache: panel j's T goes straight into slot j (and is then also built for the last panel)
+    h->tc_valid = false;
+    h->tc_fp_valid = false;
+    double *tcache = nullptr;
+    if (h->opt_tcache && !la) {
+        rc = qlb_reserve(h, &h->tcache, &h->tcache_bytes, (size_t)npanels * nb * nb * sizeof(double));
+        if (rc) return rc;
+        tcache = (double *)h->tcache;
+    }
     if (!la) {
         for (int j = 0; j < npanels; ++j) {
             const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
-            rc = factor_panel(h, st, ws, A, lda, m, n, k, c0, c1, tau, ws.Vw, ws.ldv, ws.T, (int)ws.ldt, c0 > 0);
+            double *Tj = tcache ? tcache + (size_t)j * nb * nb : ws.T;
+            rc = factor_panel(h, st, ws, A, lda, m, n, k, c0, c1, tau, ws.Vw, ws.ldv, Tj, nb, c0 > 0 || tcache != nullptr);
             if (rc) return rc;
             if (c0 > 0) {
-                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, ws.T, ws.ldt, p, ib, A, lda, c0);
+                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, Tj, nb, p, ib, A, lda, c0);
                 if (rc) return rc;
             }
+        }
+        if (tcache) {
+            h->tc_key[0] = (int64_t)(uintptr_t)(A + (int64_t)(n - k) * lda);
+            h->tc_key[1] = lda;
+            h->tc_key[2] = (int64_t)(uintptr_t)tau;
+            h->tc_key[3] = m;
+            h->tc_key[4] = k;
+            h->tc_key[5] = nb;
+            h->tc_valid = true;
         }
         return 0;
     }
@@ -300,8 +332,10 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     return 0;
 }
 
+// cache_mode: 0 = use the T cache if the pointers are the ones ql! just factored, 1 = use it (the caller validated the
+// factors by fingerprint), -1 = never.
 int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n64, int64_t k64, const double *A,
-                   int64_t lda, const double *tau, double *C, int64_t ldc) {
+                   int64_t lda, const double *tau, double *C, int64_t ldc, int cache_mode) {
     const int m = (int)m64, n = (int)n64, k = (int)k64;
     const bool left = (side == 'L' || side == 'l');
     const bool notran = (trans == 'N' || trans == 'n');
@@ -310,26 +344,44 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     const int nb = (int)h->opt_nb;
     cudaStream_t st = h->stream;
     Workspace ws;
-    int rc = get_workspace(h, nq, other, nb, 8, &ws);
+    int rc = get_workspace(h, nq, other, nb, max_w_splits(other), &ws);
     if (rc) return rc;
+    bool cached = h->opt_tcache && h->tc_valid && h->tc_key[3] == nq && h->tc_key[4] == k && h->tc_key[5] == nb && cache_mode >= 0;
+    if (cached && cache_mode == 0)
+        cached = h->tc_key[0] == (int64_t)(uintptr_t)A && h->tc_key[1] == lda && h->tc_key[2] == (int64_t)(uintptr_t)tau;
+    const double *tcache = cached ? (const double *)h->tcache : nullptr;
     const int nblk = (k + nb - 1) / nb;
-    // Q = H_k ... H_1.  Q C and C Q' apply H_1 first (ascending blocks); Q' C and C Q descending.
+    // Blocks are cut from the RIGHT like ql!'s panels (block j = reflectors [k-(j+1)nb, k-j nb)), so that cached T factors
+    // line up.  Q = H_k ... H_1: Q C and C Q' apply H_1 first (leftmost block first); Q' C and C Q the other way round.
     const bool ascending = (left && notran) || (!left && !notran);
     for (int bi = 0; bi < nblk; ++bi) {
-        const int b = ascending ? bi : nblk - 1 - bi;
-        const int i = b * nb;
-        const int ib = (k - i) < nb ? (k - i) : nb;
+        const int j = ascending ? nblk - 1 - bi : bi;
+        const int i1 = k - j * nb;
+        const int i = (i1 - nb > 0) ? i1 - nb : 0;
+        const int ib = i1 - i;
         const int p = nq - k + i + ib;          // rows of V for this block
         rc = qlb_extract_v(h, st, A + (int64_t)i * lda, lda, p, ib, nq - k + i, ws.Vw, ws.ldv);
         if (rc) return rc;
-        rc = build_T(h, st, ws, p, ib, tau + i);
-        if (rc) return rc;
+        const double *T = ws.T;
+        if (tcache) {
+            T = tcache + (size_t)j * nb * nb;
+        } else {
+            rc = build_T(h, st, ws, p, ib, tau + i);
+            if (rc) return rc;
+        }
         // left: H C = C - V T V'C -> W2 = W T' (notrans), W T (trans); right: C H = C - (C V) T V' -> W T / W T'
         const bool tt = left ? notran : !notran;
-        rc = apply_block(h, st, ws, left, tt, ws.Vw, ws.ldv, ws.T, ws.ldt, p, ib, C, ldc, other);
+        rc = apply_block(h, st, ws, left, tt, ws.Vw, ws.ldv, T, ws.ldt, p, ib, C, ldc, other);
         if (rc) return rc;
     }
     return 0;
+}
+
+// CTAs of a diagonal-block solve: one per 8 right-hand sides, at most one per SM (the 128 x 128 block fills shared memory)
+int trsm_grid(qlb200_ctx *h, int nrhs) {
+    int g = (nrhs + 7) / 8;
+    if (g > h->sm_count) g = h->sm_count;
+    return g < 1 ? 1 : g;
 }
 
 // Forward substitution with L = tril(A) (n x n, non-unit): B (n x nrhs) <- L^{-1} B, blocked by 128 rows
@@ -350,7 +402,7 @@ int qlb_trsm_lower_dev(qlb200_ctx *h, int n, int nrhs, const double *A, int64_t 
     }
     for (int i = 0; i < n; i += TB) {                                            // src/ql.jl:467
         const int tb = (n - i) < TB ? (n - i) : TB;
-        trsm_diag_kernel<TB><<<1, TB, smem, st>>>(A + i + (int64_t)i * lda, lda, tb, B + i, ldb, nrhs, i, dinfo);
+        trsm_diag_kernel<TB><<<trsm_grid(h, nrhs), TB, smem, st>>>(A + i + (int64_t)i * lda, lda, tb, B + i, ldb, nrhs, i, dinfo);
         QLB_LAUNCH_CHECK(h);
         const int rem = n - i - tb;
         if (rem > 0) {
@@ -363,10 +415,10 @@ int qlb_trsm_lower_dev(qlb200_ctx *h, int n, int nrhs, const double *A, int64_t 
 }
 
 int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A, int64_t lda, const double *tau, double *B,
-                     int64_t ldb, int32_t *dinfo) {
+                     int64_t ldb, int32_t *dinfo, int cache_mode) {
     const int n = (int)n64, nrhs = (int)nrhs64;
     if (n == 0 || nrhs == 0) return 0;
-    int rc = qlb_dormql_dev(h, 'L', 'T', n, nrhs, n, A, lda, tau, B, ldb);      // src/ql.jl:445
+    int rc = qlb_dormql_dev(h, 'L', 'T', n, nrhs, n, A, lda, tau, B, ldb, cache_mode);      // src/ql.jl:445
     if (rc) return rc;
     return qlb_trsm_lower_dev(h, n, nrhs, A, lda, B, ldb, dinfo);
 }
@@ -388,7 +440,7 @@ int qlb_dormrq_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     dim3 blk(32, 8);
     transpose_kernel<<<dim3((k + 31) / 32, (nq + 31) / 32), blk, 0, h->stream>>>(A, lda, k, nq, At, ldt);
     QLB_LAUNCH_CHECK(h);
-    return qlb_dormql_dev(h, side, notran ? 'T' : 'N', m, n, k, At, ldt, tau, C, ldc);
+    return qlb_dormql_dev(h, side, notran ? 'T' : 'N', m, n, k, At, ldt, tau, C, ldc, -1);
 }
 
 int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
@@ -404,6 +456,7 @@ int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     transpose_kernel<<<dim3((m + 31) / 32, (n + 31) / 32), blk, 0, st>>>(A, lda, m, n, At, ldt);
     QLB_LAUNCH_CHECK(h);
     rc = qlb_dgeqlf_dev(h, n, m, At, ldt, tau);
+    h->tc_valid = false;                         // those reflectors live in scratch memory
     if (rc) return rc;
     transpose_kernel<<<dim3((n + 31) / 32, (m + 31) / 32), blk, 0, st>>>(At, ldt, n, m, A, lda);
     QLB_LAUNCH_CHECK(h);

@@ -58,6 +58,7 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->stage2) cudaFree(h->stage2);
     if (h->dinfo) cudaFree(h->dinfo);
     if (h->redo) cudaFree(h->redo);
+    if (h->tcache) cudaFree(h->tcache);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->prof_ev) {
         for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
@@ -141,6 +142,10 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "trail_splits")) {
         if (value < 0 || value > 8) return qlb_fail(h, -3, "trail_splits must be in [0,8]%s");
         h->opt_trail_splits = value;
+    } else if (!strcmp(name, "tcache")) {
+        h->opt_tcache = value ? 1 : 0;
+        h->tc_valid = false;
+        h->tc_fp_valid = false;
     } else if (!strcmp(name, "graph")) {
         h->opt_graph = value ? 1 : 0;
     } else if (!strcmp(name, "bvar")) {
@@ -353,6 +358,27 @@ static int stage_out(qlb200_ctx *h, double *A, int64_t m, int64_t n, int64_t lda
 
 typedef int (*fact_fn)(qlb200_ctx *, int64_t, int64_t, double *, int64_t, double *);
 
+// Host-side fingerprint of packed QL factors (FNV-1a over tau, the dimensions and a sample of the reflector columns):
+// tells the host-pointer lmul!/ldiv! entry points whether the T cache on the device still belongs to these factors.
+static uint64_t factors_fingerprint(int64_t nq, int64_t k, const double *V, int64_t ldv, const double *tau) {
+    uint64_t hsh = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t bytes) {
+        const unsigned char *c = (const unsigned char *)p;
+        for (size_t i = 0; i < bytes; ++i) { hsh ^= c[i]; hsh *= 1099511628211ull; }
+    };
+    mix(&nq, sizeof(nq));
+    mix(&k, sizeof(k));
+    mix(tau, (size_t)k * sizeof(double));
+    const int64_t step = k > 64 ? k / 64 : 1;
+    for (int64_t j = 0; j < k; j += step) {                        // <= 64 sampled columns: head and diagonal neighbourhood
+        const double *col = V + j * ldv;
+        const int64_t mu = nq - k + j;                             // pivot row of reflector column j
+        mix(col, (size_t)(nq < 16 ? nq : 16) * sizeof(double));
+        mix(col + (mu >= 8 ? mu - 8 : 0), (size_t)(mu >= 8 ? 9 : mu + 1) * sizeof(double));
+    }
+    return hsh;
+}
+
 // ql! on device pointers, replayed as a CUDA graph when the same call comes again.  First sight of a key: plain launches
 // (workspace allocation and function attributes happen here).  Second sight: the launch sequence is captured on the
 // handle's stream and instantiated.  From then on: one cudaGraphLaunch.  Skipped while profiling, on the legacy default
@@ -370,6 +396,17 @@ static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int6
     if (h->graph_exec && !memcmp(key, h->graph_key, sizeof(key))) {
         QLB_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
         h->launches += h->graph_nodes;
+        if (h->opt_tcache && h->tcache) {          // the replay refills the T cache of exactly this factorization
+            const int64_t k = m < n ? m : n;
+            h->tc_key[0] = (int64_t)(uintptr_t)(dA + (n - k) * lda);
+            h->tc_key[1] = lda;
+            h->tc_key[2] = (int64_t)(uintptr_t)dtau;
+            h->tc_key[3] = m;
+            h->tc_key[4] = k;
+            h->tc_key[5] = h->opt_nb;
+            h->tc_valid = true;
+            h->tc_fp_valid = false;
+        }
         return 0;
     }
     if (memcmp(key, h->graph_seen_key, sizeof(key))) {           // first sight: run it plainly
@@ -425,6 +462,10 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
     if (rc) return rc;
     QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (f == geqlf_dev_graph && h->tc_valid) {      // ql!: remember which factors the device-side T cache belongs to
+        h->tc_fp = factors_fingerprint(m, k, A + (n - k) * lda, lda, tau);
+        h->tc_fp_valid = true;
+    }
     return 0;
 }
 
@@ -473,7 +514,7 @@ int qlb200_dormql_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t
     int rc = check_ormql(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
     if (rc) return rc;
     QLB_CUDA(h, cudaSetDevice(h->device));
-    return qlb_dormql_dev(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+    return qlb_dormql_dev(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc, 0);
 }
 int qlb200_dormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
                   const double *tau, double *C, int64_t ldc) {
@@ -482,6 +523,10 @@ int qlb200_dormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
     if (m == 0 || n == 0 || k == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
     const int64_t nq = (side == 'L' || side == 'l') ? m : n;
+    // the T cache survives the staging below only if nothing is reallocated; decide first whether it is ours
+    const bool fp_ok = h->opt_tcache && h->tc_valid && h->tc_fp_valid && h->tc_key[3] == nq && h->tc_key[4] == k &&
+                       factors_fingerprint(nq, k, A, lda, tau) == h->tc_fp;
+    const uint64_t fp_keep = h->tc_fp;
     double *dA, *dC;
     int64_t ldda, lddc;
     rc = stage_in(h, &h->stage, &h->stage_bytes, A, nq, k, lda, &dA, &ldda);
@@ -496,7 +541,7 @@ int qlb200_dormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
     QLB_CUDA(h, cudaMemcpy2DAsync(dC, (size_t)lddc * 8, C, (size_t)ldc * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice,
                                   h->stream));
     QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = qlb_dormql_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc);
+    rc = qlb_dormql_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc, (fp_ok && h->tc_valid && h->tc_fp == fp_keep) ? 1 : -1);
     if (rc) return rc;
     rc = stage_out(h, C, m, n, ldc, dC, lddc);
     if (rc) return rc;
@@ -522,7 +567,7 @@ int qlb200_dqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *
     int rc = check_solve(h, n, nrhs, dA, lda, dtau, dB, ldb);
     if (rc) return rc;
     QLB_CUDA(h, cudaSetDevice(h->device));
-    return qlb_dqlsolve_dev(h, n, nrhs, dA, lda, dtau, dB, ldb, nullptr);
+    return qlb_dqlsolve_dev(h, n, nrhs, dA, lda, dtau, dB, ldb, nullptr, 0);
 }
 int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
                     int64_t ldb) {
@@ -530,6 +575,9 @@ int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, i
     if (rc) return rc;
     if (n == 0 || nrhs == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
+    const bool fp_ok = h->opt_tcache && h->tc_valid && h->tc_fp_valid && h->tc_key[3] == n && h->tc_key[4] == n &&
+                       factors_fingerprint(n, n, A, lda, tau) == h->tc_fp;
+    const uint64_t fp_keep = h->tc_fp;
     double *dA, *dB;
     int64_t ldda;
     rc = stage_in(h, &h->stage, &h->stage_bytes, A, n, n, lda, &dA, &ldda);
@@ -542,7 +590,7 @@ int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, i
     QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)n * 8, (size_t)nrhs, cudaMemcpyHostToDevice,
                                   h->stream));
     QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = qlb_dqlsolve_dev(h, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo);
+    rc = qlb_dqlsolve_dev(h, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo, (fp_ok && h->tc_valid && h->tc_fp == fp_keep) ? 1 : -1);
     if (rc) return rc;
     rc = stage_out(h, B, n, nrhs, ldb, dB, lddb);
     if (rc) return rc;

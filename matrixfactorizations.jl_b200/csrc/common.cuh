@@ -38,6 +38,17 @@ struct qlb200_ctx {
     int64_t graph_key[10] = {0};
     int64_t graph_seen_key[10] = {0};
     int64_t graph_nodes = 0;
+    // T-factor cache: ql! keeps the nb x nb compact-WY T of every panel, so that lmul!/rmul!/ldiv! on the factors it just
+    // produced (same pointers, or -- for host-pointer calls -- same fingerprint of tau and sampled factors) do not rebuild
+    // them (SURVEY.md A.3 allows exactly this).  Contract for device-pointer callers: do not modify the factors between
+    // the calls, or set option "tcache" = 0.
+    int64_t opt_tcache = 1;
+    void *tcache = nullptr;
+    size_t tcache_bytes = 0;
+    bool tc_valid = false;
+    int64_t tc_key[6] = {0};               // reflector pointer (first of the last k columns), lda, tau, m, k, nb
+    uint64_t tc_fp = 0;                    // host-side fingerprint of the factors the cache belongs to
+    bool tc_fp_valid = false;
     int64_t opt_bvar = 0;                  // batched kernel variant (benchmarking)
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM
     bool strip_attr_done[8] = {false};
@@ -99,6 +110,8 @@ static inline int qlb_reserve(qlb200_ctx *h, void **buf, size_t *have, size_t ne
     }
     memset(h->graph_key, 0, sizeof(h->graph_key));
     memset(h->graph_seen_key, 0, sizeof(h->graph_seen_key));
+    h->tc_valid = false;
+    h->tc_fp_valid = false;
     if (*buf) {
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
         QLB_CUDA(h, cudaFree(*buf));

@@ -38,10 +38,11 @@ int qlb_extract_v(qlb200_ctx *h, cudaStream_t st, const double *F, int64_t ldf, 
 // blocked.cu (device pointers, asynchronous on h->stream)
 int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
 int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
-                   const double *tau, double *C, int64_t ldc);
+                   const double *tau, double *C, int64_t ldc, int cache_mode);
 int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
-                     int64_t ldb, int32_t *dinfo);
+                     int64_t ldb, int32_t *dinfo, int cache_mode);
 int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int trsm_grid(qlb200_ctx *h, int nrhs);
 int qlb_trsm_lower_dev(qlb200_ctx *h, int n, int nrhs, const double *A, int64_t lda, double *B, int64_t ldb, int32_t *dinfo);
 int qlb_dormrq_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
                    const double *tau, double *C, int64_t ldc);

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(TB) trsm_unit_upper_diag_kernel(const double *
         Us[j * (TB + 1) + i] = (i < j) ? U[i + (int64_t)j * ldu] : 0.0;
     }
     __syncthreads();
-    for (int c0 = 0; c0 < nrhs; c0 += 8) {
+    for (int c0 = blockIdx.x * 8; c0 < nrhs; c0 += gridDim.x * 8) {
         const int nc = (nrhs - c0) < 8 ? (nrhs - c0) : 8;
         double b[8];
 #pragma unroll
@@ -261,7 +261,7 @@ int qlb_dulsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A
     const int nblk = (n + TB - 1) / TB;
     for (int b = nblk - 1; b >= 0; --b) {
         const int i = b * TB, tb = (n - i) < TB ? (n - i) : TB;
-        trsm_unit_upper_diag_kernel<TB><<<1, TB, smem, st>>>(A + i + (int64_t)i * lda, lda, tb, B + i, ldb, nrhs);
+        trsm_unit_upper_diag_kernel<TB><<<trsm_grid(h, nrhs), TB, smem, st>>>(A + i + (int64_t)i * lda, lda, tb, B + i, ldb, nrhs);
         QLB_LAUNCH_CHECK(h);
         if (i > 0) {      // B[0:i] -= U[0:i, i:i+tb] * X[i:i+tb]
             int rc = qlb_gemm(h, st, nrhs <= 16 ? 2 : -1, false, true, i, nrhs, tb, -1.0, A + (int64_t)i * lda, lda, B + i, ldb, 1.0, B, ldb,

@@ -237,3 +237,38 @@ def test_device_pointer_path_large_properties(q, h):
     Lf = torch.flip(L, dims=(0, 1))
     sgn = torch.sign(torch.diagonal(R)) * torch.sign(torch.diagonal(Lf))
     assert (torch.abs(R * sgn[:, None] - Lf).max() / torch.abs(L).max()).item() <= 50 * n * EPS * 10
+
+
+def test_t_cache_hits_and_misses(q, h):
+    """ql! keeps the panels' T factors; lmul!/ldiv! reuse them only for the factors they belong to (device: same
+    pointers; host: same fingerprint).  A stale cache must never be used: interleave two factorizations."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    n = 300
+    A1 = np.asfortranarray(rng.standard_normal((n, n)))
+    A2 = np.asfortranarray(rng.standard_normal((n, n)))
+    B = np.asfortranarray(rng.standard_normal((n, 3)))
+    F1 = q.ql(A1, handle=h)
+    F2 = q.ql(A2, handle=h)                      # the cache now belongs to A2
+    tol = 50 * n * EPS * np.abs(B).max() * n
+    for F in (F1, F2, F1):                       # miss (rebuild), hit, miss
+        got = q.lmul_(F.Q.T, B.copy(order="F"))
+        ref = cport.lmul(F.factors, F.tau, B, adjoint=True)
+        assert np.abs(got - ref).max() <= tol
+    x = F2.solve(B)                              # hit
+    assert np.abs(x - cport.ldiv(F2.factors, F2.tau, B)).max() <= 50 * n * EPS * np.linalg.cond(A2) * max(1.0, np.abs(x).max())
+    # device pointers: cached and rebuilt T give the same answer
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Ad = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g).T
+    Bd = torch.randn((4, n), dtype=torch.float64, device="cuda", generator=g).T
+    Fd = q.ql_((Ad.T.clone()).T, handle=h)
+    r_hit = q.lmul_(Fd.Q, (Bd.T.clone()).T)
+    torch.cuda.synchronize()
+    h.set_option("tcache", 0)
+    try:
+        r_miss = q.lmul_(Fd.Q, (Bd.T.clone()).T)
+        torch.cuda.synchronize()
+    finally:
+        h.set_option("tcache", 1)
+    assert torch.equal(r_hit, r_miss)

@@ -38,3 +38,13 @@ elif case == "batched":
     q.lmul_batched_(A, tau, B, adjoint=True, handle=h)
 torch.cuda.synchronize()
 print("done", case, n, "launches", h.launches)
+if case == "ormql":
+    A = cm(n, n)
+    tau = torch.empty(n, dtype=torch.float64, device="cuda")
+    h.call("qlb200_dgeqlf_dev", n, n, A.data_ptr(), A.stride(1), tau.data_ptr())
+    B = cm(n, 8)
+    torch.cuda.synchronize()
+    l0 = h.launches
+    h.call("qlb200_dormql_dev", b"L", b"T", n, 8, n, A.data_ptr(), A.stride(1), tau.data_ptr(), B.data_ptr(), B.stride(1))
+    torch.cuda.synchronize()
+    print("ormql launches", h.launches - l0)
