@@ -113,8 +113,10 @@ static int build_T(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, int p, i
 //   left : C (p x nc, ldc)  <- (I - V Tm V') C      W = C' V (nc x ib)
 //   right: C (mc x p, ldc)  <- C (I - V Tm V')      W = C V  (mc x ib)
 // Tm = T (tt == false) or T' (tt == true) in W2 = W * Tm.
+// wait_T: event after which T is valid (T may still be under construction on another stream while W is computed).
 static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool left, bool tt, const double *V,
-                       int64_t ldv, const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other) {
+                       int64_t ldv, const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other,
+                       cudaEvent_t wait_T = nullptr) {
     if (other <= 0 || p <= 0 || ib <= 0) return 0;
     const bool small = ib <= 16 && other <= 128;      // in-panel strip update: many thin partials, fused reduce*T
     const int cfg_w = ib <= 16 ? 2 : -1;
@@ -143,6 +145,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     }
     if (rc) return rc;
     // 2. W2 = -(sum of partials) * Tm   (negated here, so that step 3 is a pure accumulation: alpha = beta = 1)
+    if (wait_T) QLB_CUDA(h, cudaStreamWaitEvent(st, wait_T, 0));
     if (small && !tt) {
         rc = qlb_reduce_mult_t(h, st, ws.part, S, stride, other, ib, ldp, T, (int)ldt, ws.W2, ws.ldw);
         if (rc) return rc;
@@ -265,7 +268,7 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     const int npanels = (k + nb - 1) / nb;
     const bool la = h->opt_lookahead && npanels > 1;
     Workspace ws, ws2;
-    int rc = get_workspace(h, m, n, nb, max_w_splits(0), &ws, la ? &ws2 : nullptr);
+    int rc = get_workspace(h, m, n, nb, 0, &ws, &ws2);
     if (rc) return rc;
     auto panel_c1 = [&](int j) { return n - j * nb; };
     auto panel_c0 = [&](int j) { int c = n - (j + 1) * nb; return c > n - k ? c : n - k; };
@@ -279,13 +282,34 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
         tcache = (double *)h->tcache;
     }
     if (!la) {
+        // The panel's T (Gram GEMM -> reduce -> ?larft, ~135 us of latency-bound work) is needed only for W2 = W T, not
+        // for W = C'V: it is built on the high-priority side stream while the main stream already runs the big W GEMM.
+        const bool overlap = h->opt_overlap_t != 0;
         for (int j = 0; j < npanels; ++j) {
             const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
             double *Tj = tcache ? tcache + (size_t)j * nb * nb : ws.T;
-            rc = factor_panel(h, st, ws, A, lda, m, n, k, c0, c1, tau, ws.Vw, ws.ldv, Tj, nb, c0 > 0 || tcache != nullptr);
+            const bool big = ib > 16;                  // a single-strip panel gets its T from the strip kernel
+            const bool need_T = c0 > 0 || tcache != nullptr;
+            rc = factor_panel(h, st, ws, A, lda, m, n, k, c0, c1, tau, ws.Vw, ws.ldv, Tj, nb, need_T && big && !overlap);
             if (rc) return rc;
+            cudaEvent_t wait_T = nullptr;
+            if (need_T && big && overlap) {
+                Workspace tmp = ws2;
+                tmp.Vw = ws.Vw; tmp.ldv = ws.ldv; tmp.T = Tj; tmp.ldt = nb;
+                if (c0 > 0) {
+                    QLB_CUDA(h, cudaEventRecord(h->ev_a, st));
+                    QLB_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_a, 0));
+                    rc = build_T(h, h->side_stream, tmp, p, ib, tau + (c0 - (n - k)));
+                    if (rc) return rc;
+                    QLB_CUDA(h, cudaEventRecord(h->ev_b, h->side_stream));
+                    wait_T = h->ev_b;
+                } else {
+                    rc = build_T(h, st, tmp, p, ib, tau + (c0 - (n - k)));
+                    if (rc) return rc;
+                }
+            }
             if (c0 > 0) {
-                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, Tj, nb, p, ib, A, lda, c0);
+                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, Tj, nb, p, ib, A, lda, c0, wait_T);
                 if (rc) return rc;
             }
         }

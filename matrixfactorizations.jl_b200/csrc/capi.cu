@@ -146,6 +146,8 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->opt_tcache = value ? 1 : 0;
         h->tc_valid = false;
         h->tc_fp_valid = false;
+    } else if (!strcmp(name, "overlap_t")) {
+        h->opt_overlap_t = value ? 1 : 0;
     } else if (!strcmp(name, "graph")) {
         h->opt_graph = value ? 1 : 0;
     } else if (!strcmp(name, "bvar")) {
@@ -385,7 +387,7 @@ static uint64_t factors_fingerprint(int64_t nq, int64_t k, const double *V, int6
 // stream and inside somebody else's capture.
 static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
     const int64_t key[10] = {m, n, (int64_t)(uintptr_t)dA, lda, (int64_t)(uintptr_t)dtau, h->opt_nb, h->opt_strip_rpt * 16 + h->opt_lookahead,
-                             h->opt_gemm_cfg * 16 + h->opt_trail_splits, (int64_t)(uintptr_t)h->stream, 1};
+                             h->opt_gemm_cfg * 16 + h->opt_trail_splits, (int64_t)(uintptr_t)h->stream, 1 + 2 * h->opt_overlap_t + 4 * h->opt_tcache};
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     bool usable = h->opt_graph && !h->opt_profile && !h->opt_lookahead && h->stream != nullptr && m * n >= 64 * 64;
     if (usable && (cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)) {

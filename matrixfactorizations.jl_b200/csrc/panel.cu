@@ -339,13 +339,15 @@ __global__ void __launch_bounds__(1024) reduce_mult_t_kernel(const double *__res
 __global__ void __launch_bounds__(256, 1) larft_kernel(const double *__restrict__ G, int64_t ldg, const double *__restrict__ tau,
                                                       int ib, double *__restrict__ T, int64_t ldt) {
     extern __shared__ __align__(16) double sm[];
-    double *W = sm;                                   // ib x ib, column-major pitch ib
-    double *ts = sm + (size_t)ib * ib;                // tau
+    double *W = sm;                                   // lower triangle of ib x ib, packed by columns (66 KB at ib = 128:
+                                                      // the CTA fits beside one trailing-update GEMM CTA on an SM)
+    auto PW = [&](int i, int j) -> double & { return W[j * ib - (j * (j - 1)) / 2 + (i - j)]; };      // i >= j
+    double *ts = sm + (size_t)ib * (ib + 1) / 2;      // tau
     double *Ys = ts + 128;                            // (<=112) x 17 scratch
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int idx = tid; idx < ib * ib; idx += blockDim.x) {
         const int i = idx % ib, j = idx / ib;
-        W[idx] = (i > j) ? G[i + (int64_t)j * ldg] : 0.0;
+        if (i >= j) PW(i, j) = (i > j) ? G[i + (int64_t)j * ldg] : 0.0;
     }
     if (tid < ib) ts[tid] = tau[tid];
     __syncthreads();
@@ -357,11 +359,11 @@ __global__ void __launch_bounds__(256, 1) larft_kernel(const double *__restrict_
         for (int j = r1 - 1; j >= r0; --j) {
             double s = 0.0;
             if (lane < 16 && i < r1 && i > j)
-                for (int l = j + 1; l <= i; ++l) s = fma(W[l * ib + i], W[j * ib + l], s);
+                for (int l = j + 1; l <= i; ++l) s = fma(PW(i, l), PW(l, j), s);
             __syncwarp();
             if (lane < 16 && i < r1) {
-                if (i > j) W[j * ib + i] = -ts[j] * s;
-                else if (i == j) W[j * ib + i] = ts[j];
+                if (i > j) PW(i, j) = -ts[j] * s;
+                else if (i == j) PW(i, j) = ts[j];
             }
             __syncwarp();
         }
@@ -377,9 +379,9 @@ __global__ void __launch_bounds__(256, 1) larft_kernel(const double *__restrict_
         if (ri < R) {
             const int i = R0 + ri;
             for (int l = R0; l <= i; ++l) {          // T(i,l) * G(l, c0+cg+q)
-                const double t = W[l * ib + i];
+                const double t = PW(i, l);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) y[q] = fma(t, W[(c0 + cg + q) * ib + l], y[q]);
+                for (int q = 0; q < 8; ++q) y[q] = fma(t, PW(l, c0 + cg + q), y[q]);
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) Ys[ri * 17 + cg + q] = y[q];
@@ -391,15 +393,15 @@ __global__ void __launch_bounds__(256, 1) larft_kernel(const double *__restrict_
             for (int q = 0; q < 8; ++q) {
                 const int col = cg + q;               // Z(i,col) = -sum_{c >= col} Y(i,c) T_bb(c,col)
                 double z = 0.0;
-                for (int c = col; c < 16; ++c) z = fma(Ys[ri * 17 + c], W[(c0 + col) * ib + c0 + c], z);
-                W[(c0 + col) * ib + i] = -z;
+                for (int c = col; c < 16; ++c) z = fma(Ys[ri * 17 + c], PW(c0 + c, c0 + col), z);
+                PW(i, c0 + col) = -z;
             }
         }
         __syncthreads();
     }
     for (int idx = tid; idx < ib * ib; idx += blockDim.x) {
         const int r = idx % ib, c = idx / ib;
-        T[r + (int64_t)c * ldt] = (r >= c) ? W[idx] : 0.0;
+        T[r + (int64_t)c * ldt] = (r >= c) ? PW(r, c) : 0.0;
     }
 }
 
@@ -480,10 +482,10 @@ int qlb_larft(qlb200_ctx *h, cudaStream_t st, const double *G, int64_t ldg, cons
               int64_t ldt) {
     if (ib <= 0) return 0;
     if (ib > 128) return qlb_fail(h, -2, "larft: block wider than 128%s");
-    const size_t smem = ((size_t)ib * ib + 128 + 112 * 17) * sizeof(double);
+    const size_t smem = ((size_t)ib * (ib + 1) / 2 + 128 + 112 * 17) * sizeof(double);
     if (!h->larft_attr_done) {
         QLB_CUDA(h, cudaFuncSetAttribute(qlb::larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (128 * 128 + 128 + 112 * 17) * 8));
+                                         (128 * 129 / 2 + 128 + 112 * 17) * 8));
         h->larft_attr_done = true;
     }
     qlb::larft_kernel<<<1, 256, smem, st>>>(G, ldg, tau, ib, T, ldt);
