@@ -292,6 +292,10 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             const bool need_T = c0 > 0 || tcache != nullptr;
             rc = factor_panel(h, st, ws, A, lda, m, n, k, c0, c1, tau, ws.Vw, ws.ldv, Tj, nb, need_T && big && !overlap);
             if (rc) return rc;
+            if (h->d2h.host) {      // columns [c0, c1) are final now (host-pointer ql!): mark the moment ...
+                // (the event slot was last used 8 panels ago; waits already queued keep the record they saw)
+                QLB_CUDA(h, cudaEventRecord(h->ev_panel[j & 7], st));
+            }
             cudaEvent_t wait_T = nullptr;
             if (need_T && big && overlap) {
                 Workspace tmp = ws2;
@@ -312,6 +316,19 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
                 rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, Tj, nb, p, ib, A, lda, c0, wait_T);
                 if (rc) return rc;
             }
+            if (h->d2h.host) {      // ... and send them home on the copy stream.  Queued AFTER the trailing update: a copy
+                // to pageable memory blocks the host, and the GPU must have work to do meanwhile.
+                QLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_panel[j & 7], 0));
+                QLB_CUDA(h, cudaMemcpy2DAsync(h->d2h.host + (int64_t)c0 * h->d2h.host_ld, (size_t)h->d2h.host_ld * 8,
+                                              A + (int64_t)c0 * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(c1 - c0),
+                                              cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+        }
+        if (h->d2h.host && n - k > 0) {      // wide matrix: the columns left of the reflectors are final only now
+            QLB_CUDA(h, cudaEventRecord(h->ev_panel[0], st));
+            QLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_panel[0], 0));
+            QLB_CUDA(h, cudaMemcpy2DAsync(h->d2h.host, (size_t)h->d2h.host_ld * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)(n - k),
+                                          cudaMemcpyDeviceToHost, h->copy_stream));
         }
         if (tcache) {
             h->tc_key[0] = (int64_t)(uintptr_t)(A + (int64_t)(n - k) * lda);

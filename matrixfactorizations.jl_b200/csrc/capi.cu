@@ -41,6 +41,8 @@ int qlb200_create(qlb200_handle *out, int device) {
     }
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    QLB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_panel[i], cudaEventDisableTiming));
     QLB_CUDA(h, cudaMalloc(&h->dinfo, 64 + 256 * sizeof(unsigned)));      // status word + per-SM tickets
     QLB_CUDA(h, cudaMemset(h->dinfo, 0, 64 + 256 * sizeof(unsigned)));
     h->stream = h->own_stream;
@@ -67,6 +69,9 @@ int qlb200_destroy(qlb200_handle h) {
     }
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
+    for (int i = 0; i < 8; ++i)
+        if (h->ev_panel[i]) cudaEventDestroy(h->ev_panel[i]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     delete h;
@@ -458,12 +463,26 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
     rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * sizeof(double));
     if (rc) return rc;
     double *dtau = (double *)h->stage2;
-    rc = f(h, m, n, dA, ldd, dtau);
-    if (rc) return rc;
-    rc = stage_out(h, A, m, n, lda, dA, ldd);
-    if (rc) return rc;
-    QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    // ql! of a large matrix: plain launches (no graph) with the finished panels streamed back to the host while the
+    // rest is still being factored -- the D2H copy of the result disappears behind the computation
+    const bool stream_back = (f == geqlf_dev_graph) && m * n >= ((int64_t)1 << 22) && !h->opt_lookahead;
+    if (stream_back) {
+        h->d2h.host = A;
+        h->d2h.host_ld = lda;
+        rc = qlb_dgeqlf_dev(h, m, n, dA, ldd, dtau);
+        h->d2h.host = nullptr;
+        if (rc) return rc;
+        QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+        QLB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    } else {
+        rc = f(h, m, n, dA, ldd, dtau);
+        if (rc) return rc;
+        rc = stage_out(h, A, m, n, lda, dA, ldd);
+        if (rc) return rc;
+        QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     if (f == geqlf_dev_graph && h->tc_valid) {      // ql!: remember which factors the device-side T cache belongs to
         h->tc_fp = factors_fingerprint(m, k, A + (n - k) * lda, lda, tau);
         h->tc_fp_valid = true;

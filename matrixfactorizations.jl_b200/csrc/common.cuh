@@ -16,6 +16,13 @@ struct qlb200_ctx {
     cudaStream_t stream = nullptr;         // stream `_dev` calls run on
     cudaStream_t side_stream = nullptr;    // look-ahead panel stream
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // host-pointer ql!: finished panels are copied back while the factorization of the rest is still running
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_panel[8] = {nullptr};   // ring of "panel j is final" events
+    struct {
+        double *host = nullptr;            // destination (column-major, ld = host_ld); null = disabled
+        int64_t host_ld = 0;
+    } d2h;
     void *ws = nullptr;                    // device workspace (grown on demand)
     size_t ws_bytes = 0;
     void *ws2 = nullptr;                   // second workspace (transposed copy for RQ)
