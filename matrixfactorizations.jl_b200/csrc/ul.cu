@@ -12,7 +12,8 @@
 //   DMMA GEMM         A11 -= U12 * L21 (gemm.cu).
 // ipiv is 1-based like the reference's Vector{BlasInt}; info = the largest k with a zero pivot (the first one the
 // descending loop meets, src/ul.jl:181-183), 0 if none.
-// Round-1 status: parity path; one CTA per strip and K = 16 updates (HBM-bound) -- not tuned.
+// Two-level blocking: strips of 16 update only their 128-column outer block; everything left of the block gets one
+// rank-128 DMMA update per block.  Round-1 status: the strip kernel is a single CTA (latency-bound) -- next: a cluster.
 #include "common.cuh"
 #include "internal.h"
 
@@ -123,8 +124,8 @@ __global__ void ul_laswp_kernel(double *__restrict__ A, int64_t lda, int c0, int
     }
 }
 
-// X = U22^{-1} A21 in place: U22 = unit upper triangle of A[c0:c1, c0:c1], A21 = A[c0:c1, 0:ncols).
-__global__ void ul_trsm_row_kernel(double *__restrict__ A, int64_t lda, int c0, int c1, int ncols) {
+// X = U22^{-1} A21 in place: U22 = unit upper triangle of A[c0:c1, c0:c1], A21 = A[c0:c1, col0:col0+ncols).
+__global__ void ul_trsm_row_kernel(double *__restrict__ A, int64_t lda, int c0, int c1, int col0, int ncols) {
     __shared__ double U[UL_SB][UL_SB + 1];
     const int w = c1 - c0;
     for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
@@ -134,7 +135,7 @@ __global__ void ul_trsm_row_kernel(double *__restrict__ A, int64_t lda, int c0, 
     __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
-    double *x = A + (int64_t)j * lda + c0;
+    double *x = A + (int64_t)(col0 + j) * lda + c0;
     double v[UL_SB];
 #pragma unroll
     for (int i = 0; i < UL_SB; ++i) v[i] = (i < w) ? x[i] : 0.0;
@@ -218,25 +219,49 @@ int qlb_dulfact_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t 
     QLB_LAUNCH_CHECK(h);
     // The reference's loop touches rows/columns 1..k only (k = min(m,n) ... 1), except for the row
     // interchanges which run over all n columns (src/ul.jl:155-191).
-    for (int c1 = k; c1 > 0; c1 -= UL_SB) {
-        const int c0 = (c1 - UL_SB > 0) ? c1 - UL_SB : 0;
-        ul_panel_kernel<<<1, UL_THREADS, 0, st>>>(A, lda, c0, c1, pivot, ipiv, dinfo);
-        QLB_LAUNCH_CHECK(h);
-        if (pivot) {
-            if (c0 > 0) {
-                ul_laswp_kernel<<<(c0 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, 0, c0);
-                QLB_LAUNCH_CHECK(h);
+    // Two levels: outer blocks of UL_NBO = 128 columns; inside a block the strips update only the block's own columns
+    // (K = 16, small); the columns left of the block get ONE rank-128 DMMA update per block, after the block's rows of L
+    // have been finished by a block back substitution with the block's unit upper triangle.
+    constexpr int UL_NBO = 128;
+    for (int C1 = k; C1 > 0; C1 -= UL_NBO) {
+        const int C0 = (C1 - UL_NBO > 0) ? C1 - UL_NBO : 0;
+        for (int c1 = C1; c1 > C0; c1 -= UL_SB) {
+            const int c0 = (c1 - UL_SB > C0) ? c1 - UL_SB : C0;
+            ul_panel_kernel<<<1, UL_THREADS, 0, st>>>(A, lda, c0, c1, pivot, ipiv, dinfo);
+            QLB_LAUNCH_CHECK(h);
+            if (pivot) {
+                if (c0 > 0) {
+                    ul_laswp_kernel<<<(c0 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, 0, c0);
+                    QLB_LAUNCH_CHECK(h);
+                }
+                if (n > c1) {
+                    ul_laswp_kernel<<<(n - c1 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, c1, n);
+                    QLB_LAUNCH_CHECK(h);
+                }
             }
-            if (n > c1) {
-                ul_laswp_kernel<<<(n - c1 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, c1, n);
+            if (c0 > C0) {
+                // inside the block: rows [c0,c1) of the block's columns left of the strip, then A11_block -= U12 * L21
+                ul_trsm_row_kernel<<<(c0 - C0 + 127) / 128, 128, 0, st>>>(A, lda, c0, c1, C0, c0 - C0);
                 QLB_LAUNCH_CHECK(h);
+                int rc = qlb_gemm(h, st, -1, false, true, c0, c0 - C0, c1 - c0, -1.0, A + (int64_t)c0 * lda, lda,
+                                  A + (int64_t)C0 * lda + c0, lda, 1.0, A + (int64_t)C0 * lda, lda, 1, 0);
+                if (rc) return rc;
             }
         }
-        if (c0 > 0) {
-            ul_trsm_row_kernel<<<(c0 + 127) / 128, 128, 0, st>>>(A, lda, c0, c1, c0);
-            QLB_LAUNCH_CHECK(h);
-            // A11 (c0 x c0) -= U12 (c0 x w, M-contiguous) * L21 (w x c0, K-contiguous)
-            int rc = qlb_gemm(h, st, -1, false, true, c0, c0, c1 - c0, -1.0, A + (int64_t)c0 * lda, lda, A + c0, lda, 1.0, A, lda, 1, 0);
+        if (C0 > 0) {
+            // rows [C0,C1) of the columns left of the block: X = U_block^{-1} A21, strip by strip from the bottom
+            for (int c1 = C1; c1 > C0; c1 -= UL_SB) {
+                const int c0 = (c1 - UL_SB > C0) ? c1 - UL_SB : C0;
+                if (c1 < C1) {      // A21[c0:c1, :] -= U[c0:c1, c1:C1] * X[c1:C1, :]
+                    int rc = qlb_gemm(h, st, -1, false, true, c1 - c0, C0, C1 - c1, -1.0, A + (int64_t)c1 * lda + c0, lda, A + c1, lda,
+                                      1.0, A + c0, lda, 1, 0);
+                    if (rc) return rc;
+                }
+                ul_trsm_row_kernel<<<(C0 + 127) / 128, 128, 0, st>>>(A, lda, c0, c1, 0, C0);
+                QLB_LAUNCH_CHECK(h);
+            }
+            // A11 (C0 x C0) -= U12 (C0 x nbo, M-contiguous) * L21 (nbo x C0, K-contiguous)
+            int rc = qlb_gemm(h, st, -1, false, true, C0, C0, C1 - C0, -1.0, A + (int64_t)C0 * lda, lda, A + C0, lda, 1.0, A, lda, 1, 0);
             if (rc) return rc;
         }
     }
