@@ -153,6 +153,8 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->tc_fp_valid = false;
     } else if (!strcmp(name, "overlap_t")) {
         h->opt_overlap_t = value ? 1 : 0;
+    } else if (!strcmp(name, "ul_cluster")) {
+        h->opt_ul_cluster = value ? 1 : 0;
     } else if (!strcmp(name, "graph")) {
         h->opt_graph = value ? 1 : 0;
     } else if (!strcmp(name, "bvar")) {

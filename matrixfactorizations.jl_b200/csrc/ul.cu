@@ -108,6 +108,174 @@ __global__ void __launch_bounds__(UL_THREADS) ul_panel_kernel(double *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster version of the strip kernel: the strip (rows [0,c1) x <= 16 columns) lives in the REGISTERS of one
+// thread-block cluster (<= 16 CTAs x 512 threads x 2 rows), so it is read and written once; per column two
+// hardware cluster barriers: (1) every CTA's pivot candidate has reached every CTA through distributed shared
+// memory, (2) the two rows to interchange have been published by their owners.  Same arithmetic and the same
+// first-maximum pivot rule as ul_panel_kernel (reference src/ul.jl:158-189).
+// ---------------------------------------------------------------------------------------------
+constexpr int ULC_THREADS = 512;
+constexpr int ULC_RPT = 2;
+constexpr int ULC_MAXC = 16;
+
+__device__ __forceinline__ uint32_t ulc_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t ulc_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void ulc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t ulc_map(const void *local_smem_ptr, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem_ptr)), "r"(cta));
+    return ra;
+}
+__device__ __forceinline__ void ulc_st_f64(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void ulc_st_s32(uint32_t addr, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ double ulc_ld_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+struct UlcSmem {
+    double red_v[ULC_THREADS / 32];
+    int red_i[ULC_THREADS / 32];
+    double cand_v[2][ULC_MAXC];          // every CTA's candidate, written by its owner into all CTAs (double-buffered by step parity)
+    int cand_i[2][ULC_MAXC];
+    double pub[2][2][UL_SB];             // [parity][0: row kp, 1: row k][column]: rows published by their owner threads
+    double rowk_new[UL_SB], rowk_old[UL_SB];
+};
+
+__global__ void __launch_bounds__(ULC_THREADS, 1) ul_strip_cluster_kernel(double *__restrict__ A, int64_t lda, int c0, int c1, int pivot,
+                                                                          int64_t *__restrict__ ipiv, int32_t *__restrict__ info) {
+    __shared__ UlcSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = (int)ulc_ctarank(), nc = (int)ulc_nctarank();
+    constexpr int RPC = ULC_THREADS * ULC_RPT;           // rows per CTA
+    const int w = c1 - c0, off = UL_SB - w;              // local column lc = off + (column - c0); the last column sits at 15
+    int rr[ULC_RPT];
+    double a[ULC_RPT][UL_SB];
+#pragma unroll
+    for (int i = 0; i < ULC_RPT; ++i) {
+        rr[i] = cta * RPC + tid + i * ULC_THREADS;
+#pragma unroll
+        for (int q = 0; q < UL_SB; ++q) a[i][q] = (rr[i] < c1 && q >= off) ? A[(int64_t)(c0 + q - off) * lda + rr[i]] : 0.0;
+    }
+    ulc_cluster_sync();            // every CTA of the cluster is resident before the first remote store
+#pragma unroll
+    for (int s = 0; s < UL_SB; ++s) {
+        if (s < w) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int lc = UL_SB - 1 - s;          // compile-time register column of the pivot column
+            const int k = c1 - 1 - s;              // its global index = pivot row
+            const int par = s & 1;
+            // ---- 1. pivot search: first row attaining max |a[r][k]|, r <= k ----
+            int kp = k;
+            if (pivot) {
+                ArgMax best{0.0, 0x7fffffff};
+#pragma unroll
+                for (int i = 0; i < ULC_RPT; ++i) {
+                    const double v = fabs(a[i][lc]);
+                    if (rr[i] <= k && v > best.v) best = ArgMax{v, rr[i]};      // rr ascending in i
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    ArgMax other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+                    best = argmax_combine(best, other);
+                }
+                if (lane == 0) { sm.red_v[warp] = best.v; sm.red_i[warp] = best.i; }
+                __syncthreads();
+                if (warp == 0) {
+                    ArgMax b{lane < ULC_THREADS / 32 ? sm.red_v[lane] : 0.0, lane < ULC_THREADS / 32 ? sm.red_i[lane] : 0x7fffffff};
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        ArgMax other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.i, o)};
+                        b = argmax_combine(b, other);
+                    }
+                    if (lane < nc) {               // lane c delivers this CTA's candidate to CTA c
+                        ulc_st_f64(ulc_map(&sm.cand_v[par][cta], (uint32_t)lane), b.v);
+                        ulc_st_s32(ulc_map(&sm.cand_i[par][cta], (uint32_t)lane), b.i);
+                    }
+                }
+                ulc_cluster_sync();
+                ArgMax gbest{0.0, 0x7fffffff};
+                for (int c = 0; c < nc; ++c) gbest = argmax_combine(gbest, ArgMax{sm.cand_v[par][c], sm.cand_i[par][c]});
+                kp = (gbest.i == 0x7fffffff) ? k : gbest.i;
+            }
+            // ---- 2. the owners publish rows kp and k ----
+#pragma unroll
+            for (int i = 0; i < ULC_RPT; ++i) {
+                if (rr[i] == kp) {
+#pragma unroll
+                    for (int q = 0; q < UL_SB; ++q) sm.pub[par][0][q] = a[i][q];
+                }
+                if (rr[i] == k) {
+#pragma unroll
+                    for (int q = 0; q < UL_SB; ++q) sm.pub[par][1][q] = a[i][q];
+                }
+            }
+            ulc_cluster_sync();
+            if (warp == 0) {
+                const int src_cta = (lane < 16) ? kp / RPC : k / RPC;
+                const double v = ulc_ld_f64(ulc_map(&sm.pub[par][lane < 16 ? 0 : 1][lane & 15], (uint32_t)src_cta));
+                if (lane < 16) sm.rowk_new[lane] = v;
+                else sm.rowk_old[lane & 15] = v;
+            }
+            __syncthreads();
+            const double piv = sm.rowk_new[lc];
+            if (cta == 0 && tid == 0) {
+                ipiv[k] = (int64_t)kp + 1;
+                if (piv == 0.0 && *info == 0) *info = k + 1;
+            }
+            // ---- 3. interchange (registers), scale the column above the pivot, rank-1 update to its left ----
+            const bool doswap = (piv != 0.0) && (kp != k);
+            const double pinv = (piv != 0.0) ? 1.0 / piv : 1.0;
+#pragma unroll
+            for (int i = 0; i < ULC_RPT; ++i) {
+                if (doswap && rr[i] == k) {
+#pragma unroll
+                    for (int q = 0; q < UL_SB; ++q) a[i][q] = sm.rowk_new[q];
+                }
+                if (doswap && rr[i] == kp) {
+#pragma unroll
+                    for (int q = 0; q < UL_SB; ++q) a[i][q] = sm.rowk_old[q];
+                }
+                if (rr[i] < k) {
+                    double m = a[i][lc];
+                    if (piv != 0.0) {
+                        m *= pinv;
+                        a[i][lc] = m;
+                    }
+                    // the pivot row the reference uses for the update is row k AFTER the interchange (or the untouched
+                    // row k when the pivot is zero and nothing is interchanged)
+#pragma unroll
+                    for (int q = 0; q < UL_SB; ++q)
+                        if (q < lc) a[i][q] = fma(-m, (piv != 0.0) ? sm.rowk_new[q] : sm.rowk_old[q], a[i][q]);
+                }
+            }
+            __syncthreads();       // rowk_new / rowk_old / red_* are rewritten in the next step
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ULC_RPT; ++i) {
+        if (rr[i] < c1) {
+#pragma unroll
+            for (int q = 0; q < UL_SB; ++q)
+                if (q >= off) A[(int64_t)(c0 + q - off) * lda + rr[i]] = a[i][q];
+        }
+    }
+    ulc_cluster_sync();            // no CTA exits while its shared memory may still be read remotely
+}
+
 // Row interchanges of one strip (k = c1-1 ... c0, in that order) applied to the columns [j0, j1).
 __global__ void ul_laswp_kernel(double *__restrict__ A, int64_t lda, int c0, int c1, const int64_t *__restrict__ ipiv, int j0,
                                 int j1) {
@@ -227,8 +395,32 @@ int qlb_dulfact_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t 
         const int C0 = (C1 - UL_NBO > 0) ? C1 - UL_NBO : 0;
         for (int c1 = C1; c1 > C0; c1 -= UL_SB) {
             const int c0 = (c1 - UL_SB > C0) ? c1 - UL_SB : C0;
-            ul_panel_kernel<<<1, UL_THREADS, 0, st>>>(A, lda, c0, c1, pivot, ipiv, dinfo);
-            QLB_LAUNCH_CHECK(h);
+            if (c1 <= ULC_MAXC * ULC_THREADS * ULC_RPT && h->opt_ul_cluster) {
+                int nc = (c1 + ULC_THREADS * ULC_RPT - 1) / (ULC_THREADS * ULC_RPT), ncp = 1;
+                while (ncp < nc) ncp <<= 1;
+                static bool attr_done = false;
+                if (!attr_done) {
+                    QLB_CUDA(h, cudaFuncSetAttribute(ul_strip_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                    attr_done = true;
+                }
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(ncp, 1, 1);
+                cfg.blockDim = dim3(ULC_THREADS, 1, 1);
+                cfg.dynamicSmemBytes = 0;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = ncp;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                QLB_CUDA(h, cudaLaunchKernelEx(&cfg, ul_strip_cluster_kernel, A, lda, c0, c1, pivot, ipiv, dinfo));
+                h->launches++;
+            } else {
+                ul_panel_kernel<<<1, UL_THREADS, 0, st>>>(A, lda, c0, c1, pivot, ipiv, dinfo);
+                QLB_LAUNCH_CHECK(h);
+            }
             if (pivot) {
                 if (c0 > 0) {
                     ul_laswp_kernel<<<(c0 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, 0, c0);
