@@ -49,7 +49,12 @@ def I(x):
         return 0
 
 
+seen = set()
 for b in blocks:
+    key = (b["name"], len(b["rows"]), sum(len(r) for r in b["rows"][:50]), b["rows"][0][0] if b["rows"] else "")
+    if key in seen:
+        continue
+    seen.add(key)
     h = b["hdr"]
     idx = {}
     for i, x in enumerate(h):

@@ -48,3 +48,17 @@ if case == "ormql":
     h.call("qlb200_dormql_dev", b"L", b"T", n, 8, n, A.data_ptr(), A.stride(1), tau.data_ptr(), B.data_ptr(), B.stride(1))
     torch.cuda.synchronize()
     print("ormql launches", h.launches - l0)
+if case == "ul":
+    A = cm(n, n)
+    ipiv = torch.zeros(n, dtype=torch.int64, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    h.call("qlb200_dulfact_dev", n, n, A.data_ptr(), A.stride(1), ipiv.data_ptr(), 1, info.data_ptr())
+    torch.cuda.synchronize()
+    print("ul done", h.launches)
+if case == "batched16":
+    A = torch.randn(n, 16, 16, dtype=torch.float32, device="cuda")
+    tau = torch.empty(n, 16, dtype=torch.float32, device="cuda")
+    B = torch.randn(n, 8, 16, dtype=torch.float32, device="cuda")
+    q.ql_batched_(A, tau, handle=h)
+    q.ldiv_batched_(A, tau, B, handle=h)
+    torch.cuda.synchronize()
+    print("batched16 done", h.launches)
