@@ -201,3 +201,34 @@ def test_batched_singular_info(q, h):
     info = np.zeros(4, dtype=np.int32)
     q.ldiv_batched_(Fo, tauo, np.ones((4, 1, n)), info=info, handle=h)
     assert list(info) == [0, 0, 5, 0]
+
+
+@pytest.mark.parametrize("n,dt", [(32, np.float64), (16, np.float32), (8, np.float64)])
+def test_batched_unaligned_layouts_take_the_plain_copy_path(q, h, n, dt):
+    """Odd leading dimensions / strides (not multiples of 16 bytes) cannot use TMA: the kernels fall back to plain loads
+    and stores and must give bitwise the same factors and products as the aligned layout."""
+    batch, lda, ldb, nrhs = 21, n + 1, n + 3, 5
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((batch, n, n)).astype(dt)
+    B = rng.standard_normal((batch, nrhs, n)).astype(dt)
+    F, tau = q.ql_batched_(A.copy(), handle=h)
+    W = q.lmul_batched_(F, tau, B.copy(), adjoint=True, handle=h)
+    X = q.ldiv_batched_(F, tau, B.copy(), handle=h)
+    sA, sT, sB = n * lda + 1, n + 1, nrhs * ldb + 1
+    P = np.zeros(batch * sA + 8, dtype=dt)
+    T = np.zeros(batch * sT + 8, dtype=dt)
+    PB = np.zeros(batch * sB + 8, dtype=dt)
+    for b in range(batch):
+        P[b * sA:b * sA + n * lda].reshape(n, lda)[:, :n] = A[b]
+        PB[b * sB:b * sB + nrhs * ldb].reshape(nrhs, ldb)[:, :n] = B[b]
+    pfx = "d" if dt == np.float64 else "s"
+    assert h.call(f"qlb200_{pfx}geqlf_batched", n, P.ctypes.data, lda, sA, T.ctypes.data, sT, batch) == 0
+    for b in range(batch):
+        assert np.array_equal(P[b * sA:b * sA + n * lda].reshape(n, lda)[:, :n], F[b]), b
+        assert np.array_equal(T[b * sT:b * sT + n], tau[b]), b
+    PB2 = PB.copy()
+    assert h.call(f"qlb200_{pfx}ormql_batched", b"T", n, nrhs, P.ctypes.data, lda, sA, T.ctypes.data, sT, PB.ctypes.data, ldb, sB, batch) == 0
+    assert h.call(f"qlb200_{pfx}qlsolve_batched", n, nrhs, P.ctypes.data, lda, sA, T.ctypes.data, sT, PB2.ctypes.data, ldb, sB, batch, 0) == 0
+    for b in range(batch):
+        assert np.array_equal(PB[b * sB:b * sB + nrhs * ldb].reshape(nrhs, ldb)[:, :n], W[b]), b
+        assert np.array_equal(PB2[b * sB:b * sB + nrhs * ldb].reshape(nrhs, ldb)[:, :n], X[b]), b
