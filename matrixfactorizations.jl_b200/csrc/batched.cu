@@ -829,11 +829,6 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
             if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 5) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 2>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 6) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 7) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 4>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 8) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 7>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 9) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3, 16>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
