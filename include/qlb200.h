@@ -64,9 +64,13 @@ int64_t qlb200_launch_count(qlb200_handle h);
  * event pairs on the launching stream.  This call synchronizes, returns the summed device time (ms),
  * the summed algorithmic flops and the number of launches since the last collect, and resets. */
 int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_total, int64_t *launches);
-/* Tunables: "nb" (panel width, multiple of 16 in [16,128]), "lookahead" (0/1), "gemm_cfg" (-1 auto,
- * 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V),
- * "strip_rpt" (1/2/4 minimum rows per thread in the panel kernel), "profile" (0/1, see above). */
+/* Tunables: "nb" (panel width, multiple of 16 in [16,128]), "lookahead" (0/1, measured slower: off), "gemm_cfg"
+ * (-1 auto, 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V), "strip_rpt"
+ * (1/2/4 minimum rows per thread in the panel kernel), "profile" (0/1, see above), "graph" (1: repeated ql! calls with
+ * the same arguments are replayed as a CUDA graph), "tcache" (1: ql! keeps the panels' T factors for the following
+ * lmul!/rmul!/ldiv! on the same factors -- device-pointer callers must not modify the factors in between),
+ * "overlap_t" (1: the panel's T is built on a side stream while W = C'V runs), "ul_cluster" (1: cluster strip kernel
+ * for UL), "bvar" (benchmarking variants of the batched kernel). */
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
 
 /* ---- single matrix: ql! -------------------------------------------------------------------
@@ -75,7 +79,9 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
  * A (m x n, leading dimension lda >= m) is overwritten with the packed factors; tau gets
  * min(m,n) entries.
  * Float64 only for the single-matrix path (Float32 single matrices are listed as "next" in DESIGN.md);
- * m <= 16384 (row capacity of the cluster-resident panel kernel), any n. */
+ * Any m, n; strips taller than 16384 rows (the capacity of the cluster-resident panel kernel) take a slower
+ * global-memory panel path.
+ * The host-pointer form streams finished panels back to the host while the rest is still being factored. */
 int qlb200_dgeqlf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
 int qlb200_dgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau);
 

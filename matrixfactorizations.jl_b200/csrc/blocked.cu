@@ -262,7 +262,6 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     const int m = (int)m64, n = (int)n64;
     const int k = m < n ? m : n;
     if (k == 0) return 0;
-    if (m > qlb_strip_max_rows()) return qlb_fail(h, -2, "geqlf: m exceeds the panel kernel's row capacity (16384)%s");
     const int nb = (int)h->opt_nb;
     cudaStream_t st = h->stream;
     const int npanels = (k + nb - 1) / nb;

@@ -60,6 +60,7 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->stage2) cudaFree(h->stage2);
     if (h->dinfo) cudaFree(h->dinfo);
     if (h->redo) cudaFree(h->redo);
+    if (h->tall) cudaFree(h->tall);
     if (h->tcache) cudaFree(h->tcache);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->prof_ev) {

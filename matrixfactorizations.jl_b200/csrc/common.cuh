@@ -32,6 +32,8 @@ struct qlb200_ctx {
     void *stage2 = nullptr;                // second staging buffer (C / B operands)
     size_t stage2_bytes = 0;
     int32_t *dinfo = nullptr;              // device-side status word
+    void *tall = nullptr;                  // scratch of the tall-strip fallback (partial dots, strip Gram matrix)
+    size_t tall_bytes = 0;
     void *redo = nullptr;                  // batched: counter + list of matrices for the generic kernel
     size_t redo_bytes = 0;
     int64_t launches = 0;

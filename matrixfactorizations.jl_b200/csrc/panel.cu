@@ -414,6 +414,113 @@ __global__ void extract_v_kernel(const double *__restrict__ F, int64_t ldf, int 
         Vw[r + (int64_t)j * ldv] = (r < mu) ? F[r + (int64_t)j * ldf] : ((r == mu) ? 1.0 : 0.0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strips taller than one cluster can hold (ps > 16 CTAs x 256 threads x 4 rows): the same column-by-column
+// Householder step with the strip left in global memory -- two grid kernels per column (partial dots, then
+// scalars + rank-1 update; every block re-sums the partials in the same fixed order).  Correctness path for very
+// tall matrices (ql! of 65536 x 1024 and the like); the strip's T comes from its Gram matrix afterwards.
+// ---------------------------------------------------------------------------------------------
+constexpr int TALL_THREADS = 256;
+constexpr int TALL_SB = 16;
+
+__global__ void __launch_bounds__(TALL_THREADS) tall_dots_kernel(const double *__restrict__ A, int64_t lda, int mu, int C, int w,
+                                                                 double *__restrict__ part, int rpb) {
+    __shared__ double red[TALL_THREADS / 32][TALL_SB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * rpb, r1 = min(r0 + rpb, mu);
+    double d[TALL_SB];
+#pragma unroll
+    for (int j = 0; j < TALL_SB; ++j) d[j] = 0.0;
+    for (int r = r0 + tid; r < r1; r += TALL_THREADS) {
+        const double x = A[r + (int64_t)C * lda];
+#pragma unroll
+        for (int j = 0; j < TALL_SB; ++j)
+            if (j <= C) d[j] = fma(x, A[r + (int64_t)j * lda], d[j]);      // the columns still to be updated, and x itself
+    }
+#pragma unroll
+    for (int j = 0; j < TALL_SB; ++j) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+        if (lane == 0) red[warp][j] = d[j];
+    }
+    __syncthreads();
+    if (tid < TALL_SB) {
+        double t = 0.0;
+        for (int q = 0; q < TALL_THREADS / 32; ++q) t += red[q][tid];
+        part[(int64_t)blockIdx.x * TALL_SB + tid] = t;
+        if (blockIdx.x == 0) part[(int64_t)gridDim.x * TALL_SB + tid] = (tid < w) ? A[mu + (int64_t)tid * lda] : 0.0;   // the pivot row
+    }
+}
+
+__global__ void __launch_bounds__(TALL_THREADS) tall_update_kernel(double *__restrict__ A, int64_t lda, int mu, int C, int w,
+                                                                   const double *__restrict__ part, double *__restrict__ tau_out,
+                                                                   double *__restrict__ Vw, int64_t ldv, int p, int rpb) {
+    __shared__ double tot[TALL_SB], rowv[TALL_SB], coef[TALL_SB], sc[2];
+    const int tid = threadIdx.x;
+    const int nblk = gridDim.x;
+    if (tid < TALL_SB) {
+        double t = 0.0;
+        for (int b = 0; b < nblk; ++b) t += part[(int64_t)b * TALL_SB + tid];
+        tot[tid] = t;
+        rowv[tid] = part[(int64_t)nblk * TALL_SB + tid];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double ssq = tot[C], alpha = rowv[C];
+        double beta = alpha, tauc = 0.0, scale = 0.0;
+        if (ssq != 0.0) {
+            const double nrm = sqrt(fma(alpha, alpha, ssq));
+            beta = -copysign(nrm, alpha);
+            tauc = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        sc[0] = scale;
+        sc[1] = beta;
+        for (int j = 0; j < TALL_SB; ++j) coef[j] = (j < C) ? -tauc * fma(tot[j], scale, rowv[j]) : 0.0;
+        if (blockIdx.x == 0) {
+            *tau_out = tauc;
+            A[mu + (int64_t)C * lda] = beta;
+            for (int j = 0; j < C; ++j) A[mu + (int64_t)j * lda] = rowv[j] + coef[j];      // a_j[mu] -= tau * s_j (v[mu] = 1)
+            Vw[mu + (int64_t)C * ldv] = 1.0;
+        }
+    }
+    __syncthreads();
+    const double scale = sc[0];
+    const int r0 = blockIdx.x * rpb;
+    for (int r = r0 + tid; r < r0 + rpb && r < p; r += TALL_THREADS) {
+        if (r < mu) {
+            const double v = A[r + (int64_t)C * lda] * scale;
+            A[r + (int64_t)C * lda] = v;
+            Vw[r + (int64_t)C * ldv] = v;
+#pragma unroll
+            for (int j = 0; j < TALL_SB; ++j)
+                if (j < C) A[r + (int64_t)j * lda] = fma(coef[j], v, A[r + (int64_t)j * lda]);
+        } else if (r > mu) {
+            Vw[r + (int64_t)C * ldv] = 0.0;
+        }
+    }
+}
+
+static int strip_factor_tall(qlb200_ctx *h, cudaStream_t st, double *A, int64_t lda, int ps, int w, double *tau, double *Vw, int64_t ldv,
+                             int p, double *T, int ldt) {
+    const int rpb = 2048;
+    const int nblk = (p + rpb - 1) / rpb;
+    int rc = qlb_reserve(h, &h->tall, &h->tall_bytes, ((size_t)(nblk + 1) * TALL_SB + 256 + 64) * sizeof(double));
+    if (rc) return rc;
+    double *part = (double *)h->tall, *G = part + (size_t)(nblk + 1) * TALL_SB;
+    for (int s = 0; s < w; ++s) {
+        const int C = w - 1 - s, mu = ps - 1 - s;
+        tall_dots_kernel<<<nblk, TALL_THREADS, 0, st>>>(A, lda, mu, C, w, part, rpb);
+        QLB_LAUNCH_CHECK(h);
+        tall_update_kernel<<<nblk, TALL_THREADS, 0, st>>>(A, lda, mu, C, w, part, tau + C, Vw, ldv, p, rpb);
+        QLB_LAUNCH_CHECK(h);
+    }
+    // T of the strip from the Gram matrix of its clean reflectors (?larft backward/columnwise)
+    rc = qlb_gemm(h, st, 2, true, true, w, w, p, 1.0, Vw, ldv, Vw, ldv, 0.0, G, w, 1, 0);
+    if (rc) return rc;
+    return qlb_larft(h, st, G, w, tau, w, T, ldt);
+}
+
 template <int SB, int RPT>
 static int launch_strip_t(qlb200_ctx *h, cudaStream_t st, const StripParams &p, int nc) {
     auto kern = strip_kernel<SB, RPT>;
@@ -447,7 +554,7 @@ int qlb_strip_factor(qlb200_ctx *h, cudaStream_t st, double *A, int64_t lda, int
                      int64_t ldv, int p, double *T, int ldt) {
     using namespace qlb;
     if (w < 1 || w > 16) return qlb_fail(h, -2, "strip width must be in [1,16]%s");
-    if (ps > qlb_strip_max_rows()) return qlb_fail(h, -2, "strip taller than the cluster kernel supports%s");
+    if (ps > qlb_strip_max_rows()) return qlb::strip_factor_tall(h, st, A, lda, ps, w, tau, Vw, ldv, p, T, ldt);
     // rows per thread (smallest of 1/2/4 that fits 16 CTAs, or the "strip_rpt" option), then CTAs per
     // cluster (power of two <= 16)
     int rpt = (ps + STRIP_THREADS * STRIP_MAXC - 1) / (STRIP_THREADS * STRIP_MAXC);

@@ -272,3 +272,22 @@ def test_t_cache_hits_and_misses(q, h):
     finally:
         h.set_option("tcache", 1)
     assert torch.equal(r_hit, r_miss)
+
+
+@pytest.mark.parametrize("shape", [(20000, 40), (17000, 700)])
+def test_geqlf_taller_than_the_cluster_capacity(q, h, shape):
+    """m > 16384: strips that do not fit one cluster take the global-memory panel path (mixed with the cluster kernel
+    once the strips get short enough); same LAPACK parity bar."""
+    m, n = shape
+    rng = np.random.default_rng(m)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    F = q.ql(A, handle=h)
+    lapack.set_num_threads(16)
+    Fo, tauo = lapack.geqlf(A)
+    tol = 50 * m * EPS * np.linalg.norm(A)
+    assert np.abs(F.tau - tauo).max() <= 50 * m * EPS
+    assert np.abs(F.factors - Fo).max() <= tol
+    B = np.asfortranarray(rng.standard_normal((m, 2)))
+    got = q.lmul_(F.Q.T, B.copy(order="F"))
+    ref = lapack.ormql("L", "T", np.asfortranarray(Fo), tauo, B.copy(order="F"))
+    assert np.abs(got - ref).max() <= 50 * m * EPS * np.abs(B).max() * np.sqrt(m)
