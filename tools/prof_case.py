@@ -62,3 +62,12 @@ if case == "batched16":
     q.ldiv_batched_(A, tau, B, handle=h)
     torch.cuda.synchronize()
     print("batched16 done", h.launches)
+if case == "strips":
+    # strips of different widths / heights: per-column cost vs fixed cost of the strip kernel
+    for (m, w) in [(16384, 16), (16384, 8), (16384, 1), (1024, 16), (1024, 1), (16, 16)]:
+        A = cm(m, w)
+        tau = torch.empty(w, dtype=torch.float64, device="cuda")
+        h.set_option("graph", 0)
+        h.call("qlb200_dgeqlf_dev", m, w, A.data_ptr(), A.stride(1), tau.data_ptr())
+    torch.cuda.synchronize()
+    print("strips done")
