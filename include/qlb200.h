@@ -70,7 +70,8 @@ int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_tota
  * the same arguments are replayed as a CUDA graph), "tcache" (1: ql! keeps the panels' T factors for the following
  * lmul!/rmul!/ldiv! on the same factors -- device-pointer callers must not modify the factors in between),
  * "overlap_t" (1: the panel's T is built on a side stream while W = C'V runs), "ul_cluster" (1: cluster strip kernel
- * for UL), "bvar" (benchmarking variants of the batched kernel). */
+ * for UL), "stream_in" (1: host-pointer ql! uploads the matrix in column chunks while the right-hand panels are already
+ * being factored; "chunk_cols", "join_step" tune it), "bvar" (benchmarking variants of the batched kernel). */
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
 
 /* ---- single matrix: ql! -------------------------------------------------------------------
@@ -81,7 +82,8 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
  * Float64 only for the single-matrix path (Float32 single matrices are listed as "next" in DESIGN.md);
  * Any m, n; strips taller than 16384 rows (the capacity of the cluster-resident panel kernel) take a slower
  * global-memory panel path.
- * The host-pointer form streams finished panels back to the host while the rest is still being factored. */
+ * The host-pointer form streams the matrix in by column chunks (right to left) while the right-hand panels are already
+ * being factored, and streams finished panels back while the rest is still being factored. */
 int qlb200_dgeqlf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
 int qlb200_dgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau);
 

@@ -284,8 +284,60 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
         // The panel's T (Gram GEMM -> reduce -> ?larft, ~135 us of latency-bound work) is needed only for W2 = W T, not
         // for W = C'V: it is built on the high-priority side stream while the main stream already runs the big W GEMM.
         const bool overlap = h->opt_overlap_t != 0;
+        // Host-pointer ql! (h->h2d.host set): the matrix arrives in chunks of CW columns, right to left, on the H2D stream.
+        // A chunk JOINS the trailing update at a fixed panel index (deterministic schedule: join_step panels per chunk -- 1
+        // measured best at n = 16384 --, and never later than the panel that needs its columns): the main stream waits for its arrival, applies the panels factored
+        // so far to it (clean V extracted from the packed factors, T from the cache), and from then on it takes part in
+        // the ordinary right-looking update.  Chunks that have not joined yet are simply not touched.
+        const double *hsrc = (tcache != nullptr) ? h->h2d.host : nullptr;
+        if (h->h2d.host && !hsrc) {       // no T cache: plain upload first
+            QLB_CUDA(h, cudaMemcpy2DAsync(A, (size_t)lda * 8, h->h2d.host, (size_t)h->h2d.host_ld * 8, (size_t)m * 8, (size_t)n,
+                                          cudaMemcpyHostToDevice, st));
+        }
+        int CW = (int)h->opt_chunk_cols;
+        while ((n + CW - 1) / CW > 32) CW *= 2;
+        const int nch = hsrc ? (n + CW - 1) / CW : 0;
+        int issued = nch, next_join = nch - 1, joined_lo = hsrc ? n : 0;
+        const int JSTEP = (int)h->opt_join_step;     // panels per joining chunk
+        auto issue_chunk = [&](int c) -> int {
+            const int lo = c * CW, hi = (lo + CW < n) ? lo + CW : n;
+            QLB_CUDA(h, cudaMemcpy2DAsync(A + (int64_t)lo * lda, (size_t)lda * 8, hsrc + (int64_t)lo * h->h2d.host_ld,
+                                          (size_t)h->h2d.host_ld * 8, (size_t)m * 8, (size_t)(hi - lo), cudaMemcpyHostToDevice,
+                                          h->h2d_stream));
+            QLB_CUDA(h, cudaEventRecord(h->ev_chunk[c], h->h2d_stream));
+            return 0;
+        };
+        auto join_chunk = [&](int c, int nfact) -> int {      // nfact = panels factored so far
+            const int lo = c * CW, hi = (lo + CW < n) ? lo + CW : n;
+            QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
+            for (int i = 0; i < nfact; ++i) {
+                const int c1i = panel_c1(i), c0i = panel_c0(i), ibi = c1i - c0i, pi = m - n + c1i;
+                int r = qlb_extract_v(h, st, A + (int64_t)c0i * lda, lda, pi, ibi, pi - ibi, ws.Vw, ws.ldv);
+                if (r) return r;
+                r = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, tcache + (size_t)i * nb * nb, nb, pi, ibi, A + (int64_t)lo * lda, lda,
+                                hi - lo);
+                if (r) return r;
+            }
+            joined_lo = lo;
+            return 0;
+        };
         for (int j = 0; j < npanels; ++j) {
             const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
+            if (hsrc) {
+                int cj = nch - 1 - j / JSTEP;                    // schedule: this chunk and everything right of it have joined
+                if (c0 / CW < cj) cj = c0 / CW;                  // ... and in any case the chunk holding this panel's columns
+                if (cj < 0) cj = 0;
+                while (issued > 0 && issued - 1 >= cj - 2) {     // keep two chunks in flight ahead of the joins
+                    --issued;
+                    rc = issue_chunk(issued);
+                    if (rc) return rc;
+                }
+                while (next_join >= cj) {
+                    rc = join_chunk(next_join, j);
+                    if (rc) return rc;
+                    --next_join;
+                }
+            }
             double *Tj = tcache ? tcache + (size_t)j * nb * nb : ws.T;
             const bool big = ib > 16;                  // a single-strip panel gets its T from the strip kernel
             const bool need_T = c0 > 0 || tcache != nullptr;
@@ -311,9 +363,11 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
                     if (rc) return rc;
                 }
             }
-            if (c0 > 0) {
-                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, Tj, nb, p, ib, A, lda, c0, wait_T);
+            if (c0 > joined_lo) {
+                rc = apply_block(h, st, ws, true, false, ws.Vw, ws.ldv, Tj, nb, p, ib, A + (int64_t)joined_lo * lda, lda, c0 - joined_lo, wait_T);
                 if (rc) return rc;
+            } else if (wait_T) {
+                QLB_CUDA(h, cudaStreamWaitEvent(st, wait_T, 0));      // nothing to update yet, but T must be complete before it is reused
             }
             if (h->d2h.host) {      // ... and send them home on the copy stream.  Queued AFTER the trailing update: a copy
                 // to pageable memory blocks the host, and the GPU must have work to do meanwhile.
@@ -321,6 +375,18 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
                 QLB_CUDA(h, cudaMemcpy2DAsync(h->d2h.host + (int64_t)c0 * h->d2h.host_ld, (size_t)h->d2h.host_ld * 8,
                                               A + (int64_t)c0 * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(c1 - c0),
                                               cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+        }
+        if (hsrc) {      // chunks left of every panel (wide matrices) or beyond the schedule: they join now
+            while (issued > 0) {
+                --issued;
+                rc = issue_chunk(issued);
+                if (rc) return rc;
+            }
+            while (next_join >= 0) {
+                rc = join_chunk(next_join, npanels);
+                if (rc) return rc;
+                --next_join;
             }
         }
         if (h->d2h.host && n - k > 0) {      // wide matrix: the columns left of the reflectors are final only now

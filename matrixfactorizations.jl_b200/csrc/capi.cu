@@ -42,6 +42,8 @@ int qlb200_create(qlb200_handle *out, int device) {
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     QLB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    QLB_CUDA(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 32; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_panel[i], cudaEventDisableTiming));
     QLB_CUDA(h, cudaMalloc(&h->dinfo, 64 + 256 * sizeof(unsigned)));      // status word + per-SM tickets
     QLB_CUDA(h, cudaMemset(h->dinfo, 0, 64 + 256 * sizeof(unsigned)));
@@ -73,6 +75,9 @@ int qlb200_destroy(qlb200_handle h) {
     for (int i = 0; i < 8; ++i)
         if (h->ev_panel[i]) cudaEventDestroy(h->ev_panel[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 32; ++i)
+        if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     delete h;
@@ -156,6 +161,14 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->opt_overlap_t = value ? 1 : 0;
     } else if (!strcmp(name, "ul_cluster")) {
         h->opt_ul_cluster = value ? 1 : 0;
+    } else if (!strcmp(name, "join_step")) {
+        if (value < 1 || value > 64) return qlb_fail(h, -3, "join_step must be in [1,64]%s");
+        h->opt_join_step = value;
+    } else if (!strcmp(name, "chunk_cols")) {
+        if (value < 128 || value % 128) return qlb_fail(h, -3, "chunk_cols must be a positive multiple of 128%s");
+        h->opt_chunk_cols = value;
+    } else if (!strcmp(name, "stream_in")) {
+        h->opt_stream_in = value ? 1 : 0;
     } else if (!strcmp(name, "graph")) {
         h->opt_graph = value ? 1 : 0;
     } else if (!strcmp(name, "bvar")) {
@@ -459,22 +472,40 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
     const int64_t k = m < n ? m : n;
     if (k == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
+    // ql! of a large matrix: plain launches (no graph); the matrix streams IN chunk by chunk while the right-hand panels
+    // are already being factored, and the finished panels stream OUT while the rest is still being factored -- both PCIe
+    // transfers disappear behind the computation (except the first chunk and the last panel)
+    const bool stream_back = (f == geqlf_dev_graph) && m * n >= ((int64_t)1 << 22) && !h->opt_lookahead;
+    const bool stream_in = stream_back && h->opt_stream_in && h->opt_tcache;
     double *dA;
     int64_t ldd;
-    rc = stage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, &dA, &ldd);
-    if (rc) return rc;
+    if (stream_in) {
+        ldd = (m + 1) & ~(int64_t)1;
+        rc = qlb_reserve(h, &h->stage, &h->stage_bytes, (size_t)ldd * n * sizeof(double));
+        if (rc) return rc;
+        dA = (double *)h->stage;
+    } else {
+        rc = stage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, &dA, &ldd);
+        if (rc) return rc;
+    }
     rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * sizeof(double));
     if (rc) return rc;
     double *dtau = (double *)h->stage2;
-    // ql! of a large matrix: plain launches (no graph) with the finished panels streamed back to the host while the
-    // rest is still being factored -- the D2H copy of the result disappears behind the computation
-    const bool stream_back = (f == geqlf_dev_graph) && m * n >= ((int64_t)1 << 22) && !h->opt_lookahead;
     if (stream_back) {
         h->d2h.host = A;
         h->d2h.host_ld = lda;
+        if (stream_in) {
+            h->h2d.host = A;
+            h->h2d.host_ld = lda;
+        }
         rc = qlb_dgeqlf_dev(h, m, n, dA, ldd, dtau);
         h->d2h.host = nullptr;
-        if (rc) return rc;
+        h->h2d.host = nullptr;
+        if (rc) {
+            cudaStreamSynchronize(h->h2d_stream);
+            cudaStreamSynchronize(h->copy_stream);
+            return rc;
+        }
         QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
         QLB_CUDA(h, cudaStreamSynchronize(h->copy_stream));

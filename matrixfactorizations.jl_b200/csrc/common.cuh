@@ -23,6 +23,17 @@ struct qlb200_ctx {
         double *host = nullptr;            // destination (column-major, ld = host_ld); null = disabled
         int64_t host_ld = 0;
     } d2h;
+    // host-pointer ql!: the matrix arrives in column chunks (right to left) while the panels on the right are already
+    // being factored; a chunk joins the trailing update when it has arrived and caught up with the finished panels
+    cudaStream_t h2d_stream = nullptr;
+    cudaEvent_t ev_chunk[32] = {nullptr};
+    struct {
+        const double *host = nullptr;      // source (column-major, ld = host_ld); null = the matrix is already on the device
+        int64_t host_ld = 0;
+    } h2d;
+    int64_t opt_stream_in = 1;
+    int64_t opt_chunk_cols = 1024;         // columns per H2D chunk
+    int64_t opt_join_step = 1;             // panels factored per arriving chunk before the next chunk joins
     void *ws = nullptr;                    // device workspace (grown on demand)
     size_t ws_bytes = 0;
     void *ws2 = nullptr;                   // second workspace (transposed copy for RQ)

@@ -291,3 +291,30 @@ def test_geqlf_taller_than_the_cluster_capacity(q, h, shape):
     got = q.lmul_(F.Q.T, B.copy(order="F"))
     ref = lapack.ormql("L", "T", np.asfortranarray(Fo), tauo, B.copy(order="F"))
     assert np.abs(got - ref).max() <= 50 * m * EPS * np.abs(B).max() * np.sqrt(m)
+
+
+@pytest.mark.parametrize("shape", [(2500, 2500), (2100, 2600), (3000, 2100), (4096, 4096)])
+def test_host_pointer_ql_streams_in_and_out(q, h, shape):
+    """Host-pointer ql! of a large matrix: the matrix streams in by column chunks while the right-hand panels are being
+    factored (chunks join the trailing update on a fixed schedule) and finished panels stream back.  Same parity bar as
+    the resident path, and the same answer as with streaming switched off."""
+    m, n = shape
+    rng = np.random.default_rng(m + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    F = q.ql(A, handle=h)
+    lapack.set_num_threads(16)
+    Fo, tauo = lapack.geqlf(A)
+    tol = 50 * max(m, n) * EPS * np.linalg.norm(A)
+    assert np.abs(F.tau - tauo).max() <= 50 * max(m, n) * EPS
+    assert np.abs(F.factors - Fo).max() <= tol
+    h.set_option("stream_in", 0)
+    try:
+        F0 = q.ql(A, handle=h)
+    finally:
+        h.set_option("stream_in", 1)
+    assert np.abs(F.factors - F0.factors).max() <= tol and np.abs(F.tau - F0.tau).max() <= 50 * max(m, n) * EPS
+    # the T cache filled by the streamed factorization serves the solve that follows (fingerprint hit)
+    if m == n:
+        b = np.asfortranarray(rng.standard_normal((n, 2)))
+        x = F.solve(b)
+        assert np.abs(A @ x - b).max() <= 5000 * EPS * np.linalg.cond(A)
