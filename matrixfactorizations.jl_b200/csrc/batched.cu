@@ -260,9 +260,27 @@ __device__ __forceinline__ void ql_flush_slot(T (&a)[CPL][N], T (&myscale)[CPL],
 template <int N, int LO>
 struct GroupSize { static constexpr int value = (N - LO > 16) ? 4 : 8; };
 
-template <typename T, int N, int CPL, int LO, int PD>
+// STOP > 0: leave after STOP steps (phase A of the split factorization): the live leading block (rows and columns
+// below N - STOP, held by slot 0 at register indices [STOP, N)) goes back to the image unscaled and is factored by the
+// kernel of the smaller size afterwards.
+template <typename T, int N, int CPL, int LO, int PD, int STOP = 0>
 struct GroupLoop {
     static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad) {
+        if constexpr (STOP > 0 && LO == STOP) {
+            using V = typename Vec16<T>::type;
+            constexpr int E = Vec16<T>::E;
+            static_assert((N - STOP) * CPL == N || CPL == 1, "the leading block is exactly slot 0");
+            T *dst = obuf + jl * BatchedCfg<T, N, CPL>::PITCH;
+#pragma unroll
+            for (int i = STOP; i < N; i += E) {
+                V q;
+                T *qp = reinterpret_cast<T *>(&q);
+#pragma unroll
+                for (int e = 0; e < E; ++e) qp[e] = a[0][i + e];
+                *reinterpret_cast<V *>(dst + (i - STOP)) = q;
+            }
+            return;
+        } else {
         constexpr int LPM = N / CPL, GS = GroupSize<N, LO>::value;
         constexpr int NS = (N - 1 - LO) / LPM + 1;
         constexpr bool LAST = (LO + GS == N);
@@ -271,23 +289,26 @@ struct GroupLoop {
         if constexpr (!LAST) {
             constexpr int NS_NEXT = (N - 1 - LO - GS) / LPM + 1;
             if constexpr (NS_NEXT < NS) ql_flush_slot<T, N, CPL, NS - 1>(a, myscale, obuf, jl);
-            GroupLoop<T, N, CPL, LO + GS, PD>::run(a, myscale, xg, obuf, jl, bad);
+            GroupLoop<T, N, CPL, LO + GS, PD, STOP>::run(a, myscale, xg, obuf, jl, bad);
         } else {
             // R = 0: a length-1 reflector is the identity (tau = 0, beta = alpha); row 0 leaves the tile
             const T aR = a[0][N - 1];
             obuf[jl * BatchedCfg<T, N, CPL>::PITCH] = (jl > 0) ? aR * myscale[0] : aR;
             if (jl == 0) obuf[N] = T(0);
         }
+        }
     }
 };
 
 // One warp factors G = 32/LPM matrices at a time: TMA (or plain loads) -> shared-memory image ->
 // registers -> factor (finished rows go back into the image) -> TMA bulk stores (or plain stores).
-template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA, int PD = 4>
+// STOP > 0: phase A only (see GroupLoop); flags[mi] = 1 marks the matrices it had to leave to the generic kernel.
+// skip != null: matrices with skip[mi] != 0 are not touched (phase B after a phase A that flagged them).
+template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA, int PD = 4, int STOP = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A, int64_t lda, int64_t strideA,
                      T *__restrict__ tau, int64_t strideTau, int64_t batch, int *__restrict__ redo_count,
-                     int *__restrict__ redo_list) {
+                     int *__restrict__ redo_list, int *__restrict__ flags, const int *__restrict__ skip) {
     using Cfg = BatchedCfg<T, N, CPL>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, PITCH = Cfg::PITCH;
@@ -311,7 +332,8 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
     uint32_t phase = 0;
     for (int wb = gw; wb < nwb; wb += nw) {
         const int m0 = wb * G, mi = m0 + g;
-        const bool valid = mi < nbatch;
+        const bool inb = mi < nbatch;                                  // inside the batch (its image is loaded)
+        const bool valid = inb && !(skip != nullptr && skip[mi] != 0);
         // ---- stage the matrices of this warp-batch ----
         if constexpr (USE_TMA) {
             const int nvalid = (nbatch - m0) < G ? (nbatch - m0) : G;
@@ -319,16 +341,16 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
                 mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * Cfg::IMG_BYTES));
                 for (int q = 0; q < nvalid; ++q) tma_load_3d(buf + q * N * PITCH, &tmap, 0, 0, m0 + q, bar);
             }
-            if (!valid) {      // tail of the batch: an identity keeps the arithmetic finite (results are discarded)
+            if (!inb) {        // tail of the batch: an identity keeps the arithmetic finite (results are discarded)
                 for (int idx = jl; idx < N * N; idx += LPM) obuf[(idx / N) * PITCH + (idx % N)] = (idx / N == idx % N) ? T(1) : T(0);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
             __syncwarp();
         } else {
-            const T *Am = A + (int64_t)(valid ? mi : 0) * strideA;
+            const T *Am = A + (int64_t)(inb ? mi : 0) * strideA;
             for (int idx = jl; idx < N * N; idx += LPM)
-                obuf[(idx / N) * PITCH + (idx % N)] = valid ? Am[(int64_t)(idx / N) * lda + (idx % N)] : ((idx / N == idx % N) ? T(1) : T(0));
+                obuf[(idx / N) * PITCH + (idx % N)] = inb ? Am[(int64_t)(idx / N) * lda + (idx % N)] : ((idx / N == idx % N) ? T(1) : T(0));
             __syncwarp();
         }
         T a[CPL][N];
@@ -349,16 +371,19 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
         for (int c = 0; c < CPL; ++c) myscale[c] = T(0);
 
         bool bad = false;
-        GroupLoop<T, N, CPL, 0, PD>::run(a, myscale, xg, obuf, jl, bad);
+        GroupLoop<T, N, CPL, 0, PD, STOP>::run(a, myscale, xg, obuf, jl, bad);
 
         // flagged matrices stay untouched in global memory and are redone by the generic kernel
-        if (valid && bad && jl == 0) redo_list[atomicAdd(redo_count, 1)] = mi;
+        if (valid && bad && jl == 0) {
+            redo_list[atomicAdd(redo_count, 1)] = mi;
+            if (flags != nullptr) flags[mi] = 1;
+        }
         __syncwarp();
         if (valid && !bad) {                                      // tau: one coalesced row per matrix
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const int col = jl + c * LPM;
-                tau[(int64_t)mi * strideTau + col] = obuf[col * PITCH + N];
+                if (STOP == 0 || col >= N - STOP) tau[(int64_t)mi * strideTau + col] = obuf[col * PITCH + N];      // phase A: the rest comes from phase B
             }
         }
         if constexpr (USE_TMA) {
@@ -761,9 +786,55 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     if (rc) return rc;
     int *redo_count = (int *)h->redo, *redo_list = redo_count + 4;
     QLB_CUDA(h, cudaMemsetAsync(redo_count, 0, sizeof(int), h->stream));
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, redo_count, redo_list);
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, redo_count, redo_list, nullptr,
+                                                           nullptr);
     QLB_LAUNCH_CHECK(h);
     return launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, N, redo_count, 0, redo_list);
+}
+
+// n = 32 in two kernels: phase A (R = 31 ... 16) with the 32 x 32 register tile, then the live 16 x 16 leading block is
+// an ordinary 16 x 16 QL (leading dimension lda) for the n = 16 kernel, which packs FOUR matrices into a warp instead of
+// two: the per-step fixed cost (broadcast round trip, ?larfg chain) of the 16 cheap steps is shared by twice as many
+// matrices.  Costs 4 KB of extra HBM traffic per matrix (the block is written and read once more).
+template <typename T, int WARPS, int MINB_A, int MINB_B>
+static int launch_geqlf_batched_split32(qlb200_ctx *h, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau, int64_t batch) {
+    using CfgA = BatchedCfg<T, 32, 2>;
+    using CfgB = BatchedCfg<T, 16, 2>;
+    if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
+    CUtensorMap tmA, tmB;
+    memset(&tmA, 0, sizeof(tmA));
+    memset(&tmB, 0, sizeof(tmB));
+    const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<T>(&tmA, A, 32, lda, strideA, batch, CfgA::PITCH) &&
+                     make_batch_tensor_map<T>(&tmB, A, 16, lda, strideA, batch, CfgB::PITCH);
+    auto kA = tma ? geqlf_batched_kernel<T, 32, 2, WARPS, MINB_A, true, 4, 16> : geqlf_batched_kernel<T, 32, 2, WARPS, MINB_A, false, 4, 16>;
+    auto kB = tma ? geqlf_batched_kernel<T, 16, 2, WARPS, MINB_B, true, 4, 0> : geqlf_batched_kernel<T, 16, 2, WARPS, MINB_B, false, 4, 0>;
+    const size_t smA = (size_t)WARPS * CfgA::WARP_BYTES, smB = (size_t)WARPS * CfgB::WARP_BYTES;
+    QLB_CUDA(h, cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
+    QLB_CUDA(h, cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+    int occA = 0, occB = 0;
+    QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, kA, WARPS * 32, smA));
+    QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, WARPS * 32, smB));
+    if (occA < 1 || occB < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched QL kernel does not fit on an SM%s");
+    auto grid = [&](int G, int occ) {
+        const int64_t nwb = (batch + G - 1) / G;
+        int64_t blocks = (nwb + WARPS - 1) / WARPS;
+        const int64_t cap = (int64_t)h->sm_count * occ;
+        if (blocks > cap) blocks = cap;
+        return (unsigned)(blocks < 1 ? 1 : blocks);
+    };
+    // [count A, count B, -, -][list A][list B][flags]
+    int rc = qlb_reserve(h, &h->redo, &h->redo_bytes, ((size_t)3 * batch + 4) * sizeof(int));
+    if (rc) return rc;
+    int *cntA = (int *)h->redo, *cntB = cntA + 1, *listA = cntA + 4, *listB = listA + batch, *flags = listB + batch;
+    QLB_CUDA(h, cudaMemsetAsync(cntA, 0, 4 * sizeof(int), h->stream));
+    QLB_CUDA(h, cudaMemsetAsync(flags, 0, (size_t)batch * sizeof(int), h->stream));
+    kA<<<grid(CfgA::G, occA), WARPS * 32, smA, h->stream>>>(tmA, A, lda, strideA, tau, strideTau, batch, cntA, listA, flags, nullptr);
+    QLB_LAUNCH_CHECK(h);
+    rc = launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, 32, cntA, 0, listA);
+    if (rc) return rc;
+    kB<<<grid(CfgB::G, occB), WARPS * 32, smB, h->stream>>>(tmB, A, lda, strideA, tau, strideTau, batch, cntB, listB, nullptr, flags);
+    QLB_LAUNCH_CHECK(h);
+    return launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, 16, cntB, 0, listB);
 }
 
 template <typename T, int N, int NR, int MODE>
@@ -829,7 +900,8 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
             if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
-            return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
+            if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);      // one kernel
+            return qlb::launch_geqlf_batched_split32<double, 4, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
@@ -839,7 +911,9 @@ int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64
     switch (n) {
         case 8: return qlb::launch_geqlf_batched<float, 8, 1, 4, 8>(h, A, lda, strideA, tau, strideTau, batch);
         case 16: return qlb::launch_geqlf_batched<float, 16, 2, 4, 5>(h, A, lda, strideA, tau, strideTau, batch);
-        case 32: return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
+        case 32:
+            if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
+            return qlb::launch_geqlf_batched_split32<float, 4, 3, 5>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
