@@ -257,8 +257,8 @@ __device__ __forceinline__ void ql_flush_slot(T (&a)[CPL][N], T (&myscale)[CPL],
 
 // Group sizes: 4 steps while more than 16 rows are live, 8 afterwards (short tiles: the zero rows cost
 // little, and fewer loop bodies keep the code small).  LO is the number of steps already done.
-template <int N, int LO>
-struct GroupSize { static constexpr int value = (N - LO > 16) ? 4 : 8; };
+template <int N, int LO, int LPM>
+struct GroupSize { static constexpr int value = ((N - LO > 16) ? 4 : 8) < LPM ? ((N - LO > 16) ? 4 : 8) : LPM; };
 
 // STOP > 0: leave after STOP steps (phase A of the split factorization): the live leading block (rows and columns
 // below N - STOP, held by slot 0 at register indices [STOP, N)) goes back to the image unscaled and is factored by the
@@ -281,7 +281,7 @@ struct GroupLoop {
             }
             return;
         } else {
-        constexpr int LPM = N / CPL, GS = GroupSize<N, LO>::value;
+        constexpr int LPM = N / CPL, GS = GroupSize<N, LO, LPM>::value;
         constexpr int NS = (N - 1 - LO) / LPM + 1;
         constexpr bool LAST = (LO + GS == N);
         static_assert((N - 1 - LO) / LPM == (N - LO - GS) / LPM, "a group's pivot columns live in one slot");
