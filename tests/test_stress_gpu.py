@@ -58,3 +58,31 @@ def test_interleaved_calls_on_one_handle():
                 assert np.abs(A2 @ x - B).max() <= 5000 * EPS * np.linalg.cond(A2) * max(1.0, np.abs(x).max())
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_larger_shapes_host_and_device(seed):
+    """Random tall / wide / square shapes in the streaming range (>= 4M entries go through the chunked upload) and below,
+    host and device entry points, against LAPACK."""
+    import torch
+
+    q = load_package()
+    h = q.Handle(0)
+    rng = np.random.default_rng(seed)
+    try:
+        for _ in range(3):
+            m, n = int(rng.integers(900, 3600)), int(rng.integers(900, 3600))
+            A = np.asfortranarray(rng.standard_normal((m, n)))
+            lapack.set_num_threads(16)
+            Fo, tauo = lapack.geqlf(A)
+            tol = 50 * max(m, n) * EPS * np.linalg.norm(A)
+            F = q.ql(A, handle=h)
+            assert np.abs(F.tau - tauo).max() <= 50 * max(m, n) * EPS, (m, n)
+            assert np.abs(F.factors - Fo).max() <= tol, (m, n)
+            Ad = torch.from_numpy(np.ascontiguousarray(A.T)).cuda().T
+            Fd = q.ql_(Ad, handle=h)
+            torch.cuda.synchronize()
+            assert np.abs(Fd.tau.cpu().numpy() - tauo).max() <= 50 * max(m, n) * EPS, (m, n)
+            assert np.abs(Fd.factors.cpu().numpy() - Fo).max() <= tol, (m, n)
+    finally:
+        h.close()
