@@ -71,6 +71,24 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, int c0, int 
                  : "memory");
 }
 
+// 32-bit shared-window addressing (keeps the per-step address arithmetic to one add)
+__device__ __forceinline__ double2 lds16_s(uint32_t a, double) {
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ float4 lds16_s(uint32_t a, float) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts16_s(uint32_t a, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
+__device__ __forceinline__ void sts16_s(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_s(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_s(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 template <typename T, int N, int CPL>
 struct BatchedCfg {
     static constexpr int E = Vec16<T>::E;            // elements per 16-byte vector
@@ -136,11 +154,15 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
     constexpr int P = N - 1;                         // register index of the pivot row
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(LO % E == 0 && N % E == 0, "vector alignment");
+    const uint32_t xg_s = smem_u32(xg);
+    uint32_t stash_s[NS];                            // shared address of this lane's column of slot c in the image
+#pragma unroll
+    for (int c = 0; c < NS; ++c) stash_s[c] = smem_u32(obuf + (jl + c * LPM) * PITCH);
 #pragma unroll 1
     for (int t = 0; t < nsteps; ++t) {
         const int s = LO + t, R = N - 1 - s;
         const int own_lane = R - OWN_SLOT * LPM;
-        T *xa = xg + (s & 1) * XP;
+        const uint32_t xa = xg_s + (uint32_t)((s & 1) * XP * (int)sizeof(T));
         // 1. the owner publishes its column (indices [LO, N): zeros, then the tail x, then the pivot)
         if (jl == own_lane) {
 #pragma unroll
@@ -149,7 +171,7 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
                 T *qp = reinterpret_cast<T *>(&q);
 #pragma unroll
                 for (int e = 0; e < E; ++e) qp[e] = a[OWN_SLOT][v * E + e];
-                reinterpret_cast<V *>(xa)[v] = q;
+                sts16_s(xa + (uint32_t)(v * 16), q);
             }
         }
         __syncwarp();
@@ -163,10 +185,10 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         //  cycles, one vector feeds only ~9 cycles of FP64 issue, and ptxas by itself keeps just 2 in flight)
         V qa[NVEC];
 #pragma unroll
-        for (int w = 0; w < PD && w < NVEC; ++w) qa[w] = lds16(xa + (V0 + w) * E);
+        for (int w = 0; w < PD && w < NVEC; ++w) qa[w] = lds16_s(xa + (uint32_t)((V0 + w) * 16), T());
 #pragma unroll
         for (int w = 0; w < NVEC; ++w) {
-            if (w + PD < NVEC) qa[w + PD] = lds16(xa + (V0 + w + PD) * E);
+            if (w + PD < NVEC) qa[w + PD] = lds16_s(xa + (uint32_t)((V0 + w + PD) * 16), T());
             const T *qp = reinterpret_cast<const T *>(&qa[w]);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -180,7 +202,7 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         // the update pass walks x downwards; its first PD vectors are requested now, ahead of the scalar chain
         V qb[NVEC];
 #pragma unroll
-        for (int w = 0; w < PD && w < NVEC; ++w) qb[w] = lds16(xa + (V1 - 1 - w) * E);
+        for (int w = 0; w < PD && w < NVEC; ++w) qb[w] = lds16_s(xa + (uint32_t)((V1 - 1 - w) * 16), T());
         T ds[NS];
 #pragma unroll
         for (int c = 0; c < NS; ++c) {
@@ -202,7 +224,7 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         const T g = -tauk * scale;
         if (jl == own_lane) {
             myscale[OWN_SLOT] = scale;                        // v_i = x_i / (alpha - beta), applied when row i leaves
-            obuf[(jl + OWN_SLOT * LPM) * PITCH + N] = tauk;   // tau_R waits in the padding row of its column
+            sts_s(stash_s[OWN_SLOT] + (uint32_t)(N * (int)sizeof(T)), tauk);      // tau_R waits in the padding row of its column
         }
         // 4. pivot row: finish it, send it to the output image, and the multipliers of the rank-1 update
         T dc[NS];
@@ -215,12 +237,12 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
             const T newR = t_fma(-tauk, sc, aR);
             dc[c] = g * sc;                                   // multiplier on the raw tail x
             const T val = (col > R) ? aR * myscale[c] : ((col == R) ? beta : newR);
-            obuf[col * PITCH + R] = val;
+            sts_s(stash_s[c] + (uint32_t)(R * (int)sizeof(T)), val);
         }
         // 5. a_j -= tau (v^T a_j) v on the tail rows, shifting the tile up by one index
 #pragma unroll
         for (int w = 0; w < NVEC; ++w) {
-            if (w + PD < NVEC) qb[w + PD] = lds16(xa + (V1 - 1 - w - PD) * E);
+            if (w + PD < NVEC) qb[w + PD] = lds16_s(xa + (uint32_t)((V1 - 1 - w - PD) * 16), T());
             const T *qp = reinterpret_cast<const T *>(&qb[w]);
 #pragma unroll
             for (int e = E - 1; e >= 0; --e) {
