@@ -692,17 +692,22 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                 for (int i = 0; i < RPL; ++i) b[i] = t_fma(-s, v[i], b[i]);
             }
             if constexpr (MODE == 2) {
-                // forward substitution with L = tril(factors): x_c = b_c / L_cc; b_i -= L_ic x_c (i > c)
+                // forward substitution with L = tril(factors): x_c = b_c / L_cc; b_i -= L_ic x_c (i > c).  The reciprocals of
+                // the diagonal do not depend on the substitution: they are computed up front (into the padding element of
+                // each image column), so the serial chain carries a multiplication instead of a division.
+                T *imgw = const_cast<T *>(img);
+                if (c0 == 0) {
+                    for (int c = l; c < N; c += LPM) imgw[c * PITCH + N] = T(1) / img[c * PITCH + c];
+                    __syncwarp();
+                }
                 int bad = 0;
 #pragma unroll
                 for (int c = 0; c < N; ++c) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
                     const int orow = c % RPL, org = c / RPL;       // owner row group / local row of row c
                     const T *lc = img + c * PITCH + row0;
-                    const T lcc = img[c * PITCH + c];
-                    if (lcc == T(0) && bad == 0) bad = c + 1;
-                    T xc = __shfl_sync(FULL, b[orow], jb + NR * org, LPM) / lcc;
+                    const T rcc = img[c * PITCH + N];
+                    if (img[c * PITCH + c] == T(0) && bad == 0) bad = c + 1;
+                    T xc = __shfl_sync(FULL, b[orow], jb + NR * org, LPM) * rcc;
                     const int cd = c - row0;
 #pragma unroll
                     for (int vv = 0; vv < RPL / E; ++vv) {
