@@ -311,6 +311,31 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback 6.65 TB/s",
                             "bytes_per_matrix": bytes_per, "flush": "256 MiB written between iterations"}}
 
+    # The same kernel with the FULL 262144-matrix batch on every rank (weak scaling): the strong-scaling line above shrinks
+    # the per-GPU shard to 0.2 ms at 8 GPUs, where the fill/drain of the two persistent kernels is a visible share.
+    if world > 1:
+        W0 = torch.randn((BATCH, NB, NB), dtype=torch.float64, device="cuda", generator=gB)
+        Ww = torch.empty_like(W0)
+        tw = torch.empty((BATCH, NB), dtype=torch.float64, device="cuda")
+        wt = []
+        for i in range(args.warmup + max(args.steps, 5)):
+            Ww.copy_(W0)
+            flush.fill_(i & 255)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            q.ql_batched_(Ww, tw, handle=h)
+            b1.record()
+            torch.cuda.synchronize()
+            if i >= args.warmup:
+                wt.append(b0.elapsed_time(b1) * 1e-3)
+        twm = torch.tensor([sorted(wt)[len(wt) // 2]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(twm, op=dist.ReduceOp.MAX)
+        tweak = float(twm.item())
+        batched["weak"] = {"value": world * BATCH / tweak, "unit": "matrices/s", "per_rank": BATCH, "total_matrices": world * BATCH,
+                           "ms": tweak * 1e3, "hbm_frac_per_gpu": BATCH * bytes_per / tweak / 1e9 / (hbm_peak or 6650.0)}
+        del W0, Ww, tw
+
     # ---- the other BASELINE.json configs (secondary lines; same timing hygiene: events, flush between iterations) ----
     def timed_dev(fn, reset, iters=5):
         ts = []

@@ -163,7 +163,8 @@ int qlb200_sgeqlf_batched_dev(qlb200_handle h, int64_t n, float *dA, int64_t lda
                               float *dtau, int64_t strideTau, int64_t batch);
 
 /* Batched lmul!(Q,B) (trans 'N', src/ql.jl:321-347) / lmul!(Q',B) (trans 'T', src/ql.jl:350-377):
- * B_b (n x nrhs, leading dimension ldb, matrix stride strideB) <- op(Q_b) B_b. */
+ * B_b (n x nrhs, leading dimension ldb, matrix stride strideB) <- op(Q_b) B_b.  1 <= n <= 64 like the
+ * factorization (register kernels for n in {8, 16, 32}, a generic warp-per-matrix kernel otherwise). */
 int qlb200_dormql_batched(qlb200_handle h, char trans, int64_t n, int64_t nrhs, const double *A,
                           int64_t lda, int64_t strideA, const double *tau, int64_t strideTau,
                           double *B, int64_t ldb, int64_t strideB, int64_t batch);

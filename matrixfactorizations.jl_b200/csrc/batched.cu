@@ -526,13 +526,42 @@ __global__ void __launch_bounds__(WARPS * 32) geql2_generic_kernel(T *__restrict
     }
 }
 
+// Dynamic shared memory attribute + resident blocks per SM of a batched kernel.  Both cost several microseconds of host
+// time per query, which is visible at the shard sizes of an 8-GPU run (a 32768-matrix shard takes 0.2 ms): they are
+// looked up once per handle (= per device), kernel and size.
+template <typename K>
+static int kernel_ready(qlb200_ctx *h, K kern, int threads, size_t smem, int *occ) {
+    const void *fn = (const void *)kern;
+    size_t granted = 0;                    // the attribute is per function: it only ever grows (the generic kernels' size varies with n)
+    for (int i = 0; i < h->n_ksetup; ++i)
+        if (h->ksetup[i].fn == fn) {
+            if (h->ksetup[i].smem == smem) {
+                *occ = h->ksetup[i].occ;
+                return 0;
+            }
+            if (h->ksetup[i].smem > granted) granted = h->ksetup[i].smem;
+        }
+    if (smem > granted)
+        QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem));
+    if (h->n_ksetup < 256) {
+        h->ksetup[h->n_ksetup].fn = fn;
+        h->ksetup[h->n_ksetup].smem = smem;
+        h->ksetup[h->n_ksetup].occ = *occ;
+        h->n_ksetup++;
+    }       // a full table only costs the lookup again next time: an unrecorded size above every recorded one re-sets the attribute
+    return 0;
+}
+
 template <typename T>
 static int launch_geql2_generic(qlb200_ctx *h, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau, int n,
                                 const int *count_ptr, int64_t count_val, const int *list) {
     constexpr int WARPS = 4;
     const size_t smem = (size_t)WARPS * ((size_t)(n + 1) * n + n) * sizeof(T);
     auto kern = geql2_generic_kernel<T, WARPS>;
-    QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ_unused = 0;
+    int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ_unused);
+    if (rcs) return rcs;
     int64_t blocks = list ? (int64_t)h->sm_count : (count_val + WARPS - 1) / WARPS;
     const int64_t cap = (int64_t)h->sm_count * 4;
     if (blocks > cap) blocks = cap;
@@ -798,9 +827,9 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     memset(&tmap, 0, sizeof(tmap));
     const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<T>(&tmap, A, N, lda, strideA, batch, Cfg::PITCH);
     auto kern = tma ? geqlf_batched_kernel<T, N, CPL, WARPS, MINB, true, PD> : geqlf_batched_kernel<T, N, CPL, WARPS, MINB, false, PD>;
-    QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+    int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ);
+    if (rcs) return rcs;
     if (occ < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched QL kernel does not fit on an SM%s");
     const int64_t nwb = (batch + Cfg::G - 1) / Cfg::G;
     int64_t blocks = (nwb + WARPS - 1) / WARPS;
@@ -836,11 +865,10 @@ static int launch_geqlf_batched_split32(qlb200_ctx *h, T *A, int64_t lda, int64_
     auto kA = tma ? geqlf_batched_kernel<T, 32, 2, WARPS, MINB_A, true, 4, 16> : geqlf_batched_kernel<T, 32, 2, WARPS, MINB_A, false, 4, 16>;
     auto kB = tma ? geqlf_batched_kernel<T, 16, 2, WARPS, MINB_B, true, 4, 0> : geqlf_batched_kernel<T, 16, 2, WARPS, MINB_B, false, 4, 0>;
     const size_t smA = (size_t)WARPS * CfgA::WARP_BYTES, smB = (size_t)WARPS * CfgB::WARP_BYTES;
-    QLB_CUDA(h, cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-    QLB_CUDA(h, cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
     int occA = 0, occB = 0;
-    QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, kA, WARPS * 32, smA));
-    QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, WARPS * 32, smB));
+    int rcs = kernel_ready(h, kA, WARPS * 32, smA, &occA);
+    if (!rcs) rcs = kernel_ready(h, kB, WARPS * 32, smB, &occB);
+    if (rcs) return rcs;
     if (occA < 1 || occB < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched QL kernel does not fit on an SM%s");
     auto grid = [&](int G, int occ) {
         const int64_t nwb = (batch + G - 1) / G;
@@ -849,12 +877,11 @@ static int launch_geqlf_batched_split32(qlb200_ctx *h, T *A, int64_t lda, int64_
         if (blocks > cap) blocks = cap;
         return (unsigned)(blocks < 1 ? 1 : blocks);
     };
-    // [count A, count B, -, -][list A][list B][flags]
+    // [count A, count B, -, -][flags][list A][list B]: counts and flags are cleared by one memset
     int rc = qlb_reserve(h, &h->redo, &h->redo_bytes, ((size_t)3 * batch + 4) * sizeof(int));
     if (rc) return rc;
-    int *cntA = (int *)h->redo, *cntB = cntA + 1, *listA = cntA + 4, *listB = listA + batch, *flags = listB + batch;
-    QLB_CUDA(h, cudaMemsetAsync(cntA, 0, 4 * sizeof(int), h->stream));
-    QLB_CUDA(h, cudaMemsetAsync(flags, 0, (size_t)batch * sizeof(int), h->stream));
+    int *cntA = (int *)h->redo, *cntB = cntA + 1, *flags = cntA + 4, *listA = flags + batch, *listB = listA + batch;
+    QLB_CUDA(h, cudaMemsetAsync(cntA, 0, ((size_t)batch + 4) * sizeof(int), h->stream));
     kA<<<grid(CfgA::G, occA), WARPS * 32, smA, h->stream>>>(tmA, A, lda, strideA, tau, strideTau, batch, cntA, listA, flags, nullptr);
     QLB_LAUNCH_CHECK(h);
     rc = launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, 32, cntA, 0, listA);
@@ -878,9 +905,9 @@ static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
     const bool tma = tma_ok(A, lda, strideA) && tau_ok && make_batch_tensor_map<T>(&tmap, A, N, lda, strideA, batch, Cfg::PITCH);
     const int vecB = ((uintptr_t)B % 16 == 0) && ((ldb * sizeof(T)) % 16 == 0) && ((strideB * sizeof(T)) % 16 == 0 || batch <= 1);
     auto kern = tma ? apply_batched_kernel<T, N, NR, MODE, WARPS, true> : apply_batched_kernel<T, N, NR, MODE, WARPS, false>;
-    QLB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    QLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+    int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ);
+    if (rcs) return rcs;
     if (occ < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched apply kernel does not fit on an SM%s");
     const int64_t nwb = (batch + Cfg::G - 1) / Cfg::G;
     int64_t blocks = (nwb + WARPS - 1) / WARPS;
@@ -889,6 +916,118 @@ static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch,
                                                            info_out, vecB);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic Q-apply / square solve for any n <= 64 (the sizes the register kernel above is not instantiated for; the
+// factorization accepts every n <= 64, so the apply must too).  One warp per matrix; factors (pitch n+1) and tau
+// staged in shared memory with plain loads; lane (jb, sub) = (lane % 8, lane / 8) owns rows sub, sub+4, ... of
+// column jb of an 8-column chunk of B in registers; a reflector's dot product is finished with two xor-shuffles.
+// Same MODE meaning and the same per-matrix arithmetic as apply_batched_kernel.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) apply_generic_kernel(const T *__restrict__ A, int64_t lda, int64_t strideA,
+                                                                  const T *__restrict__ tau, int64_t strideTau, T *__restrict__ B,
+                                                                  int64_t ldb, int64_t strideB, int n, int nrhs, int64_t batch,
+                                                                  int32_t *__restrict__ info_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int CB = 8, SUBS = 4, MAXR = 16;               // 8 columns x 4 row groups; 4 * 16 = 64 rows at most
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jb = lane % CB, sub = lane / CB;
+    const int P = n + 1;
+    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)warp * (P * n + 2 * n);
+    T *taus = S + P * n, *rdiag = taus + n;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+    for (int64_t mi = gw; mi < batch; mi += nw) {
+        const T *Am = A + mi * strideA;
+        __syncwarp();
+        for (int idx = lane; idx < n * n; idx += 32) S[(idx / n) * P + (idx % n)] = Am[(int64_t)(idx / n) * lda + (idx % n)];
+        for (int i = lane; i < n; i += 32) taus[i] = tau[mi * strideTau + i];
+        __syncwarp();
+        int bad = 0;
+        if constexpr (MODE == 2) {
+            for (int c = lane; c < n; c += 32) rdiag[c] = T(1) / S[c * P + c];
+            for (int c = n - 1; c >= 0; --c)
+                if (S[c * P + c] == T(0)) bad = c + 1;       // first zero on the diagonal, 1-based
+            __syncwarp();
+        }
+        for (int c0 = 0; c0 < nrhs; c0 += CB) {
+            const int col = c0 + jb;
+            const bool cvalid = col < nrhs;
+            T *Bc = B + mi * strideB + (int64_t)(cvalid ? col : 0) * ldb;
+            T b[MAXR];
+#pragma unroll
+            for (int t = 0; t < MAXR; ++t) {
+                const int i = sub + SUBS * t;
+                b[t] = (cvalid && i < n) ? Bc[i] : T(0);
+            }
+            for (int kk = 0; kk < n; ++kk) {
+                const int k = (MODE == 0) ? kk : n - 1 - kk;
+                const T *vk = S + k * P;
+                const T tk = taus[k];
+                T part = T(0);
+#pragma unroll
+                for (int t = 0; t < MAXR; ++t) {
+                    const int i = sub + SUBS * t;
+                    if (i < k) part = t_fma(vk[i], b[t], part);
+                    else if (i == k) part += b[t];
+                }
+                part += __shfl_xor_sync(FULL, part, CB);
+                part += __shfl_xor_sync(FULL, part, 2 * CB);
+                const T s = tk * part;
+#pragma unroll
+                for (int t = 0; t < MAXR; ++t) {
+                    const int i = sub + SUBS * t;
+                    if (i < k) b[t] = t_fma(-s, vk[i], b[t]);
+                    else if (i == k) b[t] -= s;
+                }
+            }
+            if constexpr (MODE == 2) {
+                for (int c = 0; c < n; ++c) {
+                    const int to = c / SUBS, so = c % SUBS;
+                    T mine = T(0);
+#pragma unroll
+                    for (int t = 0; t < MAXR; ++t)
+                        if (t == to) mine = b[t];
+                    const T xc = __shfl_sync(FULL, mine, jb + CB * so) * rdiag[c];
+                    const T *lc = S + c * P;
+#pragma unroll
+                    for (int t = 0; t < MAXR; ++t) {
+                        const int i = sub + SUBS * t;
+                        if (i == c) b[t] = xc;
+                        else if (i > c && i < n) b[t] = t_fma(-lc[i], xc, b[t]);
+                    }
+                }
+            }
+            if (cvalid) {
+#pragma unroll
+                for (int t = 0; t < MAXR; ++t) {
+                    const int i = sub + SUBS * t;
+                    if (i < n) Bc[i] = b[t];
+                }
+            }
+        }
+        if (MODE == 2 && info_out != nullptr && lane == 0) info_out[mi] = bad;
+    }
+}
+
+template <typename T, int MODE>
+static int launch_apply_generic(qlb200_ctx *h, const T *A, int64_t lda, int64_t strideA, const T *tau, int64_t strideTau,
+                                T *B, int64_t ldb, int64_t strideB, int n, int nrhs, int64_t batch, int32_t *info_out) {
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * ((size_t)(n + 1) * n + 2 * n) * sizeof(T);
+    auto kern = apply_generic_kernel<T, MODE, WARPS>;
+    int occ_unused = 0;
+    int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ_unused);
+    if (rcs) return rcs;
+    int64_t blocks = (batch + WARPS - 1) / WARPS;
+    const int64_t cap = (int64_t)h->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, B, ldb, strideB, n, nrhs, batch, info_out);
     QLB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -912,7 +1051,9 @@ static int dispatch_apply_n(qlb200_ctx *h, int64_t n, const T *A, int64_t lda, i
         case 16: return dispatch_apply_nr<T, 16, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
         case 32: return dispatch_apply_nr<T, 32, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
     }
-    return qlb_fail(h, -2, "batched apply: n must be 8, 16 or 32%s");
+    if (n >= 1 && n <= 64)
+        return launch_apply_generic<T, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, (int)n, nrhs, batch, info_out);
+    return qlb_fail(h, -2, "batched apply: n must be in [1,64]%s");
 }
 
 }  // namespace qlb

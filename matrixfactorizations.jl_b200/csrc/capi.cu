@@ -257,7 +257,7 @@ static int apply_batched_any(qlb200_ctx *h, bool host, int mode, int64_t n, int6
                              int64_t strideA, const T *tau, int64_t strideTau, T *B, int64_t ldb, int64_t strideB,
                              int64_t batch, int32_t *info_out, int argbase) {
     if (!h) return -1;
-    QLB_REQUIRE(h, n == 8 || n == 16 || n == 32, argbase, "n must be 8, 16 or 32");
+    QLB_REQUIRE(h, n >= 1 && n <= 64, argbase, "n must be in [1,64]");
     QLB_REQUIRE(h, nrhs >= 0, argbase + 1, "nrhs < 0");
     QLB_REQUIRE(h, A != nullptr || batch == 0, argbase + 2, "A is null");
     QLB_REQUIRE(h, lda >= n, argbase + 3, "lda < n");

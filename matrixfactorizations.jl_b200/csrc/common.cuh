@@ -75,7 +75,16 @@ struct qlb200_ctx {
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM
     bool strip_attr_done[8] = {false};
     bool larft_attr_done = false, trsm_attr_done = false;
+    bool ul_cluster_attr_done = false, ul_trsm_attr_done = false;
     bool gemm_attr_done[64] = {false};
+    // batched kernels: dynamic-shared-memory attribute and occupancy, looked up once per (handle, kernel, size)
+    struct KernelSetup {
+        const void *fn;
+        size_t smem;
+        int occ;
+    };
+    KernelSetup ksetup[256] = {};
+    int n_ksetup = 0;
     // optional device-side timing of the dominant kernels (trailing-update GEMMs): event pairs around
     // each launch, summed by qlb200_profile_collect (bench.py's roofline leg)
     int64_t opt_profile = 0;

@@ -398,10 +398,9 @@ int qlb_dulfact_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t 
             if (c1 <= ULC_MAXC * ULC_THREADS * ULC_RPT && h->opt_ul_cluster) {
                 int nc = (c1 + ULC_THREADS * ULC_RPT - 1) / (ULC_THREADS * ULC_RPT), ncp = 1;
                 while (ncp < nc) ncp <<= 1;
-                static bool attr_done = false;
-                if (!attr_done) {
+                if (!h->ul_cluster_attr_done) {      // per handle (= per device), like every other attribute
                     QLB_CUDA(h, cudaFuncSetAttribute(ul_strip_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                    attr_done = true;
+                    h->ul_cluster_attr_done = true;
                 }
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(ncp, 1, 1);
@@ -470,10 +469,9 @@ int qlb_dulsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A
     QLB_LAUNCH_CHECK(h);
     constexpr int TB = 128;
     const size_t smem = (size_t)TB * (TB + 1) * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!h->ul_trsm_attr_done) {
         QLB_CUDA(h, cudaFuncSetAttribute(trsm_unit_upper_diag_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        h->ul_trsm_attr_done = true;
     }
     const int nblk = (n + TB - 1) / TB;
     for (int b = nblk - 1; b >= 0; --b) {

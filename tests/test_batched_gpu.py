@@ -185,12 +185,48 @@ def test_batched_argument_errors(q, h):
     with pytest.raises(q.ArgumentError):
         q.ql_batched_(A, handle=h)                         # n > 64 unsupported
     with pytest.raises(q.ArgumentError):
-        q.lmul_batched_(np.zeros((2, 12, 12)), np.zeros((2, 12)), np.zeros((2, 1, 12)), handle=h)   # apply: 8/16/32 only
+        q.lmul_batched_(np.zeros((2, 65, 65)), np.zeros((2, 65)), np.zeros((2, 1, 65)), handle=h)   # apply: n <= 64 too
     A = np.zeros((0, 32, 32))
     F, tau = q.ql_batched_(A, handle=h)                    # empty batch is a no-op
     assert tau.shape == (0, 32)
     with pytest.raises(q.DimensionMismatch):
         q.lmul_batched_(np.zeros((2, 32, 32)), np.zeros((2, 32)), np.zeros((2, 4, 16)), handle=h)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 12, 24, 31, 33, 48, 64])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("nrhs", [1, 3, 8, 11])
+def test_batched_generic_sizes_lmul_and_solve_vs_oracle(q, h, n, dt, nrhs):
+    """Sizes without a register apply kernel go through the generic warp-per-matrix kernel (any n <= 64)."""
+    rng = np.random.default_rng(100 * n + nrhs)
+    batch = 23
+    A = rng.standard_normal((batch, n, n)).astype(dt)
+    Fo, tauo = cport.geql2_batched(A)
+    B = rng.standard_normal((batch, nrhs, n)).astype(dt)
+    tolb = 50 * n * _eps(dt) * np.abs(B).max() * np.sqrt(n)
+    for adj in (False, True):
+        got = q.lmul_batched_(Fo, tauo, B.copy(), adjoint=adj, handle=h)
+        ref = np.stack([cport.lmul(Fo[i].T, tauo[i], B[i].T, adjoint=adj).T for i in range(batch)])
+        assert np.abs(got - ref).max() <= tolb
+    info = np.full(batch, -1, dtype=np.int32)
+    X = q.ldiv_batched_(Fo, tauo, B.copy(), info=info, handle=h)
+    assert (info == 0).all()
+    Xo = np.stack([cport.ldiv(Fo[i].T, tauo[i], B[i].T).T for i in range(batch)])
+    cond = np.array([np.linalg.cond(A[i].astype(np.float64)) for i in range(batch)])
+    err = np.abs(X - Xo).reshape(batch, -1).max(axis=1)
+    scale = np.maximum(np.abs(Xo).reshape(batch, -1).max(axis=1), 1.0)
+    assert (err <= 50 * n * _eps(dt) * cond * scale).all()
+
+
+def test_batched_generic_singular_info_and_strides(q, h):
+    n = 12
+    A = np.random.default_rng(3).standard_normal((4, n, n))
+    Fo, tauo = cport.geql2_batched(A)
+    Fo[2, 4, 4] = 0.0                                      # L[5,5] = 0 in matrix 2
+    Fo[2, 9, 9] = 0.0                                      # ... and L[10,10]: the FIRST zero is reported
+    info = np.zeros(4, dtype=np.int32)
+    q.ldiv_batched_(Fo, tauo, np.ones((4, 1, n)), info=info, handle=h)
+    assert list(info) == [0, 0, 5, 0]
 
 
 def test_batched_singular_info(q, h):
