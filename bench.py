@@ -311,6 +311,26 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback 6.65 TB/s",
                             "bytes_per_matrix": bytes_per, "flush": "256 MiB written between iterations"}}
 
+    # The same workload through HOST pointers (the call a Julia user makes on Arrays): pinned host arrays, the library's
+    # upload | compute | download chunk pipeline inside the timed region (PCIe-bound: 2 x 2.1 GB per step at N = 1).
+    hA = torch.empty((mine, NB, NB), dtype=torch.float64).pin_memory()
+    hT = torch.empty((mine, NB), dtype=torch.float64).pin_memory()
+    hsrc = B0.cpu()
+    he = []
+    for i in range(3):
+        hA.copy_(hsrc)
+        barrier()
+        t0 = time.perf_counter()
+        q.ql_batched_(hA.numpy(), hT.numpy(), handle=h)
+        he.append(time.perf_counter() - t0)
+    hem = torch.tensor([min(he[1:])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(hem, op=dist.ReduceOp.MAX)
+    batched["e2e"] = {"value": BATCH / float(hem.item()), "unit": "matrices/s", "ms": float(hem.item()) * 1e3,
+                      "h2d_bytes_per_step": mine * NB * NB * 8, "d2h_bytes_per_step": mine * (NB * NB + NB) * 8,
+                      "timing": "host wall clock around the blocking host-pointer call, max over ranks"}
+    del hA, hT, hsrc
+
     # The same kernel with the FULL 262144-matrix batch on every rank (weak scaling): the strong-scaling line above shrinks
     # the per-GPU shard to 0.2 ms at 8 GPUs, where the fill/drain of the two persistent kernels is a visible share.
     if world > 1:

@@ -167,6 +167,9 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "chunk_cols")) {
         if (value < 128 || value % 128) return qlb_fail(h, -3, "chunk_cols must be a positive multiple of 128%s");
         h->opt_chunk_cols = value;
+    } else if (!strcmp(name, "batch_chunk_mb")) {
+        if (value < 0 || value > 4096) return qlb_fail(h, -3, "batch_chunk_mb must be in [0,4096]%s");
+        h->opt_batch_chunk_mb = value;
     } else if (!strcmp(name, "stream_in")) {
         h->opt_stream_in = value ? 1 : 0;
     } else if (!strcmp(name, "graph")) {
@@ -185,6 +188,52 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// host-pointer batched calls: three-stream chunk pipeline (upload | compute | download)
+// ---------------------------------------------------------------------------------------------
+static int qlb_cuda(qlb200_ctx *h, cudaError_t e) {
+    if (e == cudaSuccess) return 0;
+    return qlb_fail(h, 1000 + (int)e, "batched host pipeline: %s", cudaGetErrorString(e));
+}
+// matrices per chunk: about "batch_chunk_mb" (32) MB of operands, at least 4 chunks for batches worth splitting
+static int64_t batched_chunk(qlb200_ctx *h, int64_t bytes_per_matrix, int64_t batch) {
+    if (h->opt_batch_chunk_mb == 0) return batch;          // one chunk: upload, compute, download back to back
+    int64_t cm = (h->opt_batch_chunk_mb << 20) / (bytes_per_matrix > 0 ? bytes_per_matrix : 1);
+    if (cm < 1) cm = 1;
+    if (cm * 4 > batch && batch * bytes_per_matrix >= ((int64_t)8 << 20)) cm = (batch + 3) / 4;
+    return cm < batch ? cm : batch;
+}
+// the staging buffer may still be read by earlier work on the compute stream
+static int pipeline_begin(qlb200_ctx *h) {
+    int rc = qlb_cuda(h, cudaEventRecord(h->ev_chunk[31], h->stream));
+    if (!rc) rc = qlb_cuda(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_chunk[31], 0));
+    return rc;
+}
+// Events are reused round-robin: a wait refers to the record that precedes it in host order, so re-recording an event
+// later does not disturb waits already enqueued.
+static int pipeline_uploaded(qlb200_ctx *h, int64_t c) {
+    cudaEvent_t ev = h->ev_chunk[(2 * c) % 30];
+    int rc = qlb_cuda(h, cudaEventRecord(ev, h->h2d_stream));
+    if (!rc) rc = qlb_cuda(h, cudaStreamWaitEvent(h->stream, ev, 0));
+    return rc;
+}
+static int pipeline_computed(qlb200_ctx *h, int64_t c) {
+    cudaEvent_t ev = h->ev_chunk[(2 * c + 1) % 30];
+    int rc = qlb_cuda(h, cudaEventRecord(ev, h->stream));
+    if (!rc) rc = qlb_cuda(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
+    return rc;
+}
+// every stream is drained before the caller's host arrays are handed back, also on the error path
+static int pipeline_end(qlb200_ctx *h, int rc) {
+    cudaError_t e0 = cudaStreamSynchronize(h->h2d_stream);
+    cudaError_t e1 = cudaStreamSynchronize(h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->copy_stream);
+    if (rc) return rc;
+    if (e0 != cudaSuccess) return qlb_cuda(h, e0);
+    if (e1 != cudaSuccess) return qlb_cuda(h, e1);
+    return qlb_cuda(h, e2);
+}
 
 // ---------------------------------------------------------------------------------------------
 // batched: argument checks shared by the typed entry points
@@ -235,20 +284,29 @@ static int geqlf_batched_any(qlb200_ctx *h, bool host, int64_t n, T *A, int64_t 
     if (batch == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
     if (!host) return geqlf_batched_dev<T>(h, n, A, lda, strideA, tau, strideTau, batch);
-    // host pointers: stage the whole strided slab (H2D), factor, copy back (D2H)
+    // host pointers: the strided slab is staged on the device and processed in chunks of matrices; chunk c+1 uploads
+    // (h2d_stream) while chunk c is factored (h->stream) and chunk c-1 downloads (copy_stream), so with pinned host
+    // memory both PCIe directions are busy at once.  Pageable memory makes the copies synchronous: same result, no overlap.
     const size_t a_elems = (size_t)((batch - 1) * strideA + lda * (n - 1) + n);
     const size_t t_elems = (size_t)((batch - 1) * strideTau + n);
     const size_t a_bytes = (a_elems * sizeof(T) + 255) & ~(size_t)255;
     rc = qlb_reserve(h, &h->stage, &h->stage_bytes, a_bytes + t_elems * sizeof(T));
     if (rc) return rc;
     T *dA = (T *)h->stage, *dT = (T *)((char *)h->stage + a_bytes);
-    QLB_CUDA(h, cudaMemcpyAsync(dA, A, a_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    rc = geqlf_batched_dev<T>(h, n, dA, lda, strideA, dT, strideTau, batch);
-    if (rc) return rc;
-    QLB_CUDA(h, cudaMemcpyAsync(A, dA, a_elems * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-    QLB_CUDA(h, cudaMemcpyAsync(tau, dT, t_elems * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    return 0;
+    const int64_t cm = batched_chunk(h, strideA * (int64_t)sizeof(T), batch);
+    rc = pipeline_begin(h);
+    for (int64_t m0 = 0, c = 0; m0 < batch && !rc; m0 += cm, ++c) {
+        const int64_t mc = (batch - m0 < cm) ? batch - m0 : cm;
+        const size_t ea = (size_t)((mc - 1) * strideA + lda * (n - 1) + n), et = (size_t)((mc - 1) * strideTau + n);
+        T *dAc = dA + m0 * strideA, *dTc = dT + m0 * strideTau;
+        rc = qlb_cuda(h, cudaMemcpyAsync(dAc, A + m0 * strideA, ea * sizeof(T), cudaMemcpyHostToDevice, h->h2d_stream));
+        if (!rc) rc = pipeline_uploaded(h, c);
+        if (!rc) rc = geqlf_batched_dev<T>(h, n, dAc, lda, strideA, dTc, strideTau, mc);
+        if (!rc) rc = pipeline_computed(h, c);
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(A + m0 * strideA, dAc, ea * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(tau + m0 * strideTau, dTc, et * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    return pipeline_end(h, rc);
 }
 
 // mode 0: lmul!(Q,B); 1: lmul!(Q',B); 2: ldiv!(F,B)
@@ -281,16 +339,25 @@ static int apply_batched_any(qlb200_ctx *h, bool host, int mode, int64_t n, int6
     if (rc) return rc;
     T *dA = (T *)h->stage, *dT = (T *)((char *)h->stage + a_bytes), *dB = (T *)((char *)h->stage + a_bytes + t_bytes);
     int32_t *dI = (int32_t *)((char *)h->stage + a_bytes + t_bytes + b_bytes);
-    QLB_CUDA(h, cudaMemcpyAsync(dA, A, a_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    QLB_CUDA(h, cudaMemcpyAsync(dT, tau, t_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    QLB_CUDA(h, cudaMemcpyAsync(dB, B, b_elems * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    rc = apply_batched_dev(h, mode, n, nrhs, dA, lda, strideA, dT, strideTau, dB, ldb, strideB, batch, (mode == 2) ? dI : nullptr);
-    if (rc) return rc;
-    QLB_CUDA(h, cudaMemcpyAsync(B, dB, b_elems * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-    if (mode == 2 && info_out)
-        QLB_CUDA(h, cudaMemcpyAsync(info_out, dI, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
-    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    return 0;
+    const int64_t per = (strideA + strideB) * (int64_t)sizeof(T);
+    const int64_t cm = batched_chunk(h, per, batch);
+    rc = pipeline_begin(h);
+    for (int64_t m0 = 0, c = 0; m0 < batch && !rc; m0 += cm, ++c) {
+        const int64_t mc = (batch - m0 < cm) ? batch - m0 : cm;
+        const size_t ea = (size_t)((mc - 1) * strideA + lda * (n - 1) + n), et = (size_t)((mc - 1) * strideTau + n);
+        const size_t eb = (size_t)((mc - 1) * strideB + ldb * (nrhs - 1) + n);
+        T *dAc = dA + m0 * strideA, *dTc = dT + m0 * strideTau, *dBc = dB + m0 * strideB;
+        rc = qlb_cuda(h, cudaMemcpyAsync(dAc, A + m0 * strideA, ea * sizeof(T), cudaMemcpyHostToDevice, h->h2d_stream));
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(dTc, tau + m0 * strideTau, et * sizeof(T), cudaMemcpyHostToDevice, h->h2d_stream));
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(dBc, B + m0 * strideB, eb * sizeof(T), cudaMemcpyHostToDevice, h->h2d_stream));
+        if (!rc) rc = pipeline_uploaded(h, c);
+        if (!rc) rc = apply_batched_dev(h, mode, n, nrhs, dAc, lda, strideA, dTc, strideTau, dBc, ldb, strideB, mc, (mode == 2) ? dI + m0 : nullptr);
+        if (!rc) rc = pipeline_computed(h, c);
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(B + m0 * strideB, dBc, eb * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (!rc && mode == 2 && info_out)
+            rc = qlb_cuda(h, cudaMemcpyAsync(info_out + m0, dI + m0, (size_t)mc * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    return pipeline_end(h, rc);
 }
 
 static int trans_mode(qlb200_ctx *h, char trans, int *mode) {

@@ -33,6 +33,7 @@ struct qlb200_ctx {
     } h2d;
     int64_t opt_stream_in = 1;
     int64_t opt_chunk_cols = 1024;         // columns per H2D chunk
+    int64_t opt_batch_chunk_mb = 32;       // host-pointer batched calls: operand megabytes per pipeline chunk (0: no chunking)
     int64_t opt_join_step = 1;             // panels factored per arriving chunk before the next chunk joins
     void *ws = nullptr;                    // device workspace (grown on demand)
     size_t ws_bytes = 0;

@@ -268,3 +268,30 @@ def test_batched_unaligned_layouts_take_the_plain_copy_path(q, h, n, dt):
     for b in range(batch):
         assert np.array_equal(PB[b * sB:b * sB + nrhs * ldb].reshape(nrhs, ldb)[:, :n], W[b]), b
         assert np.array_equal(PB2[b * sB:b * sB + nrhs * ldb].reshape(nrhs, ldb)[:, :n], X[b]), b
+
+
+@pytest.mark.parametrize("n,dt", [(32, np.float64), (16, np.float32), (24, np.float64)])
+def test_batched_host_chunk_pipeline_same_bits(q, h, n, dt):
+    """Host-pointer calls run as an upload | compute | download pipeline over chunks of matrices ("batch_chunk_mb");
+    the chunking must not change a bit (chunk boundaries that split the batch unevenly, ldiv info included)."""
+    rng = np.random.default_rng(n)
+    batch = 3001
+    A = rng.standard_normal((batch, n, n)).astype(dt)
+    B = rng.standard_normal((batch, 5, n)).astype(dt)
+    A[1234, 3, 3] = 0.0
+    out = {}
+    try:
+        for mb in (0, 1):
+            h.set_option("batch_chunk_mb", mb)
+            F, tau = q.ql_batched_(A.copy(), handle=h)
+            W = q.lmul_batched_(F, tau, B.copy(), adjoint=True, handle=h)
+            Fz = F.copy()
+            Fz[77, 2, 2] = 0.0                                 # zero on the diagonal of L in matrix 77
+            info = np.full(batch, -1, dtype=np.int32)
+            X = q.ldiv_batched_(Fz, tau, B.copy(), info=info, handle=h)
+            out[mb] = (F, tau, W, X, info)
+    finally:
+        h.set_option("batch_chunk_mb", 32)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert out[1][4][77] == 3 and (np.delete(out[1][4], 77) == 0).all()
