@@ -581,7 +581,7 @@ static int launch_geql2_generic(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
 // MODE 0: B <- Q B (k ascending, src/ql.jl:321-347); MODE 1: B <- Q' B (k descending,
 // src/ql.jl:350-377); MODE 2: B <- L^{-1} Q' B (src/ql.jl:440-447,467).
 // ---------------------------------------------------------------------------------------------
-template <typename T, int N, int NR>
+template <typename T, int N, int NR, int MODE = 0>
 struct ApplyCfg {
     static constexpr int E = Vec16<T>::E;
     static constexpr int PITCH = N + E;
@@ -596,7 +596,12 @@ struct ApplyCfg {
     static constexpr int TAU_BYTES = (G * N * (int)sizeof(T) + 127) / 128 * 128;
     static constexpr int STAGE_BYTES = G * IMG_BYTES + TAU_BYTES;
     static constexpr int DBUF = (STAGE_BYTES <= 6 * 1024) ? 2 : 1;              // prefetch the next warp-batch if it is cheap
-    static constexpr int WARP_BYTES = DBUF * STAGE_BYTES + 128;                   // + mbarriers
+    // explicit reflectors (unit pivot, zeros below): made in place for the Q-apply, in a second image for the solve (which
+    // still needs L); not for n = 8, where every lane holds whole columns and the masks are cheap (measured)
+    static constexpr bool CLEAN = (MODE != 2) && (N >= 16);
+    static constexpr bool VCOPY = (MODE == 2) && (N >= 16) && (sizeof(T) == 4);     // Float64: the extra shared memory costs more than the masks (measured)
+    static constexpr int VIMG_OFF = DBUF * STAGE_BYTES + 128;                     // after the mbarriers
+    static constexpr int WARP_BYTES = VIMG_OFF + (VCOPY ? G * IMG_BYTES : 0);
     static_assert(RG >= 1 && RPL % E == 0, "row blocks are whole 16-byte vectors");
 };
 
@@ -605,9 +610,10 @@ __global__ void __launch_bounds__(WARPS * 32)
 apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ A, int64_t lda, int64_t strideA,
                      const T *__restrict__ tau, int64_t strideTau, T *__restrict__ B, int64_t ldb, int64_t strideB, int nrhs,
                      int64_t batch, int32_t *__restrict__ info_out, int vecB) {
-    using Cfg = ApplyCfg<T, N, NR>;
+    using Cfg = ApplyCfg<T, N, NR, MODE>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, RPL = Cfg::RPL, PITCH = Cfg::PITCH, DBUF = Cfg::DBUF;
+    constexpr bool CLEAN = Cfg::CLEAN, VCOPY = Cfg::VCOPY;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -693,12 +699,43 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                 }
                 __syncwarp();
                 waited = true;
+                if constexpr (CLEAN) {
+                    // Q-apply only: make the staged reflectors explicit once per warp-batch (unit pivot, zeros below it --
+                    // L is not needed), so that the reflector loop below carries no row masks.
+                    T *imw = reinterpret_cast<T *>(st);
+                    for (int col = lane; col < G * N; col += 32) {
+                        const int k = col % N;
+                        T *cp = imw + (col / N) * N * PITCH + k * PITCH;
+                        V q = *reinterpret_cast<const V *>(cp + (k / E) * E);
+                        T *qp = reinterpret_cast<T *>(&q);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) qp[e] = (e < k % E) ? qp[e] : ((e == k % E) ? T(1) : T(0));
+                        *reinterpret_cast<V *>(cp + (k / E) * E) = q;
+                        for (int v = k / E + 1; v < N / E; ++v) *reinterpret_cast<V *>(cp + v * E) = V{};
+                    }
+                    __syncwarp();
+                }
+                if constexpr (VCOPY) {
+                    const T *imr = reinterpret_cast<const T *>(st);
+                    T *vw = reinterpret_cast<T *>(wbase + Cfg::VIMG_OFF);
+                    for (int col = lane; col < G * N; col += 32) {
+                        const int k = col % N, off = (col / N) * N * PITCH + k * PITCH;
+                        for (int v = 0; v < k / E; ++v) *reinterpret_cast<V *>(vw + off + v * E) = *reinterpret_cast<const V *>(imr + off + v * E);
+                        V q = *reinterpret_cast<const V *>(imr + off + (k / E) * E);
+                        T *qp = reinterpret_cast<T *>(&q);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) qp[e] = (e < k % E) ? qp[e] : ((e == k % E) ? T(1) : T(0));
+                        *reinterpret_cast<V *>(vw + off + (k / E) * E) = q;
+                        for (int v = k / E + 1; v < N / E; ++v) *reinterpret_cast<V *>(vw + off + v * E) = V{};
+                    }
+                    __syncwarp();
+                }
             }
             // reflectors: column k (0-based) has pivot row k, tail rows 0..k-1
 #pragma unroll 4
             for (int kk = 0; kk < N; ++kk) {
                 const int k = (MODE == 0) ? kk : N - 1 - kk;
-                const T *vk = img + k * PITCH + row0;
+                const T *vk = (VCOPY ? reinterpret_cast<const T *>(wbase + Cfg::VIMG_OFF) + g * N * PITCH : img) + k * PITCH + row0;
                 const T tk = valid ? taus[k] : T(0);
                 const int kd = k - row0;                       // rows with local index < kd belong to the tail
                 T v[RPL];
@@ -710,7 +747,8 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         const int i = vv * E + e;
-                        v[i] = (i < kd) ? qp[e] : (i == kd ? T(1) : T(0));
+                        if constexpr (!CLEAN && !VCOPY) v[i] = (i < kd) ? qp[e] : (i == kd ? T(1) : T(0));
+                        else v[i] = qp[e];
                         part = t_fma(v[i], b[i], part);
                     }
                 }
@@ -774,6 +812,7 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                 phase[cur] ^= 1;
             }
         }
+        if constexpr (USE_TMA) fence_proxy_async();   // this lane's generic-proxy writes to the stage (explicit reflectors, reciprocal diagonal) before the next bulk copy into it
         __syncwarp();    // all lanes are done with this stage before it is refilled
     }
 }
@@ -896,7 +935,7 @@ static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
                                 int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch,
                                 int32_t *info_out) {
     constexpr int WARPS = 4;
-    using Cfg = ApplyCfg<T, N, NR>;
+    using Cfg = ApplyCfg<T, N, NR, MODE>;
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES;
     if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
     CUtensorMap tmap;
