@@ -1107,7 +1107,10 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
             if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
-            if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);      // one kernel
+            // One kernel for small batches: below ~48k matrices (the shard of an 8-GPU run) the second kernel's fill/drain and
+            // the two extra launches cost more than the split saves (32768 matrices: 209 vs 220 us; 262144: 1519 vs 1446 us).
+            if (h->opt_bvar == 2 || (h->opt_bvar == 0 && batch < 49152))       // bvar 3 forces the split at any batch (tests)
+                return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched_split32<double, 4, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);

@@ -295,3 +295,33 @@ def test_batched_host_chunk_pipeline_same_bits(q, h, n, dt):
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b, equal_nan=True)
     assert out[1][4][77] == 3 and (np.delete(out[1][4], 77) == 0).all()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("bvar", [2, 3])
+def test_batched_n32_single_and_split_kernels_vs_oracle(q, h, dt, bvar):
+    """n = 32 has two code paths (one kernel for small batches, the two-phase split for large ones); both are forced here
+    at a small batch, including matrices that the register kernels flag and leave to the generic kernel."""
+    rng = np.random.default_rng(bvar)
+    batch = 1537
+    A = rng.standard_normal((batch, 32, 32)).astype(dt)
+    tiny = 1e-200 if dt == np.float64 else 1e-30
+    A[5] *= tiny                                   # flagged in phase A (squares underflow)
+    A[9, :16, :16] *= tiny                         # leading block: flagged in phase B only
+    A[11, :, :8] = 0.0                             # zero rows: tau = 0 steps
+    try:
+        h.set_option("bvar", bvar)
+        F, tau = q.ql_batched_(A.copy(), handle=h)
+    finally:
+        h.set_option("bvar", 0)
+    Fo = A.copy()
+    tauo = lapack.geqlf_loop(Fo)
+    eps = _eps(dt)
+    for i in (5, 9, 11, 0, 1, batch - 1):
+        # layout F[b, col, row]: L (row >= col) scales with ||A||, the reflector tails (row < col) are O(1) whatever the scale
+        amax = float(np.abs(A[i]).max())                        # scaled norm: the squares of matrix 5 underflow
+        nrm = amax * np.linalg.norm(A[i].astype(np.float64) / amax)
+        d = np.abs(F[i].astype(np.float64) - Fo[i].astype(np.float64))
+        assert np.triu(d).max() <= 50 * 32 * eps * nrm, i
+        assert np.tril(d, -1).max() <= 50 * 32 * eps, i
+    _check_factors(F, tau, Fo, tauo, A, 32, dt)

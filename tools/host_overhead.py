@@ -24,7 +24,9 @@ for n, dt in ((32, torch.float64), (16, torch.float32)):
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         print(f"n={n} {name}: host {1e6 * (t1 - t0) / 500:.1f} us/call issue, {1e6 * (t2 - t0) / 500:.1f} us/call incl. drain")
-for batch in (32768, 65536, 131072, 262144):
+import itertools
+for bv, batch in itertools.product((0, 2), (16384, 32768, 65536, 131072, 262144)):
+    h.set_option("bvar", bv)
     A0 = torch.randn((batch, 32, 32), dtype=torch.float64, device="cuda")
     A = A0.clone()
     tau = torch.empty((batch, 32), dtype=torch.float64, device="cuda")
@@ -43,4 +45,4 @@ for batch in (32768, 65536, 131072, 262144):
         ts.append(e0.elapsed_time(e1))
     ts = sorted(ts[2:])
     med = ts[len(ts) // 2]
-    print(f"batch={batch}: {med * 1e3:.1f} us  {batch / med / 1e3:.1f} M/s  ideal-from-262144 ratio")
+    print(f"bvar={bv} batch={batch}: {med * 1e3:.1f} us  {batch / med / 1e3:.1f} M/s")
