@@ -587,11 +587,18 @@ struct ApplyCfg {
     static constexpr int PITCH = N + E;
     static constexpr int IMG_BYTES = N * PITCH * (int)sizeof(T);                 // multiple of 128
     static constexpr int pow2_floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
-    static constexpr int LPM0 = (N * NR / 8) > 32 ? 32 : (N * NR / 8);           // lanes per matrix at 8 rows per lane
+#ifndef APPLY_CL
+#define APPLY_CL 2
+#endif
+    // columns of B per lane: the kernel is bound by shared-memory wavefronts (every LDS.128 of a reflector is 4 of them, and
+    // a quarter warp reads the same 16 bytes), so one reflector load feeds CL columns
+    static constexpr int CL = (NR >= 2 && N >= 16 && !(MODE == 2 && N == 16 && sizeof(T) == 4)) ? APPLY_CL : 1;   // (that one: 6 % slower)
+    static constexpr int NRL = NR / CL;                                          // lanes across the NR columns of a pass
+    static constexpr int LPM0 = (N * NRL / 8) > 32 ? 32 : (N * NRL / 8);         // lanes per matrix at 8 rows per lane
     static constexpr int GMAX = pow2_floor((24 * 1024) / IMG_BYTES > 0 ? (24 * 1024) / IMG_BYTES : 1);   // shared-memory budget per warp
     static constexpr int G = (32 / LPM0) < GMAX ? (32 / LPM0) : GMAX;            // matrices per warp
     static constexpr int LPM = 32 / G;                    // lanes per matrix
-    static constexpr int RG = LPM / NR;                   // row groups per matrix
+    static constexpr int RG = LPM / NRL;                  // row groups per matrix
     static constexpr int RPL = N / RG;                    // rows per lane
     static constexpr int TAU_BYTES = (G * N * (int)sizeof(T) + 127) / 128 * 128;
     static constexpr int STAGE_BYTES = G * IMG_BYTES + TAU_BYTES;
@@ -613,12 +620,13 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
     using Cfg = ApplyCfg<T, N, NR, MODE>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, RPL = Cfg::RPL, PITCH = Cfg::PITCH, DBUF = Cfg::DBUF;
+    constexpr int CL = Cfg::CL, NRL = Cfg::NRL;
     constexpr bool CLEAN = Cfg::CLEAN, VCOPY = Cfg::VCOPY;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / LPM, l = lane % LPM;
-    const int jb = l % NR, rg = l / NR, row0 = rg * RPL;
+    const int jb = l % NRL, rg = l / NRL, row0 = rg * RPL;      // lane (jb, rg): columns jb*CL .. jb*CL+CL-1 of the pass, rows row0 ..
     unsigned char *wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + DBUF * Cfg::STAGE_BYTES);
     const int nbatch = (int)batch;
@@ -676,21 +684,26 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
         bool waited = false;
         // this lane's slice of B: nrhs columns are processed NR at a time
         for (int c0 = 0; c0 < nrhs; c0 += NR) {
-            const int col = c0 + jb;
-            const bool cvalid = valid && col < nrhs;
-            T b[RPL];
-            T *Bc = B + (int64_t)(valid ? mi : 0) * strideB + (int64_t)(col < nrhs ? col : 0) * ldb + row0;
-            if (vecB) {
+            bool cvalid[CL];
+            T b[CL][RPL];
+            T *Bc[CL];
 #pragma unroll
-                for (int v = 0; v < RPL / E; ++v) {
-                    V q = cvalid ? reinterpret_cast<const V *>(Bc)[v] : V{};
-                    const T *qp = reinterpret_cast<const T *>(&q);
+            for (int cc = 0; cc < CL; ++cc) {
+                const int col = c0 + jb * CL + cc;
+                cvalid[cc] = valid && col < nrhs;
+                Bc[cc] = B + (int64_t)(valid ? mi : 0) * strideB + (int64_t)(col < nrhs ? col : 0) * ldb + row0;
+                if (vecB) {
 #pragma unroll
-                    for (int e = 0; e < E; ++e) b[v * E + e] = qp[e];
+                    for (int v = 0; v < RPL / E; ++v) {
+                        V q = cvalid[cc] ? reinterpret_cast<const V *>(Bc[cc])[v] : V{};
+                        const T *qp = reinterpret_cast<const T *>(&q);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) b[cc][v * E + e] = qp[e];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) b[cc][i] = cvalid[cc] ? Bc[cc][i] : T(0);
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < RPL; ++i) b[i] = cvalid ? Bc[i] : T(0);
             }
             if (!waited) {
                 if constexpr (USE_TMA) {
@@ -739,7 +752,9 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                 const T tk = valid ? taus[k] : T(0);
                 const int kd = k - row0;                       // rows with local index < kd belong to the tail
                 T v[RPL];
-                T part = T(0);
+                T part[CL];
+#pragma unroll
+                for (int cc = 0; cc < CL; ++cc) part[cc] = T(0);
 #pragma unroll
                 for (int vv = 0; vv < RPL / E; ++vv) {
                     V q = *reinterpret_cast<const V *>(vk + vv * E);
@@ -749,14 +764,21 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                         const int i = vv * E + e;
                         if constexpr (!CLEAN && !VCOPY) v[i] = (i < kd) ? qp[e] : (i == kd ? T(1) : T(0));
                         else v[i] = qp[e];
-                        part = t_fma(v[i], b[i], part);
+#pragma unroll
+                        for (int cc = 0; cc < CL; ++cc) part[cc] = t_fma(v[i], b[cc][i], part[cc]);
                     }
                 }
 #pragma unroll
-                for (int off = NR; off < LPM; off <<= 1) part += __shfl_xor_sync(FULL, part, off);
-                const T s = tk * part;
+                for (int off = NRL; off < LPM; off <<= 1) {
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) b[i] = t_fma(-s, v[i], b[i]);
+                    for (int cc = 0; cc < CL; ++cc) part[cc] += __shfl_xor_sync(FULL, part[cc], off);
+                }
+#pragma unroll
+                for (int cc = 0; cc < CL; ++cc) {
+                    const T s = tk * part[cc];
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) b[cc][i] = t_fma(-s, v[i], b[cc][i]);
+                }
             }
             if constexpr (MODE == 2) {
                 // forward substitution with L = tril(factors): x_c = b_c / L_cc; b_i -= L_ic x_c (i > c).  The reciprocals of
@@ -774,7 +796,9 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                     const T *lc = img + c * PITCH + row0;
                     const T rcc = img[c * PITCH + N];
                     if (img[c * PITCH + c] == T(0) && bad == 0) bad = c + 1;
-                    T xc = __shfl_sync(FULL, b[orow], jb + NR * org, LPM) * rcc;
+                    T xc[CL];
+#pragma unroll
+                    for (int cc = 0; cc < CL; ++cc) xc[cc] = __shfl_sync(FULL, b[cc][orow], jb + NRL * org, LPM) * rcc;
                     const int cd = c - row0;
 #pragma unroll
                     for (int vv = 0; vv < RPL / E; ++vv) {
@@ -783,26 +807,31 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
 #pragma unroll
                         for (int e = 0; e < E; ++e) {
                             const int i = vv * E + e;
-                            if (i == cd) b[i] = xc;
-                            else if (i > cd) b[i] = t_fma(-qp[e], xc, b[i]);
+#pragma unroll
+                            for (int cc = 0; cc < CL; ++cc) {
+                                if (i == cd) b[cc][i] = xc[cc];
+                                else if (i > cd) b[cc][i] = t_fma(-qp[e], xc[cc], b[cc][i]);
+                            }
                         }
                     }
                 }
                 if (info_out != nullptr && valid && l == 0 && c0 == 0) info_out[mi] = bad;
             }
-            if (cvalid) {
+#pragma unroll
+            for (int cc = 0; cc < CL; ++cc) {
+                if (!cvalid[cc]) continue;
                 if (vecB) {
 #pragma unroll
                     for (int v = 0; v < RPL / E; ++v) {
                         V q;
                         T *qp = reinterpret_cast<T *>(&q);
 #pragma unroll
-                        for (int e = 0; e < E; ++e) qp[e] = b[v * E + e];
-                        reinterpret_cast<V *>(Bc)[v] = q;
+                        for (int e = 0; e < E; ++e) qp[e] = b[cc][v * E + e];
+                        reinterpret_cast<V *>(Bc[cc])[v] = q;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < RPL; ++i) Bc[i] = b[i];
+                    for (int i = 0; i < RPL; ++i) Bc[cc][i] = b[cc][i];
                 }
             }
         }
