@@ -199,10 +199,13 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
                 }
             }
         }
-        // the update pass walks x downwards; its first PD vectors are requested now, ahead of the scalar chain
+        // the update pass walks x downwards: its first PD vectors are the last ones of the dot pass and stay in registers
+        // (the shared-memory data pipe is the busiest unit of this kernel: 64 % of peak wavefronts, ncu)
+        // (keeping more than PD of them -- all of x for the short tiles -- was measured 1-5 % slower: registers live across the scalar chain)
+        constexpr int RU = (PD < NVEC) ? PD : NVEC;
         V qb[NVEC];
 #pragma unroll
-        for (int w = 0; w < PD && w < NVEC; ++w) qb[w] = lds16_s(xa + (uint32_t)((V1 - 1 - w) * 16), T());
+        for (int w = 0; w < RU; ++w) qb[w] = qa[NVEC - 1 - w];
         T ds[NS];
 #pragma unroll
         for (int c = 0; c < NS; ++c) {
@@ -242,7 +245,7 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         // 5. a_j -= tau (v^T a_j) v on the tail rows, shifting the tile up by one index
 #pragma unroll
         for (int w = 0; w < NVEC; ++w) {
-            if (w + PD < NVEC) qb[w + PD] = lds16_s(xa + (uint32_t)((V1 - 1 - w - PD) * 16), T());
+            if (w + PD < NVEC && w + PD >= RU) qb[w + PD] = lds16_s(xa + (uint32_t)((V1 - 1 - w - PD) * 16), T());
             const T *qp = reinterpret_cast<const T *>(&qb[w]);
 #pragma unroll
             for (int e = E - 1; e >= 0; --e) {
@@ -336,7 +339,7 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, PITCH = Cfg::PITCH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane / LPM, jl = lane % LPM;
+    const int g = lane / LPM, jl = lane % LPM;    // (matrices interleaved lane by lane instead: 10-25 % slower, bank conflicts on the images)
     unsigned char *wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
     T *buf = reinterpret_cast<T *>(wbase);
     T *obuf = buf + g * N * PITCH;                           // this matrix's image (input, then output)
