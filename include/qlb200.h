@@ -112,6 +112,17 @@ int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, i
 int qlb200_dqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
                         const double *dtau, double *dB, int64_t ldb);
 
+/* ---- tall least squares, min ||A x - b||_2 for m >= n through the QL factors.  The reference's own
+ * rectangular branch of materialize!(::Ldiv{<:QLPackedLayout}) (src/ql.jl:448-486) is wrong and @test_broken
+ * (test/test_ql.jl:148); this is the corrected tall case: B (m x nrhs) <- Q'B, then rows m-n+1..m of B <- L^{-1} (those rows).
+ * On return X = B[m-n+1:m, :] (n x nrhs) and B[1:m-n, :] holds the residual's coordinates (its norm is the residual norm).
+ * Returns 0, -i, 1000+cudaError, or i > 0 when L[i,i] == 0.  The wide minimum-norm solve needs an LQ-type factorization and
+ * is not offered. */
+int qlb200_dqllstsq(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                    const double *tau, double *B, int64_t ldb);
+int qlb200_dqllstsq_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
+                        const double *dtau, double *dB, int64_t ldb);
+
 /* ---- RQ through index reversal -------------------------------------------------------------
  * Replaces rq!(A::StridedMatrix{<:BlasFloat}) = RQ(LAPACK.gerqf!(A)...) (reference
  * src/rq.jl:401): gerqf(A) = geqlf(A^T)^T with identical tau. */
@@ -150,6 +161,20 @@ int qlb200_dulsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *
 int qlb200_dgemm_dev(qlb200_handle h, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
                      const double *dA, int64_t lda, const double *dB, int64_t ldb, double beta, double *dC,
                      int64_t ldc);
+
+/* ---- QR through index reversal ----------------------------------------------
+ * Replaces _qrfactUnblocked!(::AbstractColumnMajor, ::AbstractStridedLayout, A::AbstractMatrix{<:BlasFloat}, tau)
+ *   = QR(LAPACK.geqrf!(A, tau)...) (reference src/qr.jl:72) behind qrunblocked!/qrunblocked (src/qr.jl:73-101).
+ * With J the exchange matrix, geqrf(A) = J geqlf(J A J) J with tau reversed (the identity the reference tests at
+ * test/test_ql.jl:7-13), so the QL kernels are reused unchanged; output = LAPACK ?geqrf layout (R on and above the
+ * diagonal, reflector i below the diagonal of column i), i.e. QR.factors / QR.tau. */
+int qlb200_dgeqrf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb200_dgeqrf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau);
+/* lmul!/rmul! with QRPackedQ or its adjoint (LAPACK ?ormqr semantics: A is nq x k, reflector i in column i): Q_qr = J Q_ql J. */
+int qlb200_dormqr(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A,
+                  int64_t lda, const double *tau, double *C, int64_t ldc);
+int qlb200_dormqr_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *dA,
+                      int64_t lda, const double *dtau, double *dC, int64_t ldc);
 
 /* ---- batched small square QL (new surface; per-matrix semantics = src/ql.jl:72) ------------
  * `batch` independent n x n matrices, 1 <= n <= 64 (register kernels for n in {8, 16, 32}); matrix b starts at A + b*strideA,

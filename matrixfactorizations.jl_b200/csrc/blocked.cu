@@ -549,6 +549,101 @@ int qlb_dormrq_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     return qlb_dormql_dev(h, side, notran ? 'T' : 'N', m, n, k, At, ldt, tau, C, ldc, -1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// QR through index reversal (reference src/qr.jl:60-76 -> LAPACK.geqrf!, test/test_ql.jl:7-13):
+// with J the exchange matrix, geqrf(A) = J_m geqlf(J_m A J_n) J_n with tau reversed, and Q_qr = J Q_ql J.
+// ---------------------------------------------------------------------------------------------
+// A <- J_m A J_n in place: element (i, j) trades places with (m-1-i, n-1-j); pairs are enumerated over the dense m x n index
+__global__ void flip2d_inplace_kernel(double *__restrict__ A, int64_t lda, int m, int n) {
+    const int64_t total = (int64_t)m * n, half = total / 2;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < half; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = p / m, i = p - j * m;
+        double *x = A + i + j * lda, *y = A + (m - 1 - i) + (int64_t)(n - 1 - j) * lda;
+        const double t = *x;
+        *x = *y;
+        *y = t;
+    }
+}
+// out = J_m in J_n (out of place)
+__global__ void flip2d_kernel(const double *__restrict__ in, int64_t ldi, int m, int n, double *__restrict__ out, int64_t ldo) {
+    const int64_t total = (int64_t)m * n;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = p / m, i = p - j * m;
+        out[i + j * ldo] = in[(m - 1 - i) + (int64_t)(n - 1 - j) * ldi];
+    }
+}
+__global__ void reverse_inplace_kernel(double *__restrict__ x, int k) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k / 2; i += gridDim.x * blockDim.x) {
+        const double t = x[i];
+        x[i] = x[k - 1 - i];
+        x[k - 1 - i] = t;
+    }
+}
+__global__ void reverse_copy_kernel(const double *__restrict__ x, int k, double *__restrict__ y) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) y[i] = x[k - 1 - i];
+}
+// C <- J C (rows reversed, side 'L') or C <- C J (columns reversed, side 'R'), in place
+__global__ void flip_rows_or_cols_kernel(double *__restrict__ C, int64_t ldc, int m, int n, int rows) {
+    const int hm = rows ? m / 2 : m, hn = rows ? n : n / 2;
+    const int64_t total = (int64_t)hm * hn;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = p / hm, i = p - j * hm;
+        double *x = C + i + j * ldc, *y = rows ? C + (m - 1 - i) + j * ldc : C + i + (int64_t)(n - 1 - j) * ldc;
+        const double t = *x;
+        *x = *y;
+        *y = t;
+    }
+}
+static inline unsigned flip_grid(qlb200_ctx *h, int64_t work) {
+    int64_t b = (work + 255) / 256;
+    const int64_t cap = (int64_t)h->sm_count * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// the two halves of geqrf around the QL factorization (capi.cu puts ql! -- graph replay included -- between them)
+int qlb_qr_flip_in(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda) {
+    if (m == 0 || n == 0) return 0;
+    flip2d_inplace_kernel<<<flip_grid(h, m * n / 2), 256, 0, h->stream>>>(A, lda, (int)m, (int)n);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+int qlb_qr_flip_out(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
+    if (m == 0 || n == 0) return 0;
+    const int k = (int)(m < n ? m : n);
+    h->tc_valid = false;                         // the cached T factors belong to the flipped reflectors
+    flip2d_inplace_kernel<<<flip_grid(h, m * n / 2), 256, 0, h->stream>>>(A, lda, (int)m, (int)n);
+    QLB_LAUNCH_CHECK(h);
+    reverse_inplace_kernel<<<flip_grid(h, k / 2), 256, 0, h->stream>>>(tau, k);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// op(Q_qr) C or C op(Q_qr) with the QR reflectors in the columns of the nq x k array A (LAPACK ?ormqr layout, what
+// lmul!/rmul! with a QRPackedQ compute): Q_qr = J Q_ql J, so flip C, apply the QL reflectors J A J, flip C back.
+int qlb_dormqr_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n64, int64_t k64, const double *A, int64_t lda,
+                   const double *tau, double *C, int64_t ldc) {
+    const int m = (int)m64, n = (int)n64, k = (int)k64;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    const bool left = (side == 'L' || side == 'l');
+    const int nq = left ? m : n;
+    cudaStream_t st = h->stream;
+    const int64_t ldf = even_up(nq);
+    int rc = qlb_reserve(h, &h->ws2, &h->ws2_bytes, ((size_t)ldf * k + (size_t)k + 2) * sizeof(double));
+    if (rc) return rc;
+    double *F = (double *)h->ws2, *taur = F + (size_t)ldf * k;
+    flip2d_kernel<<<flip_grid(h, (int64_t)nq * k), 256, 0, st>>>(A, lda, nq, k, F, ldf);
+    QLB_LAUNCH_CHECK(h);
+    reverse_copy_kernel<<<flip_grid(h, k), 256, 0, st>>>(tau, k, taur);
+    QLB_LAUNCH_CHECK(h);
+    flip_rows_or_cols_kernel<<<flip_grid(h, (int64_t)m * n / 2), 256, 0, st>>>(C, ldc, m, n, left ? 1 : 0);
+    QLB_LAUNCH_CHECK(h);
+    rc = qlb_dormql_dev(h, side, trans, m, n, k, F, ldf, taur, C, ldc, -1);
+    if (rc) return rc;
+    flip_rows_or_cols_kernel<<<flip_grid(h, (int64_t)m * n / 2), 256, 0, st>>>(C, ldc, m, n, left ? 1 : 0);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
     const int m = (int)m64, n = (int)n64;
     if (m == 0 || n == 0) return 0;

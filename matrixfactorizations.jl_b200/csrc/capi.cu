@@ -723,6 +723,64 @@ int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, i
 }
 
 
+// ---- the tall least-squares solve the reference's own branch gets wrong (@test_broken, test/test_ql.jl:148).
+// A = Q [0; L] (m >= n), so min ||A x - b|| has x = L^{-1} (Q'b)[m-n+1:m]; the first m-n entries of Q'b are the residual's coordinates.
+static int check_lstsq(qlb200_ctx *h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau,
+                       const double *B, int64_t ldb) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, m >= 0 && m < (1 << 30), 2, "m out of range");
+    QLB_REQUIRE(h, n >= 0 && n <= m, 3, "n must satisfy 0 <= n <= m (tall or square)");
+    QLB_REQUIRE(h, nrhs >= 0 && nrhs < (1 << 30), 4, "nrhs out of range");
+    QLB_REQUIRE(h, A != nullptr || m * n == 0, 5, "A is null");
+    QLB_REQUIRE(h, lda >= (m > 1 ? m : 1), 6, "lda < max(1,m)");
+    QLB_REQUIRE(h, tau != nullptr || n == 0, 7, "tau is null");
+    QLB_REQUIRE(h, B != nullptr || m * nrhs == 0, 8, "B is null");
+    QLB_REQUIRE(h, ldb >= (m > 1 ? m : 1), 9, "ldb < max(1,m) (DimensionMismatch)");
+    return 0;
+}
+static int qllstsq_dev(qlb200_ctx *h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const double *dtau,
+                       double *dB, int64_t ldb, int32_t *dinfo, int cache_mode) {
+    if (n == 0 || nrhs == 0) return 0;
+    int rc = qlb_dormql_dev(h, 'L', 'T', m, nrhs, n, dA, lda, dtau, dB, ldb, cache_mode);
+    if (rc) return rc;
+    return qlb_trsm_lower_dev(h, (int)n, (int)nrhs, dA + (m - n), lda, dB + (m - n), ldb, dinfo);
+}
+int qlb200_dqllstsq_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const double *dtau,
+                        double *dB, int64_t ldb) {
+    int rc = check_lstsq(h, m, n, nrhs, dA, lda, dtau, dB, ldb);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qllstsq_dev(h, m, n, nrhs, dA, lda, dtau, dB, ldb, nullptr, 0);
+}
+int qlb200_dqllstsq(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
+                    int64_t ldb) {
+    int rc = check_lstsq(h, m, n, nrhs, A, lda, tau, B, ldb);
+    if (rc) return rc;
+    if (n == 0 || nrhs == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA, *dB;
+    int64_t ldda;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, &dA, &ldda);
+    if (rc) return rc;
+    const int64_t lddb = ((m + 1) & ~(int64_t)1) < 2 ? 2 : ((m + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)lddb * nrhs + (size_t)n + 2) * sizeof(double));
+    if (rc) return rc;
+    dB = (double *)h->stage2;
+    double *dtau = dB + (size_t)lddb * nrhs;
+    QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)m * 8, (size_t)nrhs, cudaMemcpyHostToDevice,
+                                  h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qllstsq_dev(h, m, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo, -1);
+    if (rc) return rc;
+    rc = stage_out(h, B, m, nrhs, ldb, dB, lddb);
+    if (rc) return rc;
+    int32_t info = 0;
+    QLB_CUDA(h, cudaMemcpyAsync(&info, h->dinfo, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return info == 0x7fffffff ? 0 : (int)info;       // i > 0: L[i,i] == 0 (rank deficient)
+}
+
+
 int qlb200_dormrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *dA, int64_t lda,
                       const double *dtau, double *dC, int64_t ldc) {
     if (!h) return -1;
@@ -766,6 +824,57 @@ int qlb200_dormrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
                                   h->stream));
     QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
     rc = qlb200_dormrq_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc);
+    if (rc) return rc;
+    rc = stage_out(h, C, m, n, ldc, dC, lddc);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* ---- QR through index reversal -------------------------------------------------- */
+// geqrf(A) = J geqlf(J A J) J, tau reversed; the QL in the middle is the same call as ql! (graph replay on repeated calls)
+static int geqrf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
+    int rc = qlb_qr_flip_in(h, m, n, dA, lda);
+    if (!rc) rc = geqlf_dev_graph(h, m, n, dA, lda, dtau);
+    if (!rc) rc = qlb_qr_flip_out(h, m, n, dA, lda, dtau);
+    return rc;
+}
+int qlb200_dgeqrf_dev(qlb200_handle h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
+    int rc = check_fact(h, m, n, dA, lda, dtau);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return geqrf_dev(h, m, n, dA, lda, dtau);
+}
+int qlb200_dgeqrf(qlb200_handle h, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
+    return fact_host(h, geqrf_dev, m, n, A, lda, tau);
+}
+int qlb200_dormqr_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *dA, int64_t lda,
+                      const double *dtau, double *dC, int64_t ldc) {
+    int rc = check_ormql(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dormqr_dev(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+}
+int qlb200_dormqr(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                  const double *tau, double *C, int64_t ldc) {
+    int rc = check_ormql(h, side, trans, m, n, k, A, lda, tau, C, ldc);
+    if (rc) return rc;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t nq = (side == 'L' || side == 'l') ? m : n;
+    double *dA, *dC;
+    int64_t ldda;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, nq, k, lda, &dA, &ldda);
+    if (rc) return rc;
+    const int64_t lddc = ((m + 1) & ~(int64_t)1) < 2 ? 2 : ((m + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)lddc * n + (size_t)k + 2) * sizeof(double));
+    if (rc) return rc;
+    dC = (double *)h->stage2;
+    double *dtau = dC + (size_t)lddc * n;
+    QLB_CUDA(h, cudaMemcpy2DAsync(dC, (size_t)lddc * 8, C, (size_t)ldc * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice,
+                                  h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb_dormqr_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc);
     if (rc) return rc;
     rc = stage_out(h, C, m, n, ldc, dC, lddc);
     if (rc) return rc;

@@ -97,7 +97,16 @@ materialize!(M::Rmul{<:AbstractColumnMajor,<:AdjQLPackedQLayout{<:AbstractColumn
 function materialize!(Ldv::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QL{Float64},<:StridedVecOrMat{Float64}})
     F, B = Ldv.A, Ldv.B
     m, n = size(F)
-    m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # rectangular: keep the reference's own branch (src/ql.jl:448-486)
+    if m > n      # SURVEY.md 8(f) N2: tall least squares (the reference's own branch, src/ql.jl:448-486, is @test_broken)
+        size(B, 1) == m || throw(DimensionMismatch("arguments must have the same number of rows; has $m and $(size(B,1))"))
+        h = handle()
+        info = ccall((:qlb200_dqllstsq, libqlb200), Cint,
+                     (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+                     h.ptr, m, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
+        chk(h, info; dims = (9,))
+        return B      # X = B[m-n+1:m, :]; B[1:m-n, :] = coordinates of the residual
+    end
+    m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # wide: keep the reference's own branch (src/ql.jl:448-486)
     size(B, 1) == n || throw(DimensionMismatch("arguments must have the same number of rows; has $n and $(size(B,1))"))
     h = handle()
     info = ccall((:qlb200_dqlsolve, libqlb200), Cint,
@@ -106,6 +115,35 @@ function materialize!(Ldv::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor},<:Abstra
     chk(h, info; dims = (8,))
     B
 end
+
+# ---- qrunblocked! and QR's packed Q through index reversal (SURVEY.md 8(f) N3) ------------------------------------
+function _qrfactUnblocked!(::AbstractColumnMajor, ::AbstractStridedLayout, A::AbstractMatrix{Float64}, τ::AbstractVector{Float64})   # src/qr.jl:72
+    m, n = size(A)
+    length(τ) >= min(m, n) || throw(DimensionMismatch("tau has length $(length(τ)), needs $(min(m,n))"))
+    h = handle()
+    chk(h, ccall((:qlb200_dgeqrf, libqlb200), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
+                 h.ptr, m, n, A, max(1, stride(A, 2)), τ))
+    QR(A, τ)
+end
+function _ormqr!(side::Char, trans::Char, Q::QRPackedQ{Float64,<:StridedMatrix}, C::StridedVecOrMat{Float64})
+    mA, nA = size(Q.factors)
+    k = min(mA, nA)
+    m, n = size(C, 1), size(C, 2)
+    (side == 'L' ? m : n) == mA || throw(DimensionMismatch("matrix A has dimensions ($mA,$nA) but B has dimensions ($m, $n)"))
+    h = handle()
+    chk(h, ccall((:qlb200_dormqr, libqlb200), Cint,
+                 (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+                 h.ptr, side, trans, m, n, k, Q.factors, max(1, stride(Q.factors, 2)), Q.τ, C, max(1, stride(C, 2))); dims = (6, 8))
+    C
+end
+materialize!(M::Lmul{<:QRPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QRPackedQ{Float64},<:StridedVecOrMat{Float64}}) =
+    _ormqr!('L', 'N', M.A, M.B)
+materialize!(M::Lmul{<:AdjQRPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:Any,<:StridedVecOrMat{Float64}}) =
+    _ormqr!('L', 'T', parent(M.A), M.B)
+materialize!(M::Rmul{<:AbstractColumnMajor,<:QRPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{Float64},<:QRPackedQ{Float64}}) =
+    _ormqr!('R', 'N', M.B, M.A)
+materialize!(M::Rmul{<:AbstractColumnMajor,<:AdjQRPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{Float64}}) =
+    _ormqr!('R', 'T', parent(M.B), M.A)
 
 # ---- rq! and RQ's packed Q --------------------------------------------------------------------------------------
 function rq!(A::StridedMatrix{Float64})                                                    # src/rq.jl:401

@@ -206,7 +206,9 @@ class QL:
         r"""F \ b (src/ql.jl:490-502), square only -- the reference's rectangular branches are
         @test_broken (test/test_ql.jl:148)."""
         X = _copy_colmajor(b)
-        return ldiv_(self, X)
+        ldiv_(self, X)
+        m, n = self.factors.shape
+        return X if m == n else X[m - n:]        # tall: the least-squares solution (SURVEY.md 8(f) N2)
 
 
 def ql_(A, handle=None) -> QL:
@@ -239,6 +241,47 @@ def rq_(A, handle=None):
     tau = _new_like(A, min(a.m, a.n))
     h.call(f"qlb200_{a.pfx}gerqf{a.sfx}", a.m, a.n, a.ptr, a.ld, _Mat(tau, "tau").ptr)
     return A, tau
+
+
+def qr_(A, handle=None):
+    """qrunblocked!(A) for a BlasFloat strided matrix = QR(LAPACK.geqrf!(A, tau)...) (src/qr.jl:72-76), computed by the
+    QL kernels through the flip identity (test/test_ql.jl:7-13).  Returns (factors, tau)."""
+    a = _Mat(A)
+    if a.pfx != "d":
+        raise TypeError("qr_: Float64 only")
+    h = _handle(handle, a)
+    tau = _new_like(A, min(a.m, a.n))
+    h.call(f"qlb200_dgeqrf{a.sfx}", a.m, a.n, a.ptr, a.ld, _Mat(tau, "tau").ptr)
+    return A, tau
+
+
+class QRPackedQ:
+    """QR's packed orthogonal factor: reflector i below the diagonal of column i of `factors` (m x n), size (m, m)."""
+
+    def __init__(self, factors, tau, adjoint=False, handle=None):
+        self.factors, self.tau, self.adjoint, self.handle = factors, tau, adjoint, handle
+
+    @property
+    def T(self):
+        return QRPackedQ(self.factors, self.tau, not self.adjoint, self.handle)
+
+    @property
+    def shape(self):
+        m = self.factors.shape[0]
+        return (m, m)
+
+
+def _ormqr(side, Q: QRPackedQ, C):
+    f, c, t = _Mat(Q.factors, "A(const)"), _Mat(C, "C"), _Mat(Q.tau, "tau")
+    _same_kind(f, c, t)
+    h = _handle(Q.handle, f)
+    mA, nA = f.m, f.n
+    k = min(mA, nA)
+    nq = c.m if side == "L" else c.n
+    if nq != mA:
+        raise DimensionMismatch(f"matrix A has dimensions ({mA},{nA}) but {'B' if side == 'L' else 'A'} has dimensions ({c.m}, {c.n})")
+    h.call(f"qlb200_dormqr{f.sfx}", side.encode(), (b"T" if Q.adjoint else b"N"), c.m, c.n, k, f.ptr, f.ld, t.ptr, c.ptr, c.ld)
+    return C
 
 
 class RQPackedQ:
@@ -371,11 +414,15 @@ def _ormql(side, Q: QLPackedQ, C):
 
 def lmul_(Q, B):
     """lmul!(Q,B) / lmul!(Q',B): src/ql.jl:321-347 / 350-377 (QLPackedQ), src/rq.jl:130-137,183-202 (RQPackedQ)."""
+    if isinstance(Q, QRPackedQ):
+        return _ormqr("L", Q, B)
     return _ormrq("L", Q, B) if isinstance(Q, RQPackedQ) else _ormql("L", Q, B)
 
 
 def rmul_(C, Q):
     """rmul!(C,Q) / rmul!(C,Q'): src/ql.jl:381-406 / 409-435 (QLPackedQ), src/rq.jl:234-291 (RQPackedQ)."""
+    if isinstance(Q, QRPackedQ):
+        return _ormqr("R", Q, C)
     return _ormrq("R", Q, C) if isinstance(Q, RQPackedQ) else _ormql("R", Q, C)
 
 
@@ -383,11 +430,17 @@ def ldiv_(F: QL, B):
     """ldiv!(F::QL, B), square (src/ql.jl:438-447,467)."""
     f, b, t = _Mat(F.factors, "A(const)"), _Mat(B, "B"), _Mat(F.tau, "tau")
     _same_kind(f, b, t)
-    if f.m != f.n:
-        raise DimensionMismatch("ldiv_: only the square solve is pinned by the reference (test/test_ql.jl:69,148)")
+    if f.m < f.n:
+        raise DimensionMismatch("ldiv_: square and tall only (the wide minimum-norm solve needs an LQ-type factorization; "
+                                "the reference's own branch is @test_broken, test/test_ql.jl:148)")
     if b.m != f.m:   # src/ql.jl:494
         raise DimensionMismatch(f"arguments must have the same number of rows; has {f.m} and {b.m}")
     h = _handle(F.handle, f)
+    if f.m > f.n:    # SURVEY.md 8(f) N2: least squares; X = B[m-n:, :], B[:m-n, :] = residual coordinates
+        if f.pfx != "d":
+            raise TypeError("tall ldiv_: Float64 only")
+        h.call(f"qlb200_dqllstsq{f.sfx}", f.m, f.n, b.n, f.ptr, f.ld, t.ptr, b.ptr, b.ld)
+        return B
     h.call(f"qlb200_{f.pfx}qlsolve{f.sfx}", f.n, b.n, f.ptr, f.ld, t.ptr, b.ptr, b.ld)
     return B
 

@@ -128,6 +128,11 @@ def ormql(side, trans, A, tau, C):
     return _orm("ormql", side, trans, A, tau, C)
 
 
+def ormqr(side, trans, A, tau, C):
+    """LAPACK ?ormqr -- QRPackedQ's lmul!/rmul! for BlasFloat (LinearAlgebra stdlib; QR of src/qr.jl:72)."""
+    return _orm("ormqr", side, trans, A, tau, C)
+
+
 def ormrq(side, trans, A, tau, C):
     """LAPACK ?ormrq -- RQ's Q-apply in the reference (src/rq.jl:130-137,183-202)."""
     return _orm("ormrq", side, trans, A, tau, C)
