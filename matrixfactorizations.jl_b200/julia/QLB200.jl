@@ -21,8 +21,10 @@ using LinearAlgebra, MatrixFactorizations
 using MatrixFactorizations.ArrayLayouts
 using LinearAlgebra: BlasInt
 import MatrixFactorizations: qlfactUnblocked!, rq!, ul!, QL, QLPackedQ, RQ, RQPackedQ, UL,
-                             QLPackedQLayout, AdjQLPackedQLayout, QLPackedLayout
-import ArrayLayouts: materialize!, Lmul, Rmul, Ldiv, AbstractColumnMajor
+                             QLPackedQLayout, AdjQLPackedQLayout, QLPackedLayout,
+                             _qrfactUnblocked!, QR, QRPackedQ
+import ArrayLayouts: materialize!, Lmul, Rmul, Ldiv, AbstractColumnMajor, AbstractStridedLayout,
+                     QRPackedQLayout, AdjQRPackedQLayout
 
 const libqlb200 = get(ENV, "QLB200_LIB", joinpath(@__DIR__, "..", "libqlb200.so"))
 
