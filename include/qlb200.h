@@ -176,6 +176,13 @@ int qlb200_dormqr(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
 int qlb200_dormqr_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *dA,
                       int64_t lda, const double *dtau, double *dC, int64_t ldc);
 
+/* ldiv!(F::QR, B) for m >= n (`qrunblocked(A) \ b`, reference src/qr.jl:193-204): B (m x nrhs) is overwritten, X = B[1:n, :]
+ * (exact solve for m == n, least squares for m > n, LAPACK ?gels layout); i > 0: R[i,i] == 0. */
+int qlb200_dqrsolve(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda,
+                    const double *tau, double *B, int64_t ldb);
+int qlb200_dqrsolve_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
+                        const double *dtau, double *dB, int64_t ldb);
+
 /* ---- batched small square QL (new surface; per-matrix semantics = src/ql.jl:72) ------------
  * `batch` independent n x n matrices, 1 <= n <= 64 (register kernels for n in {8, 16, 32}); matrix b starts at A + b*strideA,
  * column-major with leading dimension lda; tau of matrix b at tau + b*strideTau (n entries).

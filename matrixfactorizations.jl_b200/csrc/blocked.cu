@@ -644,6 +644,33 @@ int qlb_dormqr_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     return 0;
 }
 
+// ldiv!(F::QR, B) for m >= n (the solve behind `qrunblocked(A) \\ b`, reference src/qr.jl:193-204): with F' = J F J the QL
+// factors of J A J, A x = b  <=>  (J A J)(J x) = J b, so J x comes out of the QL solve (least squares when m > n) on the
+// flipped right-hand side; after flipping back X = B[1:n, :] (LAPACK ?gels convention).
+int qlb_dqrsolve_dev(qlb200_ctx *h, int64_t m64, int64_t n64, int64_t nrhs64, const double *A, int64_t lda, const double *tau,
+                     double *B, int64_t ldb, int32_t *dinfo) {
+    const int m = (int)m64, n = (int)n64, nrhs = (int)nrhs64;
+    if (n == 0 || nrhs == 0) return 0;
+    cudaStream_t st = h->stream;
+    const int64_t ldf = even_up(m);
+    int rc = qlb_reserve(h, &h->ws2, &h->ws2_bytes, ((size_t)ldf * n + (size_t)n + 2) * sizeof(double));
+    if (rc) return rc;
+    double *F = (double *)h->ws2, *taur = F + (size_t)ldf * n;
+    flip2d_kernel<<<flip_grid(h, (int64_t)m * n), 256, 0, st>>>(A, lda, m, n, F, ldf);
+    QLB_LAUNCH_CHECK(h);
+    reverse_copy_kernel<<<flip_grid(h, n), 256, 0, st>>>(tau, n, taur);
+    QLB_LAUNCH_CHECK(h);
+    flip_rows_or_cols_kernel<<<flip_grid(h, (int64_t)m * nrhs / 2), 256, 0, st>>>(B, ldb, m, nrhs, 1);
+    QLB_LAUNCH_CHECK(h);
+    rc = qlb_dormql_dev(h, 'L', 'T', m, nrhs, n, F, ldf, taur, B, ldb, -1);
+    if (rc) return rc;
+    rc = qlb_trsm_lower_dev(h, n, nrhs, F + (m - n), ldf, B + (m - n), ldb, dinfo);
+    if (rc) return rc;
+    flip_rows_or_cols_kernel<<<flip_grid(h, (int64_t)m * nrhs / 2), 256, 0, st>>>(B, ldb, m, nrhs, 1);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
     const int m = (int)m64, n = (int)n64;
     if (m == 0 || n == 0) return 0;

@@ -882,6 +882,42 @@ int qlb200_dormqr(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
     return 0;
 }
 
+int qlb200_dqrsolve_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const double *dtau,
+                        double *dB, int64_t ldb) {
+    int rc = check_lstsq(h, m, n, nrhs, dA, lda, dtau, dB, ldb);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dqrsolve_dev(h, m, n, nrhs, dA, lda, dtau, dB, ldb, nullptr);
+}
+int qlb200_dqrsolve(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
+                    int64_t ldb) {
+    int rc = check_lstsq(h, m, n, nrhs, A, lda, tau, B, ldb);
+    if (rc) return rc;
+    if (n == 0 || nrhs == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA, *dB;
+    int64_t ldda;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, &dA, &ldda);
+    if (rc) return rc;
+    const int64_t lddb = ((m + 1) & ~(int64_t)1) < 2 ? 2 : ((m + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)lddb * nrhs + (size_t)n + 2) * sizeof(double));
+    if (rc) return rc;
+    dB = (double *)h->stage2;
+    double *dtau = dB + (size_t)lddb * nrhs;
+    QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)m * 8, (size_t)nrhs, cudaMemcpyHostToDevice,
+                                  h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb_dqrsolve_dev(h, m, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo);
+    if (rc) return rc;
+    rc = stage_out(h, B, m, nrhs, ldb, dB, lddb);
+    if (rc) return rc;
+    int32_t info = 0;
+    QLB_CUDA(h, cudaMemcpyAsync(&info, h->dinfo, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    // the zero was found on the diagonal of L = J R J: report R's index
+    return info == 0x7fffffff ? 0 : (int)(n + 1 - info);
+}
+
 /* ---- UL ------------------------------------------------------------------------------------------- */
 static int check_ul(qlb200_ctx *h, int64_t m, int64_t n, const double *A, int64_t lda, const int64_t *ipiv) {
     if (!h) return -1;

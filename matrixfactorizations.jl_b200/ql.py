@@ -255,6 +255,20 @@ def qr_(A, handle=None):
     return A, tau
 
 
+def qr_solve(factors, tau, b, handle=None):
+    r"""`QR(factors, tau) \ b` for m >= n (src/qr.jl:193-204): exact for square, least squares for tall.  Returns X (n x nrhs)."""
+    X = _copy_colmajor(b)
+    f, bm, t = _Mat(factors, "A(const)"), _Mat(X, "B"), _Mat(tau, "tau")
+    _same_kind(f, bm, t)
+    if f.m < f.n:
+        raise DimensionMismatch("qr_solve: m >= n only")
+    if bm.m != f.m:
+        raise DimensionMismatch("Both inputs should have the same number of rows")
+    h = _handle(handle, f)
+    h.call(f"qlb200_dqrsolve{f.sfx}", f.m, f.n, bm.n, f.ptr, f.ld, t.ptr, bm.ptr, bm.ld)
+    return X[: f.n]
+
+
 class QRPackedQ:
     """QR's packed orthogonal factor: reflector i below the diagonal of column i of `factors` (m x n), size (m, m)."""
 

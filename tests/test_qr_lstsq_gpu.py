@@ -118,3 +118,33 @@ def test_wide_solve_is_refused(q, h):
     F = q.ql(A, handle=h)
     with pytest.raises(q.DimensionMismatch):
         F.solve(np.ones(5))
+
+
+@pytest.mark.parametrize("shape,nrhs", [((10, 10), 1), ((64, 64), 3), ((300, 300), 4), ((40, 7), 2), ((1500, 400), 3)])
+def test_qr_solve_square_and_tall(q, h, shape, nrhs):
+    """`qrunblocked(A) \\ b` (src/qr.jl:193-204): exact solve / least squares through the flipped QL solve."""
+    m, n = shape
+    rng = np.random.default_rng(3 * m + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    b = np.asfortranarray(rng.standard_normal((m, nrhs)))
+    Fo, tauo = lapack.geqrf(A)
+    x = q.qr_solve(Fo, tauo, b, handle=h)
+    assert x.shape == (n, nrhs)
+    xo = np.linalg.lstsq(A, b, rcond=None)[0]
+    cond = np.linalg.cond(A)
+    assert np.abs(x - xo).max() <= 50 * m * EPS * cond * max(1.0, np.abs(xo).max())
+    if m == n:
+        assert np.abs(A @ x - b).max() <= 5000 * EPS * cond
+    # with our own QR factors too
+    F, tau = q.qr_(A.copy(order="F"), handle=h)
+    x2 = q.qr_solve(F, tau, b, handle=h)
+    assert np.abs(x2 - xo).max() <= 50 * m * EPS * cond * max(1.0, np.abs(xo).max())
+
+
+def test_qr_solve_singular_reports_r_index(q, h):
+    A = np.asfortranarray(np.random.default_rng(1).standard_normal((20, 20)))
+    Fo, tauo = lapack.geqrf(A)
+    Fo[7, 7] = 0.0
+    with pytest.raises(q.SingularException) as e:
+        q.qr_solve(Fo, tauo, np.ones((20, 1), order="F"), handle=h)
+    assert e.value.info == 8
