@@ -72,7 +72,8 @@ int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_tota
  * "overlap_t" (1: the panel's T is built on a side stream while W = C'V runs), "ul_cluster" (1: cluster strip kernel
  * for UL), "stream_in" (1: host-pointer ql! uploads the matrix in column chunks while the right-hand panels are already
  * being factored; "chunk_cols", "join_step" tune it), "bvar" (n = 32 batched kernel: 0 auto, 2 always one kernel, 3 always the two-phase split),
- * "batch_chunk_mb" (default 32; host-pointer batched calls run as an upload | compute | download pipeline over chunks of
+ * "pair_sync" (default 8; GEMMs with exactly two column tiles run each pair as a 2-CTA cluster that meets every this
+ * many k-tiles so that the shared operand is read from DRAM once, 0 = off), "batch_chunk_mb" (default 32; host-pointer batched calls run as an upload | compute | download pipeline over chunks of
  * about this many megabytes, 0 = one chunk). */
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
 

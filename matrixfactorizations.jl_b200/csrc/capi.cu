@@ -167,6 +167,10 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "chunk_cols")) {
         if (value < 128 || value % 128) return qlb_fail(h, -3, "chunk_cols must be a positive multiple of 128%s");
         h->opt_chunk_cols = value;
+    } else if (!strcmp(name, "pair_sync")) {
+        if (value < 0 || value > 1024) return qlb_fail(h, -3, "pair_sync must be in [0,1024]%s");
+        h->opt_pair_sync = value;
+        h->graph_key[0] = 0;                      // a captured graph holds the old launch shape
     } else if (!strcmp(name, "batch_chunk_mb")) {
         if (value < 0 || value > 4096) return qlb_fail(h, -3, "batch_chunk_mb must be in [0,4096]%s");
         h->opt_batch_chunk_mb = value;

@@ -71,6 +71,7 @@ struct qlb200_ctx {
     uint64_t tc_fp = 0;                    // host-side fingerprint of the factors the cache belongs to
     bool tc_fp_valid = false;
     int64_t opt_overlap_t = 1;             // build the panel's T on the side stream while W = C'V runs
+    int64_t opt_pair_sync = 8;             // GEMMs with exactly two N-tiles: cluster of the pair, barrier every this many k-tiles (0: off)
     int64_t opt_ul_cluster = 1;            // UL strips factored by the cluster kernel (0: single-CTA kernel)
     int64_t opt_bvar = 0;                  // batched kernel variant (benchmarking)
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM

@@ -31,6 +31,7 @@ struct GemmParams {
     double alpha, beta;
     int kchunk;               // K range handled by one blockIdx.z (multiple of BK unless splits == 1)
     int64_t split_stride;     // elements between the partial outputs of consecutive z
+    int pair_sync;            // > 0: the two N-tiles of an M-tile form a cluster and meet every pair_sync k-tiles (see launch_cfg)
 };
 
 template <int BM_, int BN_, int BK_, int WM_, int WN_, int STAGES_, int MINB_>
@@ -271,6 +272,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_kernel(const Gem
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
+        if (p.pair_sync > 0 && kt % p.pair_sync == 0) {
+            // both CTAs of the pair stream the SAME A tile: keeping them within pair_sync k-tiles of each other turns the
+            // second read into an L2 hit (without it the pair drifts apart and DRAM traffic is 1.8x the algorithmic bytes)
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+        }
         issue(kt + STAGES - 1);
         const double *As = stage_a(kt % STAGES), *Bs = stage_b(kt % STAGES);
 #pragma unroll
@@ -317,6 +323,25 @@ static int launch_cfg(qlb200_ctx *h, int slot, const GemmParams &p, int splits, 
         h->gemm_attr_done[slot] = true;
     }
     dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, splits);
+    const int kt_total = (p.kchunk + Cfg::BK - 1) / Cfg::BK;
+    if (h->opt_pair_sync > 0 && grid.y == 2 && kt_total >= 4 * h->opt_pair_sync) {
+        GemmParams q = p;
+        q.pair_sync = (int)h->opt_pair_sync;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+        cfg.dynamicSmemBytes = Cfg::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = 2;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        QLB_CUDA(h, cudaLaunchKernelEx(&cfg, kern, q));
+        return 0;
+    }
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
     QLB_LAUNCH_CHECK(h);
     return 0;
