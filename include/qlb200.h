@@ -115,8 +115,10 @@ int qlb200_dqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *
 
 /* ---- tall least squares, min ||A x - b||_2 for m >= n through the QL factors.  The reference's own
  * rectangular branch of materialize!(::Ldiv{<:QLPackedLayout}) (src/ql.jl:448-486) is wrong and @test_broken
- * (test/test_ql.jl:148); this is the corrected tall case: B (m x nrhs) <- Q'B, then rows m-n+1..m of B <- L^{-1} (those rows).
- * On return X = B[m-n+1:m, :] (n x nrhs) and B[1:m-n, :] holds the residual's coordinates (its norm is the residual norm).
+ * (test/test_ql.jl:148); this is the corrected tall case: B (m x nrhs) <- Q'B, rows m-n+1..m of it <- L^{-1} (those rows), and
+ * the rows are rotated so that on return X = B[1:n, :] (n x nrhs) -- the rows the reference's `\` cuts out of the buffer
+ * ldiv! worked on (src/ql.jl:496-501, _cut_B(X, 1:n)); LAPACK ?gels convention, same as qlb200_dqrsolve -- and B[n+1:m, :]
+ * holds the residual's coordinates (its norm is the residual norm).
  * Returns 0, -i, 1000+cudaError, or i > 0 when L[i,i] == 0.  The wide minimum-norm solve needs an LQ-type factorization and
  * is not offered. */
 int qlb200_dqllstsq(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda,

@@ -105,6 +105,9 @@ def fn(name: str):
     """The C entry point `name` with its argtypes set (bound on first use)."""
     f = _BOUND.get(name)
     if f is None:
+        if name not in SIGNATURES:        # e.g. a complex / Float32 variant this library does not provide
+            raise TypeError(f"{name}: no such entry point in libqlb200 (element type not supported for this operation; "
+                            "see include/qlb200.h)")
         f = getattr(lib(), name)          # AttributeError if the library does not export it
         f.argtypes = [c_void_p] + SIGNATURES[name]
         f.restype = c_int

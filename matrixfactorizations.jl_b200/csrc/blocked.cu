@@ -221,9 +221,49 @@ __global__ void __launch_bounds__(TB) trsm_diag_kernel(const double *__restrict_
 
 __global__ void set_int_kernel(int32_t *p, int32_t v) { *p = v; }
 
+// 64-bit checksum of packed factors: sum (mod 2^64) over every entry of V (nq x k, any lda) and tau of a bijective mix of
+// (bit pattern, position).  Any single modified entry changes the sum; the sum does not depend on lda, the addresses or
+// the order of the additions.  It ties the T-factor cache to the CONTENT of the factors ql! produced.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long w, unsigned long long pos) {
+    unsigned long long t = (w ^ (pos * 0x9E3779B97F4A7C15ull)) * 0xBF58476D1CE4E5B9ull;
+    t ^= t >> 31;
+    return t * 0x94D049BB133111EBull;
+}
+__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+__global__ void __launch_bounds__(256) checksum_kernel(const double *__restrict__ V, int64_t ldv, int nq, int k, const double *__restrict__ tau,
+                                                       unsigned long long *__restrict__ out) {
+    const int64_t total = (int64_t)nq * k + k;
+    unsigned long long acc = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        double v;
+        if (p < (int64_t)nq * k) {
+            const int64_t j = p / nq, i = p - j * nq;
+            v = V[i + j * ldv];
+        } else {
+            v = tau[p - (int64_t)nq * k];
+        }
+        acc += mix64((unsigned long long)__double_as_longlong(v), (unsigned long long)p);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(out, acc);
+}
+
 }  // namespace qlb
 
 using namespace qlb;
+
+static int factors_checksum(qlb200_ctx *h, cudaStream_t st, const double *V, int64_t ldv, int nq, int k, const double *tau,
+                            unsigned long long *out) {
+    set_u64_kernel<<<1, 1, 0, st>>>(out, 0x5851F42D4C957F2Dull ^ ((unsigned long long)nq << 32) ^ (unsigned long long)k);
+    QLB_LAUNCH_CHECK(h);
+    int64_t blocks = ((int64_t)nq * k + k + 2047) / 2048;
+    const int64_t cap = (int64_t)h->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    checksum_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(V, ldv, nq, k, tau, out);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
 
 // Factor one panel (columns [c0, c1) of A, rows [0, p)) on stream st: strips from the right, each
 // followed by its compact-WY update of the panel columns left of it; then the panel's T.
@@ -273,7 +313,6 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     auto panel_c0 = [&](int j) { int c = n - (j + 1) * nb; return c > n - k ? c : n - k; };
     // T-factor cache: panel j's T goes straight into slot j (and is then also built for the last panel)
     h->tc_valid = false;
-    h->tc_fp_valid = false;
     double *tcache = nullptr;
     if (h->opt_tcache && !la) {
         rc = qlb_reserve(h, &h->tcache, &h->tcache_bytes, (size_t)npanels * nb * nb * sizeof(double));
@@ -403,6 +442,13 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             h->tc_key[4] = k;
             h->tc_key[5] = nb;
             h->tc_valid = true;
+            if (h->opt_tcache == 1) {      // validated mode: the cache belongs to this CONTENT
+                rc = factors_checksum(h, st, A + (int64_t)(n - k) * lda, lda, m, k, tau, h->tc_sum_dev);
+                if (rc) return rc;
+            }
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+                QLB_CUDA(h, cudaEventRecord(h->ev_tc, st));      // (under capture the caller records it after the launch)
         }
         return 0;
     }
@@ -453,8 +499,24 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     int rc = get_workspace(h, nq, other, nb, max_w_splits(other), &ws);
     if (rc) return rc;
     bool cached = h->opt_tcache && h->tc_valid && h->tc_key[3] == nq && h->tc_key[4] == k && h->tc_key[5] == nb && cache_mode >= 0;
-    if (cached && cache_mode == 0)
+    if (cached && h->opt_tcache == 2)            // trusted mode: the pointers ql! factored
         cached = h->tc_key[0] == (int64_t)(uintptr_t)A && h->tc_key[1] == lda && h->tc_key[2] == (int64_t)(uintptr_t)tau;
+    if (cached && h->opt_tcache == 1) {          // validated mode: same content (checksum of every reflector entry and tau)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+            (void)cudaGetLastError();
+            cached = false;                      // no host round trip inside a capture: rebuild T
+        } else {
+            QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_tc, 0));
+            rc = factors_checksum(h, st, A, lda, nq, k, tau, h->tc_sum_dev + 1);
+            if (rc) return rc;
+            unsigned long long sums[2] = {0, 1};
+            QLB_CUDA(h, cudaMemcpyAsync(sums, h->tc_sum_dev, sizeof(sums), cudaMemcpyDeviceToHost, st));
+            QLB_CUDA(h, cudaStreamSynchronize(st));
+            cached = sums[0] == sums[1];
+        }
+    }
+    if (cached) QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_tc, 0));
     const double *tcache = cached ? (const double *)h->tcache : nullptr;
     const int nblk = (k + nb - 1) / nb;
     // Blocks are cut from the RIGHT like ql!'s panels (block j = reflectors [k-(j+1)nb, k-j nb)), so that cached T factors
@@ -598,6 +660,29 @@ static inline unsigned flip_grid(qlb200_ctx *h, int64_t work) {
     int64_t b = (work + 255) / 256;
     const int64_t cap = (int64_t)h->sm_count * 16;
     return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// B (m x n, ldb) <- rows rotated up by `shift`: new row i = old row (i + shift) mod m (through the second workspace)
+__global__ void rotate_rows_kernel(const double *__restrict__ B, int64_t ldb, int m, int n, int shift, double *__restrict__ out,
+                                   int64_t ldo) {
+    const int64_t total = (int64_t)m * n;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = p / m, i = p - j * m;
+        int64_t src = i + shift;
+        if (src >= m) src -= m;
+        out[i + j * ldo] = B[src + j * ldb];
+    }
+}
+int qlb_rotate_rows_dev(qlb200_ctx *h, int64_t m, int64_t n, double *B, int64_t ldb, int64_t shift) {
+    if (m == 0 || n == 0 || shift % m == 0) return 0;
+    const int64_t ldo = even_up(m);
+    int rc = qlb_reserve(h, &h->ws2, &h->ws2_bytes, (size_t)ldo * n * sizeof(double));
+    if (rc) return rc;
+    double *out = (double *)h->ws2;
+    rotate_rows_kernel<<<flip_grid(h, m * n), 256, 0, h->stream>>>(B, ldb, (int)m, (int)n, (int)(shift % m), out, ldo);
+    QLB_LAUNCH_CHECK(h);
+    QLB_CUDA(h, cudaMemcpy2DAsync(B, (size_t)ldb * 8, out, (size_t)ldo * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
 }
 
 // the two halves of geqrf around the QL factorization (capi.cu puts ql! -- graph replay included -- between them)

@@ -47,6 +47,8 @@ int qlb200_create(qlb200_handle *out, int device) {
     for (int i = 0; i < 8; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_panel[i], cudaEventDisableTiming));
     QLB_CUDA(h, cudaMalloc(&h->dinfo, 64 + 256 * sizeof(unsigned)));      // status word + per-SM tickets
     QLB_CUDA(h, cudaMemset(h->dinfo, 0, 64 + 256 * sizeof(unsigned)));
+    QLB_CUDA(h, cudaMalloc(&h->tc_sum_dev, 2 * sizeof(unsigned long long)));
+    QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_tc, cudaEventDisableTiming));
     h->stream = h->own_stream;
     *out = h;
     return 0;
@@ -61,6 +63,8 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->stage) cudaFree(h->stage);
     if (h->stage2) cudaFree(h->stage2);
     if (h->dinfo) cudaFree(h->dinfo);
+    if (h->tc_sum_dev) cudaFree(h->tc_sum_dev);
+    if (h->ev_tc) cudaEventDestroy(h->ev_tc);
     if (h->redo) cudaFree(h->redo);
     if (h->tall) cudaFree(h->tall);
     if (h->tcache) cudaFree(h->tcache);
@@ -154,9 +158,9 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         if (value < 0 || value > 8) return qlb_fail(h, -3, "trail_splits must be in [0,8]%s");
         h->opt_trail_splits = value;
     } else if (!strcmp(name, "tcache")) {
-        h->opt_tcache = value ? 1 : 0;
+        if (value < 0 || value > 2) return qlb_fail(h, -3, "tcache must be 0 (off), 1 (validated by checksum) or 2 (trusted: keyed on pointers)%s");
+        h->opt_tcache = value;
         h->tc_valid = false;
-        h->tc_fp_valid = false;
     } else if (!strcmp(name, "overlap_t")) {
         h->opt_overlap_t = value ? 1 : 0;
     } else if (!strcmp(name, "ul_cluster")) {
@@ -308,7 +312,13 @@ static int geqlf_batched_any(qlb200_ctx *h, bool host, int64_t n, T *A, int64_t 
         if (!rc) rc = geqlf_batched_dev<T>(h, n, dAc, lda, strideA, dTc, strideTau, mc);
         if (!rc) rc = pipeline_computed(h, c);
         if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(A + m0 * strideA, dAc, ea * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
-        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(tau + m0 * strideTau, dTc, et * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+        // tau was never uploaded: only the n entries of each matrix come back (a contiguous copy would overwrite the caller's
+        // gaps between the tau vectors, strideTau > n, with staging-buffer contents)
+        if (!rc) {
+            if (strideTau == n) rc = qlb_cuda(h, cudaMemcpyAsync(tau + m0 * strideTau, dTc, et * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+            else rc = qlb_cuda(h, cudaMemcpy2DAsync(tau + m0 * strideTau, (size_t)strideTau * sizeof(T), dTc, (size_t)strideTau * sizeof(T),
+                                                    (size_t)n * sizeof(T), (size_t)mc, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
     }
     return pipeline_end(h, rc);
 }
@@ -452,27 +462,6 @@ static int stage_out(qlb200_ctx *h, double *A, int64_t m, int64_t n, int64_t lda
 
 typedef int (*fact_fn)(qlb200_ctx *, int64_t, int64_t, double *, int64_t, double *);
 
-// Host-side fingerprint of packed QL factors (FNV-1a over tau, the dimensions and a sample of the reflector columns):
-// tells the host-pointer lmul!/ldiv! entry points whether the T cache on the device still belongs to these factors.
-static uint64_t factors_fingerprint(int64_t nq, int64_t k, const double *V, int64_t ldv, const double *tau) {
-    uint64_t hsh = 1469598103934665603ull;
-    auto mix = [&](const void *p, size_t bytes) {
-        const unsigned char *c = (const unsigned char *)p;
-        for (size_t i = 0; i < bytes; ++i) { hsh ^= c[i]; hsh *= 1099511628211ull; }
-    };
-    mix(&nq, sizeof(nq));
-    mix(&k, sizeof(k));
-    mix(tau, (size_t)k * sizeof(double));
-    const int64_t step = k > 64 ? k / 64 : 1;
-    for (int64_t j = 0; j < k; j += step) {                        // <= 64 sampled columns: head and diagonal neighbourhood
-        const double *col = V + j * ldv;
-        const int64_t mu = nq - k + j;                             // pivot row of reflector column j
-        mix(col, (size_t)(nq < 16 ? nq : 16) * sizeof(double));
-        mix(col + (mu >= 8 ? mu - 8 : 0), (size_t)(mu >= 8 ? 9 : mu + 1) * sizeof(double));
-    }
-    return hsh;
-}
-
 // ql! on device pointers, replayed as a CUDA graph when the same call comes again.  First sight of a key: plain launches
 // (workspace allocation and function attributes happen here).  Second sight: the launch sequence is captured on the
 // handle's stream and instantiated.  From then on: one cudaGraphLaunch.  Skipped while profiling, on the legacy default
@@ -499,7 +488,7 @@ static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int6
             h->tc_key[4] = k;
             h->tc_key[5] = h->opt_nb;
             h->tc_valid = true;
-            h->tc_fp_valid = false;
+            QLB_CUDA(h, cudaEventRecord(h->ev_tc, h->stream));
         }
         return 0;
     }
@@ -534,6 +523,7 @@ static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int6
     h->graph_nodes = h->launches - l0;
     memcpy(h->graph_key, key, sizeof(key));
     QLB_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    if (h->tc_valid) QLB_CUDA(h, cudaEventRecord(h->ev_tc, h->stream));
     return 0;
 }
 
@@ -587,10 +577,6 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
         if (rc) return rc;
         QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    }
-    if (f == geqlf_dev_graph && h->tc_valid) {      // ql!: remember which factors the device-side T cache belongs to
-        h->tc_fp = factors_fingerprint(m, k, A + (n - k) * lda, lda, tau);
-        h->tc_fp_valid = true;
     }
     return 0;
 }
@@ -649,10 +635,6 @@ int qlb200_dormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
     if (m == 0 || n == 0 || k == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
     const int64_t nq = (side == 'L' || side == 'l') ? m : n;
-    // the T cache survives the staging below only if nothing is reallocated; decide first whether it is ours
-    const bool fp_ok = h->opt_tcache && h->tc_valid && h->tc_fp_valid && h->tc_key[3] == nq && h->tc_key[4] == k &&
-                       factors_fingerprint(nq, k, A, lda, tau) == h->tc_fp;
-    const uint64_t fp_keep = h->tc_fp;
     double *dA, *dC;
     int64_t ldda, lddc;
     rc = stage_in(h, &h->stage, &h->stage_bytes, A, nq, k, lda, &dA, &ldda);
@@ -667,7 +649,7 @@ int qlb200_dormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
     QLB_CUDA(h, cudaMemcpy2DAsync(dC, (size_t)lddc * 8, C, (size_t)ldc * 8, (size_t)m * 8, (size_t)n, cudaMemcpyHostToDevice,
                                   h->stream));
     QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = qlb_dormql_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc, (fp_ok && h->tc_valid && h->tc_fp == fp_keep) ? 1 : -1);
+    rc = qlb_dormql_dev(h, side, trans, m, n, k, dA, ldda, dtau, dC, lddc, h->opt_tcache == 1 ? 0 : -1);      // the staged copy is validated by checksum (never by its address)
     if (rc) return rc;
     rc = stage_out(h, C, m, n, ldc, dC, lddc);
     if (rc) return rc;
@@ -701,9 +683,6 @@ int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, i
     if (rc) return rc;
     if (n == 0 || nrhs == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
-    const bool fp_ok = h->opt_tcache && h->tc_valid && h->tc_fp_valid && h->tc_key[3] == n && h->tc_key[4] == n &&
-                       factors_fingerprint(n, n, A, lda, tau) == h->tc_fp;
-    const uint64_t fp_keep = h->tc_fp;
     double *dA, *dB;
     int64_t ldda;
     rc = stage_in(h, &h->stage, &h->stage_bytes, A, n, n, lda, &dA, &ldda);
@@ -716,7 +695,7 @@ int qlb200_dqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const double *A, i
     QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)n * 8, (size_t)nrhs, cudaMemcpyHostToDevice,
                                   h->stream));
     QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = qlb_dqlsolve_dev(h, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo, (fp_ok && h->tc_valid && h->tc_fp == fp_keep) ? 1 : -1);
+    rc = qlb_dqlsolve_dev(h, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo, h->opt_tcache == 1 ? 0 : -1);
     if (rc) return rc;
     rc = stage_out(h, B, n, nrhs, ldb, dB, lddb);
     if (rc) return rc;
@@ -747,7 +726,11 @@ static int qllstsq_dev(qlb200_ctx *h, int64_t m, int64_t n, int64_t nrhs, const 
     if (n == 0 || nrhs == 0) return 0;
     int rc = qlb_dormql_dev(h, 'L', 'T', m, nrhs, n, dA, lda, dtau, dB, ldb, cache_mode);
     if (rc) return rc;
-    return qlb_trsm_lower_dev(h, (int)n, (int)nrhs, dA + (m - n), lda, dB + (m - n), ldb, dinfo);
+    rc = qlb_trsm_lower_dev(h, (int)n, (int)nrhs, dA + (m - n), lda, dB + (m - n), ldb, dinfo);
+    if (rc || m == n) return rc;
+    // The reference's `\` returns X[1:n, :] of the buffer ldiv! worked on (src/ql.jl:496-501, _cut_B(X, 1:n)), the ?gels
+    // convention: rotate every column so that the solution comes first and the residual's coordinates follow.
+    return qlb_rotate_rows_dev(h, m, nrhs, dB, ldb, m - n);
 }
 int qlb200_dqllstsq_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const double *dtau,
                         double *dB, int64_t ldb) {
@@ -774,7 +757,7 @@ int qlb200_dqllstsq(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const d
     QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)m * 8, (size_t)nrhs, cudaMemcpyHostToDevice,
                                   h->stream));
     QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = qllstsq_dev(h, m, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo, -1);
+    rc = qllstsq_dev(h, m, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo, h->opt_tcache == 1 ? 0 : -1);
     if (rc) return rc;
     rc = stage_out(h, B, m, nrhs, ldb, dB, lddb);
     if (rc) return rc;

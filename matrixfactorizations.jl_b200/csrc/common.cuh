@@ -60,16 +60,18 @@ struct qlb200_ctx {
     int64_t graph_seen_key[10] = {0};
     int64_t graph_nodes = 0;
     // T-factor cache: ql! keeps the nb x nb compact-WY T of every panel, so that lmul!/rmul!/ldiv! on the factors it just
-    // produced (same pointers, or -- for host-pointer calls -- same fingerprint of tau and sampled factors) do not rebuild
-    // them (SURVEY.md A.3 allows exactly this).  Contract for device-pointer callers: do not modify the factors between
-    // the calls, or set option "tcache" = 0.
+    // produced do not rebuild them (SURVEY.md A.3 allows exactly this).  Option "tcache": 1 (default) = VALIDATED: ql! leaves
+    // a 64-bit position-dependent checksum of ALL reflector columns and tau on the device; lmul!/rmul!/ldiv! recompute it for
+    // the factors they are given (one pass over V, 8 bytes read back) and use the cache only on a match -- factors edited in
+    // place, or other factors at the same addresses, rebuild T.  2 = TRUSTED (opt-in fast path): the cache is keyed on the
+    // pointers alone; the caller promises not to modify the factors between the calls.  0 = off.
     int64_t opt_tcache = 1;
     void *tcache = nullptr;
     size_t tcache_bytes = 0;
     bool tc_valid = false;
     int64_t tc_key[6] = {0};               // reflector pointer (first of the last k columns), lda, tau, m, k, nb
-    uint64_t tc_fp = 0;                    // host-side fingerprint of the factors the cache belongs to
-    bool tc_fp_valid = false;
+    unsigned long long *tc_sum_dev = nullptr;   // [0] checksum left by ql!, [1] checksum of the factors under validation
+    cudaEvent_t ev_tc = nullptr;           // recorded after ql! filled the cache (readers on other streams wait for it)
     int64_t opt_overlap_t = 1;             // build the panel's T on the side stream while W = C'V runs
     int64_t opt_pair_sync = 8;             // GEMMs with exactly two N-tiles: cluster of the pair, barrier every this many k-tiles (0: off)
     int64_t opt_ul_cluster = 1;            // UL strips factored by the cluster kernel (0: single-CTA kernel)
@@ -143,8 +145,7 @@ static inline int qlb_reserve(qlb200_ctx *h, void **buf, size_t *have, size_t ne
     }
     memset(h->graph_key, 0, sizeof(h->graph_key));
     memset(h->graph_seen_key, 0, sizeof(h->graph_seen_key));
-    h->tc_valid = false;
-    h->tc_fp_valid = false;
+    if (buf == &h->tcache) h->tc_valid = false;
     if (*buf) {
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
         QLB_CUDA(h, cudaFree(*buf));

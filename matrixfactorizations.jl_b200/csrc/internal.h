@@ -48,6 +48,7 @@ int qlb_qr_flip_in(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda);
 int qlb_qr_flip_out(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
 int qlb_dormqr_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
                    const double *tau, double *C, int64_t ldc);
+int qlb_rotate_rows_dev(qlb200_ctx *h, int64_t m, int64_t n, double *B, int64_t ldb, int64_t shift);
 int trsm_grid(qlb200_ctx *h, int nrhs);
 int qlb_trsm_lower_dev(qlb200_ctx *h, int n, int nrhs, const double *A, int64_t lda, double *B, int64_t ldb, int32_t *dinfo);
 int qlb_dormrq_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,

@@ -42,6 +42,14 @@ __device__ __forceinline__ void st_async_f64(const void *local_smem_ptr, const u
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(ra), "d"(v), "r"(rb)
                  : "memory");
 }
+// 8-byte load from the shared memory of CTA `cta` of the cluster (DSMEM).
+__device__ __forceinline__ double ld_dsmem_f64(const void *local_smem_ptr, uint32_t cta) {
+    uint32_t ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem_ptr)), "r"(cta));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok) {
@@ -82,10 +90,63 @@ struct StripSmem {
     double rowv[2][SB];                   // pivot row, sent by the owner CTA (st.async target)
     double totw[NW][SB];                  // cluster-wide totals, one private copy per warp
     uint64_t mbar[2];                     // transaction barriers guarding red[par]/rowv[par]
+    double sl_w[NW][SB];                  // ?larfg slow path (scaled norm, safmin loop): per-warp partials,
+    double sl_c[SB];                      //   this CTA's partials (read by every CTA of the cluster through DSMEM),
+    double sl_tot[SB];                    //   cluster-wide results
     double Gs[SB][SB + 1];                // v_j . v_c for the T recurrence (CTA 0)
     double Ts[SB][SB + 1];
     double taus[SB];
 };
+
+// Slow-path all-reduce of K <= SB values per thread over the whole cluster (sum, or max when MAX): warp shuffles ->
+// shared memory -> hardware cluster barrier -> DSMEM reads in a fixed order (bitwise identical in every CTA).  Results
+// in sm.sl_tot[0..K).  Must be called by every thread of every CTA of the cluster.  Only the rare ?larfg special cases
+// come here (squares that under/overflow, exact zero tails), so two cluster barriers per call are acceptable.
+template <int SB, int K, bool MAX>
+__device__ __noinline__ void cluster_allreduce_slow(const double (&v)[K], StripSmem<SB> &sm, const int tid, const uint32_t nc) {
+    constexpr int NW = STRIP_THREADS / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = v[k];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double u = __shfl_xor_sync(FULL, t, o);
+            t = MAX ? fmax(t, u) : t + u;
+        }
+        if (lane == 0) sm.sl_w[warp][k] = t;
+    }
+    __syncthreads();
+    if (tid < K) {
+        double t = sm.sl_w[0][tid];
+#pragma unroll
+        for (int w8 = 1; w8 < NW; ++w8) t = MAX ? fmax(t, sm.sl_w[w8][tid]) : t + sm.sl_w[w8][tid];
+        sm.sl_c[tid] = t;
+    }
+    cluster_sync_all();
+    if (tid < K) {
+        double t = ld_dsmem_f64(&sm.sl_c[tid], 0);
+        for (uint32_t c = 1; c < nc; ++c) {
+            const double u = ld_dsmem_f64(&sm.sl_c[tid], c);
+            t = MAX ? fmax(t, u) : t + u;
+        }
+        sm.sl_tot[tid] = t;
+    }
+    cluster_sync_all();          // every CTA has read sl_c (it may be rewritten now); sl_tot is visible to the whole CTA
+}
+
+__device__ __forceinline__ double dlapy2_dev(double x, double y) {
+    const double xa = fabs(x), ya = fabs(y);
+    const double w = fmax(xa, ya), z = fmin(xa, ya);
+    if (z == 0.0) return w;
+    const double q = z / w;
+    return w * sqrt(1.0 + q * q);
+}
+// ?larfg's range of plain squares: outside of it the norm is taken in scaled form (?nrm2 / ?lapy2) and |beta| < safmin
+// triggers LAPACK's rescaling loop.  safmin = dlamch('S') / dlamch('E') = 2^-969.
+constexpr double LARFG_SSQ_LO = 1e-280, LARFG_TOT_HI = 1e280;
+constexpr double LARFG_SAFMIN = 2.2250738585072014e-308 / 1.1102230246251565e-16;
 
 // One Householder step.  The register tile is kept ROTATED so that the pivot column always sits in
 // register column SB-1 (static register indices, one loop body for every step: the fully unrolled
@@ -182,11 +243,61 @@ __device__ __forceinline__ void strip_step(double (&a)[RPT][SB], const int (&rr)
     const double ssq = tot[P], alpha = sm.rowv[par][P];
     // ---- 5. ?larfg scalars ----------------------------------------------------------------------------
     double beta = alpha, tauc = 0.0, scale = 0.0;
-    if (ssq != 0.0) {
+    const bool plain = (ssq >= LARFG_SSQ_LO) && (fma(alpha, alpha, ssq) <= LARFG_TOT_HI);      // identical in every thread of the cluster
+    if (plain) {
         const double nrm = sqrt(fma(alpha, alpha, ssq));
         beta = -copysign(nrm, alpha);
         tauc = (beta - alpha) / beta;
         scale = 1.0 / (alpha - beta);
+    } else {
+        // LAPACK ?larfg, literally (what the reference reaches through LAPACK.geqlf!, src/ql.jl:72): the tail's norm in
+        // scaled form, beta by ?lapy2, the safmin rescaling loop.  The dot products with the other columns are redone with
+        // the tail scaled by its largest entry, so that neither the squares nor the products leave the exponent range.
+        double am[1] = {0.0};
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+            if (rr[i] < mu) am[0] = fmax(am[0], fabs(a[i][P]));
+        cluster_allreduce_slow<SB, 1, true>(am, sm, tid, nc);
+        const double amax = sm.sl_tot[0];
+        __syncthreads();                                   // sl_tot is rewritten by the next reduction
+        if (amax > 0.0) {                                  // (zero tail: H = I, tau = 0, beta = alpha -- the defaults)
+            double dv[SB];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) dv[j] = 0.0;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                x[i] = (rr[i] < mu) ? a[i][P] / amax : 0.0;
+#pragma unroll
+                for (int j = 0; j < SB; ++j) dv[j] = fma(x[i], (j == P) ? x[i] : a[i][j], dv[j]);
+            }
+            cluster_allreduce_slow<SB, SB, false>(dv, sm, tid, nc);
+            const double ssq_s = sm.sl_tot[P];             // sum of (x_i / amax)^2
+            double am_s = amax, al = alpha;
+            double xnorm = am_s * sqrt(ssq_s);
+            double be = -copysign(dlapy2_dev(al, xnorm), al);
+            int knt = 0;
+            if (fabs(be) < LARFG_SAFMIN) {
+                const double rsafmn = 1.0 / LARFG_SAFMIN;
+                do {
+                    ++knt;
+                    am_s *= rsafmn;
+                    be *= rsafmn;
+                    al *= rsafmn;
+                } while (fabs(be) < LARFG_SAFMIN && knt < 20);
+                xnorm = am_s * sqrt(ssq_s);
+                be = -copysign(dlapy2_dev(al, xnorm), al);
+            }
+            tauc = (be - al) / be;
+            const double f = am_s * (1.0 / (al - be));     // v_i = (x_i / amax) f,  |f| <= 1
+            for (int q = 0; q < knt; ++q) be *= LARFG_SAFMIN;
+            beta = be;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) x[i] *= f;       // x now holds the finished reflector tail
+            scale = 1.0;
+            if (lane < SB) tot[lane] = sm.sl_tot[lane] * f;      // v(tail) . a_j
+            __syncwarp();
+        }
+        __syncthreads();
     }
     // ---- 6. rank-1 update of the unfinished columns (q >= s); the pivot becomes v (tail) and beta, and
     //         the tile rotates by one register column ----------------------------------------------------
@@ -423,19 +534,34 @@ __global__ void extract_v_kernel(const double *__restrict__ F, int64_t ldf, int 
 constexpr int TALL_THREADS = 256;
 constexpr int TALL_SB = 16;
 
+// Partial sums of one block of rows, taken with the tail SCALED by the block's largest entry (amax_b, stored behind the
+// partials): part[b][j] = sum_i (x_i / amax_b) a_ij for the columns j < C still to be updated, part[b][C] = sum_i
+// (x_i / amax_b)^2.  Neither the squares nor the products can leave the exponent range (LAPACK ?nrm2 / ?larfg semantics
+// for matrices scaled far away from 1).
 __global__ void __launch_bounds__(TALL_THREADS) tall_dots_kernel(const double *__restrict__ A, int64_t lda, int mu, int C, int w,
                                                                  double *__restrict__ part, int rpb) {
     __shared__ double red[TALL_THREADS / 32][TALL_SB];
+    __shared__ double mx[TALL_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = blockIdx.x * rpb, r1 = min(r0 + rpb, mu);
+    double am = 0.0;
+    for (int r = r0 + tid; r < r1; r += TALL_THREADS) am = fmax(am, fabs(A[r + (int64_t)C * lda]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if (lane == 0) mx[warp] = am;
+    __syncthreads();
+    am = mx[0];
+    for (int q = 1; q < TALL_THREADS / 32; ++q) am = fmax(am, mx[q]);
     double d[TALL_SB];
 #pragma unroll
     for (int j = 0; j < TALL_SB; ++j) d[j] = 0.0;
-    for (int r = r0 + tid; r < r1; r += TALL_THREADS) {
-        const double x = A[r + (int64_t)C * lda];
+    if (am > 0.0) {
+        for (int r = r0 + tid; r < r1; r += TALL_THREADS) {
+            const double x = A[r + (int64_t)C * lda] / am;
 #pragma unroll
-        for (int j = 0; j < TALL_SB; ++j)
-            if (j <= C) d[j] = fma(x, A[r + (int64_t)j * lda], d[j]);      // the columns still to be updated, and x itself
+            for (int j = 0; j < TALL_SB; ++j)
+                if (j <= C) d[j] = fma(x, (j == C) ? x : A[r + (int64_t)j * lda], d[j]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < TALL_SB; ++j) {
@@ -450,6 +576,7 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_dots_kernel(const double *_
         part[(int64_t)blockIdx.x * TALL_SB + tid] = t;
         if (blockIdx.x == 0) part[(int64_t)gridDim.x * TALL_SB + tid] = (tid < w) ? A[mu + (int64_t)tid * lda] : 0.0;   // the pivot row
     }
+    if (tid == 0) part[(int64_t)(gridDim.x + 1) * TALL_SB + blockIdx.x] = am;
 }
 
 __global__ void __launch_bounds__(TALL_THREADS) tall_update_kernel(double *__restrict__ A, int64_t lda, int mu, int C, int w,
@@ -458,25 +585,49 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_update_kernel(double *__res
     __shared__ double tot[TALL_SB], rowv[TALL_SB], coef[TALL_SB], sc[2];
     const int tid = threadIdx.x;
     const int nblk = gridDim.x;
+    const double *amaxs = part + (int64_t)(nblk + 1) * TALL_SB;
     if (tid < TALL_SB) {
+        double amax = 0.0;
+        for (int b = 0; b < nblk; ++b) amax = fmax(amax, amaxs[b]);
         double t = 0.0;
-        for (int b = 0; b < nblk; ++b) t += part[(int64_t)b * TALL_SB + tid];
-        tot[tid] = t;
+        if (amax > 0.0) {
+            for (int b = 0; b < nblk; ++b) {
+                const double wb = amaxs[b] / amax;                    // <= 1
+                t += part[(int64_t)b * TALL_SB + tid] * (tid == C ? wb * wb : wb);
+            }
+        }
+        tot[tid] = t;                                                 // x . a_j / amax  (j < C),  |x|^2 / amax^2  (j == C)
         rowv[tid] = part[(int64_t)nblk * TALL_SB + tid];
+        if (tid == 0) sc[0] = amax;
     }
     __syncthreads();
     if (tid == 0) {
-        const double ssq = tot[C], alpha = rowv[C];
-        double beta = alpha, tauc = 0.0, scale = 0.0;
-        if (ssq != 0.0) {
-            const double nrm = sqrt(fma(alpha, alpha, ssq));
-            beta = -copysign(nrm, alpha);
-            tauc = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
+        // ?larfg (LAPACK, what src/ql.jl:72 runs): scaled norm, ?lapy2, safmin loop; v_i = (x_i / amax) f
+        const double amax = sc[0], alpha = rowv[C];
+        double beta = alpha, tauc = 0.0, f = 0.0;
+        if (amax > 0.0) {
+            double am_s = amax, al = alpha;
+            double xnorm = am_s * sqrt(tot[C]);
+            double be = -copysign(dlapy2_dev(al, xnorm), al);
+            int knt = 0;
+            if (fabs(be) < LARFG_SAFMIN) {
+                const double rsafmn = 1.0 / LARFG_SAFMIN;
+                do {
+                    ++knt;
+                    am_s *= rsafmn;
+                    be *= rsafmn;
+                    al *= rsafmn;
+                } while (fabs(be) < LARFG_SAFMIN && knt < 20);
+                xnorm = am_s * sqrt(tot[C]);
+                be = -copysign(dlapy2_dev(al, xnorm), al);
+            }
+            tauc = (be - al) / be;
+            f = am_s * (1.0 / (al - be));
+            for (int q = 0; q < knt; ++q) be *= LARFG_SAFMIN;
+            beta = be;
         }
-        sc[0] = scale;
-        sc[1] = beta;
-        for (int j = 0; j < TALL_SB; ++j) coef[j] = (j < C) ? -tauc * fma(tot[j], scale, rowv[j]) : 0.0;
+        sc[1] = f;
+        for (int j = 0; j < TALL_SB; ++j) coef[j] = (j < C) ? -tauc * fma(tot[j], f, rowv[j]) : 0.0;
         if (blockIdx.x == 0) {
             *tau_out = tauc;
             A[mu + (int64_t)C * lda] = beta;
@@ -485,11 +636,11 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_update_kernel(double *__res
         }
     }
     __syncthreads();
-    const double scale = sc[0];
+    const double amax = sc[0], f = sc[1];
     const int r0 = blockIdx.x * rpb;
     for (int r = r0 + tid; r < r0 + rpb && r < p; r += TALL_THREADS) {
         if (r < mu) {
-            const double v = A[r + (int64_t)C * lda] * scale;
+            const double v = (amax > 0.0) ? (A[r + (int64_t)C * lda] / amax) * f : 0.0;
             A[r + (int64_t)C * lda] = v;
             Vw[r + (int64_t)C * ldv] = v;
 #pragma unroll
@@ -505,9 +656,9 @@ static int strip_factor_tall(qlb200_ctx *h, cudaStream_t st, double *A, int64_t 
                              int p, double *T, int ldt) {
     const int rpb = 2048;
     const int nblk = (p + rpb - 1) / rpb;
-    int rc = qlb_reserve(h, &h->tall, &h->tall_bytes, ((size_t)(nblk + 1) * TALL_SB + 256 + 64) * sizeof(double));
+    int rc = qlb_reserve(h, &h->tall, &h->tall_bytes, ((size_t)(nblk + 1) * TALL_SB + nblk + 256 + 64) * sizeof(double));
     if (rc) return rc;
-    double *part = (double *)h->tall, *G = part + (size_t)(nblk + 1) * TALL_SB;
+    double *part = (double *)h->tall, *G = part + (size_t)(nblk + 1) * TALL_SB + ((nblk + 1) & ~1);
     for (int s = 0; s < w; ++s) {
         const int C = w - 1 - s, mu = ps - 1 - s;
         tall_dots_kernel<<<nblk, TALL_THREADS, 0, st>>>(A, lda, mu, C, w, part, rpb);

@@ -106,7 +106,7 @@ function materialize!(Ldv::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor},<:Abstra
                      (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
                      h.ptr, m, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
         chk(h, info; dims = (9,))
-        return B      # X = B[m-n+1:m, :]; B[1:m-n, :] = coordinates of the residual
+        return B      # X = B[1:n, :] (what `\` cuts out, src/ql.jl:501); B[n+1:m, :] = coordinates of the residual
     end
     m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # wide: keep the reference's own branch (src/ql.jl:448-486)
     size(B, 1) == n || throw(DimensionMismatch("arguments must have the same number of rows; has $n and $(size(B,1))"))

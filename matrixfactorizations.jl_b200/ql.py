@@ -80,6 +80,7 @@ class _Mat:
                 pass
             self.ptr, self.dev, self.device_index = x.ctypes.data, False, 0
         self.pfx = _pfx(x)
+        self.itemsize = 8 if self.pfx == "d" else 4
         self.obj = x
 
     @property
@@ -116,8 +117,16 @@ def _new_like(x, n):
 
 
 def _copy_colmajor(x):
+    """A fresh column-major copy (never an alias of x: `x.T.contiguous().T` returns x itself when x is already
+    column-major, which would turn ql(A) / F.solve(b) into their in-place forms -- reference src/ql.jl:179-186 copies)."""
     if _is_torch(x):
-        return x.T.contiguous().T if x.dim() == 2 else x.clone()
+        import torch
+
+        if x.dim() != 2:
+            return x.clone()
+        out = torch.empty_strided(tuple(x.shape), (1, max(1, x.shape[0])), dtype=x.dtype, device=x.device)
+        out.copy_(x)
+        return out
     return np.array(x, order="F", copy=True)
 
 
@@ -208,7 +217,7 @@ class QL:
         X = _copy_colmajor(b)
         ldiv_(self, X)
         m, n = self.factors.shape
-        return X if m == n else X[m - n:]        # tall: the least-squares solution
+        return X if m == n else X[:n]            # `_cut_B(X, 1:n)`, src/ql.jl:501 (tall: the least-squares solution)
 
 
 def ql_(A, handle=None) -> QL:
@@ -325,7 +334,7 @@ def _ormrq(side, Q: RQPackedQ, C):
     nq = c.m if side == "L" else c.n
     if nq != nA:
         raise DimensionMismatch(f"matrix A has dimensions ({mA},{nA}) but {'B' if side == 'L' else 'A'} has dimensions ({c.m}, {c.n})")
-    aptr = f.ptr + (mA - k) * 8           # first of the last k rows
+    aptr = f.ptr + (mA - k) * f.itemsize  # first of the last k rows
     h.call(f"qlb200_{f.pfx}ormrq{f.sfx}", side.encode(), (b"T" if Q.adjoint else b"N"), c.m, c.n, k, aptr, f.ld, t.ptr,
            c.ptr, c.ld)
     return C
@@ -450,7 +459,7 @@ def ldiv_(F: QL, B):
     if b.m != f.m:   # src/ql.jl:494
         raise DimensionMismatch(f"arguments must have the same number of rows; has {f.m} and {b.m}")
     h = _handle(F.handle, f)
-    if f.m > f.n:    # least squares; X = B[m-n:, :], B[:m-n, :] = residual coordinates
+    if f.m > f.n:    # least squares; X = B[:n, :] (src/ql.jl:501), B[n:, :] = residual coordinates
         if f.pfx != "d":
             raise TypeError("tall ldiv_: Float64 only")
         h.call(f"qlb200_dqllstsq{f.sfx}", f.m, f.n, b.n, f.ptr, f.ld, t.ptr, b.ptr, b.ld)
@@ -531,5 +540,9 @@ def ql_batched_mg_(A3, tau=None, handles=None):
     if tau is None:
         tau = np.empty((batch, n), dtype=A3.dtype)
     t = _Bat(tau, "tau")
+    if handles is None:              # one handle per visible device
+        import torch
+
+        handles = [default_handle(d) for d in range(max(1, torch.cuda.device_count()))]
     _lib.call_mg(list(handles), f"qlb200_{a.pfx}geqlf_batched_mg", n, a.ptr, n, n * n, t.ptr, n, batch)
     return A3, tau

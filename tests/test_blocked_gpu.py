@@ -318,3 +318,157 @@ def test_host_pointer_ql_streams_in_and_out(q, h, shape):
         b = np.asfortranarray(rng.standard_normal((n, 2)))
         x = F.solve(b)
         assert np.abs(A @ x - b).max() <= 5000 * EPS * np.linalg.cond(A)
+
+
+def _scaled_cmp(F, tau, Fo, tauo, A, k_rows_are_reflectors=False):
+    """Elementwise comparison that stays meaningful when columns of A live at very different scales: every entry of the
+    packed factors is compared relative to max(1, ...) of ITS column -- reflector entries are O(1), L entries carry the
+    column's own scale -- at the usual 50*n*eps."""
+    m, n = A.shape
+    assert np.isfinite(F).all() and np.isfinite(tau).all()
+    scale = np.maximum(np.abs(Fo).max(axis=1 if k_rows_are_reflectors else 0, keepdims=True), np.finfo(np.float64).tiny)
+    scale = np.maximum(scale, np.abs(F).max(axis=1 if k_rows_are_reflectors else 0, keepdims=True))
+    err = np.abs(F - Fo) / scale
+    assert err.max() <= 50 * max(m, n) * EPS, err.max()
+    assert np.abs(tau - tauo).max() <= 50 * max(m, n) * EPS
+
+
+@pytest.mark.parametrize("shape", [(40, 40), (300, 200), (200, 300), (700, 700)])
+@pytest.mark.parametrize("case", ["tiny", "huge", "tiny_col", "huge_col", "denormal_col", "mixed"])
+def test_geqlf_extreme_scales_follow_lapack_larfg(q, h, shape, case):
+    """LAPACK ?larfg (what src/ql.jl:72 runs) takes the norm in scaled form and rescales when |beta| < safmin: a matrix
+    scaled by 1e-170 / 1e170, or with single columns at 1e-200 / 1e200 / in the denormal range, must factor like LAPACK
+    (the blocked path's strip kernel falls to its scaled slow step whenever plain squares would leave the range)."""
+    m, n = shape
+    rng = np.random.default_rng(m * 13 + n + len(case))
+    A = np.asfortranarray(rng.standard_normal(shape))
+    if case == "tiny":
+        A *= 1e-170
+    elif case == "huge":
+        A *= 1e170
+    elif case == "tiny_col":
+        A[:, n // 3] *= 1e-200
+        A[:, n - 1] *= 1e-180
+    elif case == "huge_col":
+        A[:, n // 2] *= 1e200
+    elif case == "denormal_col":
+        A[:, n - 2] *= 1e-300
+        A[:, 1] *= 1e-305
+    else:
+        A[:, ::3] *= 1e-165
+        A[:, 1::3] *= 1e160
+    F = q.ql(A, handle=h)
+    Fo, tauo = lapack.geqlf(A)
+    _scaled_cmp(F.factors, F.tau, Fo, tauo, A)
+
+
+@pytest.mark.parametrize("case", ["tiny", "huge", "tiny_col"])
+def test_gerqf_geqrf_extreme_scales(q, h, case):
+    rng = np.random.default_rng(len(case))
+    A = np.asfortranarray(rng.standard_normal((150, 260)))
+    if case == "tiny":
+        A *= 1e-170
+    elif case == "huge":
+        A *= 1e170
+    else:
+        A[40, :] *= 1e-200          # a tiny ROW is what a tiny column is to QL for RQ
+    F, tau = q.rq_(A.copy(order="F"), handle=h)
+    Fo, tauo = lapack.gerqf(A)
+    _scaled_cmp(F, tau, Fo, tauo, A, k_rows_are_reflectors=True)
+    At = np.asfortranarray(A.T)
+    G, gt = q.qr_(At.copy(order="F"), handle=h)
+    Go, gto = lapack.geqrf(At)
+    _scaled_cmp(G, gt, Go, gto, At)
+
+
+def test_geqlf_tall_path_extreme_scales(q, h):
+    """m > 16384 (strips in global memory): the same ?larfg semantics."""
+    rng = np.random.default_rng(4)
+    A = np.asfortranarray(rng.standard_normal((17000, 24)))
+    A[:, 5] *= 1e-200
+    A[:, 20] *= 1e190
+    A[:, 11] = 0.0
+    F = q.ql(A, handle=h)
+    Fo, tauo = lapack.geqlf(A)
+    _scaled_cmp(F.factors, F.tau, Fo, tauo, A)
+    for s in (1e-170, 1e170):
+        B = np.asfortranarray(rng.standard_normal((16500, 8)) * s)
+        F = q.ql(B, handle=h)
+        Fo, tauo = lapack.geqlf(B)
+        _scaled_cmp(F.factors, F.tau, Fo, tauo, B)
+
+
+def test_public_entry_points_copy_column_major_device_input(q, h):
+    """reference src/ql.jl:179-186: ql(A) = ql!(copy(A)); F \\ b works on a copy of b.  A column-major CUDA tensor is
+    exactly the input whose `x.T.contiguous().T` is an alias of itself."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n = 96
+    A = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g).T        # column-major
+    b = torch.randn((3, n), dtype=torch.float64, device="cuda", generator=g).T
+    A0, b0 = A.clone(), b.clone()
+    F = q.ql(A, handle=h)
+    torch.cuda.synchronize()
+    assert F.factors.data_ptr() != A.data_ptr() and torch.equal(A, A0)
+    x = F.solve(b)
+    torch.cuda.synchronize()
+    assert x.data_ptr() != b.data_ptr() and torch.equal(b, b0)
+    assert (A0 @ x - b0).abs().max().item() <= 5000 * EPS * torch.linalg.cond(A0).item()
+    Fu = q.ul(A, handle=h)
+    torch.cuda.synchronize()
+    assert torch.equal(A, A0) and Fu.factors.data_ptr() != A.data_ptr()
+    xu = Fu.solve(b)
+    torch.cuda.synchronize()
+    assert torch.equal(b, b0) and (A0 @ xu - b0).abs().max().item() <= 5000 * EPS * torch.linalg.cond(A0).item()
+
+
+def test_t_cache_is_validated_by_content(q, h):
+    """The default T cache must never serve factors it does not belong to: (a) device factors edited IN PLACE in an entry
+    no sampled fingerprint would see, tau unchanged; (b) other factors written into the SAME buffers; (c) host factors
+    edited in place.  Each time lmul! must equal the answer computed with the cache switched off."""
+    import torch
+
+    n = 700
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g).T
+    A2 = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g).T
+    B = torch.randn((5, n), dtype=torch.float64, device="cuda", generator=g).T
+
+    def apply(F, cache):
+        h.set_option("tcache", cache)
+        try:
+            out = q.lmul_(F.Q.T, (B.T.clone()).T)
+            torch.cuda.synchronize()
+        finally:
+            h.set_option("tcache", 1)
+        return out
+
+    buf = (A.T.clone()).T
+    F = q.ql_(buf, handle=h)
+    torch.cuda.synchronize()
+    hit = apply(F, 1)
+    assert torch.equal(hit, apply(F, 0))
+    F = q.ql_(buf.copy_(A), handle=h)            # refactor (the off-run above dropped the cache)
+    F.factors[333, 555] += 0.25                  # (a) one reflector entry, tau untouched
+    torch.cuda.synchronize()
+    got = apply(F, 1)
+    assert torch.equal(got, apply(F, 0)) and not torch.equal(got, hit)
+    F = q.ql_(buf.copy_(A), handle=h)
+    h2 = q.Handle(0)
+    other = q.ql_((A2.T.clone()).T, handle=h2)               # factors of another matrix, made elsewhere ...
+    torch.cuda.synchronize()
+    h2.close()
+    F.factors.copy_(other.factors)                           # (b) ... land in the buffers the cache was keyed on
+    F.tau.copy_(other.tau)
+    torch.cuda.synchronize()
+    assert torch.equal(apply(F, 1), apply(F, 0))
+    # (c) host pointers
+    rng = np.random.default_rng(8)
+    Ah = np.asfortranarray(rng.standard_normal((n, n)))
+    Bh = np.asfortranarray(rng.standard_normal((n, 2)))
+    Fh = q.ql(Ah, handle=h)
+    Fh.factors[100, 400] -= 0.5
+    got = q.lmul_(Fh.Q.T, Bh.copy(order="F"))
+    ref = cport.lmul(Fh.factors, Fh.tau, Bh, adjoint=True)
+    assert np.abs(got - ref).max() <= 50 * n * EPS * np.abs(Bh).max() * np.sqrt(n)

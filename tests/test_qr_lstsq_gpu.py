@@ -104,11 +104,12 @@ def test_tall_least_squares(q, h, shape, nrhs):
     assert np.abs(x - xo).max() <= 50 * m * EPS * cond * max(1.0, np.abs(xo).max())
     r = A @ x - b
     assert np.abs(A.T @ r).max() <= 50 * m * EPS * np.linalg.norm(A) * max(np.linalg.norm(A) * np.abs(x).max(), np.abs(b).max()) * np.sqrt(m)
-    # in-place form: the leading m-n rows carry the residual's coordinates
+    # in-place form (what the reference's unchanged `\\` works on, src/ql.jl:496-501): the solution is B[1:n, :] -- the rows
+    # `_cut_B(X, 1:n)` returns -- and the trailing m-n rows carry the residual's coordinates
     B = b.copy(order="F")
     q.ldiv_(F, B)
-    assert np.allclose(np.linalg.norm(B[: m - n], axis=0), np.linalg.norm(r, axis=0), rtol=1e-9, atol=1e-12)
-    assert np.array_equal(B[m - n:], x)
+    assert np.allclose(np.linalg.norm(B[n:], axis=0), np.linalg.norm(r, axis=0), rtol=1e-9, atol=1e-12)
+    assert np.array_equal(B[:n], x)
     v = F.solve(b[:, 0].copy())
     assert v.shape == (n,) and np.array_equal(v, x[:, 0])
 
