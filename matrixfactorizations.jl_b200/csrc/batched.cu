@@ -908,7 +908,8 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     if (occ < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched QL kernel does not fit on an SM%s");
     const int64_t nwb = (batch + Cfg::G - 1) / Cfg::G;
     int64_t blocks = (nwb + WARPS - 1) / WARPS;
-    const int64_t cap = (int64_t)h->sm_count * occ;        // persistent: one resident wave
+    int64_t cap = (int64_t)h->sm_count * occ;              // persistent: one resident wave
+    if (h->opt_bgrid > 0 && cap > h->opt_bgrid) cap = h->opt_bgrid;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     // flagged matrices (under/overflowing squares) are collected here and redone by the generic kernel

@@ -184,6 +184,8 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->opt_graph = value ? 1 : 0;
     } else if (!strcmp(name, "bvar")) {
         h->opt_bvar = value;
+    } else if (!strcmp(name, "bgrid")) {
+        h->opt_bgrid = value < 0 ? 0 : value;
     } else if (!strcmp(name, "lookahead")) {
         h->opt_lookahead = value ? 1 : 0;
     } else if (!strcmp(name, "strip")) {

@@ -76,6 +76,7 @@ struct qlb200_ctx {
     int64_t opt_pair_sync = 8;             // GEMMs with exactly two N-tiles: cluster of the pair, barrier every this many k-tiles (0: off)
     int64_t opt_ul_cluster = 1;            // UL strips factored by the cluster kernel (0: single-CTA kernel)
     int64_t opt_bvar = 0;                  // batched kernel variant (benchmarking)
+    int64_t opt_bgrid = 0;                 // batched kernels: cap on the number of CTAs (0: one resident wave; benchmarking)
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM
     bool strip_attr_done[8] = {false};
     bool larft_attr_done = false, trsm_attr_done = false;
