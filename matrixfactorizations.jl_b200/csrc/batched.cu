@@ -24,6 +24,13 @@ template <> struct Vec16<float>  { using type = float4;  static constexpr int E 
 template <typename T> struct Lim;
 template <> struct Lim<double> { static constexpr double LO = 1e-280, HI = 1e280; };
 template <> struct Lim<float>  { static constexpr float  LO = 1e-24f, HI = 1e30f; };
+// ssq >= LO && tot <= HI for non-negative ssq, tot (NaN fails), as integer compares of the high words: the two DSETP
+// of the plain form sit on the FP64 pipe, which is the scarce unit of these kernels.
+__device__ __forceinline__ bool in_plain_range(double ssq, double tot) {
+    // 1e-280 = 0x05CD0B15'A491EB84 -> high word rounded UP (conservative); 1e280 = 0x7A11A0FC'668AAC70 -> rounded DOWN
+    return ((unsigned)__double2hiint(ssq) - 0x05CD0B16u <= 0x7FEFFFFFu - 0x05CD0B16u) && ((unsigned)__double2hiint(tot) <= 0x7A11A0FCu);
+}
+__device__ __forceinline__ bool in_plain_range(float ssq, float tot) { return (ssq >= Lim<float>::LO) && (tot <= Lim<float>::HI); }
 
 __device__ __forceinline__ double fast_rsqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ float  fast_rsqrt(float x)  { return rsqrtf(x); }
@@ -158,22 +165,27 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
     uint32_t stash_s[NS];                            // shared address of this lane's column of slot c in the image
 #pragma unroll
     for (int c = 0; c < NS; ++c) stash_s[c] = smem_u32(obuf + (jl + c * LPM) * PITCH);
+    // 1. the owner of the group's first pivot column publishes it (indices [LO, N): zeros, then the tail x, then the pivot).
+    //    Inside the group the NEXT owner publishes from within the update pass (predicated stores, no divergent branch on
+    //    the step's critical path: the branch + reconvergence cost ~150 cycles of every step, ncu source page).
+    if (jl == (N - 1 - LO) - OWN_SLOT * LPM) {
+        const uint32_t xa0 = xg_s + (uint32_t)((LO & 1) * XP * (int)sizeof(T));
+#pragma unroll
+        for (int v = V0; v < V1; ++v) {
+            V q;
+            T *qp = reinterpret_cast<T *>(&q);
+#pragma unroll
+            for (int e = 0; e < E; ++e) qp[e] = a[OWN_SLOT][v * E + e];
+            sts16_s(xa0 + (uint32_t)(v * 16), q);
+        }
+    }
 #pragma unroll 1
     for (int t = 0; t < nsteps; ++t) {
         const int s = LO + t, R = N - 1 - s;
         const int own_lane = R - OWN_SLOT * LPM;
         const uint32_t xa = xg_s + (uint32_t)((s & 1) * XP * (int)sizeof(T));
-        // 1. the owner publishes its column (indices [LO, N): zeros, then the tail x, then the pivot)
-        if (jl == own_lane) {
-#pragma unroll
-            for (int v = V0; v < V1; ++v) {
-                V q;
-                T *qp = reinterpret_cast<T *>(&q);
-#pragma unroll
-                for (int e = 0; e < E; ++e) qp[e] = a[OWN_SLOT][v * E + e];
-                sts16_s(xa + (uint32_t)(v * 16), q);
-            }
-        }
+        const uint32_t xn = xg_s + (uint32_t)(((s + 1) & 1) * XP * (int)sizeof(T));      // next step's buffer
+        const bool pub = (jl == own_lane - 1) && (t + 1 < nsteps);                         // this lane owns the next pivot column
         __syncwarp();
         // 2. d_c = sum_{i < P} x_i a[c][i]  (the owner's own column gives the tail's sum of squares)
         T d[NS][NCH];
@@ -217,7 +229,7 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
         const T tot = t_fma(alpha, alpha, ssq);
         // ?larfg's special exits (zero tail -> tau = 0; under/overflowing squares -> scaled norm and the
         // safmin loop) are not taken here: the matrix is flagged and redone by geql2_generic_kernel
-        bad = bad || !((ssq >= Lim<T>::LO) && (tot <= Lim<T>::HI));
+        bad = bad || !in_plain_range(ssq, tot);
         // 3. beta = -sign(alpha) ||[alpha;x]||, tau = (beta-alpha)/beta = 1 + |alpha|/||.||, scale = 1/(alpha-beta)
         const T rinv = nr_rsqrt(tot);
         const T nrm = tot * rinv;
@@ -255,9 +267,25 @@ __device__ __forceinline__ void ql_group(T (&a)[CPL][N], T (&myscale)[CPL], T *x
                     for (int c = 0; c < NS; ++c) a[c][i + 1] = t_fma(dc[c], qp[e], a[c][i]);
                 }
             }
+            // vector (V1 - w) of the shifted tile is final now (its lowest index was written by this w, the others by w - 1):
+            // the next owner publishes it
+            if (w >= 1 && pub) {
+                V q;
+                T *qq = reinterpret_cast<T *>(&q);
+#pragma unroll
+                for (int e = 0; e < E; ++e) qq[e] = a[OWN_SLOT][(V1 - w) * E + e];
+                sts16_s(xn + (uint32_t)((V1 - w) * 16), q);
+            }
         }
 #pragma unroll
         for (int c = 0; c < NS; ++c) a[c][LO] = T(0);
+        if (pub) {      // the lowest vector: index LO is the zero that was just shifted in
+            V q;
+            T *qq = reinterpret_cast<T *>(&q);
+#pragma unroll
+            for (int e = 0; e < E; ++e) qq[e] = a[OWN_SLOT][V0 * E + e];
+            sts16_s(xn + (uint32_t)(V0 * 16), q);
+        }
     }
 }
 
@@ -325,15 +353,21 @@ struct GroupLoop {
     }
 };
 
+template <typename T>
+__device__ __noinline__ void geql2_warp(T *__restrict__ Am, int64_t lda, T *__restrict__ taum, int n, T *S, int lane);
+
 // One warp factors G = 32/LPM matrices at a time: TMA (or plain loads) -> shared-memory image ->
 // registers -> factor (finished rows go back into the image) -> TMA bulk stores (or plain stores).
-// STOP > 0: phase A only (see GroupLoop); flags[mi] = 1 marks the matrices it had to leave to the generic kernel.
-// skip != null: matrices with skip[mi] != 0 are not touched (phase B after a phase A that flagged them).
+// A matrix whose squares leave the plain range (flagged, rare) is left untouched in global memory by the register path and
+// factored right away by the same warp with the literal ?geql2 / ?larfg routine (geql2_warp) -- one launch per call, no
+// redo list, no counter to clear.
+// STOP > 0: phase A only (see GroupLoop); flags[mi] (written for EVERY matrix) = 1 marks the matrices that were flagged
+// and therefore factored completely here.  skip != null: matrices with skip[mi] != 0 are not touched (phase B).
 template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA, int PD = 4, int STOP = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A, int64_t lda, int64_t strideA,
-                     T *__restrict__ tau, int64_t strideTau, int64_t batch, int *__restrict__ redo_count,
-                     int *__restrict__ redo_list, int *__restrict__ flags, const int *__restrict__ skip) {
+                     T *__restrict__ tau, int64_t strideTau, int64_t batch, int *__restrict__ flags,
+                     const int *__restrict__ skip) {
     using Cfg = BatchedCfg<T, N, CPL>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, PITCH = Cfg::PITCH;
@@ -398,11 +432,9 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
         bool bad = false;
         GroupLoop<T, N, CPL, 0, PD, STOP>::run(a, myscale, xg, obuf, jl, bad);
 
-        // flagged matrices stay untouched in global memory and are redone by the generic kernel
-        if (valid && bad && jl == 0) {
-            redo_list[atomicAdd(redo_count, 1)] = mi;
-            if (flags != nullptr) flags[mi] = 1;
-        }
+        // flagged matrices stay untouched in global memory (no tau, no store) and are redone below
+        if (flags != nullptr && valid && jl == 0) flags[mi] = bad ? 1 : 0;
+        const unsigned redo = __ballot_sync(0xffffffffu, valid && bad && jl == 0);
         __syncwarp();
         if (valid && !bad) {                                      // tau: one coalesced row per matrix
 #pragma unroll
@@ -423,6 +455,15 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
                 T *Am = A + (int64_t)mi * strideA;
                 for (int idx = jl; idx < N * N; idx += LPM) Am[(int64_t)(idx / N) * lda + (idx % N)] = obuf[(idx / N) * PITCH + (idx % N)];
             }
+            __syncwarp();
+        }
+        if (redo) {      // warp-uniform and rare: the images have been read by the stores above, the buffer is free scratch
+            static_assert(Cfg::BUF_BYTES >= ((N + 1) * N + N) * (int)sizeof(T), "the warp's image area holds the generic routine's scratch");
+            for (unsigned rm = redo; rm; rm &= rm - 1) {
+                const int gi = (__ffs(rm) - 1) / LPM;
+                geql2_warp<T>(A + (int64_t)(m0 + gi) * strideA, lda, tau + (int64_t)(m0 + gi) * strideTau, N, buf, lane);
+            }
+            if constexpr (USE_TMA) fence_proxy_async();      // generic-proxy writes to the buffer before the next bulk load into it
             __syncwarp();
         }
     }
@@ -466,67 +507,68 @@ __device__ __forceinline__ T t_lapy2(T x, T y) {
     return w * sqrt(T(1) + q * q);
 }
 
-template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) geql2_generic_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restrict__ tau,
-                                                                  int64_t strideTau, int n, const int *__restrict__ count_ptr,
-                                                                  int64_t count_val, const int *__restrict__ list) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One warp factors one n x n matrix (column-major, leading dimension lda) in place, through the shared-memory scratch S
+// ((n + 1) * n + n elements): LAPACK ?geql2 / ?larfg literally.
+template <typename T>
+__device__ __noinline__ void geql2_warp(T *__restrict__ Am, int64_t lda, T *__restrict__ taum, int n, T *S, int lane) {
     const int P = n + 1;                                     // column pitch
-    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)warp * (P * n + n);
     T *taus = S + P * n;
-    const int64_t count = list ? (int64_t)*count_ptr : count_val;
-    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
     const T safmin = LarfgConst<T>::safmin(), rsafmn = T(1) / safmin;
-    for (int64_t it = gw; it < count; it += nw) {
-        const int64_t mi = list ? (int64_t)list[it] : it;
-        T *Am = A + mi * strideA;
-        for (int idx = lane; idx < n * n; idx += 32) S[(idx / n) * P + (idx % n)] = Am[(int64_t)(idx / n) * lda + (idx % n)];
-        __syncwarp();
-        for (int k = n - 1; k >= 0; --k) {
-            T *x = S + k * P;                                // column k: tail rows 0..k-1, pivot row k
-            T tk = T(0);
-            T xnorm = (k > 0) ? warp_nrm2<T>(x, k, lane) : T(0);
-            if (xnorm != T(0)) {
-                T alpha = x[k];
-                T beta = -t_copysign(t_lapy2(alpha, xnorm), alpha);
-                int knt = 0;
-                if (t_abs(beta) < safmin) {
-                    do {
-                        ++knt;
-                        __syncwarp();
-                        for (int i = lane; i < k; i += 32) x[i] *= rsafmn;
-                        beta *= rsafmn;
-                        alpha *= rsafmn;
-                    } while (t_abs(beta) < safmin && knt < 20);
+    for (int idx = lane; idx < n * n; idx += 32) S[(idx / n) * P + (idx % n)] = Am[(int64_t)(idx / n) * lda + (idx % n)];
+    __syncwarp();
+    for (int k = n - 1; k >= 0; --k) {
+        T *x = S + k * P;                                // column k: tail rows 0..k-1, pivot row k
+        T tk = T(0);
+        T xnorm = (k > 0) ? warp_nrm2<T>(x, k, lane) : T(0);
+        if (xnorm != T(0)) {
+            T alpha = x[k];
+            T beta = -t_copysign(t_lapy2(alpha, xnorm), alpha);
+            int knt = 0;
+            if (t_abs(beta) < safmin) {
+                do {
+                    ++knt;
                     __syncwarp();
-                    xnorm = warp_nrm2<T>(x, k, lane);
-                    beta = -t_copysign(t_lapy2(alpha, xnorm), alpha);
-                }
-                tk = (beta - alpha) / beta;
-                const T sc = T(1) / (alpha - beta);
+                    for (int i = lane; i < k; i += 32) x[i] *= rsafmn;
+                    beta *= rsafmn;
+                    alpha *= rsafmn;
+                } while (t_abs(beta) < safmin && knt < 20);
                 __syncwarp();
-                for (int i = lane; i < k; i += 32) x[i] *= sc;
-                for (int j = 0; j < knt; ++j) beta *= safmin;
-                __syncwarp();
-                if (lane == 0) x[k] = beta;
-                // apply H = I - tau v v' (v = [x(0:k-1); 1]) to columns j < k, one column per lane
-                for (int j = lane; j < k; j += 32) {
-                    T *c = S + j * P;
-                    T w = c[k];
-                    for (int i = 0; i < k; ++i) w = t_fma(x[i], c[i], w);
-                    w *= tk;
-                    c[k] -= w;
-                    for (int i = 0; i < k; ++i) c[i] = t_fma(-w, x[i], c[i]);
-                }
+                xnorm = warp_nrm2<T>(x, k, lane);
+                beta = -t_copysign(t_lapy2(alpha, xnorm), alpha);
             }
-            if (lane == 0) taus[k] = tk;
+            tk = (beta - alpha) / beta;
+            const T sc = T(1) / (alpha - beta);
             __syncwarp();
+            for (int i = lane; i < k; i += 32) x[i] *= sc;
+            for (int j = 0; j < knt; ++j) beta *= safmin;
+            __syncwarp();
+            if (lane == 0) x[k] = beta;
+            // apply H = I - tau v v' (v = [x(0:k-1); 1]) to columns j < k, one column per lane
+            for (int j = lane; j < k; j += 32) {
+                T *c = S + j * P;
+                T w = c[k];
+                for (int i = 0; i < k; ++i) w = t_fma(x[i], c[i], w);
+                w *= tk;
+                c[k] -= w;
+                for (int i = 0; i < k; ++i) c[i] = t_fma(-w, x[i], c[i]);
+            }
         }
-        for (int idx = lane; idx < n * n; idx += 32) Am[(int64_t)(idx / n) * lda + (idx % n)] = S[(idx / n) * P + (idx % n)];
-        for (int i = lane; i < n; i += 32) tau[mi * strideTau + i] = taus[i];
+        if (lane == 0) taus[k] = tk;
         __syncwarp();
     }
+    for (int idx = lane; idx < n * n; idx += 32) Am[(int64_t)(idx / n) * lda + (idx % n)] = S[(idx / n) * P + (idx % n)];
+    for (int i = lane; i < n; i += 32) taum[i] = taus[i];
+    __syncwarp();
+}
+
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) geql2_generic_kernel(T *__restrict__ A, int64_t lda, int64_t strideA, T *__restrict__ tau,
+                                                                  int64_t strideTau, int n, int64_t count) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)warp * ((n + 1) * n + n);
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+    for (int64_t mi = gw; mi < count; mi += nw) geql2_warp<T>(A + mi * strideA, lda, tau + mi * strideTau, n, S, lane);
 }
 
 // Dynamic shared memory attribute + resident blocks per SM of a batched kernel.  Both cost several microseconds of host
@@ -557,19 +599,18 @@ static int kernel_ready(qlb200_ctx *h, K kern, int threads, size_t smem, int *oc
 }
 
 template <typename T>
-static int launch_geql2_generic(qlb200_ctx *h, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau, int n,
-                                const int *count_ptr, int64_t count_val, const int *list) {
+static int launch_geql2_generic(qlb200_ctx *h, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau, int n, int64_t count) {
     constexpr int WARPS = 4;
     const size_t smem = (size_t)WARPS * ((size_t)(n + 1) * n + n) * sizeof(T);
     auto kern = geql2_generic_kernel<T, WARPS>;
     int occ_unused = 0;
     int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ_unused);
     if (rcs) return rcs;
-    int64_t blocks = list ? (int64_t)h->sm_count : (count_val + WARPS - 1) / WARPS;
+    int64_t blocks = (count + WARPS - 1) / WARPS;
     const int64_t cap = (int64_t)h->sm_count * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, n, count_ptr, count_val, list);
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(A, lda, strideA, tau, strideTau, n, count);
     QLB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -912,16 +953,10 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     if (h->opt_bgrid > 0 && cap > h->opt_bgrid) cap = h->opt_bgrid;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    // flagged matrices (under/overflowing squares) are collected here and redone by the generic kernel
     if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
-    int rc = qlb_reserve(h, &h->redo, &h->redo_bytes, ((size_t)batch + 4) * sizeof(int));
-    if (rc) return rc;
-    int *redo_count = (int *)h->redo, *redo_list = redo_count + 4;
-    QLB_CUDA(h, cudaMemsetAsync(redo_count, 0, sizeof(int), h->stream));
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, redo_count, redo_list, nullptr,
-                                                           nullptr);
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, nullptr, nullptr);      // ONE launch
     QLB_LAUNCH_CHECK(h);
-    return launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, N, redo_count, 0, redo_list);
+    return 0;
 }
 
 // n = 32 in two kernels: phase A (R = 31 ... 16) with the 32 x 32 register tile, then the live 16 x 16 leading block is
@@ -953,18 +988,15 @@ static int launch_geqlf_batched_split32(qlb200_ctx *h, T *A, int64_t lda, int64_
         if (blocks > cap) blocks = cap;
         return (unsigned)(blocks < 1 ? 1 : blocks);
     };
-    // [count A, count B, -, -][flags][list A][list B]: counts and flags are cleared by one memset
-    int rc = qlb_reserve(h, &h->redo, &h->redo_bytes, ((size_t)3 * batch + 4) * sizeof(int));
+    // flags[mi]: written by phase A for every matrix (1 = flagged and already factored completely there), read by phase B
+    int rc = qlb_reserve(h, &h->redo, &h->redo_bytes, (size_t)batch * sizeof(int));
     if (rc) return rc;
-    int *cntA = (int *)h->redo, *cntB = cntA + 1, *flags = cntA + 4, *listA = flags + batch, *listB = listA + batch;
-    QLB_CUDA(h, cudaMemsetAsync(cntA, 0, ((size_t)batch + 4) * sizeof(int), h->stream));
-    kA<<<grid(CfgA::G, occA), WARPS * 32, smA, h->stream>>>(tmA, A, lda, strideA, tau, strideTau, batch, cntA, listA, flags, nullptr);
+    int *flags = (int *)h->redo;
+    kA<<<grid(CfgA::G, occA), WARPS * 32, smA, h->stream>>>(tmA, A, lda, strideA, tau, strideTau, batch, flags, nullptr);
     QLB_LAUNCH_CHECK(h);
-    rc = launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, 32, cntA, 0, listA);
-    if (rc) return rc;
-    kB<<<grid(CfgB::G, occB), WARPS * 32, smB, h->stream>>>(tmB, A, lda, strideA, tau, strideTau, batch, cntB, listB, nullptr, flags);
+    kB<<<grid(CfgB::G, occB), WARPS * 32, smB, h->stream>>>(tmB, A, lda, strideA, tau, strideTau, batch, nullptr, flags);
     QLB_LAUNCH_CHECK(h);
-    return launch_geql2_generic<T>(h, A, lda, strideA, tau, strideTau, 16, cntB, 0, listB);
+    return 0;
 }
 
 template <typename T, int N, int NR, int MODE>
@@ -1150,7 +1182,7 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
                 return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched_split32<double, 4, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
-    if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
+    if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }
 int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
@@ -1162,7 +1194,7 @@ int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64
             if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched_split32<float, 4, 3, 5>(h, A, lda, strideA, tau, strideTau, batch);
     }
-    if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, nullptr, batch, nullptr);
+    if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }
 // mode 0: Q*B, 1: Q'*B, 2: L^{-1} Q' B
