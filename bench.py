@@ -93,25 +93,29 @@ def run_reference(args, rank, world):
 
     cores = os.cpu_count() or 1
     lapack.set_num_threads(cores)
-    n = 8192 if cores >= 8 else 4096           # bounded sample of the 16384 workload (same routine, same shape family)
+    n = args.n                                  # the SAME configuration as the GPU arm: n = 16384 (about 30 s per step on 16 cores)
     rng = np.random.default_rng(1234321)
     A0 = np.asfortranarray(rng.standard_normal((n, n)))
     A = np.empty_like(A0)
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        A[...] = A0
-        lapack.geqlf(A, inplace=True)
+    lapack.geqlf(np.asfortranarray(A0[:2048, :2048]).copy(order="F"), inplace=True)      # warm the thread pool (a full warm-up step costs 30 s)
     ts = []
+    budget = float(os.environ.get("QLB200_REF_BUDGET_S", "600"))      # the whole arm must end within minutes: stop taking steps past this
+    t_begin = time.perf_counter()
     for _ in range(args.steps):
         A[...] = A0
         t0 = time.perf_counter()
         lapack.geqlf(A, inplace=True)
         ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin + ts[-1] > budget:
+            break
     t = sum(ts) / len(ts)
     val = flops_ql(n) / t / 1e9
-    sample = f"dgeqlf (scipy-openblas {lapack.get_num_threads()} threads) on randn {n}x{n}; 4/3*n^3 flops / time"
+    sample = (f"dgeqlf (scipy-openblas {lapack.get_num_threads()} threads; the routine ql! calls, src/ql.jl:72) on randn {n}x{n}, "
+              f"{len(ts)} step(s) of {t:.1f} s; 4/3*n^3 flops / time")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": f"ql! Float64 n={N_BIG} square (CPU arm: bounded sample n={n})"},
+            "steps_timed": len(ts), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"ql! Float64 n={n} square (configs[1]); copy + in-place blocked QL per step, input resident in host memory"},
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -123,7 +127,7 @@ def cpu_baseline():
 
     cores = os.cpu_count() or 1
     lapack.set_num_threads(cores)
-    n = 8192 if cores >= 8 else 4096
+    n = N_BIG if cores >= 8 else 8192           # the workload itself (one dgeqlf of 16384 x 16384 is ~30 s on 16 cores)
     A = np.asfortranarray(np.random.default_rng(7).standard_normal((n, n)))
     lapack.geqlf(A[:1024, :1024].copy(order="F"))
     t0 = time.perf_counter()
@@ -142,6 +146,19 @@ def cpu_baseline():
     lapack.set_num_threads(cores)
     out["batched"] = {"value": nb / tb, "unit": "matrices/s", "cores": 1,
                       "sample": f"loop of dgeqlf over {nb} 32x32 matrices, 1 thread, {tb:.2f} s"}
+    # configs[0]: ql(randn(1024,1024)) + F \\ b the way the reference computes it: dgeqlf (all threads) + the scalar loops of
+    # src/ql.jl:350-377,440-447,467 (single thread, C restatement)
+    from oracle import cport
+
+    A1 = np.asfortranarray(np.random.default_rng(9).standard_normal((1024, 1024)))
+    b1 = np.asfortranarray(np.random.default_rng(10).standard_normal((1024, 1)))
+    t0 = time.perf_counter()
+    F1, tau1 = lapack.geqlf(A1)
+    t1 = time.perf_counter()
+    cport.ldiv(F1, tau1, b1)
+    t2 = time.perf_counter()
+    out["ql_1024_plus_solve"] = {"ql_ms": (t1 - t0) * 1e3, "solve_ms": (t2 - t1) * 1e3, "cores": cores,
+                                 "sample": "dgeqlf 1024x1024 (all threads) + the reference's scalar lmul!/ldiv! loops (1 thread)"}
     return out
 
 
@@ -423,10 +440,82 @@ def main():
         extras["rq_65536x1024_f64"] = {"value": fl_r / t_r / 1e9, "unit": "GFLOP/s", "ms": t_r * 1e3,
                                         "flops": "2 n^2 (m - n/3), gerqf(A) = geqlf(A')'", "frac_of_dgemm_peak": fl_r / t_r / 1e12 / peak_tflops}
         del Ar, Arw, tr_
+        # configs[3], UL half: ul! of a square 16384 x 16384 matrix, and of the tall-skinny 65536 x 1024 one -- for which the
+        # reference's loop (src/ul.jl:155-191, k = min(m,n) ... 1 over rows/cols 1:k) factors only the top 1024 x 1024 block and
+        # never reads the other rows (degenerate): both lines are stated for what they are
+        for (mu_, nu_, tag) in ((16384, 16384, "ul_16384x16384_f64"), (65536, 1024, "ul_65536x1024_f64_degenerate_top_block")):
+            Au = torch.randn((nu_, mu_), dtype=torch.float64, device="cuda", generator=gB).T
+            Auw = torch.empty((nu_, mu_), dtype=torch.float64, device="cuda").T
+            ipv = torch.zeros(min(mu_, nu_), dtype=torch.int64, device="cuda")
+            dinf = torch.zeros(1, dtype=torch.int32, device="cuda")
+            ts = []
+            for i in range(3):
+                Auw.T.copy_(Au.T)
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                h.call("qlb200_dulfact_dev", mu_, nu_, Auw.data_ptr(), Auw.stride(1), ipv.data_ptr(), 1, dinf.data_ptr())
+                b1.record()
+                torch.cuda.synchronize()
+                if i:
+                    ts.append(b0.elapsed_time(b1) * 1e-3)
+            t_u = min(ts)
+            ku = min(mu_, nu_)
+            fl_u = 2.0 / 3.0 * ku ** 3
+            extras[tag] = {"value": fl_u / t_u / 1e9, "unit": "GFLOP/s", "ms": t_u * 1e3, "flops": "2/3 k^3, k = min(m,n)",
+                           "frac_of_dgemm_peak": fl_u / t_u / 1e12 / peak_tflops}
+            del Au, Auw, ipv, dinf
+        # configs[0]: ql(randn(1024,1024)) + F \\ b -- device-resident (copy + ql! + ldiv!) and through the host API
+        n1 = 1024
+        A1 = torch.randn((n1, n1), dtype=torch.float64, device="cuda", generator=gB).T
+        A1w = torch.empty((n1, n1), dtype=torch.float64, device="cuda").T
+        b1v = torch.randn((1, n1), dtype=torch.float64, device="cuda", generator=gB).T
+        b1w = torch.empty((1, n1), dtype=torch.float64, device="cuda").T
+        tq, tsv = [], []
+        for i in range(6):
+            A1w.T.copy_(A1.T)
+            b1w.T.copy_(b1v.T)
+            c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            c0.record()
+            F1 = q.ql_(A1w, handle=h)
+            c1.record()
+            q.ldiv_(F1, b1w)
+            c2.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                tq.append(c0.elapsed_time(c1) * 1e-3)
+                tsv.append(c1.elapsed_time(c2) * 1e-3)
+        res1 = float((A1 @ b1w - b1v).abs().max().item())
+        A1h = np.asfortranarray(A1.cpu().numpy())
+        b1h = np.asfortranarray(b1v.cpu().numpy())
+        th = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            Fh = q.ql(A1h, handle=h)
+            xh = Fh.solve(b1h)
+            th.append(time.perf_counter() - t0)
+        extras["ql_1024_plus_solve_f64"] = {"ql_ms": min(tq) * 1e3, "solve_ms": min(tsv) * 1e3, "value": flops_ql(n1) / min(tq) / 1e9,
+                                            "unit": "GFLOP/s (ql! alone, 4/3 n^3)", "host_api_ql_plus_solve_ms": min(th[1:]) * 1e3,
+                                            "max_abs_residual": res1,
+                                            "note": "latency-bound on a GPU: 1024 dependent reflector steps (SURVEY.md 8(d)); parity anchor, not a throughput target"}
+        del A1, A1w, b1v, b1w
+    # the batched sizes without a register kernel (generic shared-memory kernels): n = 24, 48, 64 Float64, factor only
+    for ng in (24, 48, 64):
+        bg = 65536
+        log_, hig_ = q.shard.shard_range(bg, rank, world)
+        mg = hig_ - log_
+        Ag = torch.randn((mg, ng, ng), dtype=torch.float64, device="cuda", generator=gB)
+        Agw = torch.empty_like(Ag)
+        tg = torch.empty((mg, ng), dtype=torch.float64, device="cuda")
+        t_g = timed_dev(lambda: q.ql_batched_(Agw, tg, handle=h), lambda: Agw.copy_(Ag), iters=3)
+        by_g = (2 * ng * ng + ng) * 8
+        extras[f"batched_{ng}x{ng}_f64_ql"] = {"value": bg / t_g, "unit": "matrices/s", "ms": t_g * 1e3, "total_matrices": bg,
+                                               "hbm_frac": mg * by_g / t_g / 1e9 / hb, "bytes_per_matrix": by_g}
+        del Ag, Agw, tg
 
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        traffic = json.load(open(tp if os.path.exists(tp) else os.path.join(ROOT, "profiles", "r01_traffic.json")))
     except Exception:
         pass
     tb_ = traffic.get("batched_geqlf_n32_f64")
