@@ -116,7 +116,8 @@ static int build_T(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, int p, i
 // wait_T: event after which T is valid (T may still be under construction on another stream while W is computed).
 static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool left, bool tt, const double *V,
                        int64_t ldv, const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other,
-                       cudaEvent_t wait_T = nullptr) {
+                       cudaEvent_t wait_T = nullptr, int sms = 0) {
+    if (sms <= 0) sms = h->sm_count;               // SMs the stream can use (an SM partition in look-ahead mode)
     if (other <= 0 || p <= 0 || ib <= 0) return 0;
     const bool small = ib <= 16 && other <= 128;      // in-panel strip update: many thin partials, fused reduce*T
     const int cfg_w = ib <= 16 ? 2 : -1;
@@ -129,7 +130,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     } else if (h->opt_trail_splits > 0) {
         S = (int)h->opt_trail_splits;
     } else {
-        S = choose_splits(2 * h->sm_count, tiles, p, other >= 2048 ? 512 : 128, max_w_splits(other));
+        S = choose_splits(2 * sms, tiles, p, other >= 2048 ? 512 : 128, max_w_splits(other));
     }
     S = qlb_gemm_splits(p, S, 16);
     const bool to_part = (S > 1 || small);
@@ -269,7 +270,7 @@ static int factors_checksum(qlb200_ctx *h, cudaStream_t st, const double *V, int
 // followed by its compact-WY update of the panel columns left of it; then the panel's T.
 // Reflectors (clean copy) -> V (ldv), T -> Tp (ldt = nb).  `scr` provides Ts/G/W/partial scratch.
 static int factor_panel(qlb200_ctx *h, cudaStream_t st, const Workspace &scr, double *A, int64_t lda, int m, int n, int k,
-                        int c0, int c1, double *tau, double *V, int64_t ldv, double *Tp, int ldt, bool need_T) {
+                        int c0, int c1, double *tau, double *V, int64_t ldv, double *Tp, int ldt, bool need_T, int sms = 0) {
     const int sb = 16, ib = c1 - c0, p = m - n + c1;
     int rc;
     int s1 = c1;
@@ -284,7 +285,7 @@ static int factor_panel(qlb200_ctx *h, cudaStream_t st, const Workspace &scr, do
         if (rc) return rc;
         if (s0 > c0) {
             rc = apply_block(h, st, scr, true, false, V + (int64_t)(s0 - c0) * ldv, ldv, Tdst, ldtd, ps, w, A + (int64_t)c0 * lda,
-                             lda, s0 - c0);
+                             lda, s0 - c0, nullptr, sms);
             if (rc) return rc;
         }
         s1 = s0;
@@ -298,6 +299,11 @@ static int factor_panel(qlb200_ctx *h, cudaStream_t st, const Workspace &scr, do
     return 0;
 }
 
+bool qlb_lookahead_active(const qlb200_ctx *h, int64_t m, int64_t n) {
+    if (h->opt_lookahead == 1) return true;
+    return h->opt_lookahead == 2 && h->gc_ok && (m < n ? m : n) >= h->opt_la_min;
+}
+
 int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
     const int m = (int)m64, n = (int)n64;
     const int k = m < n ? m : n;
@@ -305,7 +311,7 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     const int nb = (int)h->opt_nb;
     cudaStream_t st = h->stream;
     const int npanels = (k + nb - 1) / nb;
-    const bool la = h->opt_lookahead && npanels > 1;
+    const bool la = npanels > 1 && !h->h2d.host && !h->d2h.host && qlb_lookahead_active(h, m64, n64);
     Workspace ws, ws2;
     int rc = get_workspace(h, m, n, nb, 0, &ws, &ws2);
     if (rc) return rc;
@@ -314,11 +320,29 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     // T-factor cache: panel j's T goes straight into slot j (and is then also built for the last panel)
     h->tc_valid = false;
     double *tcache = nullptr;
-    if (h->opt_tcache && !la) {
+    if (h->opt_tcache) {
         rc = qlb_reserve(h, &h->tcache, &h->tcache_bytes, (size_t)npanels * nb * nb * sizeof(double));
         if (rc) return rc;
         tcache = (double *)h->tcache;
     }
+    auto finish_tcache = [&](double *tc) -> int {
+        if (!tc) return 0;
+        h->tc_key[0] = (int64_t)(uintptr_t)(A + (int64_t)(n - k) * lda);
+        h->tc_key[1] = lda;
+        h->tc_key[2] = (int64_t)(uintptr_t)tau;
+        h->tc_key[3] = m;
+        h->tc_key[4] = k;
+        h->tc_key[5] = nb;
+        h->tc_valid = true;
+        if (h->opt_tcache == 1) {      // validated mode: the cache belongs to this CONTENT
+            int r = factors_checksum(h, st, A + (int64_t)(n - k) * lda, lda, m, k, tau, h->tc_sum_dev);
+            if (r) return r;
+        }
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+            QLB_CUDA(h, cudaEventRecord(h->ev_tc, st));      // (under capture the caller records it after the launch)
+        return 0;
+    };
     if (!la) {
         // The panel's T (Gram GEMM -> reduce -> ?larft, ~135 us of latency-bound work) is needed only for W2 = W T, not
         // for W = C'V: it is built on the high-priority side stream while the main stream already runs the big W GEMM.
@@ -434,54 +458,58 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             QLB_CUDA(h, cudaMemcpy2DAsync(h->d2h.host, (size_t)h->d2h.host_ld * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)(n - k),
                                           cudaMemcpyDeviceToHost, h->copy_stream));
         }
-        if (tcache) {
-            h->tc_key[0] = (int64_t)(uintptr_t)(A + (int64_t)(n - k) * lda);
-            h->tc_key[1] = lda;
-            h->tc_key[2] = (int64_t)(uintptr_t)tau;
-            h->tc_key[3] = m;
-            h->tc_key[4] = k;
-            h->tc_key[5] = nb;
-            h->tc_valid = true;
-            if (h->opt_tcache == 1) {      // validated mode: the cache belongs to this CONTENT
-                rc = factors_checksum(h, st, A + (int64_t)(n - k) * lda, lda, m, k, tau, h->tc_sum_dev);
-                if (rc) return rc;
-            }
-            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-            if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
-                QLB_CUDA(h, cudaEventRecord(h->ev_tc, st));      // (under capture the caller records it after the launch)
-        }
-        return 0;
+        return finish_tcache(tcache);
     }
-    // ---- look-ahead: panel j+1 is factored on the (high-priority) side stream while the main stream
-    // applies panel j to the columns left of panel j+1.  Vw/T alternate between the two workspaces; the
-    // main stream's GEMM scratch is ws, the side stream's is ws2.
-    cudaStream_t side = h->side_stream;
+    // ---- look-ahead: panel j+1 is factored on the panel stream P while the update stream G applies panel j to the columns
+    // left of panel j+1.  With the SM partitions (green contexts) P owns 16 SMs that G's GEMMs never occupy, so the cluster
+    // strip kernels start at once; without them P is the high-priority side stream (correct, but the strips wait for SMs).
+    // Vw alternates between the two workspaces; T goes straight into the T cache (one slot per panel) or alternates too.
+    // G's GEMM scratch is ws, P's is ws2.
+    const bool gc = h->gc_ok;
+    cudaStream_t G = (gc && !h->opt_la_gemm_all) ? h->gc_gemm : st, P = gc ? h->gc_panel : h->side_stream;
+    const int smsG = (gc && !h->opt_la_gemm_all) ? h->gc_gemm_sms : h->sm_count, smsP = gc ? h->gc_panel_sms : h->sm_count;
+    cudaEvent_t evP = h->ev_a, evN = h->ev_b;      // "panel factored" (recorded on P), "next panel's columns updated" (on G)
+    if (gc) {                                      // both partitions start after the caller's work on h->stream
+        QLB_CUDA(h, cudaEventRecord(h->ev_gc[0], st));
+        if (G != st) QLB_CUDA(h, cudaStreamWaitEvent(G, h->ev_gc[0], 0));
+        QLB_CUDA(h, cudaStreamWaitEvent(P, h->ev_gc[0], 0));
+    } else {
+        QLB_CUDA(h, cudaEventRecord(h->ev_a, st));
+        QLB_CUDA(h, cudaStreamWaitEvent(P, h->ev_a, 0));
+    }
     double *Vb[2] = {ws.Vw, ws2.Vw}, *Tb[2] = {ws.T, ws2.T};
-    rc = factor_panel(h, st, ws2, A, lda, m, n, k, panel_c0(0), panel_c1(0), tau, Vb[0], ws.ldv, Tb[0], nb, panel_c0(0) > 0);
+    auto Tslot = [&](int j) { return tcache ? tcache + (size_t)j * nb * nb : Tb[j & 1]; };
+    rc = factor_panel(h, P, ws2, A, lda, m, n, k, panel_c0(0), panel_c1(0), tau, Vb[0], ws.ldv, Tslot(0), nb, panel_c0(0) > 0 || tcache != nullptr, smsP);
     if (rc) return rc;
+    QLB_CUDA(h, cudaEventRecord(evP, P));
     for (int j = 0; j < npanels; ++j) {
         const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
-        double *V = Vb[j & 1], *T = Tb[j & 1];
+        double *V = Vb[j & 1], *T = Tslot(j);
+        QLB_CUDA(h, cudaStreamWaitEvent(G, evP, 0));            // panel j (V, T) is complete
         if (j + 1 < npanels) {
             const int d0 = panel_c0(j + 1);          // next panel = columns [d0, c0)
-            rc = apply_block(h, st, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)d0 * lda, lda, c0 - d0);
+            rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)d0 * lda, lda, c0 - d0, nullptr, smsG);
             if (rc) return rc;
-            QLB_CUDA(h, cudaEventRecord(h->ev_a, st));
-            QLB_CUDA(h, cudaStreamWaitEvent(side, h->ev_a, 0));
-            rc = factor_panel(h, side, ws2, A, lda, m, n, k, d0, c0, tau, Vb[(j + 1) & 1], ws.ldv, Tb[(j + 1) & 1], nb, d0 > 0);
+            QLB_CUDA(h, cudaEventRecord(evN, G));
+            QLB_CUDA(h, cudaStreamWaitEvent(P, evN, 0));
+            rc = factor_panel(h, P, ws2, A, lda, m, n, k, d0, c0, tau, Vb[(j + 1) & 1], ws.ldv, Tslot(j + 1), nb, d0 > 0 || tcache != nullptr, smsP);
             if (rc) return rc;
-            QLB_CUDA(h, cudaEventRecord(h->ev_b, side));
+            QLB_CUDA(h, cudaEventRecord(evP, P));
             if (d0 > 0) {
-                rc = apply_block(h, st, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, d0);
+                rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, d0, nullptr, smsG);
                 if (rc) return rc;
             }
-            QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_b, 0));
         } else if (c0 > 0) {
-            rc = apply_block(h, st, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, c0);
+            rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, c0, nullptr, smsG);
             if (rc) return rc;
         }
     }
-    return 0;
+    // the caller's stream continues after both partitions (P's last event was already waited for by G)
+    if (G != st) {
+        QLB_CUDA(h, cudaEventRecord(h->ev_gc[1], G));
+        QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_gc[1], 0));
+    }
+    return finish_tcache(tcache);
 }
 
 // cache_mode: 0 = use the T cache if the pointers are the ones ql! just factored, 1 = use it (the caller validated the

@@ -11,6 +11,68 @@
         if (!(cond)) return qlb_fail(h, -(argno), msg "%s");  \
     } while (0)
 
+#include <cuda.h>      // driver-API types; the entry points are fetched through the runtime (no link-time libcuda dependency)
+
+// SM partitions for the look-ahead ql! (see common.cuh).  Every failure simply leaves gc_ok = false.
+template <typename F>
+static bool drv(const char *name, F *fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    *fn = (F)p;
+    return true;
+}
+static void green_contexts_create(qlb200_ctx *h, unsigned panel_sms) {
+    CUresult (*pDeviceGet)(CUdevice *, int) = nullptr;
+    CUresult (*pGetRes)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+    CUresult (*pSplit)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned) = nullptr;
+    CUresult (*pDesc)(CUdevResourceDesc *, CUdevResource *, unsigned) = nullptr;
+    CUresult (*pCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned) = nullptr;
+    CUresult (*pStream)(CUstream *, CUgreenCtx, unsigned, int) = nullptr;
+    if (!drv("cuDeviceGet", &pDeviceGet) || !drv("cuDeviceGetDevResource", &pGetRes) || !drv("cuDevSmResourceSplitByCount", &pSplit) ||
+        !drv("cuDevResourceGenerateDesc", &pDesc) || !drv("cuGreenCtxCreate", &pCreate) || !drv("cuGreenCtxStreamCreate", &pStream))
+        return;
+    CUdevice dev;
+    CUdevResource all, grp, rem;
+    if (pDeviceGet(&dev, h->device) != CUDA_SUCCESS || pGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
+    unsigned ng = 1;
+    // MAX_POTENTIAL_CLUSTER_SIZE: the group must be able to host a 16-CTA cluster (SMs of one GPC)
+    if (pSplit(&grp, &ng, &all, &rem, CU_DEV_SM_RESOURCE_SPLIT_MAX_POTENTIAL_CLUSTER_SIZE, panel_sms) != CUDA_SUCCESS || ng != 1) return;
+    if (grp.sm.smCount < 16 || rem.sm.smCount < 64) return;
+    CUdevResourceDesc d0, d1;
+    if (pDesc(&d0, &grp, 1) != CUDA_SUCCESS || pDesc(&d1, &rem, 1) != CUDA_SUCCESS) return;
+    CUgreenCtx g0 = nullptr, g1 = nullptr;
+    if (pCreate(&g0, d0, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    if (pCreate(&g1, d1, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    int lo = 0, hi = 0;
+    (void)cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CUstream s0 = nullptr, s1 = nullptr;
+    if (pStream(&s0, g0, CU_STREAM_NON_BLOCKING, hi) != CUDA_SUCCESS || pStream(&s1, g1, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return;
+    for (int i = 0; i < 4; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_gc[i], cudaEventDisableTiming) != cudaSuccess) return;
+    h->gc_ctx[0] = g0;
+    h->gc_ctx[1] = g1;
+    h->gc_panel = (cudaStream_t)s0;
+    h->gc_gemm = (cudaStream_t)s1;
+    h->gc_panel_sms = (int)grp.sm.smCount;
+    h->gc_gemm_sms = (int)rem.sm.smCount;
+    h->gc_ok = true;
+}
+static void green_contexts_destroy(qlb200_ctx *h) {
+    if (h->gc_panel) cudaStreamDestroy(h->gc_panel);
+    if (h->gc_gemm) cudaStreamDestroy(h->gc_gemm);
+    CUresult (*pDestroy)(CUgreenCtx) = nullptr;
+    if (drv("cuGreenCtxDestroy", &pDestroy))
+        for (int i = 0; i < 2; ++i)
+            if (h->gc_ctx[i]) pDestroy((CUgreenCtx)h->gc_ctx[i]);
+    for (int i = 0; i < 4; ++i)
+        if (h->ev_gc[i]) cudaEventDestroy(h->ev_gc[i]);
+    h->gc_ok = false;
+}
+
 extern "C" {
 
 int qlb200_version(void) { return QLB200_VERSION; }
@@ -50,6 +112,8 @@ int qlb200_create(qlb200_handle *out, int device) {
     QLB_CUDA(h, cudaMalloc(&h->tc_sum_dev, 2 * sizeof(unsigned long long)));
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_tc, cudaEventDisableTiming));
     h->stream = h->own_stream;
+    green_contexts_create(h, 16);
+    (void)cudaGetLastError();
     *out = h;
     return 0;
 }
@@ -74,6 +138,7 @@ int qlb200_destroy(qlb200_handle h) {
         delete[] h->prof_ev;
         delete[] h->prof_flops;
     }
+    green_contexts_destroy(h);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     for (int i = 0; i < 8; ++i)
@@ -187,7 +252,16 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "bgrid")) {
         h->opt_bgrid = value < 0 ? 0 : value;
     } else if (!strcmp(name, "lookahead")) {
-        h->opt_lookahead = value ? 1 : 0;
+        if (value < 0 || value > 2) return qlb_fail(h, -3, "lookahead must be 0 (off), 1 (on) or 2 (auto)%s");
+        h->opt_lookahead = value;
+    } else if (!strcmp(name, "la_graph")) {
+        h->opt_la_graph = value ? 1 : 0;
+        h->graph_key[0] = 0;
+        h->graph_seen_key[0] = 0;
+    } else if (!strcmp(name, "la_min")) {
+        h->opt_la_min = value < 0 ? 0 : value;
+    } else if (!strcmp(name, "la_gemm_all")) {
+        h->opt_la_gemm_all = value ? 1 : 0;
     } else if (!strcmp(name, "strip")) {
         if (value != 8 && value != 16 && value != 32) return qlb_fail(h, -3, "strip must be 8, 16 or 32%s");
         h->opt_strip = value;
@@ -470,9 +544,9 @@ typedef int (*fact_fn)(qlb200_ctx *, int64_t, int64_t, double *, int64_t, double
 // stream and inside somebody else's capture.
 static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
     const int64_t key[10] = {m, n, (int64_t)(uintptr_t)dA, lda, (int64_t)(uintptr_t)dtau, h->opt_nb, h->opt_strip_rpt * 16 + h->opt_lookahead,
-                             h->opt_gemm_cfg * 16 + h->opt_trail_splits, (int64_t)(uintptr_t)h->stream, 1 + 2 * h->opt_overlap_t + 4 * h->opt_tcache};
+                             h->opt_gemm_cfg * 16 + h->opt_trail_splits, (int64_t)(uintptr_t)h->stream, 1 + 2 * h->opt_overlap_t + 4 * h->opt_tcache + 16 * h->opt_la_graph + 32 * h->opt_la_gemm_all};
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    bool usable = h->opt_graph && !h->opt_profile && !h->opt_lookahead && h->stream != nullptr && m * n >= 64 * 64;
+    bool usable = h->opt_graph && !h->opt_profile && (h->opt_la_graph || !qlb_lookahead_active(h, m, n)) && h->stream != nullptr && m * n >= 64 * 64;
     if (usable && (cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)) {
         (void)cudaGetLastError();
         usable = false;
@@ -538,7 +612,7 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
     // ql! of a large matrix: plain launches (no graph); the matrix streams IN chunk by chunk while the right-hand panels
     // are already being factored, and the finished panels stream OUT while the rest is still being factored -- both PCIe
     // transfers disappear behind the computation (except the first chunk and the last panel)
-    const bool stream_back = (f == geqlf_dev_graph) && m * n >= ((int64_t)1 << 22) && !h->opt_lookahead;
+    const bool stream_back = (f == geqlf_dev_graph) && m * n >= ((int64_t)1 << 22) && h->opt_lookahead != 1;
     const bool stream_in = stream_back && h->opt_stream_in && h->opt_tcache;
     double *dA;
     int64_t ldd;

@@ -49,7 +49,21 @@ struct qlb200_ctx {
     void *redo = nullptr;                  // batched: counter + list of matrices for the generic kernel
     size_t redo_bytes = 0;
     int64_t launches = 0;
-    int64_t opt_nb = 128, opt_strip = 16, opt_lookahead = 0;
+    int64_t opt_nb = 128, opt_strip = 16;
+    // Look-ahead (panel j+1 is factored while the trailing update of panel j runs): 0 off, 1 on, 2 (default) = on for
+    // device-resident ql! with min(m,n) >= 2048 when the SM partitions below exist.
+    int64_t opt_lookahead = 2;
+    int64_t opt_la_graph = 1;              // replay the look-ahead ql! (two streams joined by events) as a CUDA graph too
+    int64_t opt_la_min = 4096;             // look-ahead (auto) from this min(m,n) on
+    int64_t opt_la_gemm_all = 0;           // (experiment) look-ahead GEMMs on the caller's stream (all SMs) instead of the GEMM partition
+    // Two CUDA green contexts split the SMs into a small partition for the latency-bound panel kernels (the strip kernel is
+    // a 16-CTA cluster of register-filling CTAs: it can only start on 16 completely free SMs of one GPC) and the rest for the
+    // trailing-update GEMMs.  Kernels launched into gc_gemm never occupy the panel SMs, so the panel kernels start at once.
+    bool gc_ok = false;
+    void *gc_ctx[2] = {nullptr, nullptr};  // CUgreenCtx
+    cudaStream_t gc_panel = nullptr, gc_gemm = nullptr;
+    int gc_panel_sms = 0, gc_gemm_sms = 0;
+    cudaEvent_t ev_gc[4] = {nullptr};
     int64_t opt_gemm_cfg = -1;             // -1 auto, else forces a tile configuration (benchmarking)
     int64_t opt_strip_rpt = 4;             // minimum rows per thread in the strip kernel (1, 2 or 4)
     // ql! replayed as a CUDA graph: the launch sequence of one (m, n, A, lda, tau, options, stream) call is captured the

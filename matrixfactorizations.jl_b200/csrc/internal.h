@@ -35,6 +35,9 @@ int qlb_larft(qlb200_ctx *h, cudaStream_t st, const double *G, int64_t ldg, cons
 int qlb_extract_v(qlb200_ctx *h, cudaStream_t st, const double *F, int64_t ldf, int p, int ib, int mu0, double *Vw,
                   int64_t ldv);
 
+// true if ql!(m x n) on device pointers takes the look-ahead path (two streams; not replayed as a graph)
+bool qlb_lookahead_active(const qlb200_ctx *h, int64_t m, int64_t n);
+
 // blocked.cu (device pointers, asynchronous on h->stream)
 int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
 int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,

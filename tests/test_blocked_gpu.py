@@ -472,3 +472,38 @@ def test_t_cache_is_validated_by_content(q, h):
     got = q.lmul_(Fh.Q.T, Bh.copy(order="F"))
     ref = cport.lmul(Fh.factors, Fh.tau, Bh, adjoint=True)
     assert np.abs(got - ref).max() <= 50 * n * EPS * np.abs(Bh).max() * np.sqrt(n)
+
+
+@pytest.mark.parametrize("n,la", [(2304, 1), (700, 1), (4608, 2)])
+def test_lookahead_ql_plain_captured_and_replayed_agree(q, h, n, la):
+    """The look-ahead ql! (panel j+1 factored on the panel SM partition while the GEMM partition applies panel j) called three
+    times on the same buffers: plain launches, graph capture, graph replay -- bitwise the same factors, LAPACK parity, and
+    the same bits as a fresh handle (the schedule is fixed: no run-to-run variation)."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    A = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g).T
+    buf = torch.empty((n, n), dtype=torch.float64, device="cuda").T
+    outs = []
+    h.set_option("lookahead", la)
+    try:
+        for _ in range(3):
+            buf.T.copy_(A.T)
+            F = q.ql_(buf, handle=h)
+            torch.cuda.synchronize()
+            outs.append((F.factors.clone(), F.tau.clone()))
+    finally:
+        h.set_option("lookahead", 2)
+    for f, t in outs[1:]:
+        assert torch.equal(f, outs[0][0]) and torch.equal(t, outs[0][1])
+    Ah = np.asfortranarray(A.cpu().numpy())
+    lapack.set_num_threads(16)
+    Fo, tauo = lapack.geqlf(Ah)
+    tol = _tol((n, n), Ah)
+    assert np.abs(outs[0][0].cpu().numpy() - Fo).max() <= tol and np.abs(outs[0][1].cpu().numpy() - tauo).max() <= tol
+    # the T cache filled by the look-ahead path serves lmul!
+    B = torch.randn((3, n), dtype=torch.float64, device="cuda", generator=g).T
+    got = q.lmul_(F.Q.T, (B.T.clone()).T)
+    torch.cuda.synchronize()
+    ref = lapack.ormql("L", "T", np.asfortranarray(Fo), tauo, np.asfortranarray(B.cpu().numpy()))
+    assert np.abs(got.cpu().numpy() - ref).max() <= 50 * n * EPS * np.abs(ref).max() * np.sqrt(n)
