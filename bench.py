@@ -531,7 +531,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"ql! Float64 n={n} square (configs[1]); copy + in-place blocked QL per step, input resident in HBM",
                        "parallelism": "replicas only (a single matrix runs on 1 GPU); batched work shards by matrix index",
-                       "l2": "inputs (2 GiB/matrix) are larger than the 126 MB L2", "nb": 128},
+                       "l2": "inputs (2 GiB/matrix) are larger than the 126 MB L2", "nb": "auto (192 at this size)",
+                       "lookahead": "panel j+1 on a 16-SM green-context partition while the 132-SM partition applies panel j"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": (gemm_tflops / peak_tflops) if gemm_tflops else None,

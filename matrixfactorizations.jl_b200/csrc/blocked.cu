@@ -106,7 +106,21 @@ static int build_T(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, int p, i
         rc = qlb_reduce_partials(h, st, ws.part, S, stride, ib, ib, ib, ws.G, ib);
         if (rc) return rc;
     }
-    return qlb_larft(h, st, ws.G, ib, tau, ib, ws.T, ws.ldt);
+    if (ib <= 128) return qlb_larft(h, st, ws.G, ib, tau, ib, ws.T, ws.ldt);
+    // Two-level T for 128 < ib <= 256 (backward/columnwise): with the reflectors split into block 1 =
+    // [0, h1) and block 2 = [h1, ib), H = H_2 H_1 = I - [V1 V2] [[T11, 0], [T21, T22]] [V1 V2]' with
+    // T21 = -T22 (V2'V1) T11.  T11 and T22 by the ?larft recurrence on the diagonal Gram blocks, T21 by two small GEMMs
+    // (the split-K partial buffer is free again after the reduction and holds the intermediate product).
+    const int h1 = ib - 128, n2 = 128;
+    rc = qlb_larft(h, st, ws.G, ib, tau, h1, ws.T, ws.ldt);
+    if (rc) return rc;
+    rc = qlb_larft(h, st, ws.G + h1 + (int64_t)h1 * ib, ib, tau + h1, n2, ws.T + h1 + (int64_t)h1 * ws.ldt, ws.ldt);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaMemset2DAsync(ws.T + (int64_t)h1 * ws.ldt, (size_t)ws.ldt * sizeof(double), 0, (size_t)h1 * sizeof(double), (size_t)n2, st));
+    double *tmp = ws.part;                      // n2 x h1
+    rc = qlb_gemm(h, st, -1, false, true, n2, h1, n2, 1.0, ws.T + h1 + (int64_t)h1 * ws.ldt, ws.ldt, ws.G + h1, ib, 0.0, tmp, n2, 1, 0);
+    if (rc) return rc;
+    return qlb_gemm(h, st, -1, false, true, n2, h1, h1, -1.0, tmp, n2, ws.T, ws.ldt, 0.0, ws.T + h1, ws.ldt, 1, 0);
 }
 
 // Apply the block reflector H = I - V T V' (V = ws.Vw[0:p,0:ib] or Vptr) to C.
@@ -119,7 +133,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
                        cudaEvent_t wait_T = nullptr, int sms = 0) {
     if (sms <= 0) sms = h->sm_count;               // SMs the stream can use (an SM partition in look-ahead mode)
     if (other <= 0 || p <= 0 || ib <= 0) return 0;
-    const bool small = ib <= 16 && other <= 128;      // in-panel strip update: many thin partials, fused reduce*T
+    const bool small = ib <= 16 && other <= 256;      // in-panel strip update: many thin partials, fused reduce*T
     const int cfg_w = ib <= 16 ? 2 : -1;
     // 1. W partials: M = other, N = ib, K = p
     const int64_t tiles = (int64_t)((other + 127) / 128) * ((ib + 63) / 64);      // 128x64 tiles, 2 CTAs per SM
@@ -304,11 +318,19 @@ bool qlb_lookahead_active(const qlb200_ctx *h, int64_t m, int64_t n) {
     return h->opt_lookahead == 2 && h->gc_ok && (m < n ? m : n) >= h->opt_la_min;
 }
 
+// Measured on B200 (tools/sweep_geqlf.py): with the look-ahead, 192-wide panels win at n = 16384 (241 vs 248 ms: the K = 192
+// update GEMM runs at 27.4 instead of 25.9 TFLOP/s on the GEMM partition), tie at 12288 and lose below (the longer panels
+// are exposed in the tail of the factorization); widths that are not multiples of 64 lose to tile quantisation.
+int qlb_effective_nb(const qlb200_ctx *h, int64_t m, int64_t n) {
+    if (h->opt_nb > 0) return (int)h->opt_nb;
+    return (qlb_lookahead_active(h, m, n) && (m < n ? m : n) >= 14336) ? 192 : 128;
+}
+
 int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t lda, double *tau) {
     const int m = (int)m64, n = (int)n64;
     const int k = m < n ? m : n;
     if (k == 0) return 0;
-    const int nb = (int)h->opt_nb;
+    const int nb = (h->h2d.host || h->d2h.host) ? (h->opt_nb > 0 ? (int)h->opt_nb : 128) : qlb_effective_nb(h, m64, n64);
     cudaStream_t st = h->stream;
     const int npanels = (k + nb - 1) / nb;
     const bool la = npanels > 1 && !h->h2d.host && !h->d2h.host && qlb_lookahead_active(h, m64, n64);
@@ -521,7 +543,9 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     const bool notran = (trans == 'N' || trans == 'n');
     const int nq = left ? m : n, other = left ? n : m;
     if (m == 0 || n == 0 || k == 0) return 0;
-    const int nb = (int)h->opt_nb;
+    // blocks must line up with ql!'s panels for the T cache to be usable: follow the width it used when it may hit
+    const int nb = h->opt_nb > 0 ? (int)h->opt_nb
+                                 : ((h->opt_tcache && h->tc_valid && h->tc_key[3] == nq && h->tc_key[4] == k && cache_mode >= 0) ? (int)h->tc_key[5] : 128);
     cudaStream_t st = h->stream;
     Workspace ws;
     int rc = get_workspace(h, nq, other, nb, max_w_splits(other), &ws);

@@ -201,7 +201,7 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     if (!h) return -1;
     if (!name) return -2;
     if (!strcmp(name, "nb")) {
-        if (value < 16 || value > 128 || value % 16) return qlb_fail(h, -3, "nb must be a multiple of 16 in [16,128]%s");
+        if (value != 0 && (value < 16 || value > 256 || value % 16)) return qlb_fail(h, -3, "nb must be 0 (auto) or a multiple of 16 in [16,256]%s");
         h->opt_nb = value;
     } else if (!strcmp(name, "gemm_cfg")) {
         if (value < -1 || value > 3) return qlb_fail(h, -3, "gemm_cfg must be in [-1,3]%s");
@@ -543,7 +543,7 @@ typedef int (*fact_fn)(qlb200_ctx *, int64_t, int64_t, double *, int64_t, double
 // handle's stream and instantiated.  From then on: one cudaGraphLaunch.  Skipped while profiling, on the legacy default
 // stream and inside somebody else's capture.
 static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int64_t lda, double *dtau) {
-    const int64_t key[10] = {m, n, (int64_t)(uintptr_t)dA, lda, (int64_t)(uintptr_t)dtau, h->opt_nb, h->opt_strip_rpt * 16 + h->opt_lookahead,
+    const int64_t key[10] = {m, n, (int64_t)(uintptr_t)dA, lda, (int64_t)(uintptr_t)dtau, (int64_t)qlb_effective_nb(h, m, n), h->opt_strip_rpt * 16 + h->opt_lookahead,
                              h->opt_gemm_cfg * 16 + h->opt_trail_splits, (int64_t)(uintptr_t)h->stream, 1 + 2 * h->opt_overlap_t + 4 * h->opt_tcache + 16 * h->opt_la_graph + 32 * h->opt_la_gemm_all};
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     bool usable = h->opt_graph && !h->opt_profile && (h->opt_la_graph || !qlb_lookahead_active(h, m, n)) && h->stream != nullptr && m * n >= 64 * 64;
@@ -562,7 +562,7 @@ static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int6
             h->tc_key[2] = (int64_t)(uintptr_t)dtau;
             h->tc_key[3] = m;
             h->tc_key[4] = k;
-            h->tc_key[5] = h->opt_nb;
+            h->tc_key[5] = qlb_effective_nb(h, m, n);
             h->tc_valid = true;
             QLB_CUDA(h, cudaEventRecord(h->ev_tc, h->stream));
         }

@@ -49,7 +49,7 @@ struct qlb200_ctx {
     void *redo = nullptr;                  // batched: counter + list of matrices for the generic kernel
     size_t redo_bytes = 0;
     int64_t launches = 0;
-    int64_t opt_nb = 128, opt_strip = 16;
+    int64_t opt_nb = 0, opt_strip = 16;     // panel width; 0 = auto (qlb_effective_nb: 192 for look-ahead ql! with min(m,n) >= 14336, else 128)
     // Look-ahead (panel j+1 is factored while the trailing update of panel j runs): 0 off, 1 on, 2 (default) = on for
     // device-resident ql! with min(m,n) >= 2048 when the SM partitions below exist.
     int64_t opt_lookahead = 2;

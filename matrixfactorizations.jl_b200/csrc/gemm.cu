@@ -324,7 +324,7 @@ static int launch_cfg(qlb200_ctx *h, int slot, const GemmParams &p, int splits, 
     }
     dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, splits);
     const int kt_total = (p.kchunk + Cfg::BK - 1) / Cfg::BK;
-    if (h->opt_pair_sync > 0 && grid.y == 2 && kt_total >= 4 * h->opt_pair_sync) {
+    if (h->opt_pair_sync > 0 && (grid.y == 2 || grid.y == 4) && kt_total >= 4 * h->opt_pair_sync) {
         GemmParams q = p;
         q.pair_sync = (int)h->opt_pair_sync;
         cudaLaunchConfig_t cfg = {};
@@ -335,7 +335,7 @@ static int launch_cfg(qlb200_ctx *h, int slot, const GemmParams &p, int splits, 
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1;
-        attr[0].val.clusterDim.y = 2;
+        attr[0].val.clusterDim.y = grid.y;      // all N-tiles of an M-tile (2 for nb = 128, 4 for nb = 256) stream the same A tile
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;

@@ -37,6 +37,7 @@ int qlb_extract_v(qlb200_ctx *h, cudaStream_t st, const double *F, int64_t ldf, 
 
 // true if ql!(m x n) on device pointers takes the look-ahead path (two streams; not replayed as a graph)
 bool qlb_lookahead_active(const qlb200_ctx *h, int64_t m, int64_t n);
+int qlb_effective_nb(const qlb200_ctx *h, int64_t m, int64_t n);      // panel width ql!(m x n) uses (option "nb", 0 = auto)
 
 // blocked.cu (device pointers, asynchronous on h->stream)
 int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);

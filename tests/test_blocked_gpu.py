@@ -80,7 +80,7 @@ def test_geqlf_matches_lapack(q, h, shape, lookahead):
     assert np.abs(F.tau - tauo).max() <= t
 
 
-@pytest.mark.parametrize("nb", [16, 32, 64, 96, 128])
+@pytest.mark.parametrize("nb", [16, 32, 64, 96, 128, 176, 256])
 @pytest.mark.parametrize("lookahead,rpt", [(0, 4), (1, 4), (1, 1), (0, 2)])
 def test_geqlf_panel_widths(q, h, nb, lookahead, rpt):
     A = np.asfortranarray(np.random.default_rng(nb).standard_normal((700, 450)))
@@ -90,7 +90,7 @@ def test_geqlf_panel_widths(q, h, nb, lookahead, rpt):
     try:
         F = q.ql(A, handle=h)
     finally:
-        h.set_option("nb", 128)
+        h.set_option("nb", 0)
         h.set_option("lookahead", 0)
         h.set_option("strip_rpt", 4)
     Fo, tauo = lapack.geqlf(A)
