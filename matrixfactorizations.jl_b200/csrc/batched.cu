@@ -318,7 +318,9 @@ struct GroupSize { static constexpr int value = ((N - LO > 16) ? 4 : 8) < LPM ? 
 // kernel of the smaller size afterwards.
 template <typename T, int N, int CPL, int LO, int PD, int STOP = 0>
 struct GroupLoop {
-    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad) {
+    // ns = number of Householder steps = order of the matrix (ns <= N): a smaller matrix sits in the bottom-right corner of
+    // the tile (rows and columns [N - ns, N)), the rest of the tile is zero and its steps are simply not taken.
+    static __device__ __forceinline__ void run(T (&a)[CPL][N], T (&myscale)[CPL], T *xg, T *obuf, int jl, bool &bad, int ns) {
         if constexpr (STOP > 0 && LO == STOP) {
             using V = typename Vec16<T>::type;
             constexpr int E = Vec16<T>::E;
@@ -338,16 +340,26 @@ struct GroupLoop {
         constexpr int NS = (N - 1 - LO) / LPM + 1;
         constexpr bool LAST = (LO + GS == N);
         static_assert((N - 1 - LO) / LPM == (N - LO - GS) / LPM, "a group's pivot columns live in one slot");
-        ql_group<T, N, CPL, LO, NS, PD>(a, myscale, xg, obuf, jl, bad, LAST ? GS - 1 : GS);
+        // steps LO .. ns-2 are full Householder steps; step ns-1 (the matrix's first column: a length-1 reflector is the
+        // identity, tau = 0, beta = alpha) only sends the pivot row out
+        int nfull = ns - 1 - LO;
+        nfull = nfull > GS ? GS : nfull;
+        if (nfull > 0) ql_group<T, N, CPL, LO, NS, PD>(a, myscale, xg, obuf, jl, bad, nfull);
+        if (LAST || ns - 1 < LO + GS) {
+            const int R = N - ns;                       // pivot row of the last step, at register index N-1
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                const int col = jl + c * LPM;
+                const T aR = a[c][N - 1];
+                obuf[col * BatchedCfg<T, N, CPL>::PITCH + R] = (col > R) ? aR * myscale[c] : aR;
+            }
+            if (jl == R % LPM) obuf[R * BatchedCfg<T, N, CPL>::PITCH + N] = T(0);
+            return;
+        }
         if constexpr (!LAST) {
             constexpr int NS_NEXT = (N - 1 - LO - GS) / LPM + 1;
             if constexpr (NS_NEXT < NS) ql_flush_slot<T, N, CPL, NS - 1>(a, myscale, obuf, jl);
-            GroupLoop<T, N, CPL, LO + GS, PD, STOP>::run(a, myscale, xg, obuf, jl, bad);
-        } else {
-            // R = 0: a length-1 reflector is the identity (tau = 0, beta = alpha); row 0 leaves the tile
-            const T aR = a[0][N - 1];
-            obuf[jl * BatchedCfg<T, N, CPL>::PITCH] = (jl > 0) ? aR * myscale[0] : aR;
-            if (jl == 0) obuf[N] = T(0);
+            GroupLoop<T, N, CPL, LO + GS, PD, STOP>::run(a, myscale, xg, obuf, jl, bad, ns);
         }
         }
     }
@@ -363,11 +375,11 @@ __device__ __noinline__ void geql2_warp(T *__restrict__ Am, int64_t lda, T *__re
 // redo list, no counter to clear.
 // STOP > 0: phase A only (see GroupLoop); flags[mi] (written for EVERY matrix) = 1 marks the matrices that were flagged
 // and therefore factored completely here.  skip != null: matrices with skip[mi] != 0 are not touched (phase B).
-template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA, int PD = 4, int STOP = 0>
+template <typename T, int N, int CPL, int WARPS, int MINB, bool USE_TMA, int PD = 4, int STOP = 0, bool PADDED = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A, int64_t lda, int64_t strideA,
                      T *__restrict__ tau, int64_t strideTau, int64_t batch, int *__restrict__ flags,
-                     const int *__restrict__ skip) {
+                     const int *__restrict__ skip, int nr_arg) {
     using Cfg = BatchedCfg<T, N, CPL>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, PITCH = Cfg::PITCH;
@@ -383,6 +395,12 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
     const int nbatch = (int)batch;                           // < 2^31 (checked by the launcher)
     const int nwb = (nbatch + G - 1) / G;                    // warp-batches of G matrices
     const int gw = (int)blockIdx.x * WARPS + warp, nw = (int)gridDim.x * WARPS;
+    // order nr <= N: the matrix occupies rows and columns [pad, N) of the tile; the tensor copies start at (-pad, -pad), so the
+    // out-of-bounds part of the box is zero-filled on the way in and skipped on the way out
+    // (PADDED is a template parameter: the exact-size kernels keep nr = N as a constant -- the extra live registers cost the
+    //  n = 32 Float64 kernel 24 bytes of spills)
+    const int nr = PADDED ? nr_arg : N;
+    const int pad = N - nr;
 
     if constexpr (USE_TMA) {
         if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -398,7 +416,7 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
             const int nvalid = (nbatch - m0) < G ? (nbatch - m0) : G;
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * Cfg::IMG_BYTES));
-                for (int q = 0; q < nvalid; ++q) tma_load_3d(buf + q * N * PITCH, &tmap, 0, 0, m0 + q, bar);
+                for (int q = 0; q < nvalid; ++q) tma_load_3d(buf + q * N * PITCH, &tmap, -pad, -pad, m0 + q, bar);
             }
             if (!inb) {        // tail of the batch: an identity keeps the arithmetic finite (results are discarded)
                 for (int idx = jl; idx < N * N; idx += LPM) obuf[(idx / N) * PITCH + (idx % N)] = (idx / N == idx % N) ? T(1) : T(0);
@@ -408,8 +426,12 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
             __syncwarp();
         } else {
             const T *Am = A + (int64_t)(inb ? mi : 0) * strideA;
-            for (int idx = jl; idx < N * N; idx += LPM)
-                obuf[(idx / N) * PITCH + (idx % N)] = inb ? Am[(int64_t)(idx / N) * lda + (idx % N)] : ((idx / N == idx % N) ? T(1) : T(0));
+            for (int idx = jl; idx < N * N; idx += LPM) {
+                const int c = idx / N, r = idx % N;
+                T v = (c == r) ? T(1) : T(0);
+                if (inb) v = (c >= pad && r >= pad) ? Am[(int64_t)(c - pad) * lda + (r - pad)] : T(0);
+                obuf[c * PITCH + r] = v;
+            }
             __syncwarp();
         }
         T a[CPL][N];
@@ -430,7 +452,7 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
         for (int c = 0; c < CPL; ++c) myscale[c] = T(0);
 
         bool bad = false;
-        GroupLoop<T, N, CPL, 0, PD, STOP>::run(a, myscale, xg, obuf, jl, bad);
+        GroupLoop<T, N, CPL, 0, PD, STOP>::run(a, myscale, xg, obuf, jl, bad, nr);
 
         // flagged matrices stay untouched in global memory (no tau, no store) and are redone below
         if (flags != nullptr && valid && jl == 0) flags[mi] = bad ? 1 : 0;
@@ -440,10 +462,12 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const int col = jl + c * LPM;
-                if (STOP == 0 || col >= N - STOP) tau[(int64_t)mi * strideTau + col] = obuf[col * PITCH + N];      // phase A: the rest comes from phase B
+                if ((STOP == 0 || col >= N - STOP) && col >= pad) tau[(int64_t)mi * strideTau + col - pad] = obuf[col * PITCH + N];      // phase A: the rest comes from phase B
             }
         }
-        if constexpr (USE_TMA) {
+        // (tensor STORES that start at negative coordinates fault on sm_100 -- tools/ubench/tma_oob.cu: loads zero-fill, stores
+        //  raise "illegal instruction" -- so the padded variant sends its corner out with plain stores)
+        if constexpr (USE_TMA && !PADDED) {
             fence_proxy_async();                                  // generic-proxy writes -> visible to the bulk copies
             __syncwarp();
             if (valid && !bad && jl == 0) tma_store_3d(&tmap, 0, 0, mi, obuf);
@@ -453,15 +477,24 @@ geqlf_batched_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ A
         } else {
             if (valid && !bad) {
                 T *Am = A + (int64_t)mi * strideA;
-                for (int idx = jl; idx < N * N; idx += LPM) Am[(int64_t)(idx / N) * lda + (idx % N)] = obuf[(idx / N) * PITCH + (idx % N)];
+                if (PADDED && USE_TMA && (pad % E) == 0) {       // (USE_TMA: base, lda and strideA are 16-byte aligned) whole vectors
+                    const int nv = nr / E;
+                    for (int c = 0; c < nr; ++c)
+                        for (int v = jl; v < nv; v += LPM)
+                            *reinterpret_cast<V *>(Am + (int64_t)c * lda + v * E) = *reinterpret_cast<const V *>(obuf + (c + pad) * PITCH + pad + v * E);
+                } else {
+                    for (int c = 0; c < nr; ++c)
+                        for (int r = jl; r < nr; r += LPM) Am[(int64_t)c * lda + r] = obuf[(c + pad) * PITCH + pad + r];
+                }
             }
+            if constexpr (USE_TMA) fence_proxy_async();      // generic reads of the image before the next bulk load into it
             __syncwarp();
         }
         if (redo) {      // warp-uniform and rare: the images have been read by the stores above, the buffer is free scratch
             static_assert(Cfg::BUF_BYTES >= ((N + 1) * N + N) * (int)sizeof(T), "the warp's image area holds the generic routine's scratch");
             for (unsigned rm = redo; rm; rm &= rm - 1) {
                 const int gi = (__ffs(rm) - 1) / LPM;
-                geql2_warp<T>(A + (int64_t)(m0 + gi) * strideA, lda, tau + (int64_t)(m0 + gi) * strideTau, N, buf, lane);
+                geql2_warp<T>(A + (int64_t)(m0 + gi) * strideA, lda, tau + (int64_t)(m0 + gi) * strideTau, nr, buf, lane);
             }
             if constexpr (USE_TMA) fence_proxy_async();      // generic-proxy writes to the buffer before the next bulk load into it
             __syncwarp();
@@ -656,11 +689,15 @@ struct ApplyCfg {
     static_assert(RG >= 1 && RPL % E == 0, "row blocks are whole 16-byte vectors");
 };
 
-template <typename T, int N, int NR, int MODE, int WARPS, bool USE_TMA>
+template <typename T, int N, int NR, int MODE, int WARPS, bool USE_TMA, bool PADDED = false>
 __global__ void __launch_bounds__(WARPS * 32)
 apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ A, int64_t lda, int64_t strideA,
                      const T *__restrict__ tau, int64_t strideTau, T *__restrict__ B, int64_t ldb, int64_t strideB, int nrhs,
-                     int64_t batch, int32_t *__restrict__ info_out, int vecB) {
+                     int64_t batch, int32_t *__restrict__ info_out, int vecB, int nr_arg) {
+    // PADDED: factors of order nr < N in the bottom-right corner of the N x N tile (zero rows/columns and tau = 0 in front:
+    // those reflectors are the identity), B in rows [pad, N) -- same arithmetic on the real part, zeros elsewhere.
+    const int nr = PADDED ? nr_arg : N;
+    const int pad = N - nr;
     using Cfg = ApplyCfg<T, N, NR, MODE>;
     using V = typename Vec16<T>::type;
     constexpr int E = Cfg::E, LPM = Cfg::LPM, G = Cfg::G, RPL = Cfg::RPL, PITCH = Cfg::PITCH, DBUF = Cfg::DBUF;
@@ -692,23 +729,35 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
         const int nvalid = (nbatch - m0) < G ? (nbatch - m0) : G;
         if constexpr (USE_TMA) {
             if (lane == 0) {
-                mbar_arrive_expect_tx(&bars[s], (uint32_t)(nvalid * (Cfg::IMG_BYTES + N * (int)sizeof(T))));
+                mbar_arrive_expect_tx(&bars[s], (uint32_t)(nvalid * (Cfg::IMG_BYTES + nr * (int)sizeof(T))));
                 for (int q = 0; q < nvalid; ++q) {
-                    tma_load_3d(img + q * N * PITCH, &tmap, 0, 0, m0 + q, &bars[s]);
-                    tma_load_1d(taus + q * N, tau + (int64_t)(m0 + q) * strideTau, N * sizeof(T), &bars[s]);
+                    tma_load_3d(img + q * N * PITCH, &tmap, -pad, -pad, m0 + q, &bars[s]);
+                    tma_load_1d(taus + q * N + pad, tau + (int64_t)(m0 + q) * strideTau, nr * sizeof(T), &bars[s]);
                 }
             }
         } else {
             for (int q = 0; q < nvalid; ++q) {
                 const T *Am = A + (int64_t)(m0 + q) * strideA;
-                for (int idx = lane; idx < N * N; idx += 32) img[q * N * PITCH + (idx / N) * PITCH + (idx % N)] = Am[(int64_t)(idx / N) * lda + (idx % N)];
-                for (int i = lane; i < N; i += 32) taus[q * N + i] = tau[(int64_t)(m0 + q) * strideTau + i];
+                for (int idx = lane; idx < N * N; idx += 32) {
+                    const int c = idx / N, r = idx % N;
+                    img[q * N * PITCH + c * PITCH + r] = (c >= pad && r >= pad) ? Am[(int64_t)(c - pad) * lda + (r - pad)] : T(0);
+                }
+                for (int i = lane; i < N; i += 32) taus[q * N + i] = (i >= pad) ? tau[(int64_t)(m0 + q) * strideTau + i - pad] : T(0);
             }
         }
     };
     uint32_t phase[DBUF];
 #pragma unroll
     for (int s = 0; s < DBUF; ++s) phase[s] = 0;
+    if constexpr (PADDED && USE_TMA) {      // tau of the padded reflectors: zero, never overwritten by the bulk copies
+        for (int s = 0; s < DBUF; ++s) {
+            T *taus = reinterpret_cast<T *>(wbase + s * Cfg::STAGE_BYTES + G * Cfg::IMG_BYTES);
+            for (int i = lane; i < G * N; i += 32)
+                if (i % N < pad) taus[i] = T(0);
+        }
+        fence_proxy_async();
+        __syncwarp();
+    }
     if constexpr (DBUF == 2) {
         if (gw < nwb) issue(gw, 0);
     }
@@ -735,8 +784,11 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
             for (int cc = 0; cc < CL; ++cc) {
                 const int col = c0 + jb * CL + cc;
                 cvalid[cc] = valid && col < nrhs;
-                Bc[cc] = B + (int64_t)(valid ? mi : 0) * strideB + (int64_t)(col < nrhs ? col : 0) * ldb + row0;
-                if (vecB) {
+                Bc[cc] = B + (int64_t)(valid ? mi : 0) * strideB + (int64_t)(col < nrhs ? col : 0) * ldb + row0 - pad;
+                if (PADDED) {
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) b[cc][i] = (cvalid[cc] && row0 + i >= pad) ? Bc[cc][i] : T(0);
+                } else if (vecB) {
 #pragma unroll
                     for (int v = 0; v < RPL / E; ++v) {
                         V q = cvalid[cc] ? reinterpret_cast<const V *>(Bc[cc])[v] : V{};
@@ -830,7 +882,7 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                 // each image column), so the serial chain carries a multiplication instead of a division.
                 T *imgw = const_cast<T *>(img);
                 if (c0 == 0) {
-                    for (int c = l; c < N; c += LPM) imgw[c * PITCH + N] = T(1) / img[c * PITCH + c];
+                    for (int c = l; c < N; c += LPM) imgw[c * PITCH + N] = (c >= pad) ? T(1) / img[c * PITCH + c] : T(0);
                     __syncwarp();
                 }
                 int bad = 0;
@@ -839,7 +891,7 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
                     const int orow = c % RPL, org = c / RPL;       // owner row group / local row of row c
                     const T *lc = img + c * PITCH + row0;
                     const T rcc = img[c * PITCH + N];
-                    if (img[c * PITCH + c] == T(0) && bad == 0) bad = c + 1;
+                    if (img[c * PITCH + c] == T(0) && bad == 0 && c >= pad) bad = c + 1 - pad;
                     T xc[CL];
 #pragma unroll
                     for (int cc = 0; cc < CL; ++cc) xc[cc] = __shfl_sync(FULL, b[cc][orow], jb + NRL * org, LPM) * rcc;
@@ -864,7 +916,11 @@ apply_batched_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restri
 #pragma unroll
             for (int cc = 0; cc < CL; ++cc) {
                 if (!cvalid[cc]) continue;
-                if (vecB) {
+                if (PADDED) {
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i)
+                        if (row0 + i >= pad) Bc[cc][i] = b[cc][i];
+                } else if (vecB) {
 #pragma unroll
                     for (int v = 0; v < RPL / E; ++v) {
                         V q;
@@ -900,7 +956,9 @@ typedef CUresult (*qlb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuui
                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 template <typename T>
-static bool make_batch_tensor_map(CUtensorMap *tm, const T *A, int n, int64_t lda, int64_t strideA, int64_t batch, int pitch) {
+static bool make_batch_tensor_map(CUtensorMap *tm, const T *A, int n, int64_t lda, int64_t strideA, int64_t batch, int pitch,
+                                  int nbox = 0) {
+    if (nbox == 0) nbox = n;                // tile order (>= n: the copies then start at negative coordinates, see the kernels)
     static qlb_encode_tiled_fn enc = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -918,7 +976,7 @@ static bool make_batch_tensor_map(CUtensorMap *tm, const T *A, int n, int64_t ld
     // a single matrix may come with any stride: use a harmless consistent one
     const int64_t sA = batch > 1 ? strideA : (int64_t)lda * n;
     const cuuint64_t strides[2] = {(cuuint64_t)lda * sizeof(T), (cuuint64_t)sA * sizeof(T)};
-    const cuuint32_t box[3] = {(cuuint32_t)pitch, (cuuint32_t)n, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)pitch, (cuuint32_t)nbox, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     // a column shorter than 256 bytes inside a wider leading dimension (phase B of the n = 32 split: 128 of every 256 bytes)
@@ -936,13 +994,14 @@ static bool tma_ok(const T *A, int64_t lda, int64_t strideA) {
 
 template <typename T, int N, int CPL, int WARPS, int MINB, int PD = 4>
 static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t strideA, T *tau, int64_t strideTau,
-                                int64_t batch) {
+                                int64_t batch, int nr = N) {
     using Cfg = BatchedCfg<T, N, CPL>;
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<T>(&tmap, A, N, lda, strideA, batch, Cfg::PITCH);
+    const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<T>(&tmap, A, nr, lda, strideA, batch, Cfg::PITCH, N);
     auto kern = tma ? geqlf_batched_kernel<T, N, CPL, WARPS, MINB, true, PD> : geqlf_batched_kernel<T, N, CPL, WARPS, MINB, false, PD>;
+    if (nr != N) kern = tma ? geqlf_batched_kernel<T, N, CPL, WARPS, MINB, true, PD, 0, true> : geqlf_batched_kernel<T, N, CPL, WARPS, MINB, false, PD, 0, true>;
     int occ = 0;
     int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ);
     if (rcs) return rcs;
@@ -954,7 +1013,7 @@ static int launch_geqlf_batched(qlb200_ctx *h, T *A, int64_t lda, int64_t stride
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, nullptr, nullptr);      // ONE launch
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, nullptr, nullptr, nr);      // ONE launch
     QLB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -992,9 +1051,9 @@ static int launch_geqlf_batched_split32(qlb200_ctx *h, T *A, int64_t lda, int64_
     int rc = qlb_reserve(h, &h->redo, &h->redo_bytes, (size_t)batch * sizeof(int));
     if (rc) return rc;
     int *flags = (int *)h->redo;
-    kA<<<grid(CfgA::G, occA), WARPS * 32, smA, h->stream>>>(tmA, A, lda, strideA, tau, strideTau, batch, flags, nullptr);
+    kA<<<grid(CfgA::G, occA), WARPS * 32, smA, h->stream>>>(tmA, A, lda, strideA, tau, strideTau, batch, flags, nullptr, 32);
     QLB_LAUNCH_CHECK(h);
-    kB<<<grid(CfgB::G, occB), WARPS * 32, smB, h->stream>>>(tmB, A, lda, strideA, tau, strideTau, batch, nullptr, flags);
+    kB<<<grid(CfgB::G, occB), WARPS * 32, smB, h->stream>>>(tmB, A, lda, strideA, tau, strideTau, batch, nullptr, flags, 16);
     QLB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -1002,7 +1061,7 @@ static int launch_geqlf_batched_split32(qlb200_ctx *h, T *A, int64_t lda, int64_
 template <typename T, int N, int NR, int MODE>
 static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t strideA, const T *tau,
                                 int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch,
-                                int32_t *info_out) {
+                                int32_t *info_out, int nr = N) {
     constexpr int WARPS = 4;
     using Cfg = ApplyCfg<T, N, NR, MODE>;
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES;
@@ -1010,9 +1069,11 @@ static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     const bool tau_ok = ((uintptr_t)tau % 16 == 0) && ((strideTau * sizeof(T)) % 16 == 0 || batch <= 1);
-    const bool tma = tma_ok(A, lda, strideA) && tau_ok && make_batch_tensor_map<T>(&tmap, A, N, lda, strideA, batch, Cfg::PITCH);
+    const bool pad_ok = (nr == N) || (((N - nr) * sizeof(T)) % 16 == 0 && (nr * sizeof(T)) % 16 == 0);      // the 1-D bulk copy of tau
+    const bool tma = tma_ok(A, lda, strideA) && tau_ok && pad_ok && make_batch_tensor_map<T>(&tmap, A, nr, lda, strideA, batch, Cfg::PITCH, N);
     const int vecB = ((uintptr_t)B % 16 == 0) && ((ldb * sizeof(T)) % 16 == 0) && ((strideB * sizeof(T)) % 16 == 0 || batch <= 1);
     auto kern = tma ? apply_batched_kernel<T, N, NR, MODE, WARPS, true> : apply_batched_kernel<T, N, NR, MODE, WARPS, false>;
+    if (nr != N) kern = tma ? apply_batched_kernel<T, N, NR, MODE, WARPS, true, true> : apply_batched_kernel<T, N, NR, MODE, WARPS, false, true>;
     int occ = 0;
     int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ);
     if (rcs) return rcs;
@@ -1023,7 +1084,7 @@ static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch,
-                                                           info_out, vecB);
+                                                           info_out, vecB, nr);
     QLB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -1142,12 +1203,12 @@ static int launch_apply_generic(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
 
 template <typename T, int N, int MODE>
 static int dispatch_apply_nr(qlb200_ctx *h, const T *A, int64_t lda, int64_t strideA, const T *tau, int64_t strideTau,
-                             T *B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch, int32_t *info_out) {
+                             T *B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch, int32_t *info_out, int nr = N) {
     // NR = columns of B handled per pass (a power of two <= 8)
-    if (nrhs > 4) return launch_apply_batched<T, N, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
-    if (nrhs > 2) return launch_apply_batched<T, N, 4, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
-    if (nrhs > 1) return launch_apply_batched<T, N, 2, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
-    return launch_apply_batched<T, N, 1, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
+    if (nrhs > 4) return launch_apply_batched<T, N, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
+    if (nrhs > 2) return launch_apply_batched<T, N, 4, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
+    if (nrhs > 1) return launch_apply_batched<T, N, 2, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
+    return launch_apply_batched<T, N, 1, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
 }
 
 template <typename T, int MODE>
@@ -1159,6 +1220,10 @@ static int dispatch_apply_n(qlb200_ctx *h, int64_t n, const T *A, int64_t lda, i
         case 16: return dispatch_apply_nr<T, 16, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
         case 32: return dispatch_apply_nr<T, 32, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
     }
+    // other orders up to 32: the next larger tile, zero-padded in front (see the factorization)
+    if (n >= 1 && n < 8) return dispatch_apply_nr<T, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, (int)n);
+    if (n > 8 && n < 16) return dispatch_apply_nr<T, 16, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, (int)n);
+    if (n > 16 && n < 32) return dispatch_apply_nr<T, 32, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, (int)n);
     if (n >= 1 && n <= 64)
         return launch_apply_generic<T, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, (int)n, nrhs, batch, info_out);
     return qlb_fail(h, -2, "batched apply: n must be in [1,64]%s");
@@ -1182,6 +1247,11 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
                 return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched_split32<double, 4, 3, 3>(h, A, lda, strideA, tau, strideTau, batch);
     }
+    // every other order up to 32: the next larger register tile, the matrix in its bottom-right corner (zero padding, the
+    // padded steps are not taken)
+    if (n >= 1 && n < 8) return qlb::launch_geqlf_batched<double, 8, 1, 4, 6>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+    if (n > 8 && n < 16) return qlb::launch_geqlf_batched<double, 16, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+    if (n > 16 && n < 32) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }
@@ -1194,6 +1264,9 @@ int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64
             if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched_split32<float, 4, 3, 5>(h, A, lda, strideA, tau, strideTau, batch);
     }
+    if (n >= 1 && n < 8) return qlb::launch_geqlf_batched<float, 8, 1, 4, 8>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+    if (n > 8 && n < 16) return qlb::launch_geqlf_batched<float, 16, 2, 4, 5>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+    if (n > 16 && n < 32) return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }

@@ -50,10 +50,11 @@ def test_batched_geqlf_vs_oracle(q, h, n, dt, batch):
     _check_factors(F, tau, Fo, tauo, A, n, dt)
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 12, 31, 33, 48, 64])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7, 9, 12, 15, 17, 20, 24, 31, 33, 40, 48, 56, 63, 64])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_batched_generic_sizes_vs_lapack(q, h, n, dt):
-    """Sizes without a register kernel go through the generic ?geql2/?larfg kernel (any n <= 64)."""
+    """Orders other than 8/16/32: n < 32 runs on the next larger register tile (zero-padded in front, the padded steps are
+    not taken), 32 < n <= 64 on the shared-memory kernels."""
     rng = np.random.default_rng(n)
     A = rng.standard_normal((70, n, n)).astype(dt)
     F, tau = q.ql_batched_(A.copy(), handle=h)
@@ -193,7 +194,7 @@ def test_batched_argument_errors(q, h):
         q.lmul_batched_(np.zeros((2, 32, 32)), np.zeros((2, 32)), np.zeros((2, 4, 16)), handle=h)
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 12, 24, 31, 33, 48, 64])
+@pytest.mark.parametrize("n", [1, 2, 5, 7, 9, 12, 20, 24, 31, 33, 48, 64])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("nrhs", [1, 3, 8, 11])
 def test_batched_generic_sizes_lmul_and_solve_vs_oracle(q, h, n, dt, nrhs):
