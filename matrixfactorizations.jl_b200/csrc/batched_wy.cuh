@@ -1,0 +1,329 @@
+// batched_wy.cuh -- batched Float64 QL for 32 < n <= 64: matrix resident in shared memory, 8-column panel in registers,
+// compact-WY trailing update on the FP64 tensor pipe (DMMA.8x8x4).  Included by batched.cu (uses its TMA / ?larfg helpers).
+//
+// Per-matrix semantics = ql! for BlasFloat (LAPACK dgeqlf conventions, reference src/ql.jl:72, spec src/ql.jl:56-68).
+// A 64 x 64 Float64 matrix (32 KB) does not fit the register tile of geqlf_batched_kernel, so:
+//   * one warp owns one matrix; the matrix lives in the warp's shared-memory image (column pitch LD = 8 mod 16 doubles);
+//   * panels of 8 columns, from the right.  The panel is held row-distributed in registers: lane l owns rows l and l+32
+//     of all 8 columns, so the reflector dot products are lane-local FMAs finished by ONE 8-value butterfly all-reduce
+//     per step -- no shared-memory traffic inside the 8 steps of a panel;
+//   * the step body is uniform (a real loop, 8 trips): the pivot column always sits at panel index 7; after each step the
+//     columns rotate one index up and the finished reflector re-enters at index 0.  The butterfly therefore also reduces
+//     v_r' v_c for the finished reflectors c > r, which is exactly the Gram row the compact-WY factor needs:
+//         M = H_0 H_1 ... H_7 = I - V S V',  S upper triangular,  S[r][r] = tau_r,
+//         S[r][c] = -tau_r sum_{k=r+1..c} (v_r' v_k) S[k][c]      (lane c keeps column c of S, rotating with the panel);
+//   * trailing update C <- C - V S (V' C) per 8-column tile of C as three small DMMA products on fragments read straight
+//     from the image:  W = C'V (K = rows),  W2 = -W S',  C' += W2 V'.  The C fragment loaded for W (16-byte loads, rows
+//     2t, 2t+1 of column g) is the accumulator fragment of the last product: every tile of C is read and written once per
+//     panel.  tools/proto_wy_batched.py is the NumPy model of this arithmetic (checked against LAPACK dgeqlf).
+// Orders that are not a multiple of 8 use the next tile order: the matrix sits in the bottom-right corner (TMA loads from
+// negative coordinates zero-fill the rest), padded steps are skipped, the corner goes out with plain stores.
+// Matrices whose squares leave the plain range (or with an exactly zero tail) are flagged and redone by geql2_warp.
+#pragma once
+
+namespace qlb {
+
+template <int NT>
+struct WyCfg {
+    static_assert(NT % 8 == 0 && NT >= 8 && NT <= 64, "tile order");
+    static constexpr int LD = (NT % 16 == 8) ? NT : NT + 8;      // 2 adjacent columns' 64-byte row blocks -> different bank halves
+    static constexpr int NP = NT / 8;                            // panels
+    static constexpr int NSLOT = (NT + 31) / 32;                 // rows per lane
+    static constexpr int IMG_BYTES = NT * LD * 8;
+    static constexpr int S_OFF = IMG_BYTES;                      // 8 x 8 doubles: -S of the current panel
+    static constexpr int TAU_OFF = S_OFF + 512;                  // NT doubles
+    static constexpr int BAR_OFF = TAU_OFF + 512;
+    static constexpr int WARP_BYTES = BAR_OFF + 128;
+    static constexpr int WARPS_MAX = (232448 / WARP_BYTES) > 12 ? 12 : (232448 / WARP_BYTES);
+};
+
+// Trailing update of panel p (columns 8p..8p+7, NB = p+1 row blocks of 8) on the column tiles jt0 .. p-1.
+// g = lane >> 2, t = lane & 3 (DMMA fragment coordinates, common.cuh).
+template <int NT, int NB>
+__device__ __forceinline__ void wy_update(double *img, const double *sS, int jt0, int lane) {
+    constexpr int LD = WyCfg<NT>::LD;
+    constexpr int p = NB - 1;
+    const int g = lane >> 2, t = lane & 3;
+    // B fragments of W = C'V:  V[8mb + 2t + s][g]   (one 16-byte load per row block)
+    // B fragments of C' += W2 V':  V[8mb + g][2t + s]
+    double2 Vf[NB];
+    double VT[NB][2];
+    const double *vcol = img + (8 * p + g) * LD + 2 * t;
+    const double *vt0 = img + (8 * p + 2 * t) * LD + g;
+#pragma unroll
+    for (int mb = 0; mb < NB; ++mb) {
+        Vf[mb] = *reinterpret_cast<const double2 *>(vcol + 8 * mb);
+        VT[mb][0] = vt0[8 * mb];
+        VT[mb][1] = vt0[LD + 8 * mb];
+    }
+    // the image holds the PACKED panel: make the diagonal block explicit (unit pivot, zeros below it)
+    {
+        const int r0 = 2 * t, r1 = 2 * t + 1;                 // row inside the block, column g
+        Vf[p].x = (r0 < g) ? Vf[p].x : ((r0 == g) ? 1.0 : 0.0);
+        Vf[p].y = (r1 < g) ? Vf[p].y : ((r1 == g) ? 1.0 : 0.0);
+        VT[p][0] = (g < r0) ? VT[p][0] : ((g == r0) ? 1.0 : 0.0);      // row g, column 2t
+        VT[p][1] = (g < r1) ? VT[p][1] : ((g == r1) ? 1.0 : 0.0);      // row g, column 2t+1
+    }
+    const double Sf0 = sS[(2 * t) * 8 + g], Sf1 = sS[(2 * t + 1) * 8 + g];       // -S[g][2t+s]
+#pragma unroll 1
+    for (int jt = jt0; jt < p; ++jt) {
+        double2 acc[NB];
+        double *ccol = img + (8 * jt + g) * LD + 2 * t;
+        double wa0 = 0.0, wa1 = 0.0, wb0 = 0.0, wb1 = 0.0;     // two accumulation chains (DMMA dependent latency ~26 cycles)
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+            acc[mb] = *reinterpret_cast<const double2 *>(ccol + 8 * mb);
+            if (mb & 1) {
+                dmma884(wb0, wb1, acc[mb].x, Vf[mb].x);
+                dmma884(wb0, wb1, acc[mb].y, Vf[mb].y);
+            } else {
+                dmma884(wa0, wa1, acc[mb].x, Vf[mb].x);
+                dmma884(wa0, wa1, acc[mb].y, Vf[mb].y);
+            }
+        }
+        const double w0 = wa0 + wb0, w1 = wa1 + wb1;           // W[j0+g][2t], W[j0+g][2t+1]
+        double u0 = 0.0, u1 = 0.0;                             // W2 = -W S'
+        dmma884(u0, u1, w0, Sf0);
+        dmma884(u0, u1, w1, Sf1);
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+            dmma884(acc[mb].x, acc[mb].y, u0, VT[mb][0]);
+            dmma884(acc[mb].x, acc[mb].y, u1, VT[mb][1]);
+            *reinterpret_cast<double2 *>(ccol + 8 * mb) = acc[mb];
+        }
+    }
+}
+
+template <int NT, int WARPS, bool USE_TMA, bool PADDED>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A, int64_t lda, int64_t strideA,
+                double *__restrict__ tau, int64_t strideTau, int64_t batch, int nr_arg) {
+    using Cfg = WyCfg<NT>;
+    constexpr int LD = Cfg::LD, NSLOT = Cfg::NSLOT, NP = Cfg::NP;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
+    double *img = reinterpret_cast<double *>(wbase);
+    double *sS = reinterpret_cast<double *>(wbase + Cfg::S_OFF);
+    double *taus = reinterpret_cast<double *>(wbase + Cfg::TAU_OFF);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + Cfg::BAR_OFF);
+    const int nr = PADDED ? nr_arg : NT;
+    const int pad = NT - nr;
+    const int nbatch = (int)batch;
+    const int gw = (int)blockIdx.x * WARPS + warp, nw = (int)gridDim.x * WARPS;
+    if constexpr (USE_TMA) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
+    uint32_t phase = 0;
+    for (int mi = gw; mi < nbatch; mi += nw) {
+        double *Am = A + (int64_t)mi * strideA;
+        if constexpr (USE_TMA) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, (uint32_t)Cfg::IMG_BYTES);
+                tma_load_3d(img, &tmap, -pad, -pad, mi, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            __syncwarp();
+        } else {
+            for (int c = 0; c < NT; ++c)
+                for (int r = lane; r < NT; r += 32) img[c * LD + r] = (c >= pad && r >= pad) ? Am[(int64_t)(c - pad) * lda + (r - pad)] : 0.0;
+            __syncwarp();
+        }
+        bool bad = false;
+#pragma unroll 1
+        for (int p = NP - 1; p >= 0; --p) {
+            if (8 * p + 7 < pad) break;                        // the remaining panels are padding
+            // slot 0 = the 32-row half that holds this panel's pivot rows (8p .. 8p+7 never straddle a multiple of 32), slot 1 the other
+            // half: the pivot-row broadcast needs no per-column select
+            double P[8][NSLOT];
+            int row[NSLOT];
+            row[0] = lane + ((8 * p) & 32);
+            if constexpr (NSLOT == 2) row[1] = lane + (((8 * p) & 32) ^ 32);
+            const double *pcol = img + (8 * p) * LD;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) P[i][s] = (NT % 32 == 0 || row[s] < NT) ? pcol[i * LD + row[s]] : 0.0;
+            double Sr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Sr[i] = 0.0;
+#pragma unroll 2
+            for (int r = 7; r >= 0; --r) {
+                const int R = 8 * p + r;                       // pivot row = pivot column
+                const bool active = R > pad;                   // R == pad: the matrix's first column (identity, tau = 0); R < pad: padding
+                const int lp = R & 31;
+                double x7[NSLOT], xm[NSLOT];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) {
+                    x7[s] = P[7][s];
+                    xm[s] = (row[s] < R) ? x7[s] : 0.0;
+                }
+                // d_i = x' P_i over the tail rows: i = 7 -> |x|^2; live columns -> the update's dot products; finished
+                // reflectors -> the Gram row of the compact-WY factor
+                double d[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    d[i] = xm[0] * P[i][0];
+                    if constexpr (NSLOT == 2) d[i] = fma(xm[1], P[i][1], d[i]);
+                }
+                // all-reduce of the 8 sums over the 32 lanes, transposing: each stage halves the number of values a lane carries
+                // (34 shuffle instructions instead of the butterfly's 80: the shuffle unit is what bounds this loop); the total of
+                // value i ends up in lanes 4i..4i+3 and is broadcast from lane 4i, so every lane sees the same bits
+                {
+                    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                    double e[4], f[2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double send = b4 ? d[k] : d[k + 4], keep = b4 ? d[k + 4] : d[k];
+                        e[k] = keep + __shfl_xor_sync(FULL, send, 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const double send = b3 ? e[k] : e[k + 2], keep = b3 ? e[k + 2] : e[k];
+                        f[k] = keep + __shfl_xor_sync(FULL, send, 8);
+                    }
+                    const double send = b2 ? f[0] : f[1], keep = b2 ? f[1] : f[0];
+                    double hsum = keep + __shfl_xor_sync(FULL, send, 4);
+                    hsum += __shfl_xor_sync(FULL, hsum, 2);
+                    hsum += __shfl_xor_sync(FULL, hsum, 1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[i] = __shfl_sync(FULL, hsum, 4 * i);
+                }
+                double aR[8];                                  // row R of the panel
+#pragma unroll
+                for (int i = 0; i < 8; ++i) aR[i] = __shfl_sync(FULL, P[i][0], lp);
+                const double ssq = d[7], alpha = aR[7];
+                const double tot = fma(alpha, alpha, ssq);
+                bad = bad || (active && !in_plain_range(ssq, tot));
+                const double rinv = nr_rsqrt(tot);
+                const double nrm = tot * rinv;
+                double beta = -copysign(nrm, alpha);
+                double tauk = fma(fabs(alpha), rinv, 1.0);
+                double scale = nr_rcp(alpha - beta);
+                beta = active ? beta : alpha;
+                tauk = active ? tauk : 0.0;
+                scale = active ? scale : 0.0;
+                if (lane == 0) taus[R] = tauk;
+                double w[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) w[i] = fma(d[i], scale, aR[i]);
+                // S[r][c] for this lane's column c = lane (lanes 0..7 matter): Sr[i] = S[r+1+i][c]
+                double sacc = 0.0;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) sacc = fma(w[i], Sr[i], sacc);
+                const double snew = (lane == r) ? tauk : -tauk * sacc;
+#pragma unroll
+                for (int i = 7; i >= 1; --i) Sr[i] = Sr[i - 1];
+                Sr[0] = snew;
+                // rank-1 update of the live columns, every column one index up, the finished reflector to index 0
+                double vf[NSLOT], v[NSLOT];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) {
+                    v[s] = xm[s] * scale;
+                    vf[s] = (row[s] == R) ? 1.0 : v[s];
+                }
+#pragma unroll
+                for (int i = 6; i >= 0; --i) {
+                    const double si = (i + r >= 7) ? tauk * w[i] : 0.0;
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s) P[i + 1][s] = fma(-si, vf[s], P[i][s]);
+                }
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) P[0][s] = (row[s] < R) ? v[s] : ((row[s] == R) ? beta : x7[s]);
+            }
+            // the packed panel goes back into the image, -S into the scratch
+            double *pw = img + (8 * p) * LD;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (NT % 32 == 0 || row[s] < NT) pw[i * LD + row[s]] = P[i][s];
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sS[lane * 8 + i] = -Sr[i];
+            }
+            __syncwarp();
+            const int jt0 = pad >> 3;                          // column tiles left of it are padding
+            if (jt0 < p) {
+                switch (p) {
+                    case 1: wy_update<NT, 2>(img, sS, jt0, lane); break;
+                    case 2: if constexpr (NT >= 24) wy_update<NT, 3>(img, sS, jt0, lane); break;
+                    case 3: if constexpr (NT >= 32) wy_update<NT, 4>(img, sS, jt0, lane); break;
+                    case 4: if constexpr (NT >= 40) wy_update<NT, 5>(img, sS, jt0, lane); break;
+                    case 5: if constexpr (NT >= 48) wy_update<NT, 6>(img, sS, jt0, lane); break;
+                    case 6: if constexpr (NT >= 56) wy_update<NT, 7>(img, sS, jt0, lane); break;
+                    case 7: if constexpr (NT >= 64) wy_update<NT, 8>(img, sS, jt0, lane); break;
+                    default: break;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- output ----
+        if (!bad) {
+            for (int i = lane; i < nr; i += 32) tau[(int64_t)mi * strideTau + i] = taus[i + pad];
+        }
+        if constexpr (USE_TMA && !PADDED) {
+            fence_proxy_async();
+            __syncwarp();
+            if (!bad && lane == 0) tma_store_3d(&tmap, 0, 0, mi, img);
+            tma_store_commit();
+            tma_store_wait_read();
+            __syncwarp();
+        } else {
+            if (!bad) {
+                if (USE_TMA && (pad & 1) == 0) {
+                    const int nv = nr >> 1;
+                    for (int c = 0; c < nr; ++c)
+                        for (int vv = lane; vv < nv; vv += 32)
+                            *reinterpret_cast<double2 *>(Am + (int64_t)c * lda + 2 * vv) = *reinterpret_cast<const double2 *>(img + (c + pad) * LD + pad + 2 * vv);
+                } else {
+                    for (int c = 0; c < nr; ++c)
+                        for (int r = lane; r < nr; r += 32) Am[(int64_t)c * lda + r] = img[(c + pad) * LD + pad + r];
+                }
+            }
+            if constexpr (USE_TMA) fence_proxy_async();
+            __syncwarp();
+        }
+        if (bad) {        // rare: the matrix is untouched in global memory; literal ?geql2 / ?larfg with the image as scratch
+            geql2_warp<double>(Am, lda, tau + (int64_t)mi * strideTau, nr, img, lane);
+            if constexpr (USE_TMA) fence_proxy_async();
+            __syncwarp();
+        }
+    }
+    if constexpr (USE_TMA) tma_store_wait_all();
+}
+
+template <int NT>
+static int launch_geqlf_wy(qlb200_ctx *h, double *A, int64_t lda, int64_t strideA, double *tau, int64_t strideTau, int64_t batch, int nr) {
+    using Cfg = WyCfg<NT>;
+    constexpr int WARPS = Cfg::WARPS_MAX;
+    static_assert(Cfg::IMG_BYTES + 1024 >= ((NT + 1) * NT + NT) * 8, "the image + scratch hold the generic routine's scratch");
+    const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES;
+    if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<double>(&tmap, A, nr, lda, strideA, batch, Cfg::LD, NT);
+    void (*kern)(const CUtensorMap, double *, int64_t, int64_t, double *, int64_t, int64_t, int);
+    if (nr == NT) kern = tma ? geqlf_wy_kernel<NT, WARPS, true, false> : geqlf_wy_kernel<NT, WARPS, false, false>;
+    else kern = tma ? geqlf_wy_kernel<NT, WARPS, true, true> : geqlf_wy_kernel<NT, WARPS, false, true>;
+    int occ = 0;
+    int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ);
+    if (rcs) return rcs;
+    if (occ < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched WY QL kernel does not fit on an SM%s");
+    int64_t blocks = (batch + WARPS - 1) / WARPS;
+    int64_t cap = (int64_t)h->sm_count * occ;
+    if (h->opt_bgrid > 0 && cap > h->opt_bgrid) cap = h->opt_bgrid;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, nr);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+}  // namespace qlb

@@ -71,3 +71,11 @@ if case == "strips":
         h.call("qlb200_dgeqlf_dev", m, w, A.data_ptr(), A.stride(1), tau.data_ptr())
     torch.cuda.synchronize()
     print("strips done")
+if case == "bql":
+    # batched Float64 QL of order n (PROF_BATCH matrices): the shared-memory WY kernel for n > 32
+    nb = int(os.environ.get("PROF_BATCH", "32768"))
+    A = torch.randn(nb, n, n, dtype=torch.float64, device="cuda")
+    tau = torch.empty(nb, n, dtype=torch.float64, device="cuda")
+    q.ql_batched_(A, tau, handle=h)
+    torch.cuda.synchronize()
+    print("bql done", h.launches)
