@@ -126,6 +126,44 @@ int qlb200_dqllstsq(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const d
 int qlb200_dqllstsq_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
                         const double *dtau, double *dB, int64_t ldb);
 
+/* ---- SURVEY.md 8(f) N1 + the Float32 half of A4: the other BlasFloat element types of the same hook -------------------
+ * Reference src/ql.jl:72 `qlfactUnblocked!(A::StridedMatrix{T}) where T<:BlasFloat = QL(LAPACK.geqlf!(A)...)` is hit by
+ * Float32, ComplexF64 and ComplexF32 as well (the element-type sweep of test/test_ql.jl:35-56); the Q-apply loops carry the
+ * conj at src/ql.jl:336,366,368,400,426,429 and ldiv! is src/ql.jl:440-447,467.
+ *   z: ComplexF64, interleaved (re, im) = Julia's Matrix{ComplexF64}; lda/ldc/ldb in COMPLEX elements; tau complex.  LAPACK
+ *      zgeqlf / zunmql conventions (beta real, H = I - tau v v^H, trans is 'N' or 'C').  Panel: complex kernels; trailing
+ *      update: the FP64 DMMA GEMMs on the real 2x2-block form of V and T (csrc/complex.cu).
+ *   s: Float32, c: ComplexF32: widened on the device to the d / z path and narrowed again (csrc/mixed.cu states why).
+ * Same return codes as the d forms (i > 0 from ?qlsolve: L[i,i] == 0, host-pointer form only). */
+int qlb200_zgeqlf(qlb200_handle h, int64_t m, int64_t n, void *A, int64_t lda, void *tau);
+int qlb200_zgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, void *dA, int64_t lda, void *dtau);
+int qlb200_zunmql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *A, int64_t lda,
+                  const void *tau, void *C, int64_t ldc);
+int qlb200_zunmql_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *dA, int64_t lda,
+                      const void *dtau, void *dC, int64_t ldc);
+int qlb200_zqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const void *A, int64_t lda, const void *tau, void *B, int64_t ldb);
+int qlb200_zqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const void *dA, int64_t lda, const void *dtau, void *dB,
+                        int64_t ldb);
+int qlb200_cgeqlf(qlb200_handle h, int64_t m, int64_t n, void *A, int64_t lda, void *tau);
+int qlb200_cgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, void *dA, int64_t lda, void *dtau);
+int qlb200_cunmql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *A, int64_t lda,
+                  const void *tau, void *C, int64_t ldc);
+int qlb200_cunmql_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *dA, int64_t lda,
+                      const void *dtau, void *dC, int64_t ldc);
+int qlb200_cqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const void *A, int64_t lda, const void *tau, void *B, int64_t ldb);
+int qlb200_cqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const void *dA, int64_t lda, const void *dtau, void *dB,
+                        int64_t ldb);
+int qlb200_sgeqlf(qlb200_handle h, int64_t m, int64_t n, float *A, int64_t lda, float *tau);
+int qlb200_sgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, float *dA, int64_t lda, float *dtau);
+int qlb200_sormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *A, int64_t lda,
+                  const float *tau, float *C, int64_t ldc);
+int qlb200_sormql_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *dA, int64_t lda,
+                      const float *dtau, float *dC, int64_t ldc);
+int qlb200_sqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const float *A, int64_t lda, const float *tau, float *B,
+                    int64_t ldb);
+int qlb200_sqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const float *dA, int64_t lda, const float *dtau, float *dB,
+                        int64_t ldb);
+
 /* ---- RQ through index reversal -------------------------------------------------------------
  * Replaces rq!(A::StridedMatrix{<:BlasFloat}) = RQ(LAPACK.gerqf!(A)...) (reference
  * src/rq.jl:401): gerqf(A) = geqlf(A^T)^T with identical tau. */

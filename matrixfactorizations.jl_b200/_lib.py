@@ -59,6 +59,14 @@ for _sfx in ("", "_dev"):
     SIGNATURES[f"qlb200_dqrsolve{_sfx}"] = [_I, _I, _I, _P, _I, _P, _P, _I]
     SIGNATURES[f"qlb200_dulfact{_sfx}"] = _UL
     SIGNATURES[f"qlb200_dulsolve{_sfx}"] = _ULS
+    # Float32 (promoted), ComplexF64 (complex.cu) and ComplexF32 (promoted) single-matrix QL path
+    SIGNATURES[f"qlb200_sgeqlf{_sfx}"] = _FACT
+    SIGNATURES[f"qlb200_sormql{_sfx}"] = _ORM
+    SIGNATURES[f"qlb200_sqlsolve{_sfx}"] = _SOLVE
+    for _t in "zc":
+        SIGNATURES[f"qlb200_{_t}geqlf{_sfx}"] = _FACT
+        SIGNATURES[f"qlb200_{_t}unmql{_sfx}"] = _ORM
+        SIGNATURES[f"qlb200_{_t}qlsolve{_sfx}"] = _SOLVE
     for _t in "ds":
         SIGNATURES[f"qlb200_{_t}geqlf_batched{_sfx}"] = _FACT_B
         SIGNATURES[f"qlb200_{_t}ormql_batched{_sfx}"] = _ORM_B

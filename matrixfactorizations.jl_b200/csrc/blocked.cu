@@ -42,14 +42,7 @@ static int choose_splits(int sm, int64_t tiles, int K, int minchunk, int maxS) {
 // operands (a few right-hand sides) give only a handful of tiles and need deep splits to occupy the machine.
 static int max_w_splits(int64_t other) { return other >= 2048 ? 8 : (other >= 512 ? 32 : 128); }
 
-struct Workspace {
-    double *Vw;  int64_t ldv;      // clean reflector block, p x nb
-    double *T;   int64_t ldt;      // nb x nb
-    double *Ts;                    // 16 x 16 strip T
-    double *G;                     // nb x nb Gram matrix
-    double *Wsum, *W2; int64_t ldw; // (other dimension) x nb
-    double *part; int64_t part_elems;
-};
+using Workspace = ::QlbWorkspace;      // internal.h (shared with complex.cu)
 
 // Carve the handle's workspace.  rows = reflector length bound, other = largest number of operand
 // columns (rows for side 'R') a block reflector is applied to.  With `two` a second, independent set is
@@ -130,10 +123,12 @@ static int build_T(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, int p, i
 // wait_T: event after which T is valid (T may still be under construction on another stream while W is computed).
 static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool left, bool tt, const double *V,
                        int64_t ldv, const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other,
-                       cudaEvent_t wait_T = nullptr, int sms = 0) {
+                       cudaEvent_t wait_T = nullptr, int sms = 0, bool dense_T = false) {
     if (sms <= 0) sms = h->sm_count;               // SMs the stream can use (an SM partition in look-ahead mode)
     if (other <= 0 || p <= 0 || ib <= 0) return 0;
-    const bool small = ib <= 16 && other <= 256;      // in-panel strip update: many thin partials, fused reduce*T
+    // in-panel strip update: many thin partials, fused reduce*T (that kernel reads only the lower triangle of T: not for the
+    // real block form of a complex T, whose 2x2 diagonal blocks reach above the diagonal)
+    const bool small = ib <= 16 && other <= 256 && !dense_T;
     const int cfg_w = ib <= 16 ? 2 : -1;
     // 1. W partials: M = other, N = ib, K = p
     const int64_t tiles = (int64_t)((other + 127) / 128) * ((ib + 63) / 64);      // 128x64 tiles, 2 CTAs per SM
@@ -267,6 +262,28 @@ __global__ void __launch_bounds__(256) checksum_kernel(const double *__restrict_
 }  // namespace qlb
 
 using namespace qlb;
+
+// The block-reflector machinery for complex.cu: a complex block reflector is applied as a REAL one of twice the size
+// (V and T in their real 2x2-block form, C through its interleaved storage), see complex.cu.
+int qlb_block_workspace(qlb200_ctx *h, int64_t rows, int64_t other, int nb, QlbWorkspace *w) {
+    return get_workspace(h, rows, other, nb, max_w_splits(other), w);
+}
+int qlb_block_apply(qlb200_ctx *h, cudaStream_t st, const QlbWorkspace &ws, bool left, bool tt, const double *V, int64_t ldv,
+                    const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other) {
+    return apply_block(h, st, ws, left, tt, V, ldv, T, ldt, p, ib, C, ldc, other, nullptr, 0, /*dense_T=*/true);
+}
+int qlb_block_gram(qlb200_ctx *h, cudaStream_t st, const QlbWorkspace &ws, int p, int ib) {
+    // ws.G (ib x ib, ld ib) = V'V of ws.Vw[0:p, 0:ib]
+    int S = (p + 127) / 128;
+    if (S > 148) S = 148;
+    S = qlb_gemm_splits(p, S, 16);
+    const int64_t stride = (int64_t)ib * ib;
+    int rc = qlb_gemm(h, st, ib <= 16 ? 2 : -1, true, true, ib, ib, p, 1.0, ws.Vw, ws.ldv, ws.Vw, ws.ldv, 0.0, S > 1 ? ws.part : ws.G, ib,
+                      S, stride);
+    if (rc) return rc;
+    if (S > 1) rc = qlb_reduce_partials(h, st, ws.part, S, stride, ib, ib, ib, ws.G, ib);
+    return rc;
+}
 
 static int factors_checksum(qlb200_ctx *h, cudaStream_t st, const double *V, int64_t ldv, int nq, int k, const double *tau,
                             unsigned long long *out) {

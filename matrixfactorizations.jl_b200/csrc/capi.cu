@@ -130,6 +130,8 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->tc_sum_dev) cudaFree(h->tc_sum_dev);
     if (h->ev_tc) cudaEventDestroy(h->ev_tc);
     if (h->redo) cudaFree(h->redo);
+    for (int i = 0; i < 3; ++i)
+        if (h->cvt[i]) cudaFree(h->cvt[i]);
     if (h->tall) cudaFree(h->tall);
     if (h->tcache) cudaFree(h->tcache);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);

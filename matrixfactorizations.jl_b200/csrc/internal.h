@@ -4,6 +4,28 @@
 #include <stdint.h>
 struct qlb200_ctx;
 
+// carved from the handle's workspace by blocked.cu
+struct QlbWorkspace {
+    double *Vw;  int64_t ldv;      // clean reflector block, p x nb
+    double *T;   int64_t ldt;      // nb x nb
+    double *Ts;                    // 16 x 16 strip T
+    double *G;                     // nb x nb Gram matrix
+    double *Wsum, *W2; int64_t ldw; // (other dimension) x nb
+    double *part; int64_t part_elems;
+};
+int qlb_block_workspace(qlb200_ctx *h, int64_t rows, int64_t other, int nb, QlbWorkspace *w);
+// C <- (I - V Tm' V') C (left; Tm = T, or T' when tt) or C (I - V Tm V') (right): see apply_block in blocked.cu
+int qlb_block_apply(qlb200_ctx *h, cudaStream_t st, const QlbWorkspace &ws, bool left, bool tt, const double *V, int64_t ldv,
+                    const double *T, int64_t ldt, int p, int ib, double *C, int64_t ldc, int other);
+int qlb_block_gram(qlb200_ctx *h, cudaStream_t st, const QlbWorkspace &ws, int p, int ib);
+
+// complex.cu (device pointers, interleaved complex, asynchronous on h->stream)
+int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb_zunmql_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                   const double *tau, double *C, int64_t ldc);
+int qlb_zqlsolve_dev(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
+                     int64_t ldb, int32_t *dinfo);
+
 // batched.cu
 int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int64_t strideA, double *tau,
                           int64_t strideTau, int64_t batch);

@@ -44,7 +44,15 @@ def _pfx(x) -> str:
         return "d"
     if name.endswith("float32"):
         return "s"
-    raise TypeError(f"qlb200 supports Float64/Float32 (the reference's LAPACK path), got {x.dtype}")
+    if name.endswith("complex128"):
+        return "z"
+    if name.endswith("complex64"):
+        return "c"
+    raise TypeError(f"qlb200 supports the BlasFloat element types Float64/Float32/ComplexF64/ComplexF32 (the reference's LAPACK "
+                    f"path, src/ql.jl:72), got {x.dtype}")
+
+
+_ITEMSIZE = {"d": 8, "s": 4, "z": 16, "c": 8}
 
 
 class _Mat:
@@ -80,7 +88,7 @@ class _Mat:
                 pass
             self.ptr, self.dev, self.device_index = x.ctypes.data, False, 0
         self.pfx = _pfx(x)
-        self.itemsize = 8 if self.pfx == "d" else 4
+        self.itemsize = _ITEMSIZE[self.pfx]
         self.obj = x
 
     @property
@@ -236,8 +244,8 @@ def ql(A, handle=None) -> QL:
     """ql(A): copy, then ql! (src/ql.jl:179-186).  Vectors/scalars become n x 1 (src/ql.jl:187-191)."""
     if not _is_torch(A):
         A = np.asarray(A)
-        if A.dtype not in (np.float32, np.float64):
-            A = A.astype(np.float64)        # _qleltype promotion (src/ql.jl:119)
+        if A.dtype not in (np.float32, np.float64, np.complex64, np.complex128):
+            A = A.astype(np.complex128 if np.iscomplexobj(A) else np.float64)        # _qleltype promotion (src/ql.jl:119)
         if A.ndim < 2:
             A = A.reshape(-1, 1)
     return ql_(_copy_colmajor(A), handle)
@@ -426,12 +434,13 @@ def _ormql(side, Q: QLPackedQ, C):
     mA, nA = f.m, f.n
     k = min(mA, nA)
     # the reflectors live in the LAST k columns of the factors (src/ql.jl:331,361: k from nA-mA+1)
-    aptr = f.ptr + (nA - k) * f.ld * (8 if f.pfx == "d" else 4)
+    aptr = f.ptr + (nA - k) * f.ld * f.itemsize
     nq = c.m if side == "L" else c.n
     if nq != mA:     # src/ql.jl:326-328,356-358,385-387,414-416
         raise DimensionMismatch(f"matrix A has dimensions ({mA},{nA}) but {'B' if side == 'L' else 'A'} has dimensions ({c.m}, {c.n})")
-    h.call(f"qlb200_{f.pfx}ormql{f.sfx}", side.encode(), (b"T" if Q.adjoint else b"N"), c.m, c.n, k, aptr, f.ld,
-           t.ptr, c.ptr, c.ld)
+    cplx = f.pfx in "zc"          # complex: ?unmql; Q.T is the ADJOINT Q' (conj at src/ql.jl:336,366,368,400,426,429)
+    name = f"qlb200_{f.pfx}{'unmql' if cplx else 'ormql'}{f.sfx}"
+    h.call(name, side.encode(), ((b"C" if cplx else b"T") if Q.adjoint else b"N"), c.m, c.n, k, aptr, f.ld, t.ptr, c.ptr, c.ld)
     return C
 
 

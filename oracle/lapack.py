@@ -55,7 +55,7 @@ def _p(a):
 
 
 def _pre(a):
-    return {np.dtype(np.float64): "d", np.dtype(np.float32): "s"}[a.dtype]
+    return {np.dtype(np.float64): "d", np.dtype(np.float32): "s", np.dtype(np.complex128): "z", np.dtype(np.complex64): "c"}[a.dtype]
 
 
 def _real(a):
@@ -73,7 +73,7 @@ def _fact(name, A, inplace=False):
     info = c_int(0)
     wq = np.zeros(1, dtype=A.dtype)
     fn(byref(c_int(m)), byref(c_int(n)), _p(A), byref(c_int(lda)), _p(tau), _p(wq), byref(c_int(-1)), byref(info))
-    lwork = max(1, int(wq[0]))
+    lwork = max(1, int(np.real(wq[0])))
     work = np.empty(lwork, dtype=A.dtype)
     fn(byref(c_int(m)), byref(c_int(n)), _p(A), byref(c_int(lda)), _p(tau), _p(work), byref(c_int(lwork)), byref(info))
     if info.value != 0:
@@ -107,6 +107,8 @@ def _orm(name, side, trans, A, tau, C):
     lda = max(1, A.strides[1] // A.itemsize)
     ldc = max(1, C.strides[1] // C.itemsize)
     tau = np.ascontiguousarray(tau, dtype=A.dtype)
+    if _pre(A) in "zc":
+        name = name.replace("orm", "unm")          # ?unmql / ?unmqr / ?unmrq (trans 'N' or 'C')
     fn = getattr(lib(), f"scipy_{_pre(A)}{name}_")
     info = c_int(0)
     wq = np.zeros(1, dtype=A.dtype)
@@ -115,7 +117,7 @@ def _orm(name, side, trans, A, tau, C):
                           byref(c_int(lda)), _p(tau), _p(C), byref(c_int(ldc)), _p(w), byref(c_int(lw)), byref(info),
                           ctypes.c_size_t(1), ctypes.c_size_t(1))
     fn(*args(wq, -1))
-    lwork = max(1, int(wq[0]))
+    lwork = max(1, int(np.real(wq[0])))
     work = np.empty(lwork, dtype=A.dtype)
     fn(*args(work, lwork))
     if info.value != 0:
