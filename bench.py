@@ -498,7 +498,30 @@ def main():
                                             "max_abs_residual": res1,
                                             "note": "latency-bound on a GPU: 1024 dependent reflector steps (SURVEY.md 8(d)); parity anchor, not a throughput target"}
         del A1, A1w, b1v, b1w
-    # the batched sizes without a register kernel (generic shared-memory kernels): n = 24, 48, 64 Float64, factor only
+        # the other BlasFloat element types of the same hook (src/ql.jl:72): ComplexF64 (complex panel kernels
+        # + the FP64 DMMA GEMMs on the real block form), Float32 / ComplexF32 (promoted to the FP64 path); real-equivalent flops
+        for (tag, tdt, ne, mult) in (("ql_8192_c128", torch.complex128, 8192, 4.0), ("ql_8192_f32", torch.float32, 8192, 1.0),
+                                     ("ql_4096_c64", torch.complex64, 4096, 4.0)):
+            Ae = torch.empty_strided((ne, ne), (1, ne), dtype=tdt, device="cuda")
+            Ae.copy_(torch.randn((ne, ne), dtype=tdt, device="cuda", generator=gB))
+            Aew = torch.empty_strided((ne, ne), (1, ne), dtype=tdt, device="cuda")
+            ts = []
+            for i in range(3):
+                Aew.copy_(Ae)
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                q.ql_(Aew, handle=h)
+                b1.record()
+                torch.cuda.synchronize()
+                if i:
+                    ts.append(b0.elapsed_time(b1) * 1e-3)
+            t_e = min(ts)
+            extras[tag] = {"value": mult * flops_ql(ne) / t_e / 1e9, "unit": "GFLOP/s (real-equivalent: 4/3 n^3, x4 for complex)", "ms": t_e * 1e3,
+                           "frac_of_dgemm_peak": mult * flops_ql(ne) / t_e / 1e12 / peak_tflops}
+            del Ae, Aew
+    # the batched orders other than 8/16/32: n = 24 (zero-padded 32 x 32 register tile), n = 48, 64 (shared-memory resident
+    # matrix, panel in registers, DMMA compact-WY update: batched_wy.cuh), Float64, factor only.  n = 64 is bound by the FP64
+    # pipe, not HBM (350 kflop per 66 KB): fp64_frac = useful flops / the DFMA-DMMA datapath peak of 37.2 TFLOP/s
     for ng in (24, 48, 64):
         bg = 65536
         log_, hig_ = q.shard.shard_range(bg, rank, world)
@@ -509,7 +532,8 @@ def main():
         t_g = timed_dev(lambda: q.ql_batched_(Agw, tg, handle=h), lambda: Agw.copy_(Ag), iters=3)
         by_g = (2 * ng * ng + ng) * 8
         extras[f"batched_{ng}x{ng}_f64_ql"] = {"value": bg / t_g, "unit": "matrices/s", "ms": t_g * 1e3, "total_matrices": bg,
-                                               "hbm_frac": mg * by_g / t_g / 1e9 / hb, "bytes_per_matrix": by_g}
+                                               "hbm_frac": mg * by_g / t_g / 1e9 / hb, "bytes_per_matrix": by_g,
+                                               "fp64_frac": world * mg * (4.0 / 3.0 * ng ** 3) / t_g / 37.2e12 / world}
         del Ag, Agw, tg
 
     traffic = {}
@@ -543,7 +567,10 @@ def main():
                          "launches_timed": gemm_launches, "share_of_step": gemm_ms * 1e-3 / t_prof,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                         "B200 datasheet FP64 tensor = 40 TFLOP/s)",
-                         "whole_ql_frac_of_peak": value / 1e3 / world / peak_tflops},
+                         "whole_ql_frac_of_peak": value / 1e3 / world / peak_tflops,
+                         "frac_of_partition_peak": (gemm_tflops / peak_tflops * 148.0 / 132.0) if gemm_tflops else None,
+                         "partition_note": "the trailing-update GEMMs run on the 132-SM green-context partition (16 SMs factor the next "
+                                           "panel meanwhile); `frac` divides by the 148-SM cuBLAS peak, frac_of_partition_peak by 132/148 of it"},
             "batched": batched, "other_configs": extras,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -10,9 +10,9 @@
 // are expanded (kernels below), the big operand C is used in place, and the trailing update is exactly blocked.cu's
 // apply_block with (2p, 2ib) -- three DMMA GEMMs with the same 8 real flops per complex multiply-add as a complex GEMM.
 //
-// The panel (32 complex columns) is factored column by column with two grid kernels per column (partial dot products, then
-// zlarfg scalars + rank-1 update; every block re-sums the partials in the same fixed order -- bitwise reproducible), the
-// complex analogue of the tall-strip kernels in panel.cu.  Norms are taken scaled by the column's largest entry and zlarfg's
+// The panel (64 complex columns) is factored column by column with ONE grid kernel per column (the end of step C -- zlarfg
+// scalars + rank-1 update -- and the partial dot products of step C-1 on the same rows; every block re-sums the partials in
+// the same fixed order -- bitwise reproducible), the complex analogue of the tall-strip kernels in panel.cu.  Norms are taken scaled by the column's largest entry and zlarfg's
 // safmin loop is followed (LAPACK semantics for matrices scaled far away from 1).  Launch-bound for small n; the GEMMs
 // dominate from n ~ 8192 on.  ComplexF32 is promoted to ComplexF64 (mixed.cu).
 #include "common.cuh"
@@ -26,7 +26,8 @@
 namespace qlb {
 
 constexpr int ZT = 256;        // threads per block of the panel kernels
-constexpr int ZNB = 32;        // complex columns per panel (64 real columns of [[V]])
+constexpr int ZNB = 64;        // complex columns per panel (128 real columns of [[V]]: the K = 128 update GEMMs of the real path)
+constexpr int ZCH = 16;        // columns whose partial dot products a thread accumulates at a time
 constexpr double Z_SAFMIN = 2.2250738585072014e-308 / 1.1102230246251565e-16;
 
 __device__ __forceinline__ double2 zmul(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
@@ -48,13 +49,17 @@ __device__ __forceinline__ double2 zrecip(double c, double d) {
     return make_double2(e / f, -1.0 / f);
 }
 
-// Partial sums of one block of rows for panel column C (pivot row mu, tail rows [0, mu)), the tail scaled by the block's
-// largest component amax_b:  part[b][j] = sum_i conj(x_i / amax_b) a_ij  (j < C),  part[b][C] = (sum_i |x_i / amax_b|^2, 0).
-// Layout of `part` (doubles): nblk x ZNB x 2, then the pivot row ZNB x 2, then amax_b (nblk).
-__global__ void __launch_bounds__(ZT) zdots_kernel(const double2 *__restrict__ A, int64_t lda, int mu, int C, int w,
-                                                   double *__restrict__ part, int rpb) {
-    __shared__ double red[ZT / 32][ZNB][2];
-    __shared__ double mx[ZT / 32];
+// ---- the panel step ------------------------------------------------------------------------------------------------
+// Per panel column C (pivot row mu, tail rows [0, mu)) ONE kernel does, for its block of rows,
+//   (a) the end of step C: re-sum the partials of column C in a fixed order, zlarfg, scale the reflector, rank-1 update of
+//       the panel columns j < C, clean reflector in block form
+//         VV[2r, 2C] = re v_r, VV[2r+1, 2C] = im v_r, VV[2r, 2C+1] = -im v_r, VV[2r+1, 2C+1] = re v_r  (1 at the pivot, 0 below);
+//   (b) the beginning of step C-1 on the rows it has just updated: partial sums for column C-1, the tail scaled by the
+//       block's largest component amax_b:  part[b][j] = sum_i conj(x_i / amax_b) a_ij (j < C-1), part[b][C-1] = sum |x_i / amax_b|^2.
+// (a) needs all blocks' partials of step C, which the previous launch wrote: one launch per column, two partial buffers
+// alternate.  Layout of a partial buffer (doubles): nblk x ZNB x 2, then the pivot row ZNB x 2, then amax_b (nblk).
+__device__ __forceinline__ void z_dots_phase(const double2 *__restrict__ A, int64_t lda, int mu, int C, int w, double *__restrict__ part,
+                                             int rpb, double (*red)[ZCH][2], double *mx) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = blockIdx.x * rpb, r1 = min(r0 + rpb, mu);
     const double2 *xc = A + (int64_t)C * lda;
@@ -69,80 +74,102 @@ __global__ void __launch_bounds__(ZT) zdots_kernel(const double2 *__restrict__ A
     __syncthreads();
     am = mx[0];
     for (int q = 1; q < ZT / 32; ++q) am = fmax(am, mx[q]);
-    double dr[ZNB], di[ZNB];
+    const double ram = am > 0.0 ? 1.0 / am : 0.0;
+    // columns in chunks of ZCH (register accumulators); x is re-read per chunk
+    for (int c0 = 0; c0 <= C; c0 += ZCH) {
+        double dr[ZCH], di[ZCH];
 #pragma unroll
-    for (int j = 0; j < ZNB; ++j) dr[j] = di[j] = 0.0;
-    if (am > 0.0) {
-        const double ram = 1.0 / am;
-        for (int r = r0 + tid; r < r1; r += ZT) {
-            double2 x = xc[r];
-            x.x *= ram;
-            x.y *= ram;
+        for (int j = 0; j < ZCH; ++j) dr[j] = di[j] = 0.0;
+        if (am > 0.0) {
+            for (int r = r0 + tid; r < r1; r += ZT) {
+                double2 x = xc[r];
+                x.x *= ram;
+                x.y *= ram;
 #pragma unroll
-            for (int j = 0; j < ZNB; ++j) {
-                if (j < C) {
-                    const double2 a = A[r + (int64_t)j * lda];
-                    dr[j] = fma(x.x, a.x, fma(x.y, a.y, dr[j]));        // conj(x) a
-                    di[j] = fma(x.x, a.y, fma(-x.y, a.x, di[j]));
-                } else if (j == C) {
-                    dr[j] = fma(x.x, x.x, fma(x.y, x.y, dr[j]));
+                for (int j = 0; j < ZCH; ++j) {
+                    if (c0 + j < C) {
+                        const double2 a = A[r + (int64_t)(c0 + j) * lda];
+                        dr[j] = fma(x.x, a.x, fma(x.y, a.y, dr[j]));        // conj(x) a
+                        di[j] = fma(x.x, a.y, fma(-x.y, a.x, di[j]));
+                    } else if (c0 + j == C) {
+                        dr[j] = fma(x.x, x.x, fma(x.y, x.y, dr[j]));
+                    }
                 }
             }
         }
-    }
+        // warp totals of the 2 ZCH = 32 sums by a transposing reduction (31 shuffle pairs instead of 160): lane l ends up with
+        // the total of value l (l < ZCH: real parts, l >= ZCH: imaginary parts)
+        {
+            double v[2 * ZCH];
 #pragma unroll
-    for (int j = 0; j < ZNB; ++j) {
-        if (j <= C) {
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                dr[j] += __shfl_xor_sync(0xffffffffu, dr[j], o);
-                di[j] += __shfl_xor_sync(0xffffffffu, di[j], o);
+            for (int j = 0; j < ZCH; ++j) {
+                v[j] = dr[j];
+                v[ZCH + j] = di[j];
             }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = lane & off;
+#pragma unroll
+                for (int k = 0; k < off; ++k) {
+                    const double send = up ? v[k] : v[k + off], keep = up ? v[k + off] : v[k];
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            red[warp][lane & (ZCH - 1)][lane / ZCH] = v[0];
         }
-        if (lane == 0) {
-            red[warp][j][0] = dr[j];
-            red[warp][j][1] = di[j];
+        __syncthreads();
+        if (tid < 2 * ZCH) {
+            const int j = tid >> 1, c = tid & 1;
+            double t = 0.0;
+            for (int q = 0; q < ZT / 32; ++q) t += red[q][j][c];
+            if (c0 + j < ZNB) part[((int64_t)blockIdx.x * ZNB + c0 + j) * 2 + c] = t;
         }
+        __syncthreads();
     }
-    __syncthreads();
-    if (tid < 2 * ZNB) {
+    if ((int)blockIdx.x == mu / rpb && tid < 2 * ZNB) {      // the block that owns (and has just updated) the pivot row publishes it
         const int j = tid >> 1, c = tid & 1;
-        double t = 0.0;
-        for (int q = 0; q < ZT / 32; ++q) t += red[q][j][c];
-        part[((int64_t)blockIdx.x * ZNB + j) * 2 + c] = t;
-        if (blockIdx.x == 0) {
-            const double2 a = (j < w) ? A[mu + (int64_t)j * lda] : make_double2(0.0, 0.0);
-            part[((int64_t)gridDim.x * ZNB + j) * 2 + c] = c ? a.y : a.x;      // the pivot row
-        }
+        const double2 a = (j < w) ? A[mu + (int64_t)j * lda] : make_double2(0.0, 0.0);
+        part[((int64_t)gridDim.x * ZNB + j) * 2 + c] = c ? a.y : a.x;
     }
     if (tid == 0) part[(int64_t)(gridDim.x + 1) * ZNB * 2 + blockIdx.x] = am;
 }
 
-// zlarfg for column C + the rank-1 update of the panel columns j < C + the clean reflector in block form:
-//   VV[2r, 2C] = re v_r, VV[2r+1, 2C] = im v_r, VV[2r, 2C+1] = -im v_r, VV[2r+1, 2C+1] = re v_r   (v = 1 at the pivot, 0 below).
-__global__ void __launch_bounds__(ZT) zupdate_kernel(double2 *__restrict__ A, int64_t lda, int mu, int C, int w,
-                                                     const double *__restrict__ part, double2 *__restrict__ tau_out,
-                                                     double *__restrict__ VV, int64_t ldvv, int p, int rpb) {
-    __shared__ double2 tot[ZNB], rowv[ZNB], coef[ZNB];
-    __shared__ double sc[4];
+__device__ __forceinline__ void z_update_phase(double2 *__restrict__ A, int64_t lda, int mu, int C, const double *__restrict__ part,
+                                               double2 *__restrict__ tau_out, double *__restrict__ VV, int64_t ldvv, int p, int rpb,
+                                               double2 *tot, double2 *rowv, double2 *coef, double *sc, double2 (*psum)[ZNB]) {
     const int tid = threadIdx.x;
     const int nblk = gridDim.x;
     const double *amaxs = part + (int64_t)(nblk + 1) * ZNB * 2;
-    if (tid < ZNB) {
-        double amax = 0.0;
-        for (int b = 0; b < nblk; ++b) amax = fmax(amax, amaxs[b]);
+    // amax over the blocks, then the partials re-summed in a fixed order: column j by the four threads (j, g), g = blocks b = g mod 4
+    {
+        double am = 0.0;
+        for (int b = tid; b < nblk; b += ZT) am = fmax(am, amaxs[b]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if ((tid & 31) == 0) sc[8 + (tid >> 5)] = am;
+        __syncthreads();
+        am = sc[8];
+        for (int q = 1; q < ZT / 32; ++q) am = fmax(am, sc[8 + q]);
+        const int j = tid & (ZNB - 1), g = tid / ZNB;
         double tr = 0.0, ti = 0.0;
-        if (amax > 0.0) {
-            for (int b = 0; b < nblk; ++b) {
-                const double wb = amaxs[b] / amax;                    // <= 1
-                const double f = (tid == C) ? wb * wb : wb;
-                tr += part[((int64_t)b * ZNB + tid) * 2] * f;
-                ti += part[((int64_t)b * ZNB + tid) * 2 + 1] * f;
+        if (am > 0.0 && j <= C) {
+            const double ra = 1.0 / am;
+#pragma unroll 4
+            for (int b = g; b < nblk; b += ZT / ZNB) {
+                const double wb = amaxs[b] * ra;                      // <= 1
+                const double f = (j == C) ? wb * wb : wb;
+                tr = fma(part[((int64_t)b * ZNB + j) * 2], f, tr);
+                ti = fma(part[((int64_t)b * ZNB + j) * 2 + 1], f, ti);
             }
         }
-        tot[tid] = make_double2(tr, ti);
-        rowv[tid] = make_double2(part[((int64_t)nblk * ZNB + tid) * 2], part[((int64_t)nblk * ZNB + tid) * 2 + 1]);
-        if (tid == 0) sc[0] = amax;
+        psum[g][j] = make_double2(tr, ti);
+        __syncthreads();
+        if (tid < ZNB) {
+            const double2 a0 = psum[0][tid], a1 = psum[1][tid], a2 = psum[2][tid], a3 = psum[3][tid];
+            tot[tid] = make_double2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+            rowv[tid] = make_double2(part[((int64_t)nblk * ZNB + tid) * 2], part[((int64_t)nblk * ZNB + tid) * 2 + 1]);
+            if (tid == 0) sc[0] = am;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -178,22 +205,29 @@ __global__ void __launch_bounds__(ZT) zupdate_kernel(double2 *__restrict__ A, in
         }
         sc[1] = f.x;
         sc[2] = f.y;
-        const double2 nct = make_double2(-tauc.x, tauc.y);     // -conj(tau)
-        for (int j = 0; j < ZNB; ++j) {
-            double2 s = make_double2(0.0, 0.0);
-            if (j < C) s = zmul(nct, make_double2(fma(f.x, tot[j].x, fma(f.y, tot[j].y, rowv[j].x)),        // conj(f) tot + rowv
-                                                   fma(f.x, tot[j].y, fma(-f.y, tot[j].x, rowv[j].y))));
-            coef[j] = s;
-        }
-        if (blockIdx.x == 0) {
-            *tau_out = tauc;
-            A[mu + (int64_t)C * lda] = make_double2(beta, betai);
-            for (int j = 0; j < C; ++j) A[mu + (int64_t)j * lda] = make_double2(rowv[j].x + coef[j].x, rowv[j].y + coef[j].y);      // v[mu] = 1
-        }
+        sc[3] = tauc.x;
+        sc[4] = tauc.y;
+        sc[5] = beta;
+        sc[6] = betai;
     }
     __syncthreads();
     const double amax = sc[0];
     const double2 f = make_double2(sc[1], sc[2]);
+    if (tid < ZNB) {
+        const double2 nct = make_double2(-sc[3], sc[4]);       // -conj(tau)
+        double2 s = make_double2(0.0, 0.0);
+        if (tid < C) s = zmul(nct, make_double2(fma(f.x, tot[tid].x, fma(f.y, tot[tid].y, rowv[tid].x)),        // conj(f) tot + rowv
+                                                 fma(f.x, tot[tid].y, fma(-f.y, tot[tid].x, rowv[tid].y))));
+        coef[tid] = s;
+        if (blockIdx.x == 0) {
+            if (tid < C) A[mu + (int64_t)tid * lda] = make_double2(rowv[tid].x + s.x, rowv[tid].y + s.y);      // v[mu] = 1
+            if (tid == C) {
+                *tau_out = make_double2(sc[3], sc[4]);
+                A[mu + (int64_t)C * lda] = make_double2(sc[5], sc[6]);
+            }
+        }
+    }
+    __syncthreads();
     const double ram = amax > 0.0 ? 1.0 / amax : 0.0;
     const int r0 = blockIdx.x * rpb;
     double *v0 = VV + (int64_t)(2 * C) * ldvv, *v1 = v0 + ldvv;
@@ -203,13 +237,26 @@ __global__ void __launch_bounds__(ZT) zupdate_kernel(double2 *__restrict__ A, in
             const double2 x = A[r + (int64_t)C * lda];
             v = zmul(make_double2(x.x * ram, x.y * ram), f);
             A[r + (int64_t)C * lda] = v;
-#pragma unroll 4
-            for (int j = 0; j < C; ++j) {
-                double2 a = A[r + (int64_t)j * lda];
-                const double2 c = coef[j];
-                a.x = fma(c.x, v.x, fma(-c.y, v.y, a.x));
-                a.y = fma(c.x, v.y, fma(c.y, v.x, a.y));
-                A[r + (int64_t)j * lda] = a;
+            // chunks of 8 columns, the next chunk's loads issued before this chunk's stores (A may alias itself for the compiler)
+            double2 cur[8], nxt[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < C) cur[q] = A[r + (int64_t)q * lda];
+            for (int j0 = 0; j0 < C; j0 += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (j0 + 8 + q < C) nxt[q] = A[r + (int64_t)(j0 + 8 + q) * lda];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (j0 + q < C) {
+                        const double2 c = coef[j0 + q];
+                        double2 a = cur[q];
+                        a.x = fma(c.x, v.x, fma(-c.y, v.y, a.x));
+                        a.y = fma(c.x, v.y, fma(c.y, v.x, a.y));
+                        A[r + (int64_t)(j0 + q) * lda] = a;
+                    }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
             }
         } else if (r == mu) {
             v = make_double2(1.0, 0.0);
@@ -218,6 +265,27 @@ __global__ void __launch_bounds__(ZT) zupdate_kernel(double2 *__restrict__ A, in
         v0[2 * r + 1] = v.y;
         v1[2 * r] = -v.y;
         v1[2 * r + 1] = v.x;
+    }
+}
+
+// UPDATE: finish column C (pivot row mu) from part_in; DOTS: start column C-1 (pivot row mu-1) into part_out.
+template <bool UPDATE, bool DOTS>
+__global__ void __launch_bounds__(ZT) zstep_kernel(double2 *__restrict__ A, int64_t lda, int mu, int C, int w,
+                                                   const double *__restrict__ part_in, double *__restrict__ part_out,
+                                                   double2 *__restrict__ tau_out, double *__restrict__ VV, int64_t ldvv, int p, int rpb) {
+    __shared__ double red[ZT / 32][ZCH][2];
+    __shared__ double mx[ZT / 32];
+    __shared__ double2 tot[ZNB], rowv[ZNB], coef[ZNB];
+    __shared__ double2 psum[ZT / ZNB][ZNB];
+    __shared__ double sc[8 + ZT / 32];
+    static_assert(ZT / ZNB == 4 && 2 * ZCH == 32, "re-summation layout");
+    if constexpr (UPDATE) {
+        z_update_phase(A, lda, mu, C, part_in, tau_out, VV, ldvv, p, rpb, tot, rowv, coef, sc, psum);
+        __syncthreads();      // this block's rows of the panel are up to date (only this block reads them below)
+    }
+    if constexpr (DOTS) {
+        const int Cn = UPDATE ? C - 1 : C, mun = UPDATE ? mu - 1 : mu;
+        z_dots_phase(A, lda, mun, Cn, w, part_out, rpb, red, mx);
     }
 }
 
@@ -240,8 +308,9 @@ __global__ void zexpand_v_kernel(const double2 *__restrict__ F, int64_t ldf, int
 //   T(i,i) = tau_i,  T(i+1:, i) = T(i+1:, i+1:) * (-tau_i G(i+1:, i)),  G(l,i) = v_l^H v_i = GG[2l, 2i] + i GG[2l+1, 2i].
 __global__ void __launch_bounds__(64) zlarft_kernel(const double *__restrict__ GG, const double2 *__restrict__ tau, int ib,
                                                     double *__restrict__ TT, int64_t ldt) {
-    __shared__ double2 Tc[ZNB][ZNB + 1];
-    __shared__ double2 y[ZNB];
+    extern __shared__ __align__(16) unsigned char zl_smem[];
+    double2 (*Tc)[ZNB + 1] = reinterpret_cast<double2 (*)[ZNB + 1]>(zl_smem);
+    double2 *y = reinterpret_cast<double2 *>(zl_smem) + ZNB * (ZNB + 1);
     const int l = threadIdx.x;
     const int ldg = 2 * ib;
     for (int i = ib - 1; i >= 0; --i) {
@@ -337,7 +406,7 @@ __global__ void ztrsm_update_kernel(const double2 *__restrict__ L, int64_t ldl, 
 __global__ void zset_int_kernel(int32_t *p, int32_t v) { *p = v; }
 
 static int z_rows_per_block(int p) {
-    int rpb = 512;
+    int rpb = 256;
     while ((p + rpb - 1) / rpb > 148) rpb += 256;
     return rpb;
 }
@@ -347,7 +416,13 @@ static size_t z_part_doubles(int nblk) { return (size_t)(nblk + 1) * ZNB * 2 + n
 static int z_build_T(qlb200_ctx *h, cudaStream_t st, const QlbWorkspace &ws, int p, int ib, const double2 *tau) {
     int rc = qlb_block_gram(h, st, ws, 2 * p, 2 * ib);
     if (rc) return rc;
-    zlarft_kernel<<<1, 64, 0, st>>>(ws.G, tau, ib, ws.T, ws.ldt);
+    constexpr size_t smem = (size_t)(ZNB * (ZNB + 1) + ZNB) * sizeof(double2);
+    static_assert(ZNB <= 64, "zlarft_kernel: one thread per row");
+    if (!h->zlarft_attr_done) {
+        QLB_CUDA(h, cudaFuncSetAttribute(zlarft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->zlarft_attr_done = true;
+    }
+    zlarft_kernel<<<1, 64, smem, st>>>(ws.G, tau, ib, ws.T, ws.ldt);
     QLB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -365,7 +440,7 @@ int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t 
     int rc = qlb_block_workspace(h, 2 * (int64_t)m, n, 2 * ZNB, &ws);
     if (rc) return rc;
     const int rpb = z_rows_per_block(m);
-    rc = qlb_reserve(h, &h->tall, &h->tall_bytes, z_part_doubles((m + rpb - 1) / rpb) * sizeof(double));
+    rc = qlb_reserve(h, &h->tall, &h->tall_bytes, 2 * z_part_doubles((m + rpb - 1) / rpb) * sizeof(double));
     if (rc) return rc;
     double *part = (double *)h->tall;
     for (int i1 = k; i1 > 0; i1 -= ZNB) {
@@ -374,11 +449,15 @@ int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t 
         const int c0 = n - k + i0;                // its first column
         double2 *Ap = A + (int64_t)c0 * lda;
         const int nblk = (p + rpb - 1) / rpb;
+        double *pb[2] = {part, part + z_part_doubles(nblk)};
+        zstep_kernel<false, true><<<nblk, ZT, 0, st>>>(Ap, lda, p - 1, ib - 1, ib, nullptr, pb[0], nullptr, nullptr, 0, p, rpb);
+        QLB_LAUNCH_CHECK(h);
         for (int s = 0; s < ib; ++s) {
             const int C = ib - 1 - s, mu = p - 1 - s;
-            zdots_kernel<<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, part, rpb);
-            QLB_LAUNCH_CHECK(h);
-            zupdate_kernel<<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, part, tau + i0 + C, ws.Vw, ws.ldv, p, rpb);
+            if (C > 0)
+                zstep_kernel<true, true><<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, pb[s & 1], pb[(s + 1) & 1], tau + i0 + C, ws.Vw, ws.ldv, p, rpb);
+            else
+                zstep_kernel<true, false><<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, pb[s & 1], nullptr, tau + i0 + C, ws.Vw, ws.ldv, p, rpb);
             QLB_LAUNCH_CHECK(h);
         }
         if (c0 > 0) {

@@ -79,3 +79,11 @@ if case == "bql":
     q.ql_batched_(A, tau, handle=h)
     torch.cuda.synchronize()
     print("bql done", h.launches)
+if case == "zgeqlf":
+    A = torch.empty_strided((n, n), (1, n), dtype=torch.complex128, device="cuda").copy_(torch.randn(n, n, dtype=torch.complex128, device="cuda"))
+    import time
+    for it in range(2):
+        B = A.clone(memory_format=torch.preserve_format)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        q.ql_(B, handle=h); torch.cuda.synchronize()
+        print("zgeqlf", n, "ms", (time.perf_counter() - t0) * 1e3, "launches", h.launches)
