@@ -95,7 +95,7 @@ struct qlb200_ctx {
     int64_t opt_bgrid = 0;                 // batched kernels: cap on the number of CTAs (0: one resident wave; benchmarking)
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM
     bool strip_attr_done[8] = {false};
-    bool larft_attr_done = false, trsm_attr_done = false, zlarft_attr_done = false;
+    bool larft_attr_done = false, trsm_attr_done = false, zlarft_attr_done = false, zstep_attr_done = false;
     bool ul_cluster_attr_done = false, ul_trsm_attr_done = false;
     bool gemm_attr_done[64] = {false};
     // batched kernels: dynamic-shared-memory attribute and occupancy, looked up once per (handle, kernel, size)

@@ -289,6 +289,203 @@ __global__ void __launch_bounds__(ZT) zstep_kernel(double2 *__restrict__ A, int6
     }
 }
 
+// The same step with the block's rows of the panel staged in shared memory (one row per thread, ZS rows per block; for panels
+// of at most 148 * ZS rows): ONE round trip to global memory per step (cp.async of the row, overlapped with the re-summation
+// of the partials) instead of one per 8-column chunk of the update plus one per chunk of the dot products -- the step is a
+// chain of L2 latencies, not of bandwidth or flops.
+constexpr int ZS = 128;
+template <bool UPDATE, bool DOTS>
+__global__ void __launch_bounds__(ZS) zstep_smem_kernel(double2 *__restrict__ A, int64_t lda, int mu, int C, int w,
+                                                        const double *__restrict__ part_in, double *__restrict__ part_out,
+                                                        double2 *__restrict__ tau_out, double *__restrict__ VV, int64_t ldvv, int p) {
+    extern __shared__ __align__(16) unsigned char zs_raw[];
+    double2 *rb = reinterpret_cast<double2 *>(zs_raw);      // [ZNB][ZS]: column j of this block's rows
+    __shared__ double red[ZS / 32][ZCH][2];
+    __shared__ double2 tot[ZNB], rowv[ZNB], coef[ZNB];
+    __shared__ double2 psum[ZS / ZNB][ZNB];
+    __shared__ double sc[8 + ZS / 32];
+    static_assert(ZS / ZNB == 2 && 2 * ZCH == 32, "re-summation layout");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x * ZS + tid;
+    const int nblk = gridDim.x;
+    const bool staged = r < (UPDATE ? mu : mu + 1);
+    for (int j = 0; j <= C; ++j) cp_async16(&rb[j * ZS + tid], &A[(staged ? r : 0) + (int64_t)j * lda], staged);
+    cp_async_commit();
+    if constexpr (UPDATE) {
+        const double *amaxs = part_in + (int64_t)(nblk + 1) * ZNB * 2;
+        double am = 0.0;
+        for (int b = tid; b < nblk; b += ZS) am = fmax(am, amaxs[b]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if (lane == 0) sc[8 + warp] = am;
+        __syncthreads();
+        am = sc[8];
+        for (int q = 1; q < ZS / 32; ++q) am = fmax(am, sc[8 + q]);
+        {
+            const int j = tid & (ZNB - 1), g = tid / ZNB;
+            double tr = 0.0, ti = 0.0;
+            if (am > 0.0 && j <= C) {
+                const double ra = 1.0 / am;
+#pragma unroll 4
+                for (int b = g; b < nblk; b += ZS / ZNB) {
+                    const double wb = amaxs[b] * ra;
+                    const double f = (j == C) ? wb * wb : wb;
+                    tr = fma(part_in[((int64_t)b * ZNB + j) * 2], f, tr);
+                    ti = fma(part_in[((int64_t)b * ZNB + j) * 2 + 1], f, ti);
+                }
+            }
+            psum[g][j] = make_double2(tr, ti);
+        }
+        __syncthreads();
+        if (tid < ZNB) {
+            tot[tid] = make_double2(psum[0][tid].x + psum[1][tid].x, psum[0][tid].y + psum[1][tid].y);
+            rowv[tid] = make_double2(part_in[((int64_t)nblk * ZNB + tid) * 2], part_in[((int64_t)nblk * ZNB + tid) * 2 + 1]);
+        }
+        __syncthreads();
+        if (tid == 0) {      // LAPACK zlarfg (see z_update_phase)
+            double alphr = rowv[C].x, alphi = rowv[C].y;
+            double beta = alphr, betai = alphi;
+            double2 tauc = make_double2(0.0, 0.0), f = make_double2(0.0, 0.0);
+            if (am > 0.0 || alphi != 0.0) {
+                double am_s = am;
+                double xnorm = am_s * sqrt(tot[C].x);
+                double be = -copysign(dlapy3_dev(alphr, alphi, xnorm), alphr);
+                int knt = 0;
+                if (fabs(be) < Z_SAFMIN) {
+                    const double rsafmn = 1.0 / Z_SAFMIN;
+                    do {
+                        ++knt;
+                        am_s *= rsafmn;
+                        be *= rsafmn;
+                        alphr *= rsafmn;
+                        alphi *= rsafmn;
+                    } while (fabs(be) < Z_SAFMIN && knt < 20);
+                    xnorm = am_s * sqrt(tot[C].x);
+                    be = -copysign(dlapy3_dev(alphr, alphi, xnorm), alphr);
+                }
+                tauc = make_double2((be - alphr) / be, -alphi / be);
+                const double2 sr = zrecip(alphr - be, alphi);
+                f = make_double2(am_s * sr.x, am_s * sr.y);
+                for (int q = 0; q < knt; ++q) be *= Z_SAFMIN;
+                beta = be;
+                betai = 0.0;
+            }
+            sc[0] = am;
+            sc[1] = f.x;
+            sc[2] = f.y;
+            sc[3] = tauc.x;
+            sc[4] = tauc.y;
+            sc[5] = beta;
+            sc[6] = betai;
+        }
+        __syncthreads();
+        const double2 f = make_double2(sc[1], sc[2]);
+        if (tid < ZNB) {
+            const double2 nct = make_double2(-sc[3], sc[4]);       // -conj(tau)
+            double2 cf = make_double2(0.0, 0.0);
+            if (tid < C) cf = zmul(nct, make_double2(fma(f.x, tot[tid].x, fma(f.y, tot[tid].y, rowv[tid].x)),
+                                                      fma(f.x, tot[tid].y, fma(-f.y, tot[tid].x, rowv[tid].y))));
+            coef[tid] = cf;
+            if (blockIdx.x == 0) {
+                if (tid < C) A[mu + (int64_t)tid * lda] = make_double2(rowv[tid].x + cf.x, rowv[tid].y + cf.y);
+                if (tid == C) {
+                    *tau_out = make_double2(sc[3], sc[4]);
+                    A[mu + (int64_t)C * lda] = make_double2(sc[5], sc[6]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        const double ram = am > 0.0 ? 1.0 / am : 0.0;
+        if (r < p) {
+            double2 v = make_double2(0.0, 0.0);
+            if (r < mu) {
+                const double2 x = rb[C * ZS + tid];
+                v = zmul(make_double2(x.x * ram, x.y * ram), f);
+                A[r + (int64_t)C * lda] = v;
+#pragma unroll 4
+                for (int j = 0; j < C; ++j) {
+                    const double2 c = coef[j];
+                    double2 a = rb[j * ZS + tid];
+                    a.x = fma(c.x, v.x, fma(-c.y, v.y, a.x));
+                    a.y = fma(c.x, v.y, fma(c.y, v.x, a.y));
+                    rb[j * ZS + tid] = a;
+                    A[r + (int64_t)j * lda] = a;
+                }
+            } else if (r == mu) {
+                v = make_double2(1.0, 0.0);
+            }
+            double *v0 = VV + (int64_t)(2 * C) * ldvv, *v1 = v0 + ldvv;
+            v0[2 * r] = v.x;
+            v0[2 * r + 1] = v.y;
+            v1[2 * r] = -v.y;
+            v1[2 * r + 1] = v.x;
+        }
+    } else {
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    if constexpr (DOTS) {
+        // step Cn on the rows this thread has just updated (its own shared-memory entries only: no barrier needed before)
+        const int Cn = UPDATE ? C - 1 : C, mun = UPDATE ? mu - 1 : mu;
+        const bool live = r < mun;
+        double2 x = live ? rb[Cn * ZS + tid] : make_double2(0.0, 0.0);
+        double am = fmax(fabs(x.x), fabs(x.y));
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+        __syncthreads();      // (sc is reused)
+        if (lane == 0) sc[8 + warp] = am;
+        __syncthreads();
+        am = sc[8];
+        for (int q = 1; q < ZS / 32; ++q) am = fmax(am, sc[8 + q]);
+        const double ram = am > 0.0 ? 1.0 / am : 0.0;
+        x.x *= ram;
+        x.y *= ram;
+        for (int c0 = 0; c0 <= Cn; c0 += ZCH) {
+            double v[2 * ZCH];
+#pragma unroll
+            for (int j = 0; j < ZCH; ++j) {
+                double dr = 0.0, di = 0.0;
+                if (c0 + j < Cn) {
+                    const double2 a = rb[(c0 + j) * ZS + tid];
+                    dr = fma(x.x, a.x, x.y * a.y);              // conj(x) a
+                    di = fma(x.x, a.y, -x.y * a.x);
+                } else if (c0 + j == Cn) {
+                    dr = fma(x.x, x.x, x.y * x.y);
+                }
+                v[j] = dr;
+                v[ZCH + j] = di;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = lane & off;
+#pragma unroll
+                for (int k = 0; k < off; ++k) {
+                    const double send = up ? v[k] : v[k + off], keep = up ? v[k + off] : v[k];
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            red[warp][lane & (ZCH - 1)][lane / ZCH] = v[0];
+            __syncthreads();
+            if (tid < 2 * ZCH) {
+                const int j = tid >> 1, c = tid & 1;
+                double t = 0.0;
+                for (int q = 0; q < ZS / 32; ++q) t += red[q][j][c];
+                if (c0 + j < ZNB) part_out[((int64_t)blockIdx.x * ZNB + c0 + j) * 2 + c] = t;
+            }
+            __syncthreads();
+        }
+        if (r == mun) {      // the owner of the next pivot row publishes it
+            for (int j = 0; j < ZNB; ++j) {
+                const double2 a = (j <= Cn) ? rb[j * ZS + tid] : make_double2(0.0, 0.0);
+                part_out[((int64_t)nblk * ZNB + j) * 2] = a.x;
+                part_out[((int64_t)nblk * ZNB + j) * 2 + 1] = a.y;
+            }
+        }
+        if (tid == 0) part_out[(int64_t)(nblk + 1) * ZNB * 2 + blockIdx.x] = am;
+    }
+}
+
 // [[V]] (2p x 2ib, ldvv) from the packed complex factors F (column j has its pivot at row mu0 + j)
 __global__ void zexpand_v_kernel(const double2 *__restrict__ F, int64_t ldf, int p, int ib, int mu0, double *__restrict__ VV,
                                  int64_t ldvv) {
@@ -440,7 +637,7 @@ int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t 
     int rc = qlb_block_workspace(h, 2 * (int64_t)m, n, 2 * ZNB, &ws);
     if (rc) return rc;
     const int rpb = z_rows_per_block(m);
-    rc = qlb_reserve(h, &h->tall, &h->tall_bytes, 2 * z_part_doubles((m + rpb - 1) / rpb) * sizeof(double));
+    rc = qlb_reserve(h, &h->tall, &h->tall_bytes, 2 * z_part_doubles(148 + (m + rpb - 1) / rpb) * sizeof(double));
     if (rc) return rc;
     double *part = (double *)h->tall;
     for (int i1 = k; i1 > 0; i1 -= ZNB) {
@@ -449,6 +646,27 @@ int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t 
         const int c0 = n - k + i0;                // its first column
         double2 *Ap = A + (int64_t)c0 * lda;
         const int nblk = (p + rpb - 1) / rpb;
+        if (p <= 148 * ZS) {      // rows of the panel staged in shared memory, one launch per column
+            const int nb_ = (p + ZS - 1) / ZS;
+            double *pb[2] = {part, part + z_part_doubles(nb_)};
+            constexpr size_t smem = (size_t)ZNB * ZS * sizeof(double2);
+            if (!h->zstep_attr_done) {
+                QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                h->zstep_attr_done = true;
+            }
+            zstep_smem_kernel<false, true><<<nb_, ZS, smem, st>>>(Ap, lda, p - 1, ib - 1, ib, nullptr, pb[0], nullptr, nullptr, 0, p);
+            QLB_LAUNCH_CHECK(h);
+            for (int s = 0; s < ib; ++s) {
+                const int C = ib - 1 - s, mu = p - 1 - s;
+                if (C > 0)
+                    zstep_smem_kernel<true, true><<<nb_, ZS, smem, st>>>(Ap, lda, mu, C, ib, pb[s & 1], pb[(s + 1) & 1], tau + i0 + C, ws.Vw, ws.ldv, p);
+                else
+                    zstep_smem_kernel<true, false><<<nb_, ZS, smem, st>>>(Ap, lda, mu, C, ib, pb[s & 1], nullptr, tau + i0 + C, ws.Vw, ws.ldv, p);
+                QLB_LAUNCH_CHECK(h);
+            }
+        } else {
         double *pb[2] = {part, part + z_part_doubles(nblk)};
         zstep_kernel<false, true><<<nblk, ZT, 0, st>>>(Ap, lda, p - 1, ib - 1, ib, nullptr, pb[0], nullptr, nullptr, 0, p, rpb);
         QLB_LAUNCH_CHECK(h);
@@ -459,6 +677,7 @@ int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t 
             else
                 zstep_kernel<true, false><<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, pb[s & 1], nullptr, tau + i0 + C, ws.Vw, ws.ldv, p, rpb);
             QLB_LAUNCH_CHECK(h);
+        }
         }
         if (c0 > 0) {
             rc = z_build_T(h, st, ws, p, ib, tau + i0);
