@@ -401,6 +401,17 @@ def main():
     by_l = (NB * NB + NB + 2 * NB * 8) * 8
     extras["batched_32x32_f64_lmul_QtB_nrhs8"] = {"value": BATCH / t_l, "unit": "matrices/s", "ms": t_l * 1e3,
                                                   "hbm_frac": mine * by_l / t_l / 1e9 / hb, "bytes_per_matrix": by_l}
+    # configs[2] as ONE call: ql! + lmul!(Q',B) (qlb200_dgeqlf_apply_batched_dev; factors stay in L2 between the two kernels)
+    def _reset_fused():
+        Bw.copy_(B0)
+        RHw.copy_(RH)
+    t_fu = timed_dev(lambda: q.ql_apply_batched_(Bw, RHw, op="T", tau=tb, handle=h), _reset_fused)
+    by_fu = (2 * NB * NB + NB + 2 * NB * 8) * 8          # 20 736 B compulsory per matrix
+    extras["batched_32x32_f64_ql_plus_lmul_QtB_fused_call"] = {
+        "value": BATCH / t_fu, "unit": "matrices/s", "ms": t_fu * 1e3, "hbm_frac_fused_bytes": mine * by_fu / t_fu / 1e9 / hb,
+        "bytes_per_matrix": by_fu, "two_calls_ms": (tbat + t_l) * 1e3,
+        "note": "same kernels as the two separate calls, one C call; both kernels are bound by their shared-memory / FP64 pipes, "
+                "not by HBM, so re-reading the factors from L2 (fuse_chunk) buys nothing (DESIGN.md 4.1)"}
     del RH, RHw, B0, Bw, tb
     # configs[4]: 1048576 x (16 x 16) Float32 QL + ldiv! on 8 right-hand sides
     B5, N5 = 1048576, 16

@@ -269,6 +269,25 @@ int qlb200_sqlsolve_batched_dev(qlb200_handle h, int64_t n, int64_t nrhs, const 
                                 int64_t strideA, const float *dtau, int64_t strideTau, float *dB,
                                 int64_t ldb, int64_t strideB, int64_t batch, int32_t *dinfo_out);
 
+/* ---- batched, fused: ql! followed by lmul!(Q',B) / lmul!(Q,B) / ldiv!(F,B) on the factors just computed --------------
+ * BASELINE.json configs[2] ("batched QL ... with lmul!(Q',B)") and [4] ("... + ldiv! on 8 RHS") as ONE call: A and tau come
+ * back exactly as from q?geqlf_batched, B as from ?ormql_batched / ?qlsolve_batched (same kernels, same bits).  op: 'N' (Q B),
+ * 'T' or 'C' (Q'B), 'S' (L^{-1} Q'B; info[b] = i > 0 if L_b[i,i] == 0, info may be null).  Host pointers: the factors cross PCIe once in
+ * each direction instead of three times.  Device pointers: the two kernels back to back (option "fuse_chunk" = matrices per
+ * L2-sized chunk, default 0 = off: measured slower, neither kernel is HBM-bound). */
+int qlb200_dgeqlf_apply_batched(qlb200_handle h, char op, int64_t n, int64_t nrhs, double *A, int64_t lda, int64_t strideA,
+                                double *tau, int64_t strideTau, double *B, int64_t ldb, int64_t strideB, int64_t batch,
+                                int32_t *info);
+int qlb200_sgeqlf_apply_batched(qlb200_handle h, char op, int64_t n, int64_t nrhs, float *A, int64_t lda, int64_t strideA,
+                                float *tau, int64_t strideTau, float *B, int64_t ldb, int64_t strideB, int64_t batch,
+                                int32_t *info);
+int qlb200_dgeqlf_apply_batched_dev(qlb200_handle h, char op, int64_t n, int64_t nrhs, double *dA, int64_t lda, int64_t strideA,
+                                    double *dtau, int64_t strideTau, double *dB, int64_t ldb, int64_t strideB, int64_t batch,
+                                    int32_t *dinfo);
+int qlb200_sgeqlf_apply_batched_dev(qlb200_handle h, char op, int64_t n, int64_t nrhs, float *dA, int64_t lda, int64_t strideA,
+                                    float *dtau, int64_t strideTau, float *dB, int64_t ldb, int64_t strideB, int64_t batch,
+                                    int32_t *dinfo);
+
 /* ---- batched work sharded over several GPUs of one box (host pointers) ----------------------------
  * `hs[0..nh)` are handles created on the devices to use; handle g gets the contiguous matrix-index range
  * [g*batch/nh, (g+1)*batch/nh) (+ remainder on the first handles) and runs it on its own device from its

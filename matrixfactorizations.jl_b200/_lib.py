@@ -71,6 +71,7 @@ for _sfx in ("", "_dev"):
         SIGNATURES[f"qlb200_{_t}geqlf_batched{_sfx}"] = _FACT_B
         SIGNATURES[f"qlb200_{_t}ormql_batched{_sfx}"] = _ORM_B
         SIGNATURES[f"qlb200_{_t}qlsolve_batched{_sfx}"] = _SOLVE_B
+        SIGNATURES[f"qlb200_{_t}geqlf_apply_batched{_sfx}"] = [c_char, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P]
 # multi-GPU forms: the first argument is an array of handles + its length instead of one handle
 MG_SIGNATURES = {}
 for _t in "ds":

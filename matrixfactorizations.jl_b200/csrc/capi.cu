@@ -262,6 +262,8 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->graph_seen_key[0] = 0;
     } else if (!strcmp(name, "la_min")) {
         h->opt_la_min = value < 0 ? 0 : value;
+    } else if (!strcmp(name, "fuse_chunk")) {
+        h->opt_fuse_chunk = value < 0 ? 0 : value;
     } else if (!strcmp(name, "la_gemm_all")) {
         h->opt_la_gemm_all = value ? 1 : 0;
     } else if (!strcmp(name, "strip")) {
@@ -452,6 +454,68 @@ static int apply_batched_any(qlb200_ctx *h, bool host, int mode, int64_t n, int6
     return pipeline_end(h, rc);
 }
 
+// Fused factor + apply (BASELINE configs[2] and [4] as ONE call): A <- ql!(A), then B <- Q'B / Q B / L^{-1} Q'B with the
+// factors just computed.  Device pointers: the two kernels back to back (option `fuse_chunk` > 0 walks the batch in chunks
+// so that the apply finds the factors in L2 -- measured slower, see common.cuh).  Host pointers: one upload | compute |
+// download pipeline -- the factors cross PCIe once in each direction instead of up, down and up again.
+template <typename T>
+static int geqlf_apply_batched_any(qlb200_ctx *h, bool host, int mode, int64_t n, int64_t nrhs, T *A, int64_t lda, int64_t strideA,
+                                   T *tau, int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int64_t batch, int32_t *info_out) {
+    int rc = check_batched(h, n, A, lda, strideA, tau, strideTau, batch);
+    if (rc) return rc;
+    QLB_REQUIRE(h, nrhs >= 1, 4, "nrhs < 1");
+    QLB_REQUIRE(h, B != nullptr || batch == 0, 10, "B is null");
+    QLB_REQUIRE(h, ldb >= n, 11, "ldb < n (reference: DimensionMismatch)");
+    QLB_REQUIRE(h, strideB >= ldb * (nrhs - 1) + n || batch <= 1, 12, "strideB too small");
+    if (batch == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    if (!host) {
+        const int64_t cm = h->opt_fuse_chunk > 0 ? h->opt_fuse_chunk : batch;
+        for (int64_t m0 = 0; m0 < batch; m0 += cm) {
+            const int64_t mc = (batch - m0 < cm) ? batch - m0 : cm;
+            rc = geqlf_batched_dev<T>(h, n, A + m0 * strideA, lda, strideA, tau + m0 * strideTau, strideTau, mc);
+            if (!rc) rc = apply_batched_dev(h, mode, n, nrhs, A + m0 * strideA, lda, strideA, tau + m0 * strideTau, strideTau, B + m0 * strideB, ldb,
+                                            strideB, mc, (mode == 2 && info_out) ? info_out + m0 : nullptr);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    const size_t a_elems = (size_t)((batch - 1) * strideA + lda * (n - 1) + n);
+    const size_t t_elems = (size_t)((batch - 1) * strideTau + n);
+    const size_t b_elems = (size_t)((batch - 1) * strideB + ldb * (nrhs - 1) + n);
+    const size_t a_bytes = (a_elems * sizeof(T) + 255) & ~(size_t)255;
+    const size_t t_bytes = (t_elems * sizeof(T) + 255) & ~(size_t)255;
+    const size_t b_bytes = (b_elems * sizeof(T) + 255) & ~(size_t)255;
+    rc = qlb_reserve(h, &h->stage, &h->stage_bytes, a_bytes + t_bytes + b_bytes + (size_t)batch * 4);
+    if (rc) return rc;
+    T *dA = (T *)h->stage, *dT = (T *)((char *)h->stage + a_bytes), *dB = (T *)((char *)h->stage + a_bytes + t_bytes);
+    int32_t *dI = (int32_t *)((char *)h->stage + a_bytes + t_bytes + b_bytes);
+    const int64_t cm = batched_chunk(h, (strideA + strideB) * (int64_t)sizeof(T), batch);
+    rc = pipeline_begin(h);
+    for (int64_t m0 = 0, c = 0; m0 < batch && !rc; m0 += cm, ++c) {
+        const int64_t mc = (batch - m0 < cm) ? batch - m0 : cm;
+        const size_t ea = (size_t)((mc - 1) * strideA + lda * (n - 1) + n), et = (size_t)((mc - 1) * strideTau + n);
+        const size_t eb = (size_t)((mc - 1) * strideB + ldb * (nrhs - 1) + n);
+        T *dAc = dA + m0 * strideA, *dTc = dT + m0 * strideTau, *dBc = dB + m0 * strideB;
+        rc = qlb_cuda(h, cudaMemcpyAsync(dAc, A + m0 * strideA, ea * sizeof(T), cudaMemcpyHostToDevice, h->h2d_stream));
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(dBc, B + m0 * strideB, eb * sizeof(T), cudaMemcpyHostToDevice, h->h2d_stream));
+        if (!rc) rc = pipeline_uploaded(h, c);
+        if (!rc) rc = geqlf_batched_dev<T>(h, n, dAc, lda, strideA, dTc, strideTau, mc);
+        if (!rc) rc = apply_batched_dev(h, mode, n, nrhs, dAc, lda, strideA, dTc, strideTau, dBc, ldb, strideB, mc, (mode == 2) ? dI + m0 : nullptr);
+        if (!rc) rc = pipeline_computed(h, c);
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(A + m0 * strideA, dAc, ea * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (!rc) {
+            if (strideTau == n) rc = qlb_cuda(h, cudaMemcpyAsync(tau + m0 * strideTau, dTc, et * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+            else rc = qlb_cuda(h, cudaMemcpy2DAsync(tau + m0 * strideTau, (size_t)strideTau * sizeof(T), dTc, (size_t)strideTau * sizeof(T),
+                                                    (size_t)n * sizeof(T), (size_t)mc, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        if (!rc) rc = qlb_cuda(h, cudaMemcpyAsync(B + m0 * strideB, dBc, eb * sizeof(T), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (!rc && mode == 2 && info_out)
+            rc = qlb_cuda(h, cudaMemcpyAsync(info_out + m0, dI + m0, (size_t)mc * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    return pipeline_end(h, rc);
+}
+
 static int trans_mode(qlb200_ctx *h, char trans, int *mode) {
     if (trans == 'N' || trans == 'n') { *mode = 0; return 0; }
     if (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c') { *mode = 1; return 0; }
@@ -491,6 +555,23 @@ QLB_ORMQL_BATCHED(qlb200_dormql_batched, double, true)
 QLB_ORMQL_BATCHED(qlb200_sormql_batched, float, true)
 QLB_ORMQL_BATCHED(qlb200_dormql_batched_dev, double, false)
 QLB_ORMQL_BATCHED(qlb200_sormql_batched_dev, float, false)
+
+/* fused: op 'N' -> B <- Q B, 'T'/'C' -> B <- Q'B, 'S' -> B <- L^{-1} Q'B (ldiv!); info (n entries, may be null) only for 'S' */
+#define QLB_GEQLF_APPLY_BATCHED(NAME, T, HOST)                                                                     \
+    int NAME(qlb200_handle h, char op, int64_t n, int64_t nrhs, T *A, int64_t lda, int64_t strideA, T *tau,         \
+             int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int64_t batch, int32_t *info) {                 \
+        if (!h) return -1;                                                                                         \
+        int mode = 2;                                                                                              \
+        if (!(op == 'S' || op == 's')) {                                                                           \
+            int rc = trans_mode(h, op, &mode);                                                                     \
+            if (rc) return rc;                                                                                     \
+        }                                                                                                          \
+        return geqlf_apply_batched_any<T>(h, HOST, mode, n, nrhs, A, lda, strideA, tau, strideTau, B, ldb, strideB, batch, info); \
+    }
+QLB_GEQLF_APPLY_BATCHED(qlb200_dgeqlf_apply_batched, double, true)
+QLB_GEQLF_APPLY_BATCHED(qlb200_sgeqlf_apply_batched, float, true)
+QLB_GEQLF_APPLY_BATCHED(qlb200_dgeqlf_apply_batched_dev, double, false)
+QLB_GEQLF_APPLY_BATCHED(qlb200_sgeqlf_apply_batched_dev, float, false)
 
 #define QLB_QLSOLVE_BATCHED(NAME, T, HOST)                                                                         \
     int NAME(qlb200_handle h, int64_t n, int64_t nrhs, const T *A, int64_t lda, int64_t strideA, const T *tau,     \

@@ -91,6 +91,10 @@ struct qlb200_ctx {
     int64_t opt_overlap_t = 1;             // build the panel's T on the side stream while W = C'V runs
     int64_t opt_pair_sync = 8;             // GEMMs with exactly two N-tiles: cluster of the pair, barrier every this many k-tiles (0: off)
     int64_t opt_ul_cluster = 1;            // UL strips factored by the cluster kernel (0: single-CTA kernel)
+    // fused batched factor + apply on device pointers: matrices per chunk (0 = whole batch, the default).  Chunks small enough
+    // for the factors to stay in L2 between the two kernels were measured and LOSE (262144 x 32 x 32 f64 + Q'B: 2.13 ms unchunked,
+    // 2.39 / 2.71 / 3.05 ms with 32768 / 16384 / 8192-matrix chunks): neither kernel is HBM-bound, every launch pays a fill/drain.
+    int64_t opt_fuse_chunk = 0;
     int64_t opt_bvar = 0;                  // batched kernel variant (benchmarking)
     int64_t opt_bgrid = 0;                 // batched kernels: cap on the number of CTAs (0: one resident wave; benchmarking)
     int64_t opt_trail_splits = 0;          // 0 auto, else split-K count of the trailing W = C'V GEMM

@@ -537,6 +537,28 @@ def ldiv_batched_(A3, tau, B3, info=None, handle=None):
     return _apply_batched("qlsolve", None, A3, tau, B3, handle, info)
 
 
+def ql_apply_batched_(A3, B3, op="T", tau=None, info=None, handle=None):
+    """Fused `for i: F = ql!(view(A,:,:,i)); lmul!(F.Q', B_i)` (op "T"; "N": Q B_i; "S": ldiv!(F, B_i)) -- BASELINE configs[2]
+    and [4] as one call (qlb200_?geqlf_apply_batched): same kernels and bits as ql_batched_ followed by lmul_batched_ /
+    ldiv_batched_, the factors stay in L2 between the two (device) or cross PCIe once (host).  Returns (A3, tau, B3)."""
+    a, b = _Bat(A3, "A3"), _Bat(B3, "B3")
+    if len(a.shape) != 3 or a.shape[1] != a.shape[2]:
+        raise DimensionMismatch("ql_apply_batched_: expected (batch, n, n)")
+    batch, n, _ = a.shape
+    if len(b.shape) != 3 or b.shape[0] != batch or b.shape[2] != n:
+        raise DimensionMismatch(f"batched matrices {a.shape} vs right-hand sides {b.shape}")
+    if tau is None:
+        tau = _new_like(A3, batch * n).reshape(batch, n)
+    t = _Bat(tau, "tau")
+    if len({(x.dev, x.pfx) for x in (a, t, b)}) != 1:
+        raise TypeError("operands must share element type and residency")
+    nrhs = b.shape[1]
+    h = _handle(handle, a)
+    iptr = 0 if info is None else (info.data_ptr() if _is_torch(info) else info.ctypes.data)
+    h.call(f"qlb200_{a.pfx}geqlf_apply_batched{a.sfx}", op.encode(), n, nrhs, a.ptr, n, n * n, t.ptr, n, b.ptr, n, n * nrhs, batch, iptr)
+    return A3, tau, B3
+
+
 def ql_batched_mg_(A3, tau=None, handles=None):
     """Host arrays, several GPUs of one box: matrices are sharded by contiguous index ranges over `handles`
     (one per device), no cross-GPU communication; qlb200_?geqlf_batched_mg."""

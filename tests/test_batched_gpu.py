@@ -326,3 +326,40 @@ def test_batched_n32_single_and_split_kernels_vs_oracle(q, h, dt, bvar):
         assert np.triu(d).max() <= 50 * 32 * eps * nrm, i
         assert np.tril(d, -1).max() <= 50 * 32 * eps, i
     _check_factors(F, tau, Fo, tauo, A, 32, dt)
+
+
+@pytest.mark.parametrize("n,dt", [(32, np.float64), (16, np.float32), (24, np.float64), (48, np.float64)])
+@pytest.mark.parametrize("op", ["T", "N", "S"])
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_fused_factor_apply_same_bits_as_two_calls(q, h, n, dt, op, where):
+    """qlb200_?geqlf_apply_batched (BASELINE configs[2]/[4] as one call) = ql_batched_ followed by lmul_batched_ / ldiv_batched_:
+    same kernels, so the same bits -- across several L2 chunks (fuse_chunk) and host pipeline chunks."""
+    import torch
+
+    rng = np.random.default_rng(n + ord(op))
+    batch, nrhs = 1500, 8
+    A = rng.standard_normal((batch, n, n)).astype(dt)
+    B = rng.standard_normal((batch, nrhs, n)).astype(dt)
+    F2, t2 = q.ql_batched_(A.copy(), handle=h)
+    if op == "S":
+        X2 = q.ldiv_batched_(F2, t2, B.copy(), handle=h)
+    else:
+        X2 = q.lmul_batched_(F2, t2, B.copy(), adjoint=(op == "T"), handle=h)
+    h.set_option("fuse_chunk", 400)
+    h.set_option("batch_chunk_mb", 1)
+    try:
+        info = np.full(batch, -1, dtype=np.int32)
+        if where == "host":
+            F1, t1, X1 = q.ql_apply_batched_(A.copy(), B.copy(), op=op, info=info, handle=h)
+        else:
+            Ad, Bd = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+            idev = torch.from_numpy(info).cuda()
+            F1, t1, X1 = q.ql_apply_batched_(Ad, Bd, op=op, info=idev, handle=h)
+            torch.cuda.synchronize()
+            F1, t1, X1, info = F1.cpu().numpy(), t1.cpu().numpy(), X1.cpu().numpy(), idev.cpu().numpy()
+    finally:
+        h.set_option("fuse_chunk", 0)
+        h.set_option("batch_chunk_mb", 32)
+    assert np.array_equal(F1, F2) and np.array_equal(t1, t2) and np.array_equal(X1, X2)
+    if op == "S":
+        assert (info == 0).all()
