@@ -332,7 +332,11 @@ static int factor_panel(qlb200_ctx *h, cudaStream_t st, const Workspace &scr, do
 
 bool qlb_lookahead_active(const qlb200_ctx *h, int64_t m, int64_t n) {
     if (h->opt_lookahead == 1) return true;
-    return h->opt_lookahead == 2 && h->gc_ok && (m < n ? m : n) >= h->opt_la_min;
+    if (!(h->opt_lookahead == 2 && h->gc_ok)) return false;
+    if ((m < n ? m : n) >= h->opt_la_min) return true;
+    // wide matrices (the transposed tall-skinny RQ of configs[3]: 1024 x 65536): few, short panels, but every one of them is
+    // followed by a long trailing update that hides the next panel (rq 65536 x 1024: 10.0 -> 8.1 ms)
+    return m >= 1024 && n >= 8 * m && m * n >= (int64_t)4096 * 4096;
 }
 
 // Measured on B200 (tools/sweep_geqlf.py): with the look-ahead, 192-wide panels win at n = 16384 (241 vs 248 ms: the K = 192

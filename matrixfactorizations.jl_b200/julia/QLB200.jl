@@ -6,15 +6,15 @@
 # single `ccall` into the C-ABI of include/qlb200.h; nothing here does arithmetic.
 #
 # Hooks overridden (all exist in the reference, precedent: ext/MatrixFactorizationsBandedMatricesExt.jl:14-16,38,66):
-#   qlfactUnblocked!(::StridedMatrix{Float64})                         src/ql.jl:72
+#   qlfactUnblocked!(::StridedMatrix{T}), T in Float64/Float32/ComplexF64/ComplexF32   src/ql.jl:72
 #   materialize!(::Lmul{<:QLPackedQLayout{<:AbstractColumnMajor}})     src/ql.jl:321
 #   materialize!(::Lmul{<:AdjQLPackedQLayout{<:AbstractColumnMajor}})  src/ql.jl:350
 #   materialize!(::Rmul{<:Any,<:QLPackedQLayout}) / Adj                src/ql.jl:381,409
-#   materialize!(::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor}})      src/ql.jl:440 (square only)
+#   materialize!(::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor}})      src/ql.jl:440 (square; Float64 also tall least squares)
 #   rq!(::StridedMatrix{Float64})                                      src/rq.jl:401
 #   lmul!/rmul!(::RQPackedQ{Float64,<:StridedMatrix}, ...)             src/rq.jl:130,183,234,272
 #   ul!(::StridedMatrix{Float64}, pivot; check)                        src/ul.jl:146
-# plus the new batched surface ql_batched!/lmul_batched!/ldiv_batched! (SURVEY.md 0.6).
+# plus the new batched surface ql_batched!/lmul_batched!/ldiv_batched!/ql_apply_batched! (SURVEY.md 0.6; any n <= 64).
 module QLB200
 
 using LinearAlgebra, MatrixFactorizations
@@ -55,67 +55,75 @@ function chk(h::Handle, info::Integer; dims = ())
     throw(ArgumentError("libqlb200: invalid argument #$(-info): $msg"))
 end
 
-# ---- ql! -------------------------------------------------------------------------------------------------
-# replaces `QL(LAPACK.geqlf!(A)...)` (src/ql.jl:72); ql!/ql/ql_layout! reach it unchanged (src/ql.jl:114-117,179-191)
-function qlfactUnblocked!(A::StridedMatrix{Float64})
-    Base.require_one_based_indexing(A)
-    LinearAlgebra.chkstride1(A)
-    m, n = size(A)
-    τ = Vector{Float64}(undef, min(m, n))
-    h = handle()
-    info = ccall((:qlb200_dgeqlf, libqlb200), Cint,
-                 (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
-                 h.ptr, m, n, A, max(1, stride(A, 2)), τ)
-    chk(h, info)
-    QL(A, τ)
-end
+# ---- ql!, lmul!/rmul!, ldiv! for every BlasFloat element type ------------------------------------------------------
+# replaces `QL(LAPACK.geqlf!(A)...)` (src/ql.jl:72); ql!/ql/ql_layout! reach it unchanged (src/ql.jl:114-117,179-191).
+# Float64: native; ComplexF64: native complex panel + the same DMMA GEMMs (csrc/complex.cu); Float32 / ComplexF32: widened
+# on the device (csrc/mixed.cu).  For complex types the adjoint is 'C' (?unmql), the conj placements of
+# src/ql.jl:336,366,368,400,426,429 are inside the library.
+for (T, p, orm, adj) in ((Float64, :d, :ormql, 'T'), (Float32, :s, :ormql, 'T'), (ComplexF64, :z, :unmql, 'C'), (ComplexF32, :c, :unmql, 'C'))
+    geqlf = QuoteNode(Symbol(:qlb200_, p, :geqlf))
+    ormql = QuoteNode(Symbol(:qlb200_, p, orm))
+    solve = QuoteNode(Symbol(:qlb200_, p, :qlsolve))
+    @eval begin
+        function qlfactUnblocked!(A::StridedMatrix{$T})
+            Base.require_one_based_indexing(A)
+            LinearAlgebra.chkstride1(A)
+            m, n = size(A)
+            τ = Vector{$T}(undef, min(m, n))
+            h = handle()
+            info = ccall(($geqlf, libqlb200), Cint,
+                         (Ptr{Cvoid}, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}),
+                         h.ptr, m, n, A, max(1, stride(A, 2)), τ)
+            chk(h, info)
+            QL(A, τ)
+        end
+        function _ormql!(side::Char, trans::Char, A::QLPackedQ{$T,<:StridedMatrix}, C::StridedVecOrMat{$T})
+            Base.require_one_based_indexing(C)
+            mA, nA = size(A.factors)
+            k = min(mA, nA)
+            m, n = size(C, 1), size(C, 2)
+            nq = side == 'L' ? m : n
+            nq == mA || throw(DimensionMismatch("matrix A has dimensions ($mA,$nA) but $(side == 'L' ? "B" : "A") has dimensions ($m, $n)"))
+            V = view(A.factors, :, nA-k+1:nA)                  # the reflectors live in the last k columns (src/ql.jl:331)
+            h = handle()
+            info = ccall(($ormql, libqlb200), Cint,
+                         (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}, Ptr{$T}, Int64),
+                         h.ptr, side, trans == 'N' ? 'N' : $adj, m, n, k, V, max(1, stride(A.factors, 2)), A.τ, C, max(1, stride(C, 2)))
+            chk(h, info; dims = (6, 8))
+            C
+        end
+        materialize!(M::Lmul{<:QLPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QLPackedQ{$T},<:StridedVecOrMat{$T}}) =
+            _ormql!('L', 'N', M.A, M.B)                                                           # src/ql.jl:321-347
+        materialize!(M::Lmul{<:AdjQLPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:Any,<:StridedVecOrMat{$T}}) =
+            _ormql!('L', 'T', parent(M.A), M.B)                                                   # src/ql.jl:350-377
+        materialize!(M::Rmul{<:AbstractColumnMajor,<:QLPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{$T},<:QLPackedQ{$T}}) =
+            _ormql!('R', 'N', M.B, M.A)                                                           # src/ql.jl:381-406
+        materialize!(M::Rmul{<:AbstractColumnMajor,<:AdjQLPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{$T}}) =
+            _ormql!('R', 'T', parent(M.B), M.A)                                                   # src/ql.jl:409-435
 
-# ---- lmul!/rmul! with the packed Q -------------------------------------------------------------------------
-function _ormql!(side::Char, trans::Char, A::QLPackedQ{Float64,<:StridedMatrix}, C::StridedVecOrMat{Float64})
-    Base.require_one_based_indexing(C)
-    mA, nA = size(A.factors)
-    k = min(mA, nA)
-    m, n = size(C, 1), size(C, 2)
-    nq = side == 'L' ? m : n
-    nq == mA || throw(DimensionMismatch("matrix A has dimensions ($mA,$nA) but $(side == 'L' ? "B" : "A") has dimensions ($m, $n)"))
-    V = view(A.factors, :, nA-k+1:nA)                  # the reflectors live in the last k columns (src/ql.jl:331)
-    h = handle()
-    info = ccall((:qlb200_dormql, libqlb200), Cint,
-                 (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
-                 h.ptr, side, trans, m, n, k, V, max(1, stride(A.factors, 2)), A.τ, C, max(1, stride(C, 2)))
-    chk(h, info; dims = (6, 8))
-    C
-end
-materialize!(M::Lmul{<:QLPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QLPackedQ{Float64},<:StridedVecOrMat{Float64}}) =
-    _ormql!('L', 'N', M.A, M.B)                                                           # src/ql.jl:321-347
-materialize!(M::Lmul{<:AdjQLPackedQLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:Any,<:StridedVecOrMat{Float64}}) =
-    _ormql!('L', 'T', parent(M.A), M.B)                                                   # src/ql.jl:350-377
-materialize!(M::Rmul{<:AbstractColumnMajor,<:QLPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{Float64},<:QLPackedQ{Float64}}) =
-    _ormql!('R', 'N', M.B, M.A)                                                           # src/ql.jl:381-406
-materialize!(M::Rmul{<:AbstractColumnMajor,<:AdjQLPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{Float64}}) =
-    _ormql!('R', 'T', parent(M.B), M.A)                                                   # src/ql.jl:409-435
-
-# ---- ldiv!(F::QL, B), square --------------------------------------------------------------------------------
-function materialize!(Ldv::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QL{Float64},<:StridedVecOrMat{Float64}})
-    F, B = Ldv.A, Ldv.B
-    m, n = size(F)
-    if m > n      # SURVEY.md 8(f) N2: tall least squares (the reference's own branch, src/ql.jl:448-486, is @test_broken)
-        size(B, 1) == m || throw(DimensionMismatch("arguments must have the same number of rows; has $m and $(size(B,1))"))
-        h = handle()
-        info = ccall((:qlb200_dqllstsq, libqlb200), Cint,
-                     (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
-                     h.ptr, m, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
-        chk(h, info; dims = (9,))
-        return B      # X = B[1:n, :] (what `\` cuts out, src/ql.jl:501); B[n+1:m, :] = coordinates of the residual
+        # ldiv!(F::QL, B): square (src/ql.jl:440-447,467); Float64 also the tall least-squares case (SURVEY.md 8(f) N2)
+        function materialize!(Ldv::Ldiv{<:QLPackedLayout{<:AbstractColumnMajor},<:AbstractColumnMajor,<:QL{$T},<:StridedVecOrMat{$T}})
+            F, B = Ldv.A, Ldv.B
+            m, n = size(F)
+            if m > n && $T === Float64      # the reference's own branch (src/ql.jl:448-486) is @test_broken
+                size(B, 1) == m || throw(DimensionMismatch("arguments must have the same number of rows; has $m and $(size(B,1))"))
+                h = handle()
+                info = ccall((:qlb200_dqllstsq, libqlb200), Cint,
+                             (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+                             h.ptr, m, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
+                chk(h, info; dims = (9,))
+                return B      # X = B[1:n, :] (what `\` cuts out, src/ql.jl:501); B[n+1:m, :] = coordinates of the residual
+            end
+            m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # otherwise: keep the reference's own branch (src/ql.jl:448-486)
+            size(B, 1) == n || throw(DimensionMismatch("arguments must have the same number of rows; has $n and $(size(B,1))"))
+            h = handle()
+            info = ccall(($solve, libqlb200), Cint,
+                         (Ptr{Cvoid}, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}, Ptr{$T}, Int64),
+                         h.ptr, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
+            chk(h, info; dims = (8,))
+            B
+        end
     end
-    m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # wide: keep the reference's own branch (src/ql.jl:448-486)
-    size(B, 1) == n || throw(DimensionMismatch("arguments must have the same number of rows; has $n and $(size(B,1))"))
-    h = handle()
-    info = ccall((:qlb200_dqlsolve, libqlb200), Cint,
-                 (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
-                 h.ptr, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
-    chk(h, info; dims = (8,))
-    B
 end
 
 # ---- qrunblocked! and QR's packed Q through index reversal (SURVEY.md 8(f) N3) ------------------------------------
@@ -191,6 +199,7 @@ for (T, p) in ((Float64, :d), (Float32, :s))
     geqlf = QuoteNode(Symbol(:qlb200_, p, :geqlf_batched))
     ormql = QuoteNode(Symbol(:qlb200_, p, :ormql_batched))
     solve = QuoteNode(Symbol(:qlb200_, p, :qlsolve_batched))
+    fused = QuoteNode(Symbol(:qlb200_, p, :geqlf_apply_batched))
     @eval begin
         """`ql_batched!(A::Array{T,3})`: `[ql!(view(A,:,:,i)) for i]` in one call; returns the vector of `QL`s."""
         function ql_batched!(A::Array{$T,3})
@@ -210,6 +219,23 @@ for (T, p) in ((Float64, :d), (Float32, :s))
                          (Ptr{Cvoid}, Cchar, Int64, Int64, Ptr{$T}, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Int64),
                          h.ptr, trans, n, size(B, 2), A, n, n * n, τ, n, B, n, n * size(B, 2), b))
             B
+        end
+        """`ql_apply_batched!(op, A, B)`: `F_i = ql!(view(A,:,:,i))` followed by `lmul!(F_i.Q', B_i)` (op 'T'), `lmul!(F_i.Q, B_i)`
+        ('N') or `ldiv!(F_i, B_i)` ('S') in ONE call: the factors cross PCIe once.  Returns (A, τ, B)."""
+        function ql_apply_batched!(op::Char, A::Array{$T,3}, B::Array{$T,3})
+            n, n2, b = size(A)
+            n == n2 && size(B, 1) == n && size(B, 3) == b || throw(DimensionMismatch("ql_apply_batched!"))
+            τ = Matrix{$T}(undef, n, b)
+            info = Vector{Int32}(undef, b)
+            h = handle()
+            chk(h, ccall(($fused, libqlb200), Cint,
+                         (Ptr{Cvoid}, Cchar, Int64, Int64, Ptr{$T}, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}, Int64, Int64, Int64, Ptr{Int32}),
+                         h.ptr, op, n, size(B, 2), A, n, n * n, τ, n, B, n, n * size(B, 2), b, info))
+            if op == 'S'
+                i = findfirst(!iszero, info)
+                i === nothing || throw(SingularException(info[i]))
+            end
+            A, τ, B
         end
         function ldiv_batched!(A::Array{$T,3}, τ::Matrix{$T}, B::Array{$T,3})
             n, _, b = size(A)
