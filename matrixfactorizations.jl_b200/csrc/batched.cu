@@ -1242,7 +1242,7 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
         case 8: return qlb::launch_geqlf_batched<double, 8, 1, 4, 6>(h, A, lda, strideA, tau, strideTau, batch);
         case 16: return qlb::launch_geqlf_batched<double, 16, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
-            if (h->opt_bvar == 8) return qlb::launch_geqlf_wy<32>(h, A, lda, strideA, tau, strideTau, batch, 32);      // measurement only
+            if (h->opt_bvar == 8) return qlb::launch_geqlf_wy<double, 32>(h, A, lda, strideA, tau, strideTau, batch, 32);      // measurement only
             if (h->opt_bvar == 1) return qlb::launch_geqlf_batched<double, 32, 2, 4, 2>(h, A, lda, strideA, tau, strideTau, batch);
             // One kernel for small batches: below ~48k matrices (the shard of an 8-GPU run) the second kernel's fill/drain and
             // the two extra launches cost more than the split saves (32768 matrices: 209 vs 220 us; 262144: 1519 vs 1446 us).
@@ -1257,10 +1257,10 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
     if (n > 16 && n < 32) return qlb::launch_geqlf_batched<double, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
     // 32 < n <= 64: matrix in shared memory, panel in registers, DMMA trailing update (batched_wy.cuh); bvar 9 = literal ?geql2 kernel
     if (h->opt_bvar != 9) {
-        if (n > 32 && n <= 40) return qlb::launch_geqlf_wy<40>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
-        if (n > 40 && n <= 48) return qlb::launch_geqlf_wy<48>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
-        if (n > 48 && n <= 56) return qlb::launch_geqlf_wy<56>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
-        if (n > 56 && n <= 64) return qlb::launch_geqlf_wy<64>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+        if (n > 32 && n <= 40) return qlb::launch_geqlf_wy<double, 40>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+        if (n > 40 && n <= 48) return qlb::launch_geqlf_wy<double, 48>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+        if (n > 48 && n <= 56) return qlb::launch_geqlf_wy<double, 56>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+        if (n > 56 && n <= 64) return qlb::launch_geqlf_wy<double, 64>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
     }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
@@ -1277,6 +1277,13 @@ int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64
     if (n >= 1 && n < 8) return qlb::launch_geqlf_batched<float, 8, 1, 4, 8>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
     if (n > 8 && n < 16) return qlb::launch_geqlf_batched<float, 16, 2, 4, 5>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
     if (n > 16 && n < 32) return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+    // 32 < n <= 64: the Float64 shared-memory/DMMA kernel with the matrix widened while it is staged (bvar 9: literal ?geql2)
+    if (h->opt_bvar != 9) {
+        if (n > 32 && n <= 40) return qlb::launch_geqlf_wy<float, 40>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+        if (n > 40 && n <= 48) return qlb::launch_geqlf_wy<float, 48>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+        if (n > 48 && n <= 56) return qlb::launch_geqlf_wy<float, 56>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+        if (n > 56 && n <= 64) return qlb::launch_geqlf_wy<float, 64>(h, A, lda, strideA, tau, strideTau, batch, (int)n);
+    }
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }

@@ -40,7 +40,7 @@ struct WyCfg {
 // Trailing update of panel p (columns 8p..8p+7, NB = p+1 row blocks of 8) on the column tiles jt0 .. p-1.
 // g = lane >> 2, t = lane & 3 (DMMA fragment coordinates, common.cuh).
 template <int NT, int NB>
-__device__ __forceinline__ void wy_update(double *img, const double *sS, int jt0, int lane) {
+__device__ __forceinline__ void wy_update(double *img, double *sS, const double *taus8, int jt0, int lane) {
     constexpr int LD = WyCfg<NT>::LD;
     constexpr int p = NB - 1;
     const int g = lane >> 2, t = lane & 3;
@@ -63,6 +63,40 @@ __device__ __forceinline__ void wy_update(double *img, const double *sS, int jt0
         Vf[p].y = (r1 < g) ? Vf[p].y : ((r1 == g) ? 1.0 : 0.0);
         VT[p][0] = (g < r0) ? VT[p][0] : ((g == r0) ? 1.0 : 0.0);      // row g, column 2t
         VT[p][1] = (g < r1) ? VT[p][1] : ((g == r1) ? 1.0 : 0.0);      // row g, column 2t+1
+    }
+    // compact-WY factor of the panel: M = H_0 ... H_7 = I - V S V', S upper triangular, S[r][r] = tau_r,
+    // S[r][c] = -tau_r sum_{k=r+1..c} (v_r' v_k) S[k][c].  Gram matrix G = V'V on the tensor pipe (the fragments are already in
+    // registers), then lane c runs the recurrence for column c of S (G read as shared-memory broadcasts); -S goes to the scratch.
+    {
+        double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+            if (mb & 1) {
+                dmma884(h0, h1, Vf[mb].x, Vf[mb].x);
+                dmma884(h0, h1, Vf[mb].y, Vf[mb].y);
+            } else {
+                dmma884(g0, g1, Vf[mb].x, Vf[mb].x);
+                dmma884(g0, g1, Vf[mb].y, Vf[mb].y);
+            }
+        }
+        *reinterpret_cast<double2 *>(sS + g * 8 + 2 * t) = make_double2(g0 + h0, g1 + h1);      // G[g][2t], G[g][2t+1] (row-major)
+        __syncwarp();
+        double Sc[8];
+        const int c = lane & 7;
+#pragma unroll
+        for (int r = 7; r >= 0; --r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = r + 1; k < 8; ++k) acc = fma(sS[r * 8 + k], Sc[k], acc);
+            const double tr = taus8[r];
+            Sc[r] = (r == c) ? tr : ((r < c) ? -tr * acc : 0.0);
+        }
+        __syncwarp();
+        if (lane < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sS[lane * 8 + i] = -Sc[i];      // column-major -S
+        }
+        __syncwarp();
     }
     const double Sf0 = sS[(2 * t) * 8 + g], Sf1 = sS[(2 * t + 1) * 8 + g];       // -S[g][2t+s]
 #pragma unroll 1
@@ -94,10 +128,113 @@ __device__ __forceinline__ void wy_update(double *img, const double *sS, int jt0
     }
 }
 
-template <int NT, int WARPS, bool USE_TMA, bool PADDED>
+// NSTEP Householder steps of a panel (pivot rows 8p + r, r = r_hi ... r_hi - NSTEP + 1) on the NL column registers P[8-NL .. 7].
+// The pivot column always sits at index 7: after a step the finished reflector goes straight into the image (packed: tail
+// scaled, beta at the pivot, the L entries below untouched), every column moves one index up and a zero column enters at the
+// bottom (zero columns contribute exact zeros and need no masks).  Two instantiations per panel: NL = 8 for r = 7..4 and NL = 4
+// for r = 3..0 (the live columns of steps 3..0 are exactly indices 4..7).
+template <int NT, int NL, int NSLOT>
+__device__ __forceinline__ void wy_steps(double (&P)[8][NSLOT], const int (&row)[NSLOT], double *pcol, double *taus, int p, int r_hi, int pad,
+                                         int lane, bool &bad) {
+    constexpr int LD = WyCfg<NT>::LD;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int B0 = 8 - NL;                        // first register column of this body
+    constexpr int SH = (NL == 8) ? 2 : 3;             // the total of value i ends up in lanes (i << SH) ...
+#pragma unroll 1
+    for (int r = r_hi; r > r_hi - 4; --r) {
+        const int R = 8 * p + r;                       // pivot row = pivot column
+        const bool active = R > pad;                   // R == pad: the matrix's first column (identity, tau = 0); R < pad: padding
+        const int lp = R & 31;
+        double x7[NSLOT], xm[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            x7[s] = P[7][s];
+            xm[s] = (row[s] < R) ? x7[s] : 0.0;
+        }
+        double d[NL];                                  // d[NL-1] = |x|^2, the others: x' P_i over the tail rows
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            d[i] = xm[0] * P[B0 + i][0];
+            if constexpr (NSLOT == 2) d[i] = fma(xm[1], P[B0 + i][1], d[i]);
+        }
+        // transposing all-reduce over the 32 lanes (each stage halves the values a lane carries), then a broadcast: every lane
+        // sees the same bits
+        {
+            double hsum;
+            if constexpr (NL == 8) {
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                double e[4], f[2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double send = b4 ? d[k] : d[k + 4], keep = b4 ? d[k + 4] : d[k];
+                    e[k] = keep + __shfl_xor_sync(FULL, send, 16);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const double send = b3 ? e[k] : e[k + 2], keep = b3 ? e[k + 2] : e[k];
+                    f[k] = keep + __shfl_xor_sync(FULL, send, 8);
+                }
+                const double send = b2 ? f[0] : f[1], keep = b2 ? f[1] : f[0];
+                hsum = keep + __shfl_xor_sync(FULL, send, 4);
+            } else {
+                const bool b4 = lane & 16, b3 = lane & 8;
+                double f[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const double send = b4 ? d[k] : d[k + 2], keep = b4 ? d[k + 2] : d[k];
+                    f[k] = keep + __shfl_xor_sync(FULL, send, 16);
+                }
+                const double send = b3 ? f[0] : f[1], keep = b3 ? f[1] : f[0];
+                hsum = keep + __shfl_xor_sync(FULL, send, 8);
+                hsum += __shfl_xor_sync(FULL, hsum, 4);
+            }
+            hsum += __shfl_xor_sync(FULL, hsum, 2);
+            hsum += __shfl_xor_sync(FULL, hsum, 1);
+#pragma unroll
+            for (int i = 0; i < NL; ++i) d[i] = __shfl_sync(FULL, hsum, i << SH);
+        }
+        double aR[NL];                                 // row R of the panel (slot 0 holds the pivot rows)
+#pragma unroll
+        for (int i = 0; i < NL; ++i) aR[i] = __shfl_sync(FULL, P[B0 + i][0], lp);
+        const double ssq = d[NL - 1], alpha = aR[NL - 1];
+        const double tot = fma(alpha, alpha, ssq);
+        bad = bad || (active && !in_plain_range(ssq, tot));
+        const double rinv = nr_rsqrt(tot);
+        const double nrm = tot * rinv;
+        double beta = -copysign(nrm, alpha);
+        double tauk = fma(fabs(alpha), rinv, 1.0);
+        double scale = nr_rcp(alpha - beta);
+        beta = active ? beta : alpha;
+        tauk = active ? tauk : 0.0;
+        scale = active ? scale : 0.0;
+        if (lane == 0) taus[R] = tauk;
+        double v[NSLOT], vf[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            v[s] = xm[s] * scale;
+            vf[s] = (row[s] == R) ? 1.0 : v[s];
+            // the finished column, packed
+            const double outv = (row[s] < R) ? v[s] : ((row[s] == R) ? beta : x7[s]);
+            if (NT % 32 == 0 || row[s] < NT) pcol[r * LD + row[s]] = outv;
+        }
+#pragma unroll
+        for (int i = NL - 2; i >= 0; --i) {
+            const double si = tauk * fma(d[i], scale, aR[i]);          // tau * v' a_i
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) P[B0 + i + 1][s] = fma(-si, vf[s], P[B0 + i][s]);
+        }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) P[B0][s] = 0.0;
+    }
+}
+
+// TI = element type in global memory: double, or float (Float32 matrices are widened while they are staged -- plain loads,
+// no TMA -- factored in Float64 and narrowed on the way out; flagged matrices are redone by the Float32 ?geql2 routine).
+template <typename TI, int NT, int WARPS, bool USE_TMA, bool PADDED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A, int64_t lda, int64_t strideA,
-                double *__restrict__ tau, int64_t strideTau, int64_t batch, int nr_arg) {
+geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, TI *__restrict__ A, int64_t lda, int64_t strideA,
+                TI *__restrict__ tau, int64_t strideTau, int64_t batch, int nr_arg) {
+    static_assert(!USE_TMA || sizeof(TI) == 8, "the tensor map describes Float64 matrices");
     using Cfg = WyCfg<NT>;
     constexpr int LD = Cfg::LD, NSLOT = Cfg::NSLOT, NP = Cfg::NP;
     constexpr unsigned FULL = 0xffffffffu;
@@ -112,6 +249,8 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A
     const int pad = NT - nr;
     const int nbatch = (int)batch;
     const int gw = (int)blockIdx.x * WARPS + warp, nw = (int)gridDim.x * WARPS;
+    const bool flat4 = sizeof(TI) == 4 && lda == NT && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && ((strideA * sizeof(TI)) & 15) == 0;
+    (void)flat4;
     if constexpr (USE_TMA) {
         if (lane == 0) {
             mbar_init(bar, 1);
@@ -121,7 +260,7 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A
     }
     uint32_t phase = 0;
     for (int mi = gw; mi < nbatch; mi += nw) {
-        double *Am = A + (int64_t)mi * strideA;
+        TI *Am = A + (int64_t)mi * strideA;
         if constexpr (USE_TMA) {
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)Cfg::IMG_BYTES);
@@ -131,8 +270,23 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A
             phase ^= 1;
             __syncwarp();
         } else {
-            for (int c = 0; c < NT; ++c)
-                for (int r = lane; r < NT; r += 32) img[c * LD + r] = (c >= pad && r >= pad) ? Am[(int64_t)(c - pad) * lda + (r - pad)] : 0.0;
+            bool staged = false;
+            if constexpr (sizeof(TI) == 4 && !PADDED) {
+                if (flat4) {      // contiguous Float32 matrix: whole-warp 16-byte loads (4 rows of one column each)
+#pragma unroll 8
+                    for (int idx = lane * 4; idx < NT * NT; idx += 128) {
+                        const float4 v = *reinterpret_cast<const float4 *>(Am + idx);
+                        double *d = img + (idx / NT) * LD + (idx % NT);
+                        *reinterpret_cast<double2 *>(d) = make_double2((double)v.x, (double)v.y);
+                        *reinterpret_cast<double2 *>(d + 2) = make_double2((double)v.z, (double)v.w);
+                    }
+                    staged = true;
+                }
+            }
+            if (!staged) {
+                for (int c = 0; c < NT; ++c)
+                    for (int r = lane; r < NT; r += 32) img[c * LD + r] = (c >= pad && r >= pad) ? (double)Am[(int64_t)(c - pad) * lda + (r - pad)] : 0.0;
+            }
             __syncwarp();
         }
         bool bad = false;
@@ -150,115 +304,20 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s) P[i][s] = (NT % 32 == 0 || row[s] < NT) ? pcol[i * LD + row[s]] : 0.0;
-            double Sr[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) Sr[i] = 0.0;
-#pragma unroll 2
-            for (int r = 7; r >= 0; --r) {
-                const int R = 8 * p + r;                       // pivot row = pivot column
-                const bool active = R > pad;                   // R == pad: the matrix's first column (identity, tau = 0); R < pad: padding
-                const int lp = R & 31;
-                double x7[NSLOT], xm[NSLOT];
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
-                    x7[s] = P[7][s];
-                    xm[s] = (row[s] < R) ? x7[s] : 0.0;
-                }
-                // d_i = x' P_i over the tail rows: i = 7 -> |x|^2; live columns -> the update's dot products; finished
-                // reflectors -> the Gram row of the compact-WY factor
-                double d[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    d[i] = xm[0] * P[i][0];
-                    if constexpr (NSLOT == 2) d[i] = fma(xm[1], P[i][1], d[i]);
-                }
-                // all-reduce of the 8 sums over the 32 lanes, transposing: each stage halves the number of values a lane carries
-                // (34 shuffle instructions instead of the butterfly's 80: the shuffle unit is what bounds this loop); the total of
-                // value i ends up in lanes 4i..4i+3 and is broadcast from lane 4i, so every lane sees the same bits
-                {
-                    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-                    double e[4], f[2];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double send = b4 ? d[k] : d[k + 4], keep = b4 ? d[k + 4] : d[k];
-                        e[k] = keep + __shfl_xor_sync(FULL, send, 16);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const double send = b3 ? e[k] : e[k + 2], keep = b3 ? e[k + 2] : e[k];
-                        f[k] = keep + __shfl_xor_sync(FULL, send, 8);
-                    }
-                    const double send = b2 ? f[0] : f[1], keep = b2 ? f[1] : f[0];
-                    double hsum = keep + __shfl_xor_sync(FULL, send, 4);
-                    hsum += __shfl_xor_sync(FULL, hsum, 2);
-                    hsum += __shfl_xor_sync(FULL, hsum, 1);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) d[i] = __shfl_sync(FULL, hsum, 4 * i);
-                }
-                double aR[8];                                  // row R of the panel
-#pragma unroll
-                for (int i = 0; i < 8; ++i) aR[i] = __shfl_sync(FULL, P[i][0], lp);
-                const double ssq = d[7], alpha = aR[7];
-                const double tot = fma(alpha, alpha, ssq);
-                bad = bad || (active && !in_plain_range(ssq, tot));
-                const double rinv = nr_rsqrt(tot);
-                const double nrm = tot * rinv;
-                double beta = -copysign(nrm, alpha);
-                double tauk = fma(fabs(alpha), rinv, 1.0);
-                double scale = nr_rcp(alpha - beta);
-                beta = active ? beta : alpha;
-                tauk = active ? tauk : 0.0;
-                scale = active ? scale : 0.0;
-                if (lane == 0) taus[R] = tauk;
-                double w[7];
-#pragma unroll
-                for (int i = 0; i < 7; ++i) w[i] = fma(d[i], scale, aR[i]);
-                // S[r][c] for this lane's column c = lane (lanes 0..7 matter): Sr[i] = S[r+1+i][c]
-                double sacc = 0.0;
-#pragma unroll
-                for (int i = 0; i < 7; ++i) sacc = fma(w[i], Sr[i], sacc);
-                const double snew = (lane == r) ? tauk : -tauk * sacc;
-#pragma unroll
-                for (int i = 7; i >= 1; --i) Sr[i] = Sr[i - 1];
-                Sr[0] = snew;
-                // rank-1 update of the live columns, every column one index up, the finished reflector to index 0
-                double vf[NSLOT], v[NSLOT];
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
-                    v[s] = xm[s] * scale;
-                    vf[s] = (row[s] == R) ? 1.0 : v[s];
-                }
-#pragma unroll
-                for (int i = 6; i >= 0; --i) {
-                    const double si = (i + r >= 7) ? tauk * w[i] : 0.0;
-#pragma unroll
-                    for (int s = 0; s < NSLOT; ++s) P[i + 1][s] = fma(-si, vf[s], P[i][s]);
-                }
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) P[0][s] = (row[s] < R) ? v[s] : ((row[s] == R) ? beta : x7[s]);
-            }
-            // the packed panel goes back into the image, -S into the scratch
             double *pw = img + (8 * p) * LD;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-                    if (NT % 32 == 0 || row[s] < NT) pw[i * LD + row[s]] = P[i][s];
-            if (lane < 8) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) sS[lane * 8 + i] = -Sr[i];
-            }
+            wy_steps<NT, 8, NSLOT>(P, row, pw, taus, p, 7, pad, lane, bad);
+            wy_steps<NT, 4, NSLOT>(P, row, pw, taus, p, 3, pad, lane, bad);
             __syncwarp();
             const int jt0 = pad >> 3;                          // column tiles left of it are padding
             if (jt0 < p) {
                 switch (p) {
-                    case 1: wy_update<NT, 2>(img, sS, jt0, lane); break;
-                    case 2: if constexpr (NT >= 24) wy_update<NT, 3>(img, sS, jt0, lane); break;
-                    case 3: if constexpr (NT >= 32) wy_update<NT, 4>(img, sS, jt0, lane); break;
-                    case 4: if constexpr (NT >= 40) wy_update<NT, 5>(img, sS, jt0, lane); break;
-                    case 5: if constexpr (NT >= 48) wy_update<NT, 6>(img, sS, jt0, lane); break;
-                    case 6: if constexpr (NT >= 56) wy_update<NT, 7>(img, sS, jt0, lane); break;
-                    case 7: if constexpr (NT >= 64) wy_update<NT, 8>(img, sS, jt0, lane); break;
+                    case 1: wy_update<NT, 2>(img, sS, taus + 8 * p, jt0, lane); break;
+                    case 2: if constexpr (NT >= 24) wy_update<NT, 3>(img, sS, taus + 8 * p, jt0, lane); break;
+                    case 3: if constexpr (NT >= 32) wy_update<NT, 4>(img, sS, taus + 8 * p, jt0, lane); break;
+                    case 4: if constexpr (NT >= 40) wy_update<NT, 5>(img, sS, taus + 8 * p, jt0, lane); break;
+                    case 5: if constexpr (NT >= 48) wy_update<NT, 6>(img, sS, taus + 8 * p, jt0, lane); break;
+                    case 6: if constexpr (NT >= 56) wy_update<NT, 7>(img, sS, taus + 8 * p, jt0, lane); break;
+                    case 7: if constexpr (NT >= 64) wy_update<NT, 8>(img, sS, taus + 8 * p, jt0, lane); break;
                     default: break;
                 }
             }
@@ -266,7 +325,7 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A
         }
         // ---- output ----
         if (!bad) {
-            for (int i = lane; i < nr; i += 32) tau[(int64_t)mi * strideTau + i] = taus[i + pad];
+            for (int i = lane; i < nr; i += 32) tau[(int64_t)mi * strideTau + i] = (TI)taus[i + pad];
         }
         if constexpr (USE_TMA && !PADDED) {
             fence_proxy_async();
@@ -277,21 +336,37 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A
             __syncwarp();
         } else {
             if (!bad) {
-                if (USE_TMA && (pad & 1) == 0) {
-                    const int nv = nr >> 1;
+                bool done = false;
+                if constexpr (USE_TMA) {
+                    if ((pad & 1) == 0) {
+                        const int nv = nr >> 1;
+                        for (int c = 0; c < nr; ++c)
+                            for (int vv = lane; vv < nv; vv += 32)
+                                *reinterpret_cast<double2 *>(Am + (int64_t)c * lda + 2 * vv) = *reinterpret_cast<const double2 *>(img + (c + pad) * LD + pad + 2 * vv);
+                        done = true;
+                    }
+                }
+                if constexpr (sizeof(TI) == 4 && !PADDED) {
+                    if (flat4) {
+#pragma unroll 8
+                        for (int idx = lane * 4; idx < NT * NT; idx += 128) {
+                            const double *d = img + (idx / NT) * LD + (idx % NT);
+                            const double2 a0 = *reinterpret_cast<const double2 *>(d), a1 = *reinterpret_cast<const double2 *>(d + 2);
+                            *reinterpret_cast<float4 *>(Am + idx) = make_float4((float)a0.x, (float)a0.y, (float)a1.x, (float)a1.y);
+                        }
+                        done = true;
+                    }
+                }
+                if (!done) {
                     for (int c = 0; c < nr; ++c)
-                        for (int vv = lane; vv < nv; vv += 32)
-                            *reinterpret_cast<double2 *>(Am + (int64_t)c * lda + 2 * vv) = *reinterpret_cast<const double2 *>(img + (c + pad) * LD + pad + 2 * vv);
-                } else {
-                    for (int c = 0; c < nr; ++c)
-                        for (int r = lane; r < nr; r += 32) Am[(int64_t)c * lda + r] = img[(c + pad) * LD + pad + r];
+                        for (int r = lane; r < nr; r += 32) Am[(int64_t)c * lda + r] = (TI)img[(c + pad) * LD + pad + r];
                 }
             }
             if constexpr (USE_TMA) fence_proxy_async();
             __syncwarp();
         }
         if (bad) {        // rare: the matrix is untouched in global memory; literal ?geql2 / ?larfg with the image as scratch
-            geql2_warp<double>(Am, lda, tau + (int64_t)mi * strideTau, nr, img, lane);
+            geql2_warp<TI>(Am, lda, tau + (int64_t)mi * strideTau, nr, reinterpret_cast<TI *>(img), lane);
             if constexpr (USE_TMA) fence_proxy_async();
             __syncwarp();
         }
@@ -299,8 +374,8 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ A
     if constexpr (USE_TMA) tma_store_wait_all();
 }
 
-template <int NT>
-static int launch_geqlf_wy(qlb200_ctx *h, double *A, int64_t lda, int64_t strideA, double *tau, int64_t strideTau, int64_t batch, int nr) {
+template <typename TI, int NT>
+static int launch_geqlf_wy(qlb200_ctx *h, TI *A, int64_t lda, int64_t strideA, TI *tau, int64_t strideTau, int64_t batch, int nr) {
     using Cfg = WyCfg<NT>;
     constexpr int WARPS = Cfg::WARPS_MAX;
     static_assert(Cfg::IMG_BYTES + 1024 >= ((NT + 1) * NT + NT) * 8, "the image + scratch hold the generic routine's scratch");
@@ -308,10 +383,14 @@ static int launch_geqlf_wy(qlb200_ctx *h, double *A, int64_t lda, int64_t stride
     if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<double>(&tmap, A, nr, lda, strideA, batch, Cfg::LD, NT);
-    void (*kern)(const CUtensorMap, double *, int64_t, int64_t, double *, int64_t, int64_t, int);
-    if (nr == NT) kern = tma ? geqlf_wy_kernel<NT, WARPS, true, false> : geqlf_wy_kernel<NT, WARPS, false, false>;
-    else kern = tma ? geqlf_wy_kernel<NT, WARPS, true, true> : geqlf_wy_kernel<NT, WARPS, false, true>;
+    void (*kern)(const CUtensorMap, TI *, int64_t, int64_t, TI *, int64_t, int64_t, int);
+    if constexpr (sizeof(TI) == 8) {
+        const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<double>(&tmap, A, nr, lda, strideA, batch, Cfg::LD, NT);
+        if (nr == NT) kern = tma ? geqlf_wy_kernel<TI, NT, WARPS, true, false> : geqlf_wy_kernel<TI, NT, WARPS, false, false>;
+        else kern = tma ? geqlf_wy_kernel<TI, NT, WARPS, true, true> : geqlf_wy_kernel<TI, NT, WARPS, false, true>;
+    } else {
+        kern = (nr == NT) ? geqlf_wy_kernel<TI, NT, WARPS, false, false> : geqlf_wy_kernel<TI, NT, WARPS, false, true>;
+    }
     int occ = 0;
     int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ);
     if (rcs) return rcs;
