@@ -391,8 +391,10 @@ int qlb_dulfact_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t 
     // (K = 16, small); the columns left of the block get ONE rank-128 DMMA update per block, after the block's rows of L
     // have been finished by a block back substitution with the block's unit upper triangle.
     constexpr int UL_NBO = 128;
-    for (int C1 = k; C1 > 0; C1 -= UL_NBO) {
-        const int C0 = (C1 - UL_NBO > 0) ? C1 - UL_NBO : 0;
+    // One outer block [C0, C1): its strips from the right, the row interchanges applied at once only INSIDE the block's own
+    // columns (nothing outside the block is read until the block is complete, so the interchanges of the other columns are
+    // deferred and applied in one pass, see below), the in-block rows of L and the in-block rank-16 updates.
+    auto factor_block = [&](cudaStream_t s, int C0, int C1) -> int {
         for (int c1 = C1; c1 > C0; c1 -= UL_SB) {
             const int c0 = (c1 - UL_SB > C0) ? c1 - UL_SB : C0;
             if (c1 <= ULC_MAXC * ULC_THREADS * ULC_RPT && h->opt_ul_cluster) {
@@ -406,7 +408,7 @@ int qlb_dulfact_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t 
                 cfg.gridDim = dim3(ncp, 1, 1);
                 cfg.blockDim = dim3(ULC_THREADS, 1, 1);
                 cfg.dynamicSmemBytes = 0;
-                cfg.stream = st;
+                cfg.stream = s;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeClusterDimension;
                 attr[0].val.clusterDim.x = ncp;
@@ -417,45 +419,111 @@ int qlb_dulfact_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t 
                 QLB_CUDA(h, cudaLaunchKernelEx(&cfg, ul_strip_cluster_kernel, A, lda, c0, c1, pivot, ipiv, dinfo));
                 h->launches++;
             } else {
-                ul_panel_kernel<<<1, UL_THREADS, 0, st>>>(A, lda, c0, c1, pivot, ipiv, dinfo);
+                ul_panel_kernel<<<1, UL_THREADS, 0, s>>>(A, lda, c0, c1, pivot, ipiv, dinfo);
                 QLB_LAUNCH_CHECK(h);
             }
             if (pivot) {
-                if (c0 > 0) {
-                    ul_laswp_kernel<<<(c0 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, 0, c0);
+                if (c0 > C0) {
+                    ul_laswp_kernel<<<(c0 - C0 + 255) / 256, 256, 0, s>>>(A, lda, c0, c1, ipiv, C0, c0);
                     QLB_LAUNCH_CHECK(h);
                 }
-                if (n > c1) {
-                    ul_laswp_kernel<<<(n - c1 + 255) / 256, 256, 0, st>>>(A, lda, c0, c1, ipiv, c1, n);
+                if (C1 > c1) {
+                    ul_laswp_kernel<<<(C1 - c1 + 255) / 256, 256, 0, s>>>(A, lda, c0, c1, ipiv, c1, C1);
                     QLB_LAUNCH_CHECK(h);
                 }
             }
             if (c0 > C0) {
                 // inside the block: rows [c0,c1) of the block's columns left of the strip, then A11_block -= U12 * L21
-                ul_trsm_row_kernel<<<(c0 - C0 + 127) / 128, 128, 0, st>>>(A, lda, c0, c1, C0, c0 - C0);
+                ul_trsm_row_kernel<<<(c0 - C0 + 127) / 128, 128, 0, s>>>(A, lda, c0, c1, C0, c0 - C0);
                 QLB_LAUNCH_CHECK(h);
-                int rc = qlb_gemm(h, st, -1, false, true, c0, c0 - C0, c1 - c0, -1.0, A + (int64_t)c0 * lda, lda,
+                int rc = qlb_gemm(h, s, -1, false, true, c0, c0 - C0, c1 - c0, -1.0, A + (int64_t)c0 * lda, lda,
                                   A + (int64_t)C0 * lda + c0, lda, 1.0, A + (int64_t)C0 * lda, lda, 1, 0);
                 if (rc) return rc;
             }
         }
+        return 0;
+    };
+    // The block's interchanges on the columns outside the block (left of it: still to be updated; right of it: finished)
+    auto deferred_swaps = [&](cudaStream_t s, int C0, int C1) -> int {
+        if (!pivot) return 0;
         if (C0 > 0) {
-            // rows [C0,C1) of the columns left of the block: X = U_block^{-1} A21, strip by strip from the bottom
-            for (int c1 = C1; c1 > C0; c1 -= UL_SB) {
-                const int c0 = (c1 - UL_SB > C0) ? c1 - UL_SB : C0;
-                if (c1 < C1) {      // A21[c0:c1, :] -= U[c0:c1, c1:C1] * X[c1:C1, :]
-                    int rc = qlb_gemm(h, st, -1, false, true, c1 - c0, C0, C1 - c1, -1.0, A + (int64_t)c1 * lda + c0, lda, A + c1, lda,
-                                      1.0, A + c0, lda, 1, 0);
-                    if (rc) return rc;
-                }
-                ul_trsm_row_kernel<<<(C0 + 127) / 128, 128, 0, st>>>(A, lda, c0, c1, 0, C0);
-                QLB_LAUNCH_CHECK(h);
+            ul_laswp_kernel<<<(C0 + 255) / 256, 256, 0, s>>>(A, lda, C0, C1, ipiv, 0, C0);
+            QLB_LAUNCH_CHECK(h);
+        }
+        if (n > C1) {
+            ul_laswp_kernel<<<(n - C1 + 255) / 256, 256, 0, s>>>(A, lda, C0, C1, ipiv, C1, n);
+            QLB_LAUNCH_CHECK(h);
+        }
+        return 0;
+    };
+    // rows [C0,C1) of the columns left of the block: X = U_block^{-1} A21, strip by strip from the bottom
+    auto block_rows = [&](cudaStream_t s, int C0, int C1) -> int {
+        for (int c1 = C1; c1 > C0; c1 -= UL_SB) {
+            const int c0 = (c1 - UL_SB > C0) ? c1 - UL_SB : C0;
+            if (c1 < C1) {      // A21[c0:c1, :] -= U[c0:c1, c1:C1] * X[c1:C1, :]
+                int rc = qlb_gemm(h, s, -1, false, true, c1 - c0, C0, C1 - c1, -1.0, A + (int64_t)c1 * lda + c0, lda, A + c1, lda,
+                                  1.0, A + c0, lda, 1, 0);
+                if (rc) return rc;
             }
-            // A11 (C0 x C0) -= U12 (C0 x nbo, M-contiguous) * L21 (nbo x C0, K-contiguous)
-            int rc = qlb_gemm(h, st, -1, false, true, C0, C0, C1 - C0, -1.0, A + (int64_t)C0 * lda, lda, A + C0, lda, 1.0, A, lda, 1, 0);
+            ul_trsm_row_kernel<<<(C0 + 127) / 128, 128, 0, s>>>(A, lda, c0, c1, 0, C0);
+            QLB_LAUNCH_CHECK(h);
+        }
+        return 0;
+    };
+    // A11[0:C0, j0:j1) -= U12 (C0 x nbo, M-contiguous) * L21[:, j0:j1) (nbo x cols, K-contiguous)
+    auto trailing = [&](cudaStream_t s, int C0, int C1, int j0, int j1) -> int {
+        if (j1 <= j0) return 0;
+        return qlb_gemm(h, s, -1, false, true, C0, j1 - j0, C1 - C0, -1.0, A + (int64_t)C0 * lda, lda, A + (int64_t)j0 * lda + C0, lda, 1.0,
+                        A + (int64_t)j0 * lda, lda, 1, 0);
+    };
+    // Look-ahead on the SM partitions (as in ql!, blocked.cu): block b+1 is factored on the 16-SM panel partition while the
+    // other partition applies block b to the columns left of block b+1 -- the 16 384 latency-bound column steps of the strips
+    // (about half of the run time at n = 16384) disappear behind the rank-128 updates.
+    const bool la = h->gc_ok && h->opt_lookahead != 0 && k >= 2048;
+    if (!la) {
+        for (int C1 = k; C1 > 0; C1 -= UL_NBO) {
+            const int C0 = (C1 - UL_NBO > 0) ? C1 - UL_NBO : 0;
+            int rc = factor_block(st, C0, C1);
+            if (!rc) rc = deferred_swaps(st, C0, C1);
+            if (!rc && C0 > 0) rc = block_rows(st, C0, C1);
+            if (!rc && C0 > 0) rc = trailing(st, C0, C1, 0, C0);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    cudaStream_t G = h->gc_gemm, P = h->gc_panel;
+    cudaEvent_t evP = h->ev_a, evN = h->ev_b;
+    QLB_CUDA(h, cudaEventRecord(h->ev_gc[0], st));
+    QLB_CUDA(h, cudaStreamWaitEvent(G, h->ev_gc[0], 0));
+    QLB_CUDA(h, cudaStreamWaitEvent(P, h->ev_gc[0], 0));
+    {
+        const int C1 = k, C0 = (C1 - UL_NBO > 0) ? C1 - UL_NBO : 0;
+        int rc = factor_block(P, C0, C1);
+        if (rc) return rc;
+        QLB_CUDA(h, cudaEventRecord(evP, P));
+    }
+    for (int C1 = k; C1 > 0; C1 -= UL_NBO) {
+        const int C0 = (C1 - UL_NBO > 0) ? C1 - UL_NBO : 0;
+        QLB_CUDA(h, cudaStreamWaitEvent(G, evP, 0));            // block [C0, C1) is factored
+        int rc = deferred_swaps(G, C0, C1);
+        if (rc) return rc;
+        if (C0 > 0) {
+            rc = block_rows(G, C0, C1);
+            if (rc) return rc;
+            const int D0 = (C0 - UL_NBO > 0) ? C0 - UL_NBO : 0;      // next block = columns [D0, C0)
+            rc = trailing(G, C0, C1, D0, C0);
+            if (rc) return rc;
+            QLB_CUDA(h, cudaEventRecord(evN, G));
+            QLB_CUDA(h, cudaStreamWaitEvent(P, evN, 0));
+            rc = factor_block(P, D0, C0);
+            if (rc) return rc;
+            QLB_CUDA(h, cudaEventRecord(evP, P));
+            rc = trailing(G, C0, C1, 0, D0);
             if (rc) return rc;
         }
     }
+    QLB_CUDA(h, cudaEventRecord(h->ev_gc[1], G));
+    QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_gc[1], 0));
     return 0;
 }
 

@@ -34,3 +34,43 @@ def test_proto_ormql_matches_lapack(shape, side, trans):
     # and the reference's scalar loops (src/ql.jl:321-435)
     ref2 = cport.lmul(F, tau, C, adjoint=(trans == "T")) if side == "L" else cport.rmul(C, F, tau, adjoint=(trans == "T"))
     assert np.abs(got - ref2).max() <= 1e-12
+
+
+@pytest.mark.parametrize("n,pad", [(8, 0), (16, 0), (32, 0), (48, 0), (64, 0), (32, 8), (32, 5), (40, 7), (64, 17), (64, 31)])
+def test_proto_batched_wy_matches_lapack(n, pad):
+    """NumPy model of the shared-memory batched kernel (csrc/batched_wy.cuh): rotating panel steps, compact-WY factor
+    S from the Gram rows, C <- C - V S (V'C), zero-padded tile for orders that are not a multiple of 8."""
+    from tools.proto_wy_batched import ql_wy
+
+    nr = n - pad
+    Ar = np.random.default_rng(n * 100 + pad).standard_normal((nr, nr))
+    A = np.zeros((n, n))
+    A[pad:, pad:] = Ar
+    F, tau = ql_wy(A, pad)
+    Fo, tauo = lapack.geqlf(np.asfortranarray(Ar))
+    t = 50 * n * np.finfo(float).eps * np.linalg.norm(Ar)
+    assert np.abs(F[pad:, pad:] - Fo).max() <= t and np.abs(tau[pad:] - tauo).max() <= t
+
+
+@pytest.mark.parametrize("dt", [np.complex128, np.complex64])
+@pytest.mark.parametrize("shape", [(9, 9), (12, 7), (7, 12)])
+def test_lapack_binding_complex(dt, shape):
+    """The complex half of the LAPACK binding (z/c geqlf, unmql: what src/ql.jl:72 calls for Complex BlasFloat) -- used as the
+    parity reference of tests/test_eltypes_gpu.py: Q unitary, Q [0; L] = A, Q^H via 'C'."""
+    m, n = shape
+    rng = np.random.default_rng(m * 10 + n)
+    A = np.asfortranarray((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dt))
+    F, tau = lapack.geqlf(A)
+    k = min(m, n)
+    V = np.asfortranarray(F[:, n - k:])
+    Q = lapack.ormql("L", "N", V, tau, np.eye(m, dtype=dt))
+    QH = lapack.ormql("L", "C", V, tau, np.eye(m, dtype=dt))
+    eps = np.finfo(dt).eps
+    assert np.abs(Q.conj().T @ Q - np.eye(m)).max() <= 50 * m * eps
+    assert np.abs(QH - Q.conj().T).max() <= 50 * m * eps
+    L = np.zeros((m, n), dtype=dt)
+    L[m - k:, :] = np.tril(F[m - k:, :], max(n - m, 0))
+    assert np.abs(Q @ L - A).max() <= 50 * max(m, n) * eps * np.linalg.norm(A)
+    if k > 1:      # zlarfg: beta is real
+        d = np.array([F[m - k + i, n - k + i] for i in range(1, k)])
+        assert np.abs(d.imag).max() == 0

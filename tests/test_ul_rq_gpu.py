@@ -167,3 +167,32 @@ def test_batched_mg_single_device_sharding(q, h):
         assert np.array_equal(F1, F2) and np.array_equal(t1, t2)
     finally:
         h2.close()
+
+
+@pytest.mark.parametrize("shape", [(2500, 2500), (3000, 2300), (2300, 3000)])
+@pytest.mark.parametrize("pivot", [True, False])
+def test_ul_lookahead_same_bits_and_flipped_getrf(q, h, shape, pivot):
+    """From min(m,n) >= 2048 on ul! factors block b+1 on the panel SM partition while block b is applied (look-ahead, row
+    interchanges outside the block deferred): same operations in the same order per entry, so the same bits as the
+    sequential schedule (option lookahead = 0); pivots and factors vs LAPACK getrf of the flipped matrix (SURVEY.md A.4,
+    test/test_ul.jl:30-35) for the square pivoted case."""
+    import torch
+
+    m, n = shape
+    rng = np.random.default_rng(m + n + int(pivot))
+    A = np.asfortranarray(rng.standard_normal((m, n)) + (0 if pivot else 4.0) * np.eye(m, n))
+    Ad = torch.empty_strided((m, n), (1, m), dtype=torch.float64, device="cuda").copy_(torch.from_numpy(A))
+    F1 = q.ul_(Ad.clone(memory_format=torch.preserve_format), pivot=pivot, check=False, handle=h)
+    h.set_option("lookahead", 0)
+    try:
+        F0 = q.ul_(Ad.clone(memory_format=torch.preserve_format), pivot=pivot, check=False, handle=h)
+    finally:
+        h.set_option("lookahead", 2)
+    torch.cuda.synchronize()
+    assert torch.equal(F1.factors, F0.factors) and torch.equal(F1.ipiv, F0.ipiv) and F1.info == F0.info
+    if pivot and m == n:
+        LU, ipiv, info = lapack.getrf(A[::-1, ::-1])
+        want = LU[::-1, ::-1]
+        got = F1.factors.cpu().numpy()
+        assert np.array_equal(F1.ipiv.cpu().numpy(), (n + 1 - ipiv)[::-1])
+        assert np.abs(got - want).max() <= 50 * n * EPS * np.linalg.norm(A)
