@@ -4,13 +4,15 @@
 // conventions, reference src/ql.jl:72 with the unblocked spec at src/ql.jl:56-68), lmul!(Q,B) /
 // lmul!(Q',B) (src/ql.jl:321-347 / 350-377) and the square ldiv!(F::QL,B) (src/ql.jl:440-447,467).
 //
-// Factorization kernel: a group of LPM = N/CPL lanes owns one matrix; every lane keeps CPL whole
-// columns in registers, so the reflector dot products v^T a_j and the rank-1 update are lane-local
-// FMAs (no shuffles); only the pivot column is broadcast (through shared memory) and two scalars
-// are shuffled per step.  Matrices are staged global -> shared by TMA 1-D bulk copies (one per
-// column, padded pitch => conflict-free column reads), prefetched one warp-batch ahead; factors go
-// back with 16-byte stores straight from registers.  HBM traffic = read A + write factors + write
-// tau = (2 n^2 + n) * sizeof(T) bytes per matrix, the compulsory minimum.
+// Factorization kernel (n <= 32): a group of LPM = N/CPL lanes owns one matrix; every lane keeps CPL whole columns in registers
+// (a SHIFTED tile: the pivot row always sits at register index N-1, finished rows leave into the shared-memory image of the
+// output), so the reflector dot products v^T a_j and the rank-1 update are lane-local FMAs (no shuffles); only the pivot
+// column is broadcast (through shared memory) and two scalars are shuffled per step.  A matrix is staged global -> shared by
+// ONE TMA tensor copy (3-D tensor map {rows, cols, matrix}, box {N+E, N, 1}: the E out-of-bounds rows give the padded,
+// conflict-free image for free) and leaves the same way (one TMA tensor store of the image).  HBM traffic = read A + write
+// factors + write tau = (2 n^2 + n) * sizeof(T) bytes per matrix, the compulsory minimum (n = 32 Float64 above 48k matrices
+// runs as two kernels and re-reads/re-writes the live 16 x 16 block: 1.22x).  Orders other than 8/16/32 use the next larger
+// tile with the matrix in its bottom-right corner; 32 < n <= 64: batched_wy.cuh.
 #include "common.cuh"
 #include "internal.h"
 #include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
