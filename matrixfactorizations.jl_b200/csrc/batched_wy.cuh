@@ -40,7 +40,8 @@ struct WyCfg {
 // Trailing update of panel p (columns 8p..8p+7, NB = p+1 row blocks of 8) on the column tiles jt0 .. p-1.
 // g = lane >> 2, t = lane & 3 (DMMA fragment coordinates, common.cuh).
 template <int NT, int NB>
-__device__ __forceinline__ void wy_update(double *img, double *sS, const double *taus8, int jt0, int lane) {
+__device__ __forceinline__ void wy_update(double *img, double *sS, const double *taus8, int jt0, int lane, int jt1 = NB - 1,
+                                          bool build_s = true) {
     constexpr int LD = WyCfg<NT>::LD;
     constexpr int p = NB - 1;
     const int g = lane >> 2, t = lane & 3;
@@ -67,7 +68,7 @@ __device__ __forceinline__ void wy_update(double *img, double *sS, const double 
     // compact-WY factor of the panel: M = H_0 ... H_7 = I - V S V', S upper triangular, S[r][r] = tau_r,
     // S[r][c] = -tau_r sum_{k=r+1..c} (v_r' v_k) S[k][c].  Gram matrix G = V'V on the tensor pipe (the fragments are already in
     // registers), then lane c runs the recurrence for column c of S (G read as shared-memory broadcasts); -S goes to the scratch.
-    {
+    if (build_s) {
         double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
         for (int mb = 0; mb < NB; ++mb) {
@@ -100,7 +101,7 @@ __device__ __forceinline__ void wy_update(double *img, double *sS, const double 
     }
     const double Sf0 = sS[(2 * t) * 8 + g], Sf1 = sS[(2 * t + 1) * 8 + g];       // -S[g][2t+s]
 #pragma unroll 1
-    for (int jt = jt0; jt < p; ++jt) {
+    for (int jt = jt0; jt < jt1; ++jt) {
         double2 acc[NB];
         double *ccol = img + (8 * jt + g) * LD + 2 * t;
         double wa0 = 0.0, wa1 = 0.0, wb0 = 0.0, wb1 = 0.0;     // two accumulation chains (DMMA dependent latency ~26 cycles)
@@ -374,6 +375,188 @@ geqlf_wy_kernel(const __grid_constant__ CUtensorMap tmap, TI *__restrict__ A, in
     if constexpr (USE_TMA) tma_store_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-pair variant: TWO warps per matrix.  The panel warp runs the Householder steps, the update warp the tensor-core
+// trailing updates, with a one-panel look-ahead inside the matrix: as soon as the update warp has applied panel p to the 8
+// columns of panel p-1 it hands them over, and the panel warp factors panel p-1 while the update warp applies panel p to the
+// rest.  The kernel is bound by the latency of the dependent step chain with only NT-limited matrices resident per SM
+// (shared memory); this takes the update off that chain and doubles the warps per SM.  Hand-offs are mbarriers in shared
+// memory (release/acquire at CTA scope), the pair meets on a named barrier around staging and output.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int NT>
+__device__ __forceinline__ void wy_update_dispatch(int p, double *img, double *sS, const double *taus8, int jt0, int lane, int jt1, bool build_s) {
+    switch (p) {
+        case 1: wy_update<NT, 2>(img, sS, taus8, jt0, lane, jt1, build_s); break;
+        case 2: if constexpr (NT >= 24) wy_update<NT, 3>(img, sS, taus8, jt0, lane, jt1, build_s); break;
+        case 3: if constexpr (NT >= 32) wy_update<NT, 4>(img, sS, taus8, jt0, lane, jt1, build_s); break;
+        case 4: if constexpr (NT >= 40) wy_update<NT, 5>(img, sS, taus8, jt0, lane, jt1, build_s); break;
+        case 5: if constexpr (NT >= 48) wy_update<NT, 6>(img, sS, taus8, jt0, lane, jt1, build_s); break;
+        case 6: if constexpr (NT >= 56) wy_update<NT, 7>(img, sS, taus8, jt0, lane, jt1, build_s); break;
+        case 7: if constexpr (NT >= 64) wy_update<NT, 8>(img, sS, taus8, jt0, lane, jt1, build_s); break;
+        default: break;
+    }
+}
+
+template <typename TI, int NT, int PAIRS, bool USE_TMA, bool PADDED>
+__global__ void __launch_bounds__(PAIRS * 64, 1)
+geqlf_wy_pair_kernel(const __grid_constant__ CUtensorMap tmap, TI *__restrict__ A, int64_t lda, int64_t strideA,
+                     TI *__restrict__ tau, int64_t strideTau, int64_t batch, int nr_arg) {
+    static_assert(!USE_TMA || sizeof(TI) == 8, "the tensor map describes Float64 matrices");
+    using Cfg = WyCfg<NT>;
+    constexpr int LD = Cfg::LD, NSLOT = Cfg::NSLOT, NP = Cfg::NP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp >> 1, role = warp & 1;            // role 0: panel warp, role 1: update warp
+    const int l64 = (role << 5) | lane;                     // index inside the pair
+    unsigned char *wbase = smem_raw + (size_t)slot * Cfg::WARP_BYTES;
+    double *img = reinterpret_cast<double *>(wbase);
+    double *sS = reinterpret_cast<double *>(wbase + Cfg::S_OFF);
+    double *taus = reinterpret_cast<double *>(wbase + Cfg::TAU_OFF);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + Cfg::BAR_OFF);      // [0] TMA, [1] "panel ready", [2] "next panel's columns updated"
+    int *badflag = reinterpret_cast<int *>(wbase + Cfg::BAR_OFF + 32);
+    const int nr = PADDED ? nr_arg : NT;
+    const int pad = NT - nr;
+    const int jt0 = pad >> 3;                               // column tiles left of it are padding
+    const int nbatch = (int)batch;
+    const int gp = (int)blockIdx.x * PAIRS + slot, npairs = (int)gridDim.x * PAIRS;
+    const bool flat4 = sizeof(TI) == 4 && lda == NT && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && ((strideA * sizeof(TI)) & 15) == 0;
+    (void)flat4;
+    if (l64 == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
+        mbar_fence_init();
+    }
+    pair_sync(1 + slot);
+    uint32_t ph_tma = 0, ph_a = 0, ph_b = 0;
+    for (int mi = gp; mi < nbatch; mi += npairs) {
+        TI *Am = A + (int64_t)mi * strideA;
+        if constexpr (USE_TMA) {
+            if (l64 == 0) {
+                mbar_arrive_expect_tx(&bar[0], (uint32_t)Cfg::IMG_BYTES);
+                tma_load_3d(img, &tmap, -pad, -pad, mi, &bar[0]);
+            }
+            mbar_wait(&bar[0], ph_tma);
+            ph_tma ^= 1;
+        } else {
+            bool staged = false;
+            if constexpr (sizeof(TI) == 4 && !PADDED) {
+                if (flat4) {
+#pragma unroll 8
+                    for (int idx = l64 * 4; idx < NT * NT; idx += 256) {
+                        const float4 v = *reinterpret_cast<const float4 *>(Am + idx);
+                        double *d = img + (idx / NT) * LD + (idx % NT);
+                        *reinterpret_cast<double2 *>(d) = make_double2((double)v.x, (double)v.y);
+                        *reinterpret_cast<double2 *>(d + 2) = make_double2((double)v.z, (double)v.w);
+                    }
+                    staged = true;
+                }
+            }
+            if (!staged) {
+                for (int c = role; c < NT; c += 2)
+                    for (int r = lane; r < NT; r += 32) img[c * LD + r] = (c >= pad && r >= pad) ? (double)Am[(int64_t)(c - pad) * lda + (r - pad)] : 0.0;
+            }
+            pair_sync(1 + slot);
+        }
+        if (role == 0) {
+            bool bad = false;
+#pragma unroll 1
+            for (int p = NP - 1; p >= 0; --p) {
+                if (8 * p + 7 < pad) break;                        // the remaining panels are padding
+                if (p + 1 < NP && jt0 < p + 1) {                   // panel p+1 has been applied to these 8 columns
+                    mbar_wait(&bar[2], ph_b);
+                    ph_b ^= 1;
+                }
+                double P[8][NSLOT];
+                int row[NSLOT];
+                row[0] = lane + ((8 * p) & 32);
+                if constexpr (NSLOT == 2) row[1] = lane + (((8 * p) & 32) ^ 32);
+                double *pw = img + (8 * p) * LD;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s) P[i][s] = (NT % 32 == 0 || row[s] < NT) ? pw[i * LD + row[s]] : 0.0;
+                wy_steps<NT, 8, NSLOT>(P, row, pw, taus, p, 7, pad, lane, bad);
+                wy_steps<NT, 4, NSLOT>(P, row, pw, taus, p, 3, pad, lane, bad);
+                __syncwarp();
+                if (p >= 1 && jt0 < p && lane == 0) mbar_arrive(&bar[1]);      // release: the panel's columns and tau are in shared memory
+            }
+            if (lane == 0) *badflag = bad ? 1 : 0;
+        } else {
+#pragma unroll 1
+            for (int q = NP - 1; q >= 1; --q) {
+                if (!(jt0 < q)) break;
+                mbar_wait(&bar[1], ph_a);
+                ph_a ^= 1;
+                wy_update_dispatch<NT>(q, img, sS, taus + 8 * q, q - 1, lane, q, true);        // look-ahead: the next panel's columns first
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[2]);
+                if (jt0 < q - 1) wy_update_dispatch<NT>(q, img, sS, taus + 8 * q, jt0, lane, q - 1, false);
+                __syncwarp();
+            }
+        }
+        pair_sync(1 + slot);
+        const bool bad = *badflag != 0;
+        // ---- output ----
+        if (!bad) {
+            for (int i = l64; i < nr; i += 64) tau[(int64_t)mi * strideTau + i] = (TI)taus[i + pad];
+        }
+        if constexpr (USE_TMA && !PADDED) {
+            fence_proxy_async();
+            pair_sync(1 + slot);
+            if (l64 == 0) {
+                if (!bad) tma_store_3d(&tmap, 0, 0, mi, img);
+                tma_store_commit();
+                tma_store_wait_read();
+            }
+            pair_sync(1 + slot);
+        } else {
+            if (!bad) {
+                bool done = false;
+                if constexpr (USE_TMA) {
+                    if ((pad & 1) == 0) {
+                        const int nv = nr >> 1;
+                        for (int c = role; c < nr; c += 2)
+                            for (int vv = lane; vv < nv; vv += 32)
+                                *reinterpret_cast<double2 *>(Am + (int64_t)c * lda + 2 * vv) = *reinterpret_cast<const double2 *>(img + (c + pad) * LD + pad + 2 * vv);
+                        done = true;
+                    }
+                }
+                if constexpr (sizeof(TI) == 4 && !PADDED) {
+                    if (flat4) {
+#pragma unroll 8
+                        for (int idx = l64 * 4; idx < NT * NT; idx += 256) {
+                            const double *d = img + (idx / NT) * LD + (idx % NT);
+                            const double2 a0 = *reinterpret_cast<const double2 *>(d), a1 = *reinterpret_cast<const double2 *>(d + 2);
+                            *reinterpret_cast<float4 *>(Am + idx) = make_float4((float)a0.x, (float)a0.y, (float)a1.x, (float)a1.y);
+                        }
+                        done = true;
+                    }
+                }
+                if (!done) {
+                    for (int c = role; c < nr; c += 2)
+                        for (int r = lane; r < nr; r += 32) Am[(int64_t)c * lda + r] = (TI)img[(c + pad) * LD + pad + r];
+                }
+            }
+            if constexpr (USE_TMA) fence_proxy_async();
+            pair_sync(1 + slot);
+        }
+        if (bad) {        // rare: the matrix is untouched in global memory; literal ?geql2 / ?larfg with the image as scratch
+            if (role == 0) geql2_warp<TI>(Am, lda, tau + (int64_t)mi * strideTau, nr, reinterpret_cast<TI *>(img), lane);
+            if constexpr (USE_TMA) fence_proxy_async();
+            pair_sync(1 + slot);
+        }
+    }
+    if constexpr (USE_TMA) {
+        if (l64 == 0) tma_store_wait_all();
+    }
+}
+
 template <typename TI, int NT>
 static int launch_geqlf_wy(qlb200_ctx *h, TI *A, int64_t lda, int64_t strideA, TI *tau, int64_t strideTau, int64_t batch, int nr) {
     using Cfg = WyCfg<NT>;
@@ -391,16 +574,34 @@ static int launch_geqlf_wy(qlb200_ctx *h, TI *A, int64_t lda, int64_t strideA, T
     } else {
         kern = (nr == NT) ? geqlf_wy_kernel<TI, NT, WARPS, false, false> : geqlf_wy_kernel<TI, NT, WARPS, false, true>;
     }
+    // The warp-pair kernel (two warps per matrix, look-ahead inside the matrix) wins where shared memory allows at most ~7
+    // matrices per SM anyway (n > 56: 3.01 vs 3.32 ms per 65 536 64 x 64 matrices); below, one warp per matrix keeps more
+    // matrices resident and wins (n = 48: 1.61 vs 2.06 ms, n = 40: 1.05 vs 1.66 ms).  bvar 6 / 7 force pair / single (tests).
+    constexpr int PAIRS = WARPS < 7 ? WARPS : 7;
+    int threads = WARPS * 32, per_cta = WARPS;
+    size_t smem_used = smem;
+    if (h->opt_bvar == 6 || (h->opt_bvar != 7 && NT >= 64)) {
+        if constexpr (sizeof(TI) == 8) {
+            const bool tma = tma_ok(A, lda, strideA) && make_batch_tensor_map<double>(&tmap, A, nr, lda, strideA, batch, Cfg::LD, NT);
+            if (nr == NT) kern = tma ? geqlf_wy_pair_kernel<TI, NT, PAIRS, true, false> : geqlf_wy_pair_kernel<TI, NT, PAIRS, false, false>;
+            else kern = tma ? geqlf_wy_pair_kernel<TI, NT, PAIRS, true, true> : geqlf_wy_pair_kernel<TI, NT, PAIRS, false, true>;
+        } else {
+            kern = (nr == NT) ? geqlf_wy_pair_kernel<TI, NT, PAIRS, false, false> : geqlf_wy_pair_kernel<TI, NT, PAIRS, false, true>;
+        }
+        threads = PAIRS * 64;
+        per_cta = PAIRS;
+        smem_used = (size_t)PAIRS * Cfg::WARP_BYTES;
+    }
     int occ = 0;
-    int rcs = kernel_ready(h, kern, WARPS * 32, smem, &occ);
+    int rcs = kernel_ready(h, kern, threads, smem_used, &occ);
     if (rcs) return rcs;
     if (occ < 1) return qlb_fail(h, 1000 + (int)cudaErrorLaunchOutOfResources, "batched WY QL kernel does not fit on an SM%s");
-    int64_t blocks = (batch + WARPS - 1) / WARPS;
+    int64_t blocks = (batch + per_cta - 1) / per_cta;
     int64_t cap = (int64_t)h->sm_count * occ;
     if (h->opt_bgrid > 0 && cap > h->opt_bgrid) cap = h->opt_bgrid;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, WARPS * 32, smem, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, nr);
+    kern<<<(unsigned)blocks, threads, smem_used, h->stream>>>(tmap, A, lda, strideA, tau, strideTau, batch, nr);
     QLB_LAUNCH_CHECK(h);
     return 0;
 }

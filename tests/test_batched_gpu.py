@@ -363,3 +363,23 @@ def test_fused_factor_apply_same_bits_as_two_calls(q, h, n, dt, op, where):
     assert np.array_equal(F1, F2) and np.array_equal(t1, t2) and np.array_equal(X1, X2)
     if op == "S":
         assert (info == 0).all()
+
+
+@pytest.mark.parametrize("n", [33, 40, 47, 48, 56, 64])
+@pytest.mark.parametrize("bvar", [6, 7])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_batched_wy_pair_and_single_warp_kernels_same_bits(q, h, n, bvar, dt):
+    """32 < n <= 64: the warp-pair kernel (panel warp + update warp, look-ahead inside the matrix; default for n > 56) and the
+    one-warp-per-matrix kernel execute the same arithmetic per matrix: identical bits, and both match LAPACK."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((150, n, n)).astype(dt)
+    F0, t0 = q.ql_batched_(A.copy(), handle=h)
+    h.set_option("bvar", bvar)
+    try:
+        F1, t1 = q.ql_batched_(A.copy(), handle=h)
+    finally:
+        h.set_option("bvar", 0)
+    assert np.array_equal(F0, F1) and np.array_equal(t0, t1)
+    Fo = A.copy()
+    tauo = lapack.geqlf_loop(Fo)
+    _check_factors(F1, t1, Fo, tauo, A, n, dt)
