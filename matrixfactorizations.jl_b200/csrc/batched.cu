@@ -1271,7 +1271,10 @@ int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64
                           int64_t strideTau, int64_t batch) {
     switch (n) {
         case 8: return qlb::launch_geqlf_batched<float, 8, 1, 4, 8>(h, A, lda, strideA, tau, strideTau, batch);
-        case 16: return qlb::launch_geqlf_batched<float, 16, 2, 4, 5>(h, A, lda, strideA, tau, strideTau, batch);
+        case 16:
+            if (h->opt_bvar == 5) return qlb::launch_geqlf_batched<float, 16, 2, 4, 6>(h, A, lda, strideA, tau, strideTau, batch);      // experiment
+            if (h->opt_bvar == 4) return qlb::launch_geqlf_batched<float, 16, 2, 4, 4>(h, A, lda, strideA, tau, strideTau, batch);      // experiment
+            return qlb::launch_geqlf_batched<float, 16, 2, 4, 5>(h, A, lda, strideA, tau, strideTau, batch);
         case 32:
             if (h->opt_bvar == 2) return qlb::launch_geqlf_batched<float, 32, 2, 4, 3>(h, A, lda, strideA, tau, strideTau, batch);
             return qlb::launch_geqlf_batched_split32<float, 4, 3, 5>(h, A, lda, strideA, tau, strideTau, batch);
