@@ -688,7 +688,7 @@ struct ApplyCfg {
     static constexpr bool VCOPY = (MODE == 2) && (N >= 16) && (sizeof(T) == 4);     // Float64: the extra shared memory costs more than the masks (measured)
     static constexpr int VIMG_OFF = DBUF * STAGE_BYTES + 128;                     // after the mbarriers
     static constexpr int WARP_BYTES = VIMG_OFF + (VCOPY ? G * IMG_BYTES : 0);
-    static_assert(RG >= 1 && RPL % E == 0, "row blocks are whole 16-byte vectors");
+    static constexpr bool VALID = RG >= 1 && RPL % E == 0;      // row blocks are whole 16-byte vectors (else: the next wider NR)
 };
 
 template <typename T, int N, int NR, int MODE, int WARPS, bool USE_TMA, bool PADDED = false>
@@ -1206,11 +1206,19 @@ static int launch_apply_generic(qlb200_ctx *h, const T *A, int64_t lda, int64_t 
 template <typename T, int N, int MODE>
 static int dispatch_apply_nr(qlb200_ctx *h, const T *A, int64_t lda, int64_t strideA, const T *tau, int64_t strideTau,
                              T *B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch, int32_t *info_out, int nr = N) {
-    // NR = columns of B handled per pass (a power of two <= 8)
-    if (nrhs > 4) return launch_apply_batched<T, N, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
-    if (nrhs > 2) return launch_apply_batched<T, N, 4, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
-    if (nrhs > 1) return launch_apply_batched<T, N, 2, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
-    return launch_apply_batched<T, N, 1, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
+    // NR = columns of B handled per pass (a power of two <= 8; a configuration whose row blocks would not be whole vectors
+    // falls through to the next wider one, which masks the missing columns)
+    if constexpr (ApplyCfg<T, N, 1, MODE>::VALID) {
+        if (nrhs <= 1) return launch_apply_batched<T, N, 1, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
+    }
+    if constexpr (ApplyCfg<T, N, 2, MODE>::VALID) {
+        if (nrhs <= 2) return launch_apply_batched<T, N, 2, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
+    }
+    if constexpr (ApplyCfg<T, N, 4, MODE>::VALID) {
+        if (nrhs <= 4) return launch_apply_batched<T, N, 4, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
+    }
+    static_assert(ApplyCfg<T, N, 8, MODE>::VALID, "the widest configuration must exist");
+    return launch_apply_batched<T, N, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, nr);
 }
 
 template <typename T, int MODE>
@@ -1221,11 +1229,15 @@ static int dispatch_apply_n(qlb200_ctx *h, int64_t n, const T *A, int64_t lda, i
         case 8: return dispatch_apply_nr<T, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
         case 16: return dispatch_apply_nr<T, 16, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
         case 32: return dispatch_apply_nr<T, 32, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
+        case 64:
+            if (h->opt_bvar != 9) return dispatch_apply_nr<T, 64, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out);
+            break;
     }
     // other orders up to 32: the next larger tile, zero-padded in front (see the factorization)
     if (n >= 1 && n < 8) return dispatch_apply_nr<T, 8, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, (int)n);
     if (n > 8 && n < 16) return dispatch_apply_nr<T, 16, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, (int)n);
     if (n > 16 && n < 32) return dispatch_apply_nr<T, 32, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, (int)n);
+    if (n > 32 && n < 64 && h->opt_bvar != 9) return dispatch_apply_nr<T, 64, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, nrhs, batch, info_out, (int)n);
     if (n >= 1 && n <= 64)
         return launch_apply_generic<T, MODE>(h, A, lda, strideA, tau, strideTau, B, ldb, strideB, (int)n, nrhs, batch, info_out);
     return qlb_fail(h, -2, "batched apply: n must be in [1,64]%s");
