@@ -153,6 +153,26 @@ int qlb200_cunmql_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t
 int qlb200_cqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const void *A, int64_t lda, const void *tau, void *B, int64_t ldb);
 int qlb200_cqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const void *dA, int64_t lda, const void *dtau, void *dB,
                         int64_t ldb);
+/* rq! / RQPackedQ for the same element types (reference src/rq.jl:401 -> LAPACK.gerqf!, :130-291 -> LAPACK.ormrq!):
+ * ?gerqf(A) = (?geqlf(A^H))^H with identical tau; ?unmrq on the conjugate-transposed reflectors with the other op. */
+int qlb200_zgerqf(qlb200_handle h, int64_t m, int64_t n, void *A, int64_t lda, void *tau);
+int qlb200_zgerqf_dev(qlb200_handle h, int64_t m, int64_t n, void *dA, int64_t lda, void *dtau);
+int qlb200_zunmrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *A, int64_t lda,
+                  const void *tau, void *C, int64_t ldc);
+int qlb200_zunmrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *dA, int64_t lda,
+                      const void *dtau, void *dC, int64_t ldc);
+int qlb200_cgerqf(qlb200_handle h, int64_t m, int64_t n, void *A, int64_t lda, void *tau);
+int qlb200_cgerqf_dev(qlb200_handle h, int64_t m, int64_t n, void *dA, int64_t lda, void *dtau);
+int qlb200_cunmrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *A, int64_t lda,
+                  const void *tau, void *C, int64_t ldc);
+int qlb200_cunmrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *dA, int64_t lda,
+                      const void *dtau, void *dC, int64_t ldc);
+int qlb200_sgerqf(qlb200_handle h, int64_t m, int64_t n, float *A, int64_t lda, float *tau);
+int qlb200_sgerqf_dev(qlb200_handle h, int64_t m, int64_t n, float *dA, int64_t lda, float *dtau);
+int qlb200_sormrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *A, int64_t lda,
+                  const float *tau, float *C, int64_t ldc);
+int qlb200_sormrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *dA, int64_t lda,
+                      const float *dtau, float *dC, int64_t ldc);
 int qlb200_sgeqlf(qlb200_handle h, int64_t m, int64_t n, float *A, int64_t lda, float *tau);
 int qlb200_sgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, float *dA, int64_t lda, float *dtau);
 int qlb200_sormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *A, int64_t lda,

@@ -63,10 +63,14 @@ for _sfx in ("", "_dev"):
     SIGNATURES[f"qlb200_sgeqlf{_sfx}"] = _FACT
     SIGNATURES[f"qlb200_sormql{_sfx}"] = _ORM
     SIGNATURES[f"qlb200_sqlsolve{_sfx}"] = _SOLVE
+    SIGNATURES[f"qlb200_sgerqf{_sfx}"] = _FACT
+    SIGNATURES[f"qlb200_sormrq{_sfx}"] = _ORM
     for _t in "zc":
         SIGNATURES[f"qlb200_{_t}geqlf{_sfx}"] = _FACT
         SIGNATURES[f"qlb200_{_t}unmql{_sfx}"] = _ORM
         SIGNATURES[f"qlb200_{_t}qlsolve{_sfx}"] = _SOLVE
+        SIGNATURES[f"qlb200_{_t}gerqf{_sfx}"] = _FACT
+        SIGNATURES[f"qlb200_{_t}unmrq{_sfx}"] = _ORM
     for _t in "ds":
         SIGNATURES[f"qlb200_{_t}geqlf_batched{_sfx}"] = _FACT_B
         SIGNATURES[f"qlb200_{_t}ormql_batched{_sfx}"] = _ORM_B

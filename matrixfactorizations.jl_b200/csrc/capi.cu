@@ -132,6 +132,7 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->redo) cudaFree(h->redo);
     for (int i = 0; i < 3; ++i)
         if (h->cvt[i]) cudaFree(h->cvt[i]);
+    if (h->zws) cudaFree(h->zws);
     if (h->tall) cudaFree(h->tall);
     if (h->tcache) cudaFree(h->tcache);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);

@@ -46,6 +46,8 @@ struct qlb200_ctx {
     int32_t *dinfo = nullptr;              // device-side status word
     void *tall = nullptr;                  // scratch of the tall-strip fallback (partial dots, strip Gram matrix)
     size_t tall_bytes = 0;
+    void *zws = nullptr;                   // complex RQ: the conjugate-transposed reflectors (complex.cu)
+    size_t zws_bytes = 0;
     void *cvt[3] = {nullptr, nullptr, nullptr};   // Float32 / ComplexF32 entry points: the widened operands (mixed.cu)
     size_t cvt_bytes[3] = {0, 0, 0};
     void *redo = nullptr;                  // batched: counter + list of matrices for the generic kernel

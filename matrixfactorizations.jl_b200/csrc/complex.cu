@@ -764,6 +764,45 @@ int qlb_zqlsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A
     return 0;
 }
 
+// rq!(A) for ComplexF64 (reference src/rq.jl:401 -> LAPACK.gerqf!): zgerqf(A) = (zgeqlf(A^H))^H with identical tau -- the RQ
+// reflectors are stored conjugated in the rows (H(i) = I - tau v v^H, conj(v) in row i), which is exactly the conjugate
+// transpose of the QL reflectors of A^H; R = L^H.
+int qlb_zgerqf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t lda, double *taud) {
+    const int m = (int)m64, n = (int)n64;
+    if (m == 0 || n == 0) return 0;
+    cudaStream_t st = h->stream;
+    const int64_t ldt = n;
+    int rc = qlb_reserve(h, &h->ws2, &h->ws2_bytes, (size_t)ldt * m * 2 * sizeof(double));
+    if (rc) return rc;
+    double2 *At = (double2 *)h->ws2;
+    dim3 b(32, 8), g1((m + 31) / 32, (n + 31) / 32), g2((n + 31) / 32, (m + 31) / 32);
+    zctranspose_kernel<<<g1, b, 0, st>>>(reinterpret_cast<const double2 *>(Ad), lda, m, n, At, ldt);
+    QLB_LAUNCH_CHECK(h);
+    rc = qlb_zgeqlf_dev(h, n, m, (double *)At, ldt, taud);
+    if (rc) return rc;
+    zctranspose_kernel<<<g2, b, 0, st>>>(At, ldt, n, m, reinterpret_cast<double2 *>(Ad), lda);
+    QLB_LAUNCH_CHECK(h);
+    return 0;
+}
+// lmul!/rmul! with RQ's packed Q (reference src/rq.jl:130-137,183-202,234-291 -> LAPACK.ormrq! = zunmrq): A is k x nq, row i
+// holds conj(v_i); Q_rq = H(1)^H ... H(k)^H = Q_ql^H for the QL reflectors A^H, so op(Q_rq) is the other op of Q_ql.
+int qlb_zunmrq_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n64, int64_t k64, const double *Ad, int64_t lda,
+                   const double *taud, double *Cd, int64_t ldc) {
+    const int m = (int)m64, n = (int)n64, k = (int)k64;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    const bool left = (side == 'L' || side == 'l');
+    const bool notran = (trans == 'N' || trans == 'n');
+    const int nq = left ? m : n;
+    const int64_t ldt = nq;
+    int rc = qlb_reserve(h, &h->zws, &h->zws_bytes, (size_t)ldt * k * 2 * sizeof(double));
+    if (rc) return rc;
+    double2 *At = (double2 *)h->zws;                // nq x k: column i = v_i
+    dim3 b(32, 8), g((k + 31) / 32, (nq + 31) / 32);
+    zctranspose_kernel<<<g, b, 0, h->stream>>>(reinterpret_cast<const double2 *>(Ad), lda, k, nq, At, ldt);
+    QLB_LAUNCH_CHECK(h);
+    return qlb_zunmql_dev(h, side, notran ? 'C' : 'N', m, n, k, (const double *)At, ldt, taud, Cd, ldc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // extern "C" entry points (include/qlb200.h)
 // ---------------------------------------------------------------------------------------------
@@ -864,6 +903,76 @@ int qlb200_zunmql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, 
     double *dtau = dC + (size_t)m * n * 2;
     QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 16, cudaMemcpyHostToDevice, h->stream));
     rc = qlb_zunmql_dev(h, side, trans, m, n, k, dA, nq, dtau, dC, m);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaMemcpy2DAsync(C, (size_t)ldc * 16, dC, (size_t)m * 16, (size_t)m * 16, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int qlb200_zgerqf_dev(qlb200_handle h, int64_t m, int64_t n, void *dA, int64_t lda, void *dtau) {
+    int rc = zcheck_fact(h, m, n, dA, lda, dtau);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_zgerqf_dev(h, m, n, (double *)dA, lda, (double *)dtau);
+}
+int qlb200_zgerqf(qlb200_handle h, int64_t m, int64_t n, void *A, int64_t lda, void *tau) {
+    int rc = zcheck_fact(h, m, n, A, lda, tau);
+    if (rc) return rc;
+    const int64_t k = m < n ? m : n;
+    if (k == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA;
+    rc = zstage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, 0, &dA);
+    if (rc) return rc;
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * 16);
+    if (rc) return rc;
+    double *dtau = (double *)h->stage2;
+    rc = qlb_zgerqf_dev(h, m, n, dA, m, dtau);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaMemcpy2DAsync(A, (size_t)lda * 16, dA, (size_t)m * 16, (size_t)m * 16, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * 16, cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+static int zcheck_unmrq(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *A, int64_t lda,
+                        const void *tau, const void *C, int64_t ldc) {
+    if (!h) return -1;
+    const bool left = side == 'L' || side == 'l', right = side == 'R' || side == 'r';
+    QLB_REQUIRE(h, left || right, 2, "side must be 'L' or 'R'");
+    QLB_REQUIRE(h, trans == 'N' || trans == 'n' || trans == 'C' || trans == 'c', 3, "trans must be 'N' or 'C'");
+    QLB_REQUIRE(h, m >= 0 && m < (1 << 29), 4, "m out of range");
+    QLB_REQUIRE(h, n >= 0 && n < (1 << 29), 5, "n out of range");
+    const int64_t nq = left ? m : n;
+    QLB_REQUIRE(h, k >= 0 && k <= nq, 6, "k must satisfy 0 <= k <= order of Q (DimensionMismatch)");
+    QLB_REQUIRE(h, A != nullptr || k == 0, 7, "A is null");
+    QLB_REQUIRE(h, lda >= (k > 1 ? k : 1), 8, "lda < max(1,k)");
+    QLB_REQUIRE(h, tau != nullptr || k == 0, 9, "tau is null");
+    QLB_REQUIRE(h, C != nullptr || m * n == 0, 10, "C is null");
+    QLB_REQUIRE(h, ldc >= (m > 1 ? m : 1), 11, "ldc < max(1,m)");
+    return 0;
+}
+int qlb200_zunmrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *dA, int64_t lda,
+                      const void *dtau, void *dC, int64_t ldc) {
+    int rc = zcheck_unmrq(h, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_zunmrq_dev(h, side, trans, m, n, k, (const double *)dA, lda, (const double *)dtau, (double *)dC, ldc);
+}
+int qlb200_zunmrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *A, int64_t lda,
+                  const void *tau, void *C, int64_t ldc) {
+    int rc = zcheck_unmrq(h, side, trans, m, n, k, A, lda, tau, C, ldc);
+    if (rc) return rc;
+    if (m == 0 || n == 0 || k == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t nq = (side == 'L' || side == 'l') ? m : n;
+    double *dA, *dC;
+    rc = zstage_in(h, &h->stage, &h->stage_bytes, A, k, nq, lda, 0, &dA);
+    if (rc) return rc;
+    rc = zstage_in(h, &h->stage2, &h->stage2_bytes, C, m, n, ldc, (size_t)k + 1, &dC);
+    if (rc) return rc;
+    double *dtau = dC + (size_t)m * n * 2;
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)k * 16, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb_zunmrq_dev(h, side, trans, m, n, k, dA, k, dtau, dC, m);
     if (rc) return rc;
     QLB_CUDA(h, cudaMemcpy2DAsync(C, (size_t)ldc * 16, dC, (size_t)m * 16, (size_t)m * 16, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     QLB_CUDA(h, cudaStreamSynchronize(h->stream));

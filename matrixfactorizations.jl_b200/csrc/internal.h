@@ -23,6 +23,9 @@ int qlb_block_gram(qlb200_ctx *h, cudaStream_t st, const QlbWorkspace &ws, int p
 int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
 int qlb_zunmql_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
                    const double *tau, double *C, int64_t ldc);
+int qlb_zgerqf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb_zunmrq_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                   const double *tau, double *C, int64_t ldc);
 int qlb_zqlsolve_dev(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
                      int64_t ldb, int32_t *dinfo);
 

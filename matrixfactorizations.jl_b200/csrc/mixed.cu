@@ -35,7 +35,7 @@ static inline int64_t ev(int64_t x) { return x < 2 ? 2 : ((x + 1) & ~(int64_t)1)
 
 // MULT = 1: Float32 -> the d path; MULT = 2: ComplexF32 (interleaved) -> the z path.  All pointers are device pointers; leading
 // dimensions in elements of the caller's type.
-template <int MULT>
+template <int MULT, bool RQ = false>
 static int geqlf_promoted(qlb200_ctx *h, int64_t m, int64_t n, float *A, int64_t lda, float *tau) {
     const int64_t k = m < n ? m : n;
     if (k == 0) return 0;
@@ -46,29 +46,36 @@ static int geqlf_promoted(qlb200_ctx *h, int64_t m, int64_t n, float *A, int64_t
     double *dA = (double *)h->cvt[0], *dT = (double *)h->cvt[2];
     rc = cvt(h, A, MULT * lda, dA, ldd, rows, n);
     if (rc) return rc;
-    rc = (MULT == 1) ? qlb_dgeqlf_dev(h, m, n, dA, ldd, dT) : qlb_zgeqlf_dev(h, m, n, dA, ldd / 2, dT);
+    if constexpr (RQ) rc = (MULT == 1) ? qlb_dgerqf_dev(h, m, n, dA, ldd, dT) : qlb_zgerqf_dev(h, m, n, dA, ldd / 2, dT);
+    else rc = (MULT == 1) ? qlb_dgeqlf_dev(h, m, n, dA, ldd, dT) : qlb_zgeqlf_dev(h, m, n, dA, ldd / 2, dT);
     if (rc) return rc;
     rc = cvt(h, dA, ldd, A, MULT * lda, rows, n);
     if (rc) return rc;
     return cvt(h, dT, MULT * k, tau, MULT * k, MULT * k, 1);
 }
-template <int MULT>
+// RQ: A is k x nq (rows = reflectors, LAPACK ?ormrq / ?unmrq), else nq x k (?ormql / ?unmql)
+template <int MULT, bool RQ = false>
 static int ormql_promoted(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *A, int64_t lda,
                           const float *tau, float *C, int64_t ldc) {
     if (m == 0 || n == 0 || k == 0) return 0;
     const int64_t nq = (side == 'L' || side == 'l') ? m : n;
-    const int64_t ra = MULT * nq, lda2 = ev(ra), rc_ = MULT * m, ldc2 = ev(rc_);
-    int rc = qlb_reserve(h, &h->cvt[0], &h->cvt_bytes[0], (size_t)lda2 * k * sizeof(double));
+    const int64_t arows = RQ ? k : nq, acols = RQ ? nq : k;
+    const int64_t ra = MULT * arows, lda2 = ev(ra), rc_ = MULT * m, ldc2 = ev(rc_);
+    int rc = qlb_reserve(h, &h->cvt[0], &h->cvt_bytes[0], (size_t)lda2 * acols * sizeof(double));
     if (!rc) rc = qlb_reserve(h, &h->cvt[1], &h->cvt_bytes[1], (size_t)ldc2 * n * sizeof(double));
     if (!rc) rc = qlb_reserve(h, &h->cvt[2], &h->cvt_bytes[2], (size_t)(MULT * k + 2) * sizeof(double));
     if (rc) return rc;
     double *dA = (double *)h->cvt[0], *dC = (double *)h->cvt[1], *dT = (double *)h->cvt[2];
-    rc = cvt(h, A, MULT * lda, dA, lda2, ra, k);
+    rc = cvt(h, A, MULT * lda, dA, lda2, ra, acols);
     if (!rc) rc = cvt(h, C, MULT * ldc, dC, ldc2, rc_, n);
     if (!rc) rc = cvt(h, tau, MULT * k, dT, MULT * k, MULT * k, 1);
     if (rc) return rc;
-    rc = (MULT == 1) ? qlb_dormql_dev(h, side, trans, m, n, k, dA, lda2, dT, dC, ldc2, -1)
-                     : qlb_zunmql_dev(h, side, trans, m, n, k, dA, lda2 / 2, dT, dC, ldc2 / 2);
+    if constexpr (RQ)
+        rc = (MULT == 1) ? qlb_dormrq_dev(h, side, trans, m, n, k, dA, lda2, dT, dC, ldc2)
+                         : qlb_zunmrq_dev(h, side, trans, m, n, k, dA, lda2 / 2, dT, dC, ldc2 / 2);
+    else
+        rc = (MULT == 1) ? qlb_dormql_dev(h, side, trans, m, n, k, dA, lda2, dT, dC, ldc2, -1)
+                         : qlb_zunmql_dev(h, side, trans, m, n, k, dA, lda2 / 2, dT, dC, ldc2 / 2);
     if (rc) return rc;
     return cvt(h, dC, ldc2, C, MULT * ldc, rc_, n);
 }
@@ -107,7 +114,7 @@ static int down(qlb200_ctx *h, float *A, int64_t rows, int64_t cols, int64_t ld,
     return 0;
 }
 
-template <int MULT>
+template <int MULT, bool RQ = false>
 static int geqlf_any(qlb200_ctx *h, bool host, int64_t m, int64_t n, float *A, int64_t lda, float *tau) {
     if (!h) return -1;
     QLB_REQUIRE(h, m >= 0 && m < (1 << 29), 2, "m out of range");
@@ -118,12 +125,12 @@ static int geqlf_any(qlb200_ctx *h, bool host, int64_t m, int64_t n, float *A, i
     const int64_t k = m < n ? m : n;
     if (k == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
-    if (!host) return geqlf_promoted<MULT>(h, m, n, A, lda, tau);
+    if (!host) return geqlf_promoted<MULT, RQ>(h, m, n, A, lda, tau);
     float *dA;
     int rc = up(h, &h->stage, &h->stage_bytes, A, MULT * m, n, MULT * lda, (size_t)MULT * k + 4, &dA);
     if (rc) return rc;
     float *dT = dA + (size_t)MULT * m * n;
-    rc = geqlf_promoted<MULT>(h, m, n, dA, m, dT);
+    rc = geqlf_promoted<MULT, RQ>(h, m, n, dA, m, dT);
     if (rc) return rc;
     rc = down(h, A, MULT * m, n, MULT * lda, dA);
     if (rc) return rc;
@@ -131,7 +138,7 @@ static int geqlf_any(qlb200_ctx *h, bool host, int64_t m, int64_t n, float *A, i
     QLB_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
-template <int MULT>
+template <int MULT, bool RQ = false>
 static int ormql_any(qlb200_ctx *h, bool host, char side, char trans, int64_t m, int64_t n, int64_t k, const float *A, int64_t lda,
                      const float *tau, float *C, int64_t ldc) {
     if (!h) return -1;
@@ -144,20 +151,21 @@ static int ormql_any(qlb200_ctx *h, bool host, char side, char trans, int64_t m,
     const int64_t nq = left ? m : n;
     QLB_REQUIRE(h, k >= 0 && k <= nq, 6, "k must satisfy 0 <= k <= order of Q (DimensionMismatch)");
     QLB_REQUIRE(h, A != nullptr || k == 0, 7, "A is null");
-    QLB_REQUIRE(h, lda >= (nq > 1 ? nq : 1), 8, "lda < order of Q (DimensionMismatch)");
+    const int64_t arows = RQ ? k : nq, acols = RQ ? nq : k;
+    QLB_REQUIRE(h, lda >= (arows > 1 ? arows : 1), 8, "lda too small (DimensionMismatch)");
     QLB_REQUIRE(h, tau != nullptr || k == 0, 9, "tau is null");
     QLB_REQUIRE(h, C != nullptr || m * n == 0, 10, "C is null");
     QLB_REQUIRE(h, ldc >= (m > 1 ? m : 1), 11, "ldc < max(1,m)");
     if (m == 0 || n == 0 || k == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
-    if (!host) return ormql_promoted<MULT>(h, side, trans, m, n, k, A, lda, tau, C, ldc);
+    if (!host) return ormql_promoted<MULT, RQ>(h, side, trans, m, n, k, A, lda, tau, C, ldc);
     float *dA, *dC;
-    int rc = up(h, &h->stage, &h->stage_bytes, A, MULT * nq, k, MULT * lda, (size_t)MULT * k + 4, &dA);
+    int rc = up(h, &h->stage, &h->stage_bytes, A, MULT * arows, acols, MULT * lda, (size_t)MULT * k + 4, &dA);
     if (!rc) rc = up(h, &h->stage2, &h->stage2_bytes, C, MULT * m, n, MULT * ldc, 0, &dC);
     if (rc) return rc;
     float *dT = dA + (size_t)MULT * nq * k;
     QLB_CUDA(h, cudaMemcpyAsync(dT, tau, (size_t)MULT * k * 4, cudaMemcpyHostToDevice, h->stream));
-    rc = ormql_promoted<MULT>(h, side, trans, m, n, k, dA, nq, dT, dC, m);
+    rc = ormql_promoted<MULT, RQ>(h, side, trans, m, n, k, dA, arows, dT, dC, m);
     if (rc) return rc;
     rc = down(h, C, MULT * m, n, MULT * ldc, dC);
     if (rc) return rc;
@@ -201,6 +209,26 @@ int qlb200_sgeqlf(qlb200_handle h, int64_t m, int64_t n, float *A, int64_t lda, 
 int qlb200_sgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, float *dA, int64_t lda, float *dtau) { return geqlf_any<1>(h, false, m, n, dA, lda, dtau); }
 int qlb200_cgeqlf(qlb200_handle h, int64_t m, int64_t n, void *A, int64_t lda, void *tau) { return geqlf_any<2>(h, true, m, n, (float *)A, lda, (float *)tau); }
 int qlb200_cgeqlf_dev(qlb200_handle h, int64_t m, int64_t n, void *dA, int64_t lda, void *dtau) { return geqlf_any<2>(h, false, m, n, (float *)dA, lda, (float *)dtau); }
+int qlb200_sgerqf(qlb200_handle h, int64_t m, int64_t n, float *A, int64_t lda, float *tau) { return geqlf_any<1, true>(h, true, m, n, A, lda, tau); }
+int qlb200_sgerqf_dev(qlb200_handle h, int64_t m, int64_t n, float *dA, int64_t lda, float *dtau) { return geqlf_any<1, true>(h, false, m, n, dA, lda, dtau); }
+int qlb200_cgerqf(qlb200_handle h, int64_t m, int64_t n, void *A, int64_t lda, void *tau) { return geqlf_any<2, true>(h, true, m, n, (float *)A, lda, (float *)tau); }
+int qlb200_cgerqf_dev(qlb200_handle h, int64_t m, int64_t n, void *dA, int64_t lda, void *dtau) { return geqlf_any<2, true>(h, false, m, n, (float *)dA, lda, (float *)dtau); }
+int qlb200_sormrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *A, int64_t lda, const float *tau,
+                  float *C, int64_t ldc) {
+    return ormql_any<1, true>(h, true, side, trans, m, n, k, A, lda, tau, C, ldc);
+}
+int qlb200_sormrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *dA, int64_t lda,
+                      const float *dtau, float *dC, int64_t ldc) {
+    return ormql_any<1, true>(h, false, side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+}
+int qlb200_cunmrq(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *A, int64_t lda, const void *tau,
+                  void *C, int64_t ldc) {
+    return ormql_any<2, true>(h, true, side, trans, m, n, k, (const float *)A, lda, (const float *)tau, (float *)C, ldc);
+}
+int qlb200_cunmrq_dev(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const void *dA, int64_t lda,
+                      const void *dtau, void *dC, int64_t ldc) {
+    return ormql_any<2, true>(h, false, side, trans, m, n, k, (const float *)dA, lda, (const float *)dtau, (float *)dC, ldc);
+}
 int qlb200_sormql(qlb200_handle h, char side, char trans, int64_t m, int64_t n, int64_t k, const float *A, int64_t lda, const float *tau,
                   float *C, int64_t ldc) {
     return ormql_any<1>(h, true, side, trans, m, n, k, A, lda, tau, C, ldc);

@@ -155,31 +155,37 @@ materialize!(M::Rmul{<:AbstractColumnMajor,<:QRPackedQLayout{<:AbstractColumnMaj
 materialize!(M::Rmul{<:AbstractColumnMajor,<:AdjQRPackedQLayout{<:AbstractColumnMajor},<:StridedMatrix{Float64}}) =
     _ormqr!('R', 'T', parent(M.B), M.A)
 
-# ---- rq! and RQ's packed Q --------------------------------------------------------------------------------------
-function rq!(A::StridedMatrix{Float64})                                                    # src/rq.jl:401
-    m, n = size(A)
-    τ = Vector{Float64}(undef, min(m, n))
-    h = handle()
-    chk(h, ccall((:qlb200_dgerqf, libqlb200), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
-                 h.ptr, m, n, A, max(1, stride(A, 2)), τ))
-    RQ(A, τ)
+# ---- rq! and RQ's packed Q (every BlasFloat element type) ---------------------------------------------------------------
+for (T, p, orm, adj) in ((Float64, :d, :ormrq, 'T'), (Float32, :s, :ormrq, 'T'), (ComplexF64, :z, :unmrq, 'C'), (ComplexF32, :c, :unmrq, 'C'))
+    gerqf = QuoteNode(Symbol(:qlb200_, p, :gerqf))
+    ormrq = QuoteNode(Symbol(:qlb200_, p, orm))
+    @eval begin
+        function rq!(A::StridedMatrix{$T})                                                    # src/rq.jl:401
+            m, n = size(A)
+            τ = Vector{$T}(undef, min(m, n))
+            h = handle()
+            chk(h, ccall(($gerqf, libqlb200), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}),
+                         h.ptr, m, n, A, max(1, stride(A, 2)), τ))
+            RQ(A, τ)
+        end
+        function _ormrq!(side::Char, trans::Char, Q::RQPackedQ{$T,<:StridedMatrix}, C::StridedVecOrMat{$T})
+            mA, nA = size(Q.factors)
+            k = min(mA, nA)
+            m, n = size(C, 1), size(C, 2)
+            (side == 'L' ? m : n) == nA || throw(DimensionMismatch("matrix A has dimensions ($mA,$nA) but B has dimensions ($m, $n)"))
+            V = view(Q.factors, mA-k+1:mA, :)                  # the last k rows hold the reflectors (LAPACK ?ormrq / ?unmrq)
+            h = handle()
+            chk(h, ccall(($ormrq, libqlb200), Cint,
+                         (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Ptr{$T}, Int64, Ptr{$T}, Ptr{$T}, Int64),
+                         h.ptr, side, trans == 'N' ? 'N' : $adj, m, n, k, V, max(1, stride(Q.factors, 2)), Q.τ, C, max(1, stride(C, 2))); dims = (6, 8))
+            C
+        end
+        LinearAlgebra.lmul!(Q::RQPackedQ{$T,<:StridedMatrix}, B::StridedVecOrMat{$T}) = _ormrq!('L', 'N', Q, B)          # src/rq.jl:130-137
+        LinearAlgebra.lmul!(Q::Adjoint{<:Any,<:RQPackedQ{$T,<:StridedMatrix}}, B::StridedVecOrMat{$T}) = _ormrq!('L', 'T', parent(Q), B)   # :183-202
+        LinearAlgebra.rmul!(A::StridedMatrix{$T}, Q::RQPackedQ{$T,<:StridedMatrix}) = _ormrq!('R', 'N', Q, A)           # :234-242
+        LinearAlgebra.rmul!(A::StridedMatrix{$T}, Q::Adjoint{<:Any,<:RQPackedQ{$T,<:StridedMatrix}}) = _ormrq!('R', 'T', parent(Q), A)   # :272-291
+    end
 end
-function _ormrq!(side::Char, trans::Char, Q::RQPackedQ{Float64,<:StridedMatrix}, C::StridedVecOrMat{Float64})
-    mA, nA = size(Q.factors)
-    k = min(mA, nA)
-    m, n = size(C, 1), size(C, 2)
-    (side == 'L' ? m : n) == nA || throw(DimensionMismatch("matrix A has dimensions ($mA,$nA) but B has dimensions ($m, $n)"))
-    V = view(Q.factors, mA-k+1:mA, :)                  # the last k rows hold the reflectors (LAPACK ?ormrq)
-    h = handle()
-    chk(h, ccall((:qlb200_dormrq, libqlb200), Cint,
-                 (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
-                 h.ptr, side, trans, m, n, k, V, max(1, stride(Q.factors, 2)), Q.τ, C, max(1, stride(C, 2))); dims = (6, 8))
-    C
-end
-LinearAlgebra.lmul!(Q::RQPackedQ{Float64,<:StridedMatrix}, B::StridedVecOrMat{Float64}) = _ormrq!('L', 'N', Q, B)          # src/rq.jl:130-137
-LinearAlgebra.lmul!(Q::Adjoint{<:Any,<:RQPackedQ{Float64,<:StridedMatrix}}, B::StridedVecOrMat{Float64}) = _ormrq!('L', 'T', parent(Q), B)   # :183-202
-LinearAlgebra.rmul!(A::StridedMatrix{Float64}, Q::RQPackedQ{Float64,<:StridedMatrix}) = _ormrq!('R', 'N', Q, A)           # :234-242
-LinearAlgebra.rmul!(A::StridedMatrix{Float64}, Q::Adjoint{<:Any,<:RQPackedQ{Float64,<:StridedMatrix}}) = _ormrq!('R', 'T', parent(Q), A)   # :272-291
 
 # ---- ul! -----------------------------------------------------------------------------------------------------------
 function ul!(A::StridedMatrix{Float64}, ::Val{Pivot} = Val(true); check::Bool = true) where Pivot        # src/ul.jl:146-196

@@ -343,8 +343,9 @@ def _ormrq(side, Q: RQPackedQ, C):
     if nq != nA:
         raise DimensionMismatch(f"matrix A has dimensions ({mA},{nA}) but {'B' if side == 'L' else 'A'} has dimensions ({c.m}, {c.n})")
     aptr = f.ptr + (mA - k) * f.itemsize  # first of the last k rows
-    h.call(f"qlb200_{f.pfx}ormrq{f.sfx}", side.encode(), (b"T" if Q.adjoint else b"N"), c.m, c.n, k, aptr, f.ld, t.ptr,
-           c.ptr, c.ld)
+    cplx = f.pfx in "zc"
+    h.call(f"qlb200_{f.pfx}{'unmrq' if cplx else 'ormrq'}{f.sfx}", side.encode(), ((b"C" if cplx else b"T") if Q.adjoint else b"N"),
+           c.m, c.n, k, aptr, f.ld, t.ptr, c.ptr, c.ld)
     return C
 
 

@@ -183,3 +183,29 @@ def test_dimension_errors_complex(q, h):
         q.lmul_(F.Q, np.zeros((5, 2), dtype=np.complex128, order="F"))
     with pytest.raises(q.DimensionMismatch):
         F.solve(np.zeros((5, 1), dtype=np.complex128, order="F"))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(40, 40), (130, 70), (70, 130), (1, 9), (9, 1)])
+def test_rq_factors_and_q_apply_other_types(q, h, dt, shape):
+    """rq!(A) = RQ(LAPACK.gerqf!(A)...) (src/rq.jl:401) and lmul!/rmul! with RQPackedQ (src/rq.jl:130-291 -> LAPACK.ormrq!) for
+    Float32 / ComplexF64 / ComplexF32: ?gerqf(A) = (?geqlf(A^H))^H, ?unmrq through the conjugate-transposed reflectors."""
+    m, n = shape
+    rng = np.random.default_rng(m * 7 + n)
+    A = _rand(rng, (m, n), dt)
+    F, tau = q.rq_(A.copy(order="F"), handle=h)
+    Fo, tauo = lapack.gerqf(A)
+    tol = 50 * max(m, n) * _eps(dt) * max(np.linalg.norm(A), 1.0)
+    assert np.abs(F - Fo).max() <= tol
+    assert np.abs(tau - tauo).max() <= 50 * max(m, n) * _eps(dt)
+    k = min(m, n)
+    V = np.asfortranarray(Fo[m - k:, :])
+    Qo = q.RQPackedQ(Fo, tauo, handle=h)
+    adj = "C" if np.issubdtype(dt, np.complexfloating) else "T"
+    B = _rand(rng, (n, 3), dt)
+    C = _rand(rng, (3, n), dt)
+    t2 = 50 * max(m, n) * _eps(dt) * np.sqrt(n)
+    assert np.abs(q.lmul_(Qo, B.copy(order="F")) - lapack.ormrq("L", "N", V, tauo, B)).max() <= t2 * max(1.0, np.abs(B).max())
+    assert np.abs(q.lmul_(Qo.T, B.copy(order="F")) - lapack.ormrq("L", adj, V, tauo, B)).max() <= t2 * max(1.0, np.abs(B).max())
+    assert np.abs(q.rmul_(C.copy(order="F"), Qo) - lapack.ormrq("R", "N", V, tauo, C)).max() <= t2 * max(1.0, np.abs(C).max())
+    assert np.abs(q.rmul_(C.copy(order="F"), Qo.T) - lapack.ormrq("R", adj, V, tauo, C)).max() <= t2 * max(1.0, np.abs(C).max())
