@@ -84,6 +84,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(n):
+    """`config` of the bench line -- the SAME dict for both arms (the reference arm runs this workload with LAPACK dgeqlf on the host
+    cores; where its input lives and how it is threaded is stated in its cpu_baseline.sample)."""
+    return {"workload": f"ql! Float64 n={n} square (configs[1]); copy + in-place blocked QL per step",
+            "parallelism": "replicas only (a single matrix runs on 1 GPU); batched work shards by matrix index",
+            "l2": "inputs (2 GiB/matrix) are larger than the 126 MB L2", "nb": "auto (192 at this size)",
+            "lookahead": "panel j+1 on a 16-SM green-context partition while the 132-SM partition applies panel j",
+            "residency": "GPU arm: input resident in HBM for `value`, in pinned host memory for `e2e`; reference arm: host memory"}
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path: LAPACK dgeqlf (src/ql.jl:72) on the host cores."""
     if rank != 0:
@@ -115,7 +125,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "steps_timed": len(ts), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"ql! Float64 n={n} square (configs[1]); copy + in-place blocked QL per step, input resident in host memory"},
+            "config": workload_config(n),
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -564,10 +574,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"ql! Float64 n={n} square (configs[1]); copy + in-place blocked QL per step, input resident in HBM",
-                       "parallelism": "replicas only (a single matrix runs on 1 GPU); batched work shards by matrix index",
-                       "l2": "inputs (2 GiB/matrix) are larger than the 126 MB L2", "nb": "auto (192 at this size)",
-                       "lookahead": "panel j+1 on a 16-SM green-context partition while the 132-SM partition applies panel j"},
+            "config": workload_config(n),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": (gemm_tflops / peak_tflops) if gemm_tflops else None,
