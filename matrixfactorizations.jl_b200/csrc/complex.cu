@@ -627,6 +627,50 @@ static int z_build_T(qlb200_ctx *h, cudaStream_t st, const QlbWorkspace &ws, int
 }  // namespace qlb
 using namespace qlb;
 
+// Factor one panel (complex columns [c0, c0+ib), rows [0, p)) on stream st: one launch per column; reflectors in block form
+// -> VV (ldvv).  smem_rows: the block's rows staged in shared memory (fast, but one 128 KB block per SM: for a stream that
+// owns the whole GPU); otherwise the global-memory variant (two blocks per SM: for the 16-SM panel partition).
+static int z_factor_panel(qlb200_ctx *h, cudaStream_t st, double2 *A, int64_t lda, int p, int c0, int ib, double2 *tau_panel, double *VV,
+                          int64_t ldvv, double *part, bool smem_rows) {
+    double2 *Ap = A + (int64_t)c0 * lda;
+    if (smem_rows && p <= 148 * ZS) {
+        const int nb_ = (p + ZS - 1) / ZS;
+        double *pb[2] = {part, part + z_part_doubles(nb_)};
+        constexpr size_t smem = (size_t)ZNB * ZS * sizeof(double2);
+        if (!h->zstep_attr_done) {
+            QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            h->zstep_attr_done = true;
+        }
+        zstep_smem_kernel<false, true><<<nb_, ZS, smem, st>>>(Ap, lda, p - 1, ib - 1, ib, nullptr, pb[0], nullptr, nullptr, 0, p);
+        QLB_LAUNCH_CHECK(h);
+        for (int s = 0; s < ib; ++s) {
+            const int C = ib - 1 - s, mu = p - 1 - s;
+            if (C > 0)
+                zstep_smem_kernel<true, true><<<nb_, ZS, smem, st>>>(Ap, lda, mu, C, ib, pb[s & 1], pb[(s + 1) & 1], tau_panel + C, VV, ldvv, p);
+            else
+                zstep_smem_kernel<true, false><<<nb_, ZS, smem, st>>>(Ap, lda, mu, C, ib, pb[s & 1], nullptr, tau_panel + C, VV, ldvv, p);
+            QLB_LAUNCH_CHECK(h);
+        }
+        return 0;
+    }
+    const int rpb = z_rows_per_block(p);
+    const int nblk = (p + rpb - 1) / rpb;
+    double *pb[2] = {part, part + z_part_doubles(nblk)};
+    zstep_kernel<false, true><<<nblk, ZT, 0, st>>>(Ap, lda, p - 1, ib - 1, ib, nullptr, pb[0], nullptr, nullptr, 0, p, rpb);
+    QLB_LAUNCH_CHECK(h);
+    for (int s = 0; s < ib; ++s) {
+        const int C = ib - 1 - s, mu = p - 1 - s;
+        if (C > 0)
+            zstep_kernel<true, true><<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, pb[s & 1], pb[(s + 1) & 1], tau_panel + C, VV, ldvv, p, rpb);
+        else
+            zstep_kernel<true, false><<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, pb[s & 1], nullptr, tau_panel + C, VV, ldvv, p, rpb);
+        QLB_LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
 int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t lda, double *taud) {
     const int m = (int)m64, n = (int)n64, k = m < n ? m : n;
     if (k == 0) return 0;
@@ -640,53 +684,86 @@ int qlb_zgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *Ad, int64_t 
     rc = qlb_reserve(h, &h->tall, &h->tall_bytes, 2 * z_part_doubles(148 + (m + rpb - 1) / rpb) * sizeof(double));
     if (rc) return rc;
     double *part = (double *)h->tall;
-    for (int i1 = k; i1 > 0; i1 -= ZNB) {
-        const int i0 = i1 - ZNB > 0 ? i1 - ZNB : 0, ib = i1 - i0;
-        const int p = m - k + i1;                 // rows of the panel
-        const int c0 = n - k + i0;                // its first column
-        double2 *Ap = A + (int64_t)c0 * lda;
-        const int nblk = (p + rpb - 1) / rpb;
-        if (p <= 148 * ZS) {      // rows of the panel staged in shared memory, one launch per column
-            const int nb_ = (p + ZS - 1) / ZS;
-            double *pb[2] = {part, part + z_part_doubles(nb_)};
-            constexpr size_t smem = (size_t)ZNB * ZS * sizeof(double2);
-            if (!h->zstep_attr_done) {
-                QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                QLB_CUDA(h, cudaFuncSetAttribute(zstep_smem_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                h->zstep_attr_done = true;
-            }
-            zstep_smem_kernel<false, true><<<nb_, ZS, smem, st>>>(Ap, lda, p - 1, ib - 1, ib, nullptr, pb[0], nullptr, nullptr, 0, p);
-            QLB_LAUNCH_CHECK(h);
-            for (int s = 0; s < ib; ++s) {
-                const int C = ib - 1 - s, mu = p - 1 - s;
-                if (C > 0)
-                    zstep_smem_kernel<true, true><<<nb_, ZS, smem, st>>>(Ap, lda, mu, C, ib, pb[s & 1], pb[(s + 1) & 1], tau + i0 + C, ws.Vw, ws.ldv, p);
-                else
-                    zstep_smem_kernel<true, false><<<nb_, ZS, smem, st>>>(Ap, lda, mu, C, ib, pb[s & 1], nullptr, tau + i0 + C, ws.Vw, ws.ldv, p);
-                QLB_LAUNCH_CHECK(h);
-            }
-        } else {
-        double *pb[2] = {part, part + z_part_doubles(nblk)};
-        zstep_kernel<false, true><<<nblk, ZT, 0, st>>>(Ap, lda, p - 1, ib - 1, ib, nullptr, pb[0], nullptr, nullptr, 0, p, rpb);
-        QLB_LAUNCH_CHECK(h);
-        for (int s = 0; s < ib; ++s) {
-            const int C = ib - 1 - s, mu = p - 1 - s;
-            if (C > 0)
-                zstep_kernel<true, true><<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, pb[s & 1], pb[(s + 1) & 1], tau + i0 + C, ws.Vw, ws.ldv, p, rpb);
-            else
-                zstep_kernel<true, false><<<nblk, ZT, 0, st>>>(Ap, lda, mu, C, ib, pb[s & 1], nullptr, tau + i0 + C, ws.Vw, ws.ldv, p, rpb);
-            QLB_LAUNCH_CHECK(h);
-        }
-        }
-        if (c0 > 0) {
-            rc = z_build_T(h, st, ws, p, ib, tau + i0);
+    const int npanels = (k + ZNB - 1) / ZNB;
+    auto P1 = [&](int j) { return k - j * ZNB; };                            // reflector range of panel j: [P0(j), P1(j))
+    auto P0 = [&](int j) { const int i0 = k - (j + 1) * ZNB; return i0 > 0 ? i0 : 0; };
+    // Look-ahead on the SM partitions (as ql! and ul!): panel j+1 is factored on the 16-SM partition (global-memory step kernel,
+    // two blocks per SM) while the other partition applies panel j.  The reflectors / T of consecutive panels alternate
+    // between the handle's workspace and a second set carved from h->zws.
+    // Pays only where the panel (8 192 column steps x ~25 us on 16 SMs at n = 8192) is shorter than the update: n = 8192 218 -> 207 ms,
+    // n = 4096 68 -> 80 ms; so from min(m,n) = 8192 on (option lookahead = 1 forces it: tests).
+    const bool la = h->gc_ok && h->opt_lookahead != 0 && npanels > 2 && (h->opt_lookahead == 1 || k >= 8192);
+    if (!la) {
+        for (int j = 0; j < npanels; ++j) {
+            const int i0 = P0(j), ib = P1(j) - i0;
+            const int p = m - k + P1(j), c0 = n - k + i0;
+            rc = z_factor_panel(h, st, A, lda, p, c0, ib, tau + i0, ws.Vw, ws.ldv, part, true);
             if (rc) return rc;
-            // C <- H^H C = (I - V T^H V^H) C:  [[T]]^T = [[T^H]]  ->  apply_block with tt = false
-            rc = qlb_block_apply(h, st, ws, true, false, ws.Vw, ws.ldv, ws.T, ws.ldt, 2 * p, 2 * ib, Ad, 2 * lda, c0);
+            if (c0 > 0) {
+                rc = z_build_T(h, st, ws, p, ib, tau + i0);
+                if (rc) return rc;
+                // C <- H^H C = (I - V T^H V^H) C:  [[T]]^T = [[T^H]]  ->  apply_block with tt = false
+                rc = qlb_block_apply(h, st, ws, true, false, ws.Vw, ws.ldv, ws.T, ws.ldt, 2 * p, 2 * ib, Ad, 2 * lda, c0);
+                if (rc) return rc;
+            }
+        }
+        return 0;
+    }
+    constexpr int NB2 = 2 * ZNB;
+    const size_t gram_part = (size_t)160 * NB2 * NB2;
+    rc = qlb_reserve(h, &h->zws, &h->zws_bytes, ((size_t)ws.ldv * NB2 + 2 * (size_t)NB2 * NB2 + gram_part + 64) * sizeof(double));
+    if (rc) return rc;
+    QlbWorkspace wp[2];                       // panel-stream views: own V, T, Gram and split-K scratch
+    wp[0] = ws;
+    wp[1] = ws;
+    {
+        double *q = (double *)h->zws;
+        wp[1].Vw = q;  q += (size_t)ws.ldv * NB2;
+        wp[1].T = q;   q += (size_t)NB2 * NB2;
+        wp[0].G = wp[1].G = q;  q += (size_t)NB2 * NB2;
+        wp[0].part = wp[1].part = q;
+        wp[0].part_elems = wp[1].part_elems = (int64_t)gram_part;
+    }
+    cudaStream_t G = h->gc_gemm, P = h->gc_panel;
+    cudaEvent_t evP = h->ev_a, evN = h->ev_b;
+    QLB_CUDA(h, cudaEventRecord(h->ev_gc[0], st));
+    QLB_CUDA(h, cudaStreamWaitEvent(G, h->ev_gc[0], 0));
+    QLB_CUDA(h, cudaStreamWaitEvent(P, h->ev_gc[0], 0));
+    auto factor = [&](int j) -> int {         // on P: panel j into set j & 1, and its T when there is something left of it
+        const int i0 = P0(j), ib = P1(j) - i0;
+        const int p = m - k + P1(j), c0 = n - k + i0;
+        int r = z_factor_panel(h, P, A, lda, p, c0, ib, tau + i0, wp[j & 1].Vw, ws.ldv, part, false);
+        if (!r && c0 > 0) r = z_build_T(h, P, wp[j & 1], p, ib, tau + i0);
+        return r;
+    };
+    rc = factor(0);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaEventRecord(evP, P));
+    for (int j = 0; j < npanels; ++j) {
+        const int i0 = P0(j), ib = P1(j) - i0;
+        const int p = m - k + P1(j), c0 = n - k + i0;
+        const QlbWorkspace &w = wp[j & 1];
+        QLB_CUDA(h, cudaStreamWaitEvent(G, evP, 0));            // panel j (V, T) is complete
+        if (j + 1 < npanels) {
+            const int d0 = n - k + P0(j + 1);                   // next panel = columns [d0, c0)
+            rc = qlb_block_apply(h, G, ws, true, false, w.Vw, ws.ldv, w.T, ws.ldt, 2 * p, 2 * ib, Ad + (int64_t)d0 * lda * 2, 2 * lda, c0 - d0);
+            if (rc) return rc;
+            QLB_CUDA(h, cudaEventRecord(evN, G));
+            QLB_CUDA(h, cudaStreamWaitEvent(P, evN, 0));
+            rc = factor(j + 1);
+            if (rc) return rc;
+            QLB_CUDA(h, cudaEventRecord(evP, P));
+            if (d0 > 0) {
+                rc = qlb_block_apply(h, G, ws, true, false, w.Vw, ws.ldv, w.T, ws.ldt, 2 * p, 2 * ib, Ad, 2 * lda, d0);
+                if (rc) return rc;
+            }
+        } else if (c0 > 0) {
+            rc = qlb_block_apply(h, G, ws, true, false, w.Vw, ws.ldv, w.T, ws.ldt, 2 * p, 2 * ib, Ad, 2 * lda, c0);
             if (rc) return rc;
         }
     }
+    QLB_CUDA(h, cudaEventRecord(h->ev_gc[1], G));
+    QLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_gc[1], 0));
     return 0;
 }
 

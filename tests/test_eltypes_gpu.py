@@ -209,3 +209,22 @@ def test_rq_factors_and_q_apply_other_types(q, h, dt, shape):
     assert np.abs(q.lmul_(Qo.T, B.copy(order="F")) - lapack.ormrq("L", adj, V, tauo, B)).max() <= t2 * max(1.0, np.abs(B).max())
     assert np.abs(q.rmul_(C.copy(order="F"), Qo) - lapack.ormrq("R", "N", V, tauo, C)).max() <= t2 * max(1.0, np.abs(C).max())
     assert np.abs(q.rmul_(C.copy(order="F"), Qo.T) - lapack.ormrq("R", adj, V, tauo, C)).max() <= t2 * max(1.0, np.abs(C).max())
+
+
+@pytest.mark.parametrize("shape", [(2100, 2100), (2100, 2600), (2600, 2100)])
+def test_complex_ql_lookahead_vs_lapack(q, h, shape):
+    """The ComplexF64 ql! with the look-ahead schedule (panel j+1 on the panel SM partition while panel j is applied; automatic
+    from min(m,n) = 8192 on, forced here with lookahead = 1): same parity bar against LAPACK zgeqlf as the sequential schedule."""
+    m, n = shape
+    rng = np.random.default_rng(m + 3 * n)
+    A = _rand(rng, (m, n), np.complex128)
+    Fo, tauo = lapack.geqlf(A)
+    tol = 50 * max(m, n) * _eps(np.complex128) * np.linalg.norm(A)
+    for la in (1, 0):
+        h.set_option("lookahead", la)
+        try:
+            F = q.ql(A, handle=h)
+        finally:
+            h.set_option("lookahead", 2)
+        assert np.abs(F.factors - Fo).max() <= tol
+        assert np.abs(F.tau - tauo).max() <= 50 * max(m, n) * _eps(np.complex128)
