@@ -1250,6 +1250,9 @@ static int dispatch_apply_n(qlb200_ctx *h, int64_t n, const T *A, int64_t lda, i
 // ---------------------------------------------------------------------------------------------
 // typed internal entry points used by capi.cu
 // ---------------------------------------------------------------------------------------------
+// (the Makefile compiles this file twice, -DQLB_BATCHED_ONLY_F64 / -DQLB_BATCHED_ONLY_F32: the two element types' kernel
+//  instantiations build in parallel)
+#ifndef QLB_BATCHED_ONLY_F32
 int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int64_t strideA, double *tau,
                           int64_t strideTau, int64_t batch) {
     switch (n) {
@@ -1279,6 +1282,8 @@ int qlb_geqlf_batched_f64(qlb200_ctx *h, int64_t n, double *A, int64_t lda, int6
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<double>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }
+#endif
+#ifndef QLB_BATCHED_ONLY_F64
 int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64_t strideA, float *tau,
                           int64_t strideTau, int64_t batch) {
     switch (n) {
@@ -1304,6 +1309,8 @@ int qlb_geqlf_batched_f32(qlb200_ctx *h, int64_t n, float *A, int64_t lda, int64
     if (n >= 1 && n <= 64) return qlb::launch_geql2_generic<float>(h, A, lda, strideA, tau, strideTau, (int)n, batch);
     return qlb_fail(h, -2, "batched QL: n must be in [1,64]%s");
 }
+#endif
+#ifndef QLB_BATCHED_ONLY_F32
 // mode 0: Q*B, 1: Q'*B, 2: L^{-1} Q' B
 int qlb_apply_batched_f64(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, const double *A, int64_t lda,
                           int64_t strideA, const double *tau, int64_t strideTau, double *B, int64_t ldb,
@@ -1312,6 +1319,8 @@ int qlb_apply_batched_f64(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, cons
     if (mode == 1) return qlb::dispatch_apply_n<double, 1>(h, n, A, lda, strideA, tau, strideTau, B, ldb, strideB, (int)nrhs, batch, info_out);
     return qlb::dispatch_apply_n<double, 2>(h, n, A, lda, strideA, tau, strideTau, B, ldb, strideB, (int)nrhs, batch, info_out);
 }
+#endif
+#ifndef QLB_BATCHED_ONLY_F64
 int qlb_apply_batched_f32(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, const float *A, int64_t lda,
                           int64_t strideA, const float *tau, int64_t strideTau, float *B, int64_t ldb,
                           int64_t strideB, int64_t batch, int32_t *info_out) {
@@ -1319,3 +1328,4 @@ int qlb_apply_batched_f32(qlb200_ctx *h, int mode, int64_t n, int64_t nrhs, cons
     if (mode == 1) return qlb::dispatch_apply_n<float, 1>(h, n, A, lda, strideA, tau, strideTau, B, ldb, strideB, (int)nrhs, batch, info_out);
     return qlb::dispatch_apply_n<float, 2>(h, n, A, lda, strideA, tau, strideTau, B, ldb, strideB, (int)nrhs, batch, info_out);
 }
+#endif
