@@ -351,10 +351,11 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     const int m = (int)m64, n = (int)n64;
     const int k = m < n ? m : n;
     if (k == 0) return 0;
-    const int nb = (h->h2d.host || h->d2h.host) ? (h->opt_nb > 0 ? (int)h->opt_nb : 128) : qlb_effective_nb(h, m64, n64);
+    const bool seq_host = h->h2d.host || (h->d2h.host && !h->d2h.la);      // the chunk-joining host schedule (no look-ahead)
+    const int nb = seq_host ? (h->opt_nb > 0 ? (int)h->opt_nb : 128) : qlb_effective_nb(h, m64, n64);
     cudaStream_t st = h->stream;
     const int npanels = (k + nb - 1) / nb;
-    const bool la = npanels > 1 && !h->h2d.host && !h->d2h.host && qlb_lookahead_active(h, m64, n64);
+    const bool la = npanels > 1 && !seq_host && qlb_lookahead_active(h, m64, n64);
     Workspace ws, ws2;
     int rc = get_workspace(h, m, n, nb, 0, &ws, &ws2);
     if (rc) return rc;
@@ -479,7 +480,7 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
                 // to pageable memory blocks the host, and the GPU must have work to do meanwhile.
                 QLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_panel[j & 7], 0));
                 QLB_CUDA(h, cudaMemcpy2DAsync(h->d2h.host + (int64_t)c0 * h->d2h.host_ld, (size_t)h->d2h.host_ld * 8,
-                                              A + (int64_t)c0 * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(c1 - c0),
+                                              A + (int64_t)c0 * lda, (size_t)lda * 8, (size_t)(h->d2h.rows > 0 ? h->d2h.rows : m) * 8, (size_t)(c1 - c0),
                                               cudaMemcpyDeviceToHost, h->copy_stream));
             }
         }
@@ -522,9 +523,23 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     }
     double *Vb[2] = {ws.Vw, ws2.Vw}, *Tb[2] = {ws.T, ws2.T};
     auto Tslot = [&](int j) { return tcache ? tcache + (size_t)j * nb * nb : Tb[j & 1]; };
+    // host destination given (split host-pointer ql!, capi.cu): the columns of a panel are final once it is factored -- they go
+    // home on the copy stream behind an event of their own (ring of 8; the panel stream is never more than one panel ahead)
+    auto send_home = [&](int j) -> int {
+        if (!h->d2h.host) return 0;
+        const int c0 = panel_c0(j), c1 = panel_c1(j);
+        const int64_t rows = h->d2h.rows > 0 ? h->d2h.rows : m;
+        QLB_CUDA(h, cudaEventRecord(h->ev_panel[j & 7], P));
+        QLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_panel[j & 7], 0));
+        QLB_CUDA(h, cudaMemcpy2DAsync(h->d2h.host + (int64_t)c0 * h->d2h.host_ld, (size_t)h->d2h.host_ld * 8, A + (int64_t)c0 * lda, (size_t)lda * 8,
+                                      (size_t)rows * 8, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, h->copy_stream));
+        return 0;
+    };
     rc = factor_panel(h, P, ws2, A, lda, m, n, k, panel_c0(0), panel_c1(0), tau, Vb[0], ws.ldv, Tslot(0), nb, panel_c0(0) > 0 || tcache != nullptr, smsP);
     if (rc) return rc;
     QLB_CUDA(h, cudaEventRecord(evP, P));
+    rc = send_home(0);
+    if (rc) return rc;
     for (int j = 0; j < npanels; ++j) {
         const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
         double *V = Vb[j & 1], *T = Tslot(j);
@@ -538,6 +553,8 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             rc = factor_panel(h, P, ws2, A, lda, m, n, k, d0, c0, tau, Vb[(j + 1) & 1], ws.ldv, Tslot(j + 1), nb, d0 > 0 || tcache != nullptr, smsP);
             if (rc) return rc;
             QLB_CUDA(h, cudaEventRecord(evP, P));
+            rc = send_home(j + 1);
+            if (rc) return rc;
             if (d0 > 0) {
                 rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, d0, nullptr, smsG);
                 if (rc) return rc;

@@ -263,6 +263,11 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->graph_seen_key[0] = 0;
     } else if (!strcmp(name, "la_min")) {
         h->opt_la_min = value < 0 ? 0 : value;
+    } else if (!strcmp(name, "host_split")) {
+        h->opt_host_split = value ? 1 : 0;
+    } else if (!strcmp(name, "host_split_min")) {
+        if (value < 512) return qlb_fail(h, -3, "host_split_min must be >= 512%s");
+        h->opt_host_split_min = value;
     } else if (!strcmp(name, "fuse_chunk")) {
         h->opt_fuse_chunk = value < 0 ? 0 : value;
     } else if (!strcmp(name, "la_gemm_all")) {
@@ -696,6 +701,53 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
     // ql! of a large matrix: plain launches (no graph); the matrix streams IN chunk by chunk while the right-hand panels
     // are already being factored, and the finished panels stream OUT while the rest is still being factored -- both PCIe
     // transfers disappear behind the computation (except the first chunk and the last panel)
+    // Large tall/square ql! with the SM partitions available: SPLIT schedule.  The right quarter of the columns is uploaded and
+    // factored first (look-ahead ql! of the m x wR block) while the rest is still on its way; then Q_R' is applied to the left
+    // part (blocked ormql with the cached T factors, all SMs), then the leading (m - wR) x wL block is factored (look-ahead
+    // again).  Same arithmetic as one ql! (LAPACK's right-to-left order restricted to column blocks); finished panels stream
+    // home behind the computation in both factorizations.  Option "host_split" = 0 falls back to the chunk-joining schedule.
+    if (f == geqlf_dev_graph && h->opt_host_split && h->gc_ok && h->opt_lookahead == 2 && m >= n && n >= h->opt_host_split_min && h->opt_tcache) {
+        const int64_t ldd = (m + 1) & ~(int64_t)1;
+        rc = qlb_reserve(h, &h->stage, &h->stage_bytes, (size_t)ldd * n * sizeof(double));
+        if (!rc) rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * sizeof(double));
+        if (rc) return rc;
+        double *dA = (double *)h->stage, *dtau = (double *)h->stage2;
+        int64_t wR = ((n / 4 + 127) / 128) * 128;
+        const int64_t wL = n - wR;
+        QLB_CUDA(h, cudaMemcpy2DAsync(dA + wL * ldd, (size_t)ldd * 8, A + wL * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)wR,
+                                      cudaMemcpyHostToDevice, h->h2d_stream));
+        QLB_CUDA(h, cudaEventRecord(h->ev_chunk[0], h->h2d_stream));
+        QLB_CUDA(h, cudaMemcpy2DAsync(dA, (size_t)ldd * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)wL, cudaMemcpyHostToDevice, h->h2d_stream));
+        QLB_CUDA(h, cudaEventRecord(h->ev_chunk[1], h->h2d_stream));
+        QLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[0], 0));
+        h->d2h.la = true;
+        h->d2h.rows = m;
+        h->d2h.host_ld = lda;
+        h->d2h.host = A + wL * lda;
+        rc = qlb_dgeqlf_dev(h, m, wR, dA + wL * ldd, ldd, dtau + wL);
+        h->d2h.host = nullptr;
+        if (!rc) {
+            QLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[1], 0));
+            rc = qlb_dormql_dev(h, 'L', 'T', m, wL, wR, dA + wL * ldd, ldd, dtau + wL, dA, ldd, 0);
+        }
+        if (!rc) {
+            h->d2h.host = A;
+            rc = qlb_dgeqlf_dev(h, m - wR, wL, dA, ldd, dtau);
+            h->d2h.host = nullptr;
+        }
+        h->d2h.la = false;
+        h->d2h.rows = 0;
+        h->tc_valid = false;                 // the cache now holds the T factors of the leading block only
+        if (rc) {
+            cudaStreamSynchronize(h->h2d_stream);
+            cudaStreamSynchronize(h->copy_stream);
+            return rc;
+        }
+        QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+        QLB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+        return 0;
+    }
     const bool stream_back = (f == geqlf_dev_graph) && m * n >= ((int64_t)1 << 22) && h->opt_lookahead != 1;
     const bool stream_in = stream_back && h->opt_stream_in && h->opt_tcache;
     double *dA;

@@ -22,6 +22,8 @@ struct qlb200_ctx {
     struct {
         double *host = nullptr;            // destination (column-major, ld = host_ld); null = disabled
         int64_t host_ld = 0;
+        int64_t rows = 0;                  // rows copied per finished column (0: the m of the call; the split host path copies whole columns of the parent matrix)
+        bool la = false;                   // the caller wants the look-ahead schedule (device-resident input, finished panels streamed out)
     } d2h;
     // host-pointer ql!: the matrix arrives in column chunks (right to left) while the panels on the right are already
     // being factored; a chunk joins the trailing update when it has arrived and caught up with the finished panels
@@ -31,6 +33,8 @@ struct qlb200_ctx {
         const double *host = nullptr;      // source (column-major, ld = host_ld); null = the matrix is already on the device
         int64_t host_ld = 0;
     } h2d;
+    int64_t opt_host_split = 1;            // host-pointer ql!, large tall/square matrices: split schedule (capi.cu fact_host)
+    int64_t opt_host_split_min = 8192;     // ... from this number of columns on
     int64_t opt_stream_in = 1;
     int64_t opt_chunk_cols = 1024;         // columns per H2D chunk
     int64_t opt_batch_chunk_mb = 32;       // host-pointer batched calls: operand megabytes per pipeline chunk (0: no chunking)

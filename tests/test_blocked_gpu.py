@@ -320,6 +320,40 @@ def test_host_pointer_ql_streams_in_and_out(q, h, shape):
         assert np.abs(A @ x - b).max() <= 5000 * EPS * np.linalg.cond(A)
 
 
+@pytest.mark.parametrize("shape,split_min", [((2500, 2500), 1024), ((3000, 2100), 1024), ((5000, 4600), 1024), ((8192, 8192), 8192)])
+def test_host_pointer_ql_split_schedule(q, h, shape, split_min):
+    """Host-pointer ql! of a large tall/square matrix, split schedule (capi.cu): the right quarter of the columns is uploaded
+    and factored while the rest is on its way, Q_R' is applied to the left part, then the leading block is factored; finished
+    panels stream home.  Same arithmetic as one ql! (column blocks, right to left): the parity bar against LAPACK dgeqlf,
+    agreement with the chunk-joining schedule (host_split = 0), nothing outside the matrix touched (lda > m)."""
+    m, n = shape
+    rng = np.random.default_rng(m + n)
+    lda = m + 3
+    buf = np.zeros((lda, n), order="F")
+    buf[:m, :] = rng.standard_normal((m, n))
+    A = buf[:m, :]
+    h.set_option("host_split_min", split_min)
+    try:
+        F = q.ql_(np.asfortranarray(A.copy()), handle=h)
+        Fv = buf.copy(order="F")
+        Av = Fv[:m, :]
+        q.ql_(Av, handle=h)                                   # a view with lda > m
+    finally:
+        h.set_option("host_split_min", 8192)
+    lapack.set_num_threads(16)
+    Fo, tauo = lapack.geqlf(np.asfortranarray(A.copy()))
+    tol = 50 * max(m, n) * EPS * np.linalg.norm(A)
+    assert np.abs(F.tau - tauo).max() <= 50 * max(m, n) * EPS
+    assert np.abs(F.factors - Fo).max() <= tol
+    assert np.array_equal(Av, F.factors) and np.all(Fv[m:, :] == 0.0)
+    h.set_option("host_split", 0)
+    try:
+        F0 = q.ql(np.asfortranarray(A.copy()), handle=h)
+    finally:
+        h.set_option("host_split", 1)
+    assert np.abs(F.factors - F0.factors).max() <= tol and np.abs(F.tau - F0.tau).max() <= 50 * max(m, n) * EPS
+
+
 def _scaled_cmp(F, tau, Fo, tauo, A, k_rows_are_reflectors=False):
     """Elementwise comparison that stays meaningful when columns of A live at very different scales: every entry of the
     packed factors is compared relative to max(1, ...) of ITS column -- reflector entries are O(1), L entries carry the
