@@ -148,6 +148,24 @@ __device__ __forceinline__ double dlapy2_dev(double x, double y) {
 constexpr double LARFG_SSQ_LO = 1e-280, LARFG_TOT_HI = 1e280;
 constexpr double LARFG_SAFMIN = 2.2250738585072014e-308 / 1.1102230246251565e-16;
 
+// (in the plain range only: no special-case branches)
+__device__ __forceinline__ double strip_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);               // 1 - x y^2
+    const double p = fma(0.375, e, 0.5);
+    const double q = y * e;
+    return fma(q, p, y);                            // y (1 + e/2 + 3 e^2/8)
+}
+__device__ __forceinline__ double strip_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y, p, y);                            // y (1 + e + e^2)
+}
+
 // One Householder step.  The register tile is kept ROTATED so that the pivot column always sits in
 // register column SB-1 (static register indices, one loop body for every step: the fully unrolled
 // variant was instruction-cache bound).  At step s (0-based) register column q holds
@@ -245,10 +263,15 @@ __device__ __forceinline__ void strip_step(double (&a)[RPT][SB], const int (&rr)
     double beta = alpha, tauc = 0.0, scale = 0.0;
     const bool plain = (ssq >= LARFG_SSQ_LO) && (fma(alpha, alpha, ssq) <= LARFG_TOT_HI);      // identical in every thread of the cluster
     if (plain) {
-        const double nrm = sqrt(fma(alpha, alpha, ssq));
+        // 1/sqrt and 1/x from the hardware seeds + one third-order FMA correction (below half an ulp before the final rounding,
+        // the same arithmetic as the batched kernels): the IEEE sqrt and the two divisions were ~110 of the ~830 instructions
+        // every warp issues per column, all of them on the serial chain
+        const double totsq = fma(alpha, alpha, ssq);
+        const double rinv = strip_rsqrt(totsq);
+        const double nrm = totsq * rinv;
         beta = -copysign(nrm, alpha);
-        tauc = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
+        tauc = fma(fabs(alpha), rinv, 1.0);            // (beta - alpha) / beta = 1 + |alpha| / nrm
+        scale = strip_rcp(alpha - beta);
     } else {
         // LAPACK ?larfg, literally (what the reference reaches through LAPACK.geqlf!, src/ql.jl:72): the tail's norm in
         // scaled form, beta by ?lapy2, the safmin rescaling loop.  The dot products with the other columns are redone with
@@ -307,19 +330,23 @@ __device__ __forceinline__ void strip_step(double (&a)[RPT][SB], const int (&rr)
     double newp[RPT];
 #pragma unroll
     for (int i = 0; i < RPT; ++i) newp[i] = (rr[i] < mu) ? vi[i] : ((rr[i] == mu) ? beta : a[i][P]);
+    // the update multipliers once per warp (lane j: column j) instead of once per thread and column, in place of the totals
+    // (v_f . v_C of the finished columns is taken from them first)
+    if (lane < SB) {
+        const double w = fma(tot[lane], scale, sm.rowv[par][lane]);
+        if (cta == 0 && warp == 0 && lane < s) sm.Gs[SB - s + lane][C] = w;
+        if (cta == 0 && tid == 0) sm.taus[C] = tauc;
+        tot[lane] = (lane >= s) ? -tauc * w : 0.0;
+    }
+    __syncwarp();
 #pragma unroll
     for (int j = P - 1; j >= 0; --j) {
-        const double coef = (j >= s) ? -tauc * fma(tot[j], scale, sm.rowv[par][j]) : 0.0;
+        const double coef = tot[j];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) a[i][j + 1] = fma(coef, vi[i], a[i][j]);
     }
 #pragma unroll
     for (int i = 0; i < RPT; ++i) a[i][0] = newp[i];
-    if (cta == 0) {
-        // v_f . v_C for every finished column f = SB-s+q (register column q < s); warp 0 only
-        if (tid < s) sm.Gs[SB - s + tid][C] = fma(scale, tot[tid], sm.rowv[par][tid]);
-        if (tid == 0) sm.taus[C] = tauc;
-    }
     __syncwarp();      // this warp's totals are rewritten in the next step
 }
 
