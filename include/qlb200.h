@@ -119,12 +119,20 @@ int qlb200_dqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const double *
  * the rows are rotated so that on return X = B[1:n, :] (n x nrhs) -- the rows the reference's `\` cuts out of the buffer
  * ldiv! worked on (src/ql.jl:496-501, _cut_B(X, 1:n)); LAPACK ?gels convention, same as qlb200_dqrsolve -- and B[n+1:m, :]
  * holds the residual's coordinates (its norm is the residual norm).
- * Returns 0, -i, 1000+cudaError, or i > 0 when L[i,i] == 0.  The wide minimum-norm solve needs an LQ-type factorization and
- * is not offered. */
+ * Returns 0, -i, 1000+cudaError, or i > 0 when L[i,i] == 0.  (The wide minimum-norm solve: qlb200_dqlminnorm below.) */
 int qlb200_dqllstsq(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda,
                     const double *tau, double *B, int64_t ldb);
 int qlb200_dqllstsq_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
                         const double *dtau, double *dB, int64_t ldb);
+/* N2, wide half (m < n): the minimum-norm solution of A x = b from the QL factors of the wide A -- what the reference's branch at
+ * src/ql.jl:448-483 is meant to compute (it is @test_broken, test/test_ql.jl:148; README.md:40 advertises `ql(A) \ b`).  A = Q L with the
+ * trapezoid L = tril(factors, n-m): c = Q'b, RQ of the trapezoid L = [0 R] Z, y = R^{-1} c, x = Z' [0; y].  B is n x nrhs (ldb >= n):
+ * rows 1..m hold b on entry, rows 1..n hold x on exit -- the buffer the reference's `\` allocates (src/ql.jl:496-501).
+ * Returns 0, -i, 1000+cudaError, or i > 0 when R[i,i] == 0 (rank deficient). */
+int qlb200_dqlminnorm(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau,
+                      double *B, int64_t ldb);
+int qlb200_dqlminnorm_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda,
+                          const double *dtau, double *dB, int64_t ldb);
 
 /* ---- SURVEY.md 8(f) N1 + the Float32 half of A4: the other BlasFloat element types of the same hook -------------------
  * Reference src/ql.jl:72 `qlfactUnblocked!(A::StridedMatrix{T}) where T<:BlasFloat = QL(LAPACK.geqlf!(A)...)` is hit by

@@ -635,6 +635,76 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     return 0;
 }
 
+// Back substitution with one tb x tb NON-unit upper-triangular diagonal block: X = U^{-1} B in place (the wide minimum-norm
+// solve, qlb_dqlminnorm_dev).  dinfo: 1-based index (i0 + c + 1) of the first zero on the diagonal, kept by atomicMin.
+template <int TB>
+__global__ void __launch_bounds__(TB) trsm_upper_diag_kernel(const double *__restrict__ U, int64_t ldu, int tb, double *__restrict__ B,
+                                                            int64_t ldb, int nrhs, int i0, int32_t *__restrict__ dinfo) {
+    extern __shared__ __align__(16) double sm[];
+    double *Us = sm;                       // tb x tb, pitch TB+1
+    __shared__ double xs[8];
+    __shared__ double rd[TB];
+    const int r = threadIdx.x;
+    for (int idx = threadIdx.x; idx < tb * tb; idx += TB) {
+        const int i = idx % tb, j = idx / tb;
+        Us[j * (TB + 1) + i] = (i < j) ? U[i + (int64_t)j * ldu] : 0.0;
+    }
+    if (r < tb) {
+        const double d = U[r + (int64_t)r * ldu];
+        rd[r] = 1.0 / d;
+        if (d == 0.0 && dinfo && blockIdx.x == 0) atomicMin(dinfo, i0 + r + 1);
+    }
+    __syncthreads();
+    for (int c0 = blockIdx.x * 8; c0 < nrhs; c0 += gridDim.x * 8) {
+        const int nc = (nrhs - c0) < 8 ? (nrhs - c0) : 8;
+        double b[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[q] = (r < tb && q < nc) ? B[r + (int64_t)(c0 + q) * ldb] : 0.0;
+        for (int c = tb - 1; c >= 0; --c) {
+            if (r == c) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    b[q] *= rd[c];
+                    xs[q] = b[q];
+                }
+            }
+            __syncthreads();
+            if (r < c) {
+                const double u = Us[c * (TB + 1) + r];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b[q] = fma(-u, xs[q], b[q]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (r < tb && q < nc) B[r + (int64_t)(c0 + q) * ldb] = b[q];
+    }
+}
+
+// W (m x n, ldw) = L of a wide QL (getL, reference src/ql.jl:214-217): tril(factors, n - m)
+__global__ void extract_l_wide_kernel(const double *__restrict__ F, int64_t ldf, int m, int n, double *__restrict__ W, int64_t ldw) {
+    const int64_t total = (int64_t)m * n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % m), j = (int)(idx / m);
+        W[i + (int64_t)j * ldw] = (j <= i + (n - m)) ? F[i + (int64_t)j * ldf] : 0.0;
+    }
+}
+// B (n x nrhs): rows [0, m) move to rows [n - m, n) (through the scratch S, m x nrhs), rows [0, n - m) become zero
+__global__ void stash_rows_kernel(const double *__restrict__ B, int64_t ldb, int m, int nrhs, double *__restrict__ S) {
+    const int64_t total = (int64_t)m * nrhs;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
+        S[idx] = B[idx % m + (idx / m) * ldb];
+}
+__global__ void place_rows_kernel(double *__restrict__ B, int64_t ldb, int m, int n, int nrhs, const double *__restrict__ S) {
+    const int64_t total = (int64_t)n * nrhs;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % n);
+        const int64_t c = idx / n;
+        B[i + c * ldb] = (i < n - m) ? 0.0 : S[(i - (n - m)) + c * m];
+    }
+}
+
 // CTAs of a diagonal-block solve: one per 8 right-hand sides, at most one per SM (the 128 x 128 block fills shared memory)
 int trsm_grid(qlb200_ctx *h, int nrhs) {
     int g = (nrhs + 7) / 8;
@@ -679,6 +749,53 @@ int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n64, int64_t nrhs64, const double *A
     int rc = qlb_dormql_dev(h, 'L', 'T', n, nrhs, n, A, lda, tau, B, ldb, cache_mode);      // src/ql.jl:445
     if (rc) return rc;
     return qlb_trsm_lower_dev(h, n, nrhs, A, lda, B, ldb, dinfo);
+}
+
+// SURVEY.md 8(f) N2, wide half: the minimum-norm solution of A x = b for m < n from the QL factors.  The reference's own branch
+// (src/ql.jl:448-483: a QR-derived "trapezoid to triangular" loop) is @test_broken (test/test_ql.jl:148); this is the same idea
+// done correctly with the kernels at hand: A = Q L, L = [L1 L2] (m x n, L2 lower triangular) -> c = Q'b; RQ of the trapezoid,
+// L = [0 R] Z (qlb_dgerqf_dev on a copy of L); y = R^{-1} c; x = Z' [0; y].  B is n x nrhs: rows [0, m) hold b on entry, rows
+// [0, n) hold x on exit (the buffer the reference's `\` allocates, src/ql.jl:496-501).  dinfo: first zero on R's diagonal.
+int qlb_dqlminnorm_dev(qlb200_ctx *h, int64_t m64, int64_t n64, int64_t nrhs64, const double *A, int64_t lda, const double *tau, double *B,
+                       int64_t ldb, int32_t *dinfo) {
+    const int m = (int)m64, n = (int)n64, nrhs = (int)nrhs64;
+    if (m == 0 || nrhs == 0) return 0;
+    cudaStream_t st = h->stream;
+    int rc = qlb_dormql_dev(h, 'L', 'T', m, nrhs, m, A + (int64_t)(n - m) * lda, lda, tau, B, ldb, -1);      // c = Q'b
+    if (rc) return rc;
+    const int64_t ldw = even_up(m);
+    rc = qlb_reserve(h, &h->zws, &h->zws_bytes, ((size_t)ldw * n + (size_t)m + 2 + (size_t)m * nrhs) * sizeof(double));
+    if (rc) return rc;
+    double *W = (double *)h->zws, *tau2 = W + (size_t)ldw * n, *S = tau2 + m + 2;
+    const unsigned gb = (unsigned)(h->sm_count * 8);
+    extract_l_wide_kernel<<<gb, 256, 0, st>>>(A, lda, m, n, W, ldw);
+    QLB_LAUNCH_CHECK(h);
+    rc = qlb_dgerqf_dev(h, m, n, W, ldw, tau2);
+    if (rc) return rc;
+    if (dinfo) {
+        set_int_kernel<<<1, 1, 0, st>>>(dinfo, 0x7fffffff);
+        QLB_LAUNCH_CHECK(h);
+    }
+    constexpr int TB = 128;
+    const size_t smem = (size_t)TB * (TB + 1) * sizeof(double);
+    static_assert(TB * (TB + 1) * 8 + TB * 8 + 64 <= 227 * 1024, "diag block must fit in shared memory");
+    QLB_CUDA(h, cudaFuncSetAttribute(trsm_upper_diag_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double *R = W + (int64_t)(n - m) * ldw;               // upper triangular m x m
+    const int nblk = (m + TB - 1) / TB;
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int i = b * TB, tb = (m - i) < TB ? (m - i) : TB;
+        trsm_upper_diag_kernel<TB><<<trsm_grid(h, nrhs), TB, smem, st>>>(R + i + (int64_t)i * ldw, ldw, tb, B + i, ldb, nrhs, i, dinfo);
+        QLB_LAUNCH_CHECK(h);
+        if (i > 0) {      // B[0:i] -= R[0:i, i:i+tb] * X[i:i+tb]
+            rc = qlb_gemm(h, st, nrhs <= 16 ? 2 : -1, false, true, i, nrhs, tb, -1.0, R + (int64_t)i * ldw, ldw, B + i, ldb, 1.0, B, ldb, 1, 0);
+            if (rc) return rc;
+        }
+    }
+    stash_rows_kernel<<<gb, 256, 0, st>>>(B, ldb, m, nrhs, S);
+    QLB_LAUNCH_CHECK(h);
+    place_rows_kernel<<<gb, 256, 0, st>>>(B, ldb, m, n, nrhs, S);
+    QLB_LAUNCH_CHECK(h);
+    return qlb_dormrq_dev(h, 'L', 'T', n, nrhs, m, W, ldw, tau2, B, ldb);      // x = Z' [0; y]
 }
 
 // ormrq through index reversal: gerqf(A) = geqlf(A')' (SURVEY.md A.4), so the RQ reflectors (rows of the k x nq

@@ -944,6 +944,53 @@ static int qllstsq_dev(qlb200_ctx *h, int64_t m, int64_t n, int64_t nrhs, const 
     // convention: rotate every column so that the solution comes first and the residual's coordinates follow.
     return qlb_rotate_rows_dev(h, m, nrhs, dB, ldb, m - n);
 }
+// wide minimum-norm solve (m < n); B is n x nrhs
+static int check_minnorm(qlb200_ctx *h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau,
+                         const double *B, int64_t ldb) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, m >= 0 && m < (1 << 30), 2, "m out of range");
+    QLB_REQUIRE(h, n >= m && n < (1 << 30), 3, "minimum-norm solve needs m <= n");
+    QLB_REQUIRE(h, nrhs >= 0 && nrhs < (1 << 30), 4, "nrhs out of range");
+    QLB_REQUIRE(h, A != nullptr || m * n == 0, 5, "A is null");
+    QLB_REQUIRE(h, lda >= (m > 1 ? m : 1), 6, "lda < max(1,m)");
+    QLB_REQUIRE(h, tau != nullptr || m == 0, 7, "tau is null");
+    QLB_REQUIRE(h, B != nullptr || n * nrhs == 0, 8, "B is null");
+    QLB_REQUIRE(h, ldb >= (n > 1 ? n : 1), 9, "ldb < max(1,n) (DimensionMismatch)");
+    return 0;
+}
+int qlb200_dqlminnorm_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const double *dtau,
+                          double *dB, int64_t ldb) {
+    int rc = check_minnorm(h, m, n, nrhs, dA, lda, dtau, dB, ldb);
+    if (rc) return rc;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    return qlb_dqlminnorm_dev(h, m, n, nrhs, dA, lda, dtau, dB, ldb, nullptr);
+}
+int qlb200_dqlminnorm(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
+                      int64_t ldb) {
+    int rc = check_minnorm(h, m, n, nrhs, A, lda, tau, B, ldb);
+    if (rc) return rc;
+    if (m == 0 || nrhs == 0) return 0;
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    double *dA, *dB;
+    int64_t ldda;
+    rc = stage_in(h, &h->stage, &h->stage_bytes, A, m, n, lda, &dA, &ldda);
+    if (rc) return rc;
+    const int64_t lddb = ((n + 1) & ~(int64_t)1) < 2 ? 2 : ((n + 1) & ~(int64_t)1);
+    rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, ((size_t)lddb * nrhs + (size_t)m + 2) * sizeof(double));
+    if (rc) return rc;
+    dB = (double *)h->stage2;
+    double *dtau = dB + (size_t)lddb * nrhs;
+    QLB_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)lddb * 8, B, (size_t)ldb * 8, (size_t)m * 8, (size_t)nrhs, cudaMemcpyHostToDevice, h->stream));
+    QLB_CUDA(h, cudaMemcpyAsync(dtau, tau, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = qlb_dqlminnorm_dev(h, m, n, nrhs, dA, ldda, dtau, dB, lddb, h->dinfo);
+    if (rc) return rc;
+    rc = stage_out(h, B, n, nrhs, ldb, dB, lddb);
+    if (rc) return rc;
+    int32_t info = 0;
+    QLB_CUDA(h, cudaMemcpyAsync(&info, h->dinfo, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return info == 0x7fffffff ? 0 : (int)info;       // i > 0: rank deficient
+}
 int qlb200_dqllstsq_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, const double *dA, int64_t lda, const double *dtau,
                         double *dB, int64_t ldb) {
     int rc = check_lstsq(h, m, n, nrhs, dA, lda, dtau, dB, ldb);

@@ -71,6 +71,8 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m, int64_t n, i
 int qlb_dqlsolve_dev(qlb200_ctx *h, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
                      int64_t ldb, int32_t *dinfo, int cache_mode);
 int qlb_dgerqf_dev(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda, double *tau);
+int qlb_dqlminnorm_dev(qlb200_ctx *h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
+                       int64_t ldb, int32_t *dinfo);
 int qlb_dqrsolve_dev(qlb200_ctx *h, int64_t m, int64_t n, int64_t nrhs, const double *A, int64_t lda, const double *tau, double *B,
                      int64_t ldb, int32_t *dinfo);
 int qlb_qr_flip_in(qlb200_ctx *h, int64_t m, int64_t n, double *A, int64_t lda);

@@ -114,7 +114,16 @@ for (T, p, orm, adj) in ((Float64, :d, :ormql, 'T'), (Float32, :s, :ormql, 'T'),
                 chk(h, info; dims = (9,))
                 return B      # X = B[1:n, :] (what `\` cuts out, src/ql.jl:501); B[n+1:m, :] = coordinates of the residual
             end
-            m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # otherwise: keep the reference's own branch (src/ql.jl:448-486)
+            if m < n && $T === Float64      # wide: minimum-norm solution on the n-row buffer `\` allocates (src/ql.jl:496-501)
+                size(B, 1) == n || throw(DimensionMismatch("wide ldiv!: B must have $n rows (b in the first $m); has $(size(B,1))"))
+                h = handle()
+                info = ccall((:qlb200_dqlminnorm, libqlb200), Cint,
+                             (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+                             h.ptr, m, n, size(B, 2), F.factors, max(1, stride(F.factors, 2)), F.τ, B, max(1, stride(B, 2)))
+                chk(h, info; dims = (9,))
+                return B
+            end
+            m == n || return invoke(materialize!, Tuple{Ldiv{<:QLPackedLayout}}, Ldv)   # other element types, rectangular: the reference's own branch (src/ql.jl:448-486)
             size(B, 1) == n || throw(DimensionMismatch("arguments must have the same number of rows; has $n and $(size(B,1))"))
             h = handle()
             info = ccall(($solve, libqlb200), Cint,

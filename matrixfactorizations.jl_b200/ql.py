@@ -222,9 +222,24 @@ class QL:
     def solve(self, b):
         r"""F \ b (src/ql.jl:490-502), square only -- the reference's rectangular branches are
         @test_broken (test/test_ql.jl:148)."""
+        m, n = self.factors.shape
+        if m < n:                                # wide: X = zeros(n, ...); X[1:m, :] = b (src/ql.jl:498-499); minimum-norm solution
+            if b.shape[0] != m:
+                raise DimensionMismatch(f"left hand side has {m} rows, but right hand side has {b.shape[0]} rows")
+            if _is_torch(b):
+                import torch
+
+                cols = 1 if b.dim() == 1 else b.shape[1]
+                X = torch.zeros((cols, n), dtype=b.dtype, device=b.device).T
+                X[:m, :] = b.reshape(m, cols)
+            else:
+                cols = 1 if b.ndim == 1 else b.shape[1]
+                X = np.zeros((n, cols), dtype=self.factors.dtype, order="F")
+                X[:m, :] = np.reshape(b, (m, cols))
+            ldiv_(self, X)
+            return X[:, 0] if (b.dim() if _is_torch(b) else b.ndim) == 1 else X
         X = _copy_colmajor(b)
         ldiv_(self, X)
-        m, n = self.factors.shape
         return X if m == n else X[:n]            # `_cut_B(X, 1:n)`, src/ql.jl:501 (tall: the least-squares solution, SURVEY.md 8(f) N2)
 
 
@@ -463,12 +478,16 @@ def ldiv_(F: QL, B):
     """ldiv!(F::QL, B), square (src/ql.jl:438-447,467)."""
     f, b, t = _Mat(F.factors, "A(const)"), _Mat(B, "B"), _Mat(F.tau, "tau")
     _same_kind(f, b, t)
-    if f.m < f.n:
-        raise DimensionMismatch("ldiv_: square and tall only (the wide minimum-norm solve needs an LQ-type factorization; "
-                                "the reference's own branch is @test_broken, test/test_ql.jl:148)")
+    h = _handle(F.handle, f)
+    if f.m < f.n:    # SURVEY.md 8(f) N2, wide: minimum-norm solution; B is the n-row buffer of src/ql.jl:496-501 (b in its first m rows)
+        if f.pfx != "d":
+            raise TypeError("wide ldiv_: Float64 only")
+        if b.m != f.n:
+            raise DimensionMismatch(f"wide ldiv_: B must have {f.n} rows (b in the first {f.m}); has {b.m}")
+        h.call(f"qlb200_dqlminnorm{f.sfx}", f.m, f.n, b.n, f.ptr, f.ld, t.ptr, b.ptr, b.ld)
+        return B
     if b.m != f.m:   # src/ql.jl:494
         raise DimensionMismatch(f"arguments must have the same number of rows; has {f.m} and {b.m}")
-    h = _handle(F.handle, f)
     if f.m > f.n:    # SURVEY.md 8(f) N2: least squares; X = B[:n, :] (src/ql.jl:501), B[n:, :] = residual coordinates
         if f.pfx != "d":
             raise TypeError("tall ldiv_: Float64 only")

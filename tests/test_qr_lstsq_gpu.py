@@ -114,11 +114,37 @@ def test_tall_least_squares(q, h, shape, nrhs):
     assert v.shape == (n,) and np.array_equal(v, x[:, 0])
 
 
-def test_wide_solve_is_refused(q, h):
-    A = np.asfortranarray(np.random.default_rng(2).standard_normal((5, 9)))
+@pytest.mark.parametrize("shape,nrhs", [((5, 9), 1), ((1, 6), 2), ((30, 47), 3), ((100, 101), 2), ((300, 1200), 5), ((1100, 1500), 2)])
+def test_wide_minimum_norm_solve(q, h, shape, nrhs):
+    r"""SURVEY.md 8(f) N2, wide half: `ql(A) \ b` for m < n returns the minimum-norm solution (what README.md:40 of the reference
+    advertises; its own branch, src/ql.jl:448-483, is @test_broken at test/test_ql.jl:148): against numpy's lstsq (pinv solution)."""
+    import torch
+
+    m, n = shape
+    rng = np.random.default_rng(m + 11 * n)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    b = np.asfortranarray(rng.standard_normal((m, nrhs)))
     F = q.ql(A, handle=h)
+    x = F.solve(b)
+    assert x.shape == (n, nrhs)
+    xo = np.linalg.lstsq(A, b, rcond=None)[0]
+    cond = np.linalg.cond(A)
+    assert np.abs(x - xo).max() <= 50 * n * EPS * cond * max(1.0, np.abs(xo).max())
+    assert np.abs(A @ x - b).max() <= 5000 * EPS * cond * max(1.0, np.abs(b).max())
+    # minimum norm: x lies in the row space of A (orthogonal to its null space)
+    Q0 = np.linalg.qr(A.T, mode="complete")[0][:, m:]
+    assert np.abs(Q0.T @ x).max() <= 50 * n * EPS * cond * max(1.0, np.abs(xo).max())
+    v = F.solve(b[:, 0].copy())
+    assert v.shape == (n,) and np.array_equal(v, x[:, 0])
+    # device pointers, in-place form on the n-row buffer of src/ql.jl:496-501
+    Fd = q.QL(torch.from_numpy(F.factors.T.copy()).cuda().T, torch.from_numpy(F.tau).cuda(), handle=h)
+    X = torch.zeros((nrhs, n), dtype=torch.float64, device="cuda").T
+    X[:m, :] = torch.from_numpy(b).cuda()
+    q.ldiv_(Fd, X)
+    torch.cuda.synchronize()
+    assert np.array_equal(X.cpu().numpy(), x)
     with pytest.raises(q.DimensionMismatch):
-        F.solve(np.ones(5))
+        F.solve(np.ones(m + 1))
 
 
 @pytest.mark.parametrize("shape,nrhs", [((10, 10), 1), ((64, 64), 3), ((300, 300), 4), ((40, 7), 2), ((1500, 400), 3)])
