@@ -192,6 +192,15 @@ int qlb200_sqlsolve(qlb200_handle h, int64_t n, int64_t nrhs, const float *A, in
 int qlb200_sqlsolve_dev(qlb200_handle h, int64_t n, int64_t nrhs, const float *dA, int64_t lda, const float *dtau, float *dB,
                         int64_t ldb);
 
+/* ---- banded QL in BandedMatrices.jl storage ------------------------------------------------------
+ * Replaces banded_ql!(L::BandedMatrix{Float64}) (reference ext/MatrixFactorizationsBandedMatricesExt.jl:18-36) behind
+ * ql(::BandedMatrix) / ql!(::BandedMatrix) (ext:14-16; the caller widens the lower bandwidth to max(l, l+u+m-n) first, as ext:14
+ * does).  D = bandeddata(L): (l+u+1) x n, column-major with leading dimension ldd, A[i,j] = D[u+i-j, j] (0-based); tau has min(m,n)
+ * entries.  LinearAlgebra.reflector! conventions (a pivot with a zero or empty tail gets tau = 2, beta = -alpha).  One CTA walks the
+ * n dependent column steps: latency-bound by construction (csrc/banded.cu) -- a completeness path, not a throughput path. */
+int qlb200_dgbqlf(qlb200_handle h, int64_t m, int64_t n, int64_t l, int64_t u, double *D, int64_t ldd, double *tau);
+int qlb200_dgbqlf_dev(qlb200_handle h, int64_t m, int64_t n, int64_t l, int64_t u, double *dD, int64_t ldd, double *dtau);
+
 /* ---- RQ through index reversal -------------------------------------------------------------
  * Replaces rq!(A::StridedMatrix{<:BlasFloat}) = RQ(LAPACK.gerqf!(A)...) (reference
  * src/rq.jl:401): gerqf(A) = geqlf(A^T)^T with identical tau. */

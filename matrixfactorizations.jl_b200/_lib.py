@@ -58,6 +58,7 @@ for _sfx in ("", "_dev"):
     SIGNATURES[f"qlb200_dqllstsq{_sfx}"] = [_I, _I, _I, _P, _I, _P, _P, _I]
     SIGNATURES[f"qlb200_dqrsolve{_sfx}"] = [_I, _I, _I, _P, _I, _P, _P, _I]
     SIGNATURES[f"qlb200_dqlminnorm{_sfx}"] = [_I, _I, _I, _P, _I, _P, _P, _I]
+    SIGNATURES[f"qlb200_dgbqlf{_sfx}"] = [_I, _I, _I, _I, _P, _I, _P]
     SIGNATURES[f"qlb200_dulfact{_sfx}"] = _UL
     SIGNATURES[f"qlb200_dulsolve{_sfx}"] = _ULS
     # Float32 (promoted), ComplexF64 (complex.cu) and ComplexF32 (promoted) single-matrix QL path

@@ -498,6 +498,21 @@ def ldiv_(F: QL, B):
 
 
 # ---- batched (new surface; per-matrix semantics = ql!, lmul!, ldiv!) ---------------------------
+def banded_ql_(D, m, n, l, u, handle=None):
+    """banded_ql!(L::BandedMatrix) (reference ext/MatrixFactorizationsBandedMatricesExt.jl:18-36) on the band data
+    D = bandeddata(L) ((l+u+1) x n, column-major; the lower bandwidth already widened as ql(::BandedMatrix) does, ext:14).
+    In place; returns (D, tau)."""
+    d = _Mat(D, "D")
+    if d.pfx != "d":
+        raise TypeError("banded_ql_: Float64 only")
+    if d.m != l + u + 1 or d.n != n:
+        raise DimensionMismatch(f"band data must be {l + u + 1} x {n}, got {d.m} x {d.n}")
+    h = _handle(handle, d)
+    tau = _new_like(D, min(m, n))
+    h.call(f"qlb200_dgbqlf{d.sfx}", m, n, l, u, d.ptr, d.ld, _Mat(tau, "tau").ptr)
+    return D, tau
+
+
 class _Bat:
     def __init__(self, x, what):
         if _is_torch(x):
