@@ -228,3 +228,30 @@ def test_complex_ql_lookahead_vs_lapack(q, h, shape):
             h.set_option("lookahead", 2)
         assert np.abs(F.factors - Fo).max() <= tol
         assert np.abs(F.tau - tauo).max() <= 50 * max(m, n) * _eps(np.complex128)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(30, 30), (45, 28), (28, 45)])
+def test_q_apply_and_solve_vs_the_reference_loops(q, h, dt, shape):
+    """lmul!/rmul! (Q and Q') and the square ldiv! against the NumPy restatement of the reference's OWN generic loops
+    (oracle/loops.py: src/ql.jl:318-435 with the conj placements, :440-447,467), on the GPU-computed factors."""
+    from oracle import loops
+
+    m, n = shape
+    rng = np.random.default_rng(m * 3 + n)
+    A = _rand(rng, (m, n), dt)
+    F = q.ql(A, handle=h)
+    hi = np.complex128 if np.issubdtype(dt, np.complexfloating) else np.float64
+    Fh, th = F.factors.astype(hi), F.tau.astype(hi)
+    B = _rand(rng, (m, 4), dt)
+    C = _rand(rng, (4, m), dt)
+    tol = 50 * max(m, n) * _eps(dt) * np.sqrt(m) * max(1.0, np.abs(B).max(), np.abs(C).max())
+    assert np.abs(q.lmul_(F.Q, B.copy(order="F")) - loops.lmul(Fh, th, B.astype(hi))).max() <= tol
+    assert np.abs(q.lmul_(F.Q.T, B.copy(order="F")) - loops.lmul(Fh, th, B.astype(hi), adjoint=True)).max() <= tol
+    assert np.abs(q.rmul_(C.copy(order="F"), F.Q) - loops.rmul(C.astype(hi), Fh, th)).max() <= tol
+    assert np.abs(q.rmul_(C.copy(order="F"), F.Q.T) - loops.rmul(C.astype(hi), Fh, th, adjoint=True)).max() <= tol
+    if m == n:
+        x = F.solve(B)
+        xo = loops.ldiv_square(Fh, th, B.astype(hi))
+        cond = np.linalg.cond(A.astype(hi))
+        assert np.abs(x - xo).max() <= 50 * n * _eps(dt) * cond * max(1.0, np.abs(xo).max())

@@ -74,3 +74,32 @@ def test_lapack_binding_complex(dt, shape):
     if k > 1:      # zlarfg: beta is real
         d = np.array([F[m - k + i, n - k + i] for i in range(1, k)])
         assert np.abs(d.imag).max() == 0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("shape", [(9, 9), (12, 7), (7, 12)])
+def test_generic_loops_restatement_vs_lapack(dt, shape):
+    """oracle/loops.py (the reference's generic lmul!/rmul! loops for any element type, src/ql.jl:318-435, incl. the conj
+    placements) against LAPACK ?ormql / ?unmql on LAPACK-computed factors, and against the real C port."""
+    from oracle import loops
+
+    m, n = shape
+    rng = np.random.default_rng(m + 31 * n)
+    A = rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if dt == np.complex128 else 0)
+    A = np.asfortranarray(A.astype(dt))
+    F, tau = lapack.geqlf(A)
+    k = min(m, n)
+    V = np.asfortranarray(F[:, n - k:])
+    B = np.asfortranarray((rng.standard_normal((m, 3)) + (1j * rng.standard_normal((m, 3)) if dt == np.complex128 else 0)).astype(dt))
+    C = np.asfortranarray((rng.standard_normal((3, m)) + (1j * rng.standard_normal((3, m)) if dt == np.complex128 else 0)).astype(dt))
+    adj = "C" if dt == np.complex128 else "T"
+    assert np.abs(loops.lmul(F, tau, B) - lapack.ormql("L", "N", V, tau, B)).max() <= 1e-12
+    assert np.abs(loops.lmul(F, tau, B, adjoint=True) - lapack.ormql("L", adj, V, tau, B)).max() <= 1e-12
+    assert np.abs(loops.rmul(C, F, tau) - lapack.ormql("R", "N", V, tau, C)).max() <= 1e-12
+    assert np.abs(loops.rmul(C, F, tau, adjoint=True) - lapack.ormql("R", adj, V, tau, C)).max() <= 1e-12
+    if dt == np.float64:
+        assert np.abs(loops.lmul(F, tau, B) - cport.lmul(F, tau, B)).max() <= 1e-12
+        assert np.abs(loops.rmul(C, F, tau, adjoint=True) - cport.rmul(C, F, tau, adjoint=True)).max() <= 1e-12
+    if m == n:
+        x = loops.ldiv_square(F, tau, B)
+        assert np.abs(A @ x - B).max() <= 1e-10 * np.linalg.cond(A)
