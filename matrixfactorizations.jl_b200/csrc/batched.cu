@@ -1064,8 +1064,8 @@ template <typename T, int N, int NR, int MODE>
 static int launch_apply_batched(qlb200_ctx *h, const T *A, int64_t lda, int64_t strideA, const T *tau,
                                 int64_t strideTau, T *B, int64_t ldb, int64_t strideB, int nrhs, int64_t batch,
                                 int32_t *info_out, int nr = N) {
-    constexpr int WARPS = 4;
     using Cfg = ApplyCfg<T, N, NR, MODE>;
+    constexpr int WARPS = (N == 64 && 6 * Cfg::WARP_BYTES <= 232448) ? 6 : 4;      // 64-row tiles: one CTA per SM, fill its shared memory
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES;
     if (batch >= ((int64_t)1 << 31)) return qlb_fail(h, -8, "batch too large%s");
     CUtensorMap tmap;
