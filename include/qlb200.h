@@ -64,14 +64,18 @@ int64_t qlb200_launch_count(qlb200_handle h);
  * event pairs on the launching stream.  This call synchronizes, returns the summed device time (ms),
  * the summed algorithmic flops and the number of launches since the last collect, and resets. */
 int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_total, int64_t *launches);
-/* Tunables: "nb" (panel width, multiple of 16 in [16,128]), "lookahead" (0/1, measured slower: off), "gemm_cfg"
+/* Tunables: "nb" (panel width, multiple of 16 in [16,256]; 0 = auto: 192 for look-ahead ql! with min(m,n) >= 14336, else 128),
+ * "lookahead" (2 = default: ql!/ul!/complex ql! factor the next panel on a 16-SM green-context partition while the other SMs apply
+ * the previous one, for large matrices; 1 = always; 0 = sequential schedule), "la_min", "host_split" / "host_split_min" (host-pointer
+ * ql! of large tall/square matrices: split schedule), "fuse_chunk" (fused batched factor + apply: matrices per
+ * chunk, 0 = whole batch), "gemm_cfg"
  * (-1 auto, 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V), "strip_rpt"
  * (1/2/4 minimum rows per thread in the panel kernel), "profile" (0/1, see above), "graph" (1: repeated ql! calls with
  * the same arguments are replayed as a CUDA graph), "tcache" (1: ql! keeps the panels' T factors for the following
  * lmul!/rmul!/ldiv! on the same factors -- device-pointer callers must not modify the factors in between),
  * "overlap_t" (1: the panel's T is built on a side stream while W = C'V runs), "ul_cluster" (1: cluster strip kernel
  * for UL), "stream_in" (1: host-pointer ql! uploads the matrix in column chunks while the right-hand panels are already
- * being factored; "chunk_cols", "join_step" tune it), "bvar" (n = 32 batched kernel: 0 auto, 2 always one kernel, 3 always the two-phase split),
+ * being factored; "chunk_cols", "join_step" tune it), "bvar" (batched kernel variants: 0 auto; n = 32: 2 always one kernel, 3 always the two-phase split; 32 < n <= 64: 6 warp-pair kernel, 7 one warp per matrix, 9 the literal ?geql2 kernels),
  * "pair_sync" (default 8; GEMMs with exactly two column tiles run each pair as a 2-CTA cluster that meets every this
  * many k-tiles so that the shared operand is read from DRAM once, 0 = off), "batch_chunk_mb" (default 32; host-pointer batched calls run as an upload | compute | download pipeline over chunks of
  * about this many megabytes, 0 = one chunk). */
@@ -262,7 +266,8 @@ int qlb200_dqrsolve_dev(qlb200_handle h, int64_t m, int64_t n, int64_t nrhs, con
                         const double *dtau, double *dB, int64_t ldb);
 
 /* ---- batched small square QL (new surface; per-matrix semantics = src/ql.jl:72) ------------
- * `batch` independent n x n matrices, 1 <= n <= 64 (register kernels for n in {8, 16, 32}); matrix b starts at A + b*strideA,
+ * `batch` independent n x n matrices, 1 <= n <= 64 -- register-tile kernels for n <= 32 (8/16/32 exactly, other orders zero-padded
+ * into the next tile), shared-memory + DMMA compact-WY kernels for 32 < n <= 64; matrix b starts at A + b*strideA,
  * column-major with leading dimension lda; tau of matrix b at tau + b*strideTau (n entries).
  * Reference-equivalent workload: `for i: ql!(view(A,:,:,i))`. */
 int qlb200_dgeqlf_batched(qlb200_handle h, int64_t n, double *A, int64_t lda, int64_t strideA,
@@ -276,7 +281,7 @@ int qlb200_sgeqlf_batched_dev(qlb200_handle h, int64_t n, float *dA, int64_t lda
 
 /* Batched lmul!(Q,B) (trans 'N', src/ql.jl:321-347) / lmul!(Q',B) (trans 'T', src/ql.jl:350-377):
  * B_b (n x nrhs, leading dimension ldb, matrix stride strideB) <- op(Q_b) B_b.  1 <= n <= 64 like the
- * factorization (register kernels for n in {8, 16, 32}, a generic warp-per-matrix kernel otherwise). */
+ * factorization (register kernels on 8/16/32/64-row tiles, other orders zero-padded into the next tile). */
 int qlb200_dormql_batched(qlb200_handle h, char trans, int64_t n, int64_t nrhs, const double *A,
                           int64_t lda, int64_t strideA, const double *tau, int64_t strideTau,
                           double *B, int64_t ldb, int64_t strideB, int64_t batch);
