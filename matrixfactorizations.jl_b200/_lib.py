@@ -87,7 +87,7 @@ for _t in "ds":
 SIGNATURES["qlb200_dgemm_dev"] = [c_char, c_char, _I, _I, _I, ctypes.c_double, _P, _I, _P, _I, ctypes.c_double, _P, _I]
 HANDLE_FUNCS = ["qlb200_version", "qlb200_create", "qlb200_destroy", "qlb200_set_stream", "qlb200_sync",
                 "qlb200_last_error", "qlb200_launch_count", "qlb200_set_option", "qlb200_reset_stream",
-                "qlb200_profile_collect"]
+                "qlb200_profile_collect", "qlb200_upload_rate"]
 
 
 def lib() -> ctypes.CDLL:
@@ -109,6 +109,8 @@ def lib() -> ctypes.CDLL:
         L.qlb200_launch_count.argtypes = [c_void_p]
         L.qlb200_launch_count.restype = c_int64
         L.qlb200_set_option.argtypes = [c_void_p, c_char_p, c_int64]
+        L.qlb200_upload_rate.argtypes = [c_void_p]
+        L.qlb200_upload_rate.restype = ctypes.c_double
         _LIB = L
     return _LIB
 
@@ -192,6 +194,10 @@ class Handle:
     @property
     def launches(self) -> int:
         return int(lib().qlb200_launch_count(self._h))
+
+    def upload_rate(self) -> float:
+        """GB/s the first upload piece of the last large host-pointer ql! saw (0.0: none yet)."""
+        return float(lib().qlb200_upload_rate(self._h))
 
     def last_error(self) -> str:
         return lib().qlb200_last_error(self._h).decode(errors="replace")

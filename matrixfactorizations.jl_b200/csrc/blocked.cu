@@ -408,10 +408,15 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
         const int JSTEP = (int)h->opt_join_step;     // panels per joining chunk
         auto issue_chunk = [&](int c) -> int {
             const int lo = c * CW, hi = (lo + CW < n) ? lo + CW : n;
+            if (c == nch - 1) QLB_CUDA(h, cudaEventRecord(h->ev_up[0], h->h2d_stream));
             QLB_CUDA(h, cudaMemcpy2DAsync(A + (int64_t)lo * lda, (size_t)lda * 8, hsrc + (int64_t)lo * h->h2d.host_ld,
                                           (size_t)h->h2d.host_ld * 8, (size_t)m * 8, (size_t)(hi - lo), cudaMemcpyHostToDevice,
                                           h->h2d_stream));
             QLB_CUDA(h, cudaEventRecord(h->ev_chunk[c], h->h2d_stream));
+            if (c == nch - 1) {             // the first chunk on its way: its upload rate steers the host schedule choice
+                QLB_CUDA(h, cudaEventRecord(h->ev_up[1], h->h2d_stream));
+                h->up_bytes = (double)m * 8.0 * (double)(hi - lo);
+            }
             return 0;
         };
         auto join_chunk = [&](int c, int nfact) -> int {      // nfact = panels factored so far
@@ -591,7 +596,7 @@ int qlb_dormql_dev(qlb200_ctx *h, char side, char trans, int64_t m64, int64_t n6
     bool cached = h->opt_tcache && h->tc_valid && h->tc_key[3] == nq && h->tc_key[4] == k && h->tc_key[5] == nb && cache_mode >= 0;
     if (cached && h->opt_tcache == 2)            // trusted mode: the pointers ql! factored
         cached = h->tc_key[0] == (int64_t)(uintptr_t)A && h->tc_key[1] == lda && h->tc_key[2] == (int64_t)(uintptr_t)tau;
-    if (cached && h->opt_tcache == 1) {          // validated mode: same content (checksum of every reflector entry and tau)
+    if (cached && h->opt_tcache == 1 && cache_mode != 2) {          // validated mode: same content (checksum of every reflector entry and tau); cache_mode 2: the caller (the split host schedule) applies the factors ql! has just left
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
             (void)cudaGetLastError();

@@ -106,6 +106,7 @@ int qlb200_create(qlb200_handle *out, int device) {
     QLB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     QLB_CUDA(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 32; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) QLB_CUDA(h, cudaEventCreate(&h->ev_up[i]));
     for (int i = 0; i < 8; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_panel[i], cudaEventDisableTiming));
     QLB_CUDA(h, cudaMalloc(&h->dinfo, 64 + 256 * sizeof(unsigned)));      // status word + per-SM tickets
     QLB_CUDA(h, cudaMemset(h->dinfo, 0, 64 + 256 * sizeof(unsigned)));
@@ -149,6 +150,8 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 32; ++i)
         if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+    for (int i = 0; i < 2; ++i)
+        if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -199,6 +202,7 @@ int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_tota
 }
 
 int64_t qlb200_launch_count(qlb200_handle h) { return h ? h->launches : -1; }
+double qlb200_upload_rate(qlb200_handle h) { return h ? h->h2d_gbps : -1.0; }
 
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     if (!h) return -1;
@@ -264,10 +268,18 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     } else if (!strcmp(name, "la_min")) {
         h->opt_la_min = value < 0 ? 0 : value;
     } else if (!strcmp(name, "host_split")) {
-        h->opt_host_split = value ? 1 : 0;
+        if (value < 0 || value > 2) return qlb_fail(h, -3, "host_split must be 0, 1 or 2%s");
+        h->opt_host_split = (int)value;
+        h->h2d_gbps = 0.0;
+    } else if (!strcmp(name, "host_split_gbps")) {
+        if (value < 0) return qlb_fail(h, -3, "host_split_gbps must be >= 0%s");
+        h->opt_host_split_gbps = value;
     } else if (!strcmp(name, "host_split_min")) {
         if (value < 512) return qlb_fail(h, -3, "host_split_min must be >= 512%s");
         h->opt_host_split_min = value;
+    } else if (!strcmp(name, "host_split_chunk")) {
+        if (value < 0) return qlb_fail(h, -3, "host_split_chunk must be >= 0%s");
+        h->opt_host_split_chunk = value;
     } else if (!strcmp(name, "fuse_chunk")) {
         h->opt_fuse_chunk = value < 0 ? 0 : value;
     } else if (!strcmp(name, "la_gemm_all")) {
@@ -692,6 +704,16 @@ static int geqlf_dev_graph(qlb200_ctx *h, int64_t m, int64_t n, double *dA, int6
     return 0;
 }
 
+// Upload rate of the first piece of a host-pointer ql! (events ev_up[0..1] on the H2D stream, read after the call's final sync).
+static void note_upload_rate(qlb200_ctx *h) {
+    float ms = 0.f;
+    if (h->up_bytes > 0.0 && cudaEventElapsedTime(&ms, h->ev_up[0], h->ev_up[1]) == cudaSuccess && ms > 0.f)
+        h->h2d_gbps = h->up_bytes / (ms * 1e6);
+    else
+        cudaGetLastError();
+    h->up_bytes = 0.0;
+}
+
 static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, int64_t lda, double *tau) {
     int rc = check_fact(h, m, n, A, lda, tau);
     if (rc) return rc;
@@ -706,7 +728,13 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
     // part (blocked ormql with the cached T factors, all SMs), then the leading (m - wR) x wL block is factored (look-ahead
     // again).  Same arithmetic as one ql! (LAPACK's right-to-left order restricted to column blocks); finished panels stream
     // home behind the computation in both factorizations.  Option "host_split" = 0 falls back to the chunk-joining schedule.
-    if (f == geqlf_dev_graph && h->opt_host_split && h->gc_ok && h->opt_lookahead == 2 && m >= n && n >= h->opt_host_split_min && h->opt_tcache) {
+    // "host_split" = 2 (default) picks per call: the split schedule while the previous call's first upload ran at PCIe speed,
+    // the chunk-joining schedule (which hides a slow upload better: 8 GPUs uploading at once share the host's memory system)
+    // while it did not.  Both schedules time their first upload piece, so the choice follows the load.
+    const bool split_now = h->opt_host_split == 1 ||
+                           (h->opt_host_split == 2 && (h->h2d_gbps == 0.0 || h->h2d_gbps >= (double)h->opt_host_split_gbps));
+    if (f == geqlf_dev_graph && split_now && h->gc_ok && h->opt_lookahead == 2 && m >= n && n >= h->opt_host_split_min && h->opt_tcache &&
+        (h->opt_host_split_chunk == 0 || n <= 31 * h->opt_host_split_chunk)) {      // (one event per chunk)
         const int64_t ldd = (m + 1) & ~(int64_t)1;
         rc = qlb_reserve(h, &h->stage, &h->stage_bytes, (size_t)ldd * n * sizeof(double));
         if (!rc) rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * sizeof(double));
@@ -714,11 +742,22 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
         double *dA = (double *)h->stage, *dtau = (double *)h->stage2;
         int64_t wR = ((n / 4 + 127) / 128) * 128;
         const int64_t wL = n - wR;
+        QLB_CUDA(h, cudaEventRecord(h->ev_up[0], h->h2d_stream));
         QLB_CUDA(h, cudaMemcpy2DAsync(dA + wL * ldd, (size_t)ldd * 8, A + wL * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)wR,
                                       cudaMemcpyHostToDevice, h->h2d_stream));
+        QLB_CUDA(h, cudaEventRecord(h->ev_up[1], h->h2d_stream));
+        h->up_bytes = (double)m * 8.0 * (double)wR;
         QLB_CUDA(h, cudaEventRecord(h->ev_chunk[0], h->h2d_stream));
-        QLB_CUDA(h, cudaMemcpy2DAsync(dA, (size_t)ldd * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)wL, cudaMemcpyHostToDevice, h->h2d_stream));
-        QLB_CUDA(h, cudaEventRecord(h->ev_chunk[1], h->h2d_stream));
+        // the left part follows in column chunks, right to left: Q_R' is applied to a chunk as soon as it has arrived, so a slow
+        // upload (several GPUs sharing the host's memory system) hides behind the applies instead of stalling them
+        const int64_t CW = h->opt_host_split_chunk > 0 ? ((h->opt_host_split_chunk + 127) / 128) * 128 : wL;
+        const int nchunks = (int)((wL + CW - 1) / CW);
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t hi = wL - (int64_t)c * CW, lo = hi - CW > 0 ? hi - CW : 0;
+            QLB_CUDA(h, cudaMemcpy2DAsync(dA + lo * ldd, (size_t)ldd * 8, A + lo * lda, (size_t)lda * 8, (size_t)m * 8, (size_t)(hi - lo),
+                                          cudaMemcpyHostToDevice, h->h2d_stream));
+            QLB_CUDA(h, cudaEventRecord(h->ev_chunk[1 + c], h->h2d_stream));
+        }
         QLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[0], 0));
         h->d2h.la = true;
         h->d2h.rows = m;
@@ -726,9 +765,10 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
         h->d2h.host = A + wL * lda;
         rc = qlb_dgeqlf_dev(h, m, wR, dA + wL * ldd, ldd, dtau + wL);
         h->d2h.host = nullptr;
-        if (!rc) {
-            QLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[1], 0));
-            rc = qlb_dormql_dev(h, 'L', 'T', m, wL, wR, dA + wL * ldd, ldd, dtau + wL, dA, ldd, 0);
+        for (int c = 0; c < nchunks && !rc; ++c) {
+            const int64_t hi = wL - (int64_t)c * CW, lo = hi - CW > 0 ? hi - CW : 0;
+            QLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[1 + c], 0));
+            rc = qlb_dormql_dev(h, 'L', 'T', m, hi - lo, wR, dA + wL * ldd, ldd, dtau + wL, dA + lo * ldd, ldd, 2);
         }
         if (!rc) {
             h->d2h.host = A;
@@ -746,6 +786,7 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
         QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
         QLB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+        note_upload_rate(h);
         return 0;
     }
     const bool stream_back = (f == geqlf_dev_graph) && m * n >= ((int64_t)1 << 22) && h->opt_lookahead != 1;
@@ -770,6 +811,7 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
         if (stream_in) {
             h->h2d.host = A;
             h->h2d.host_ld = lda;
+            h->up_bytes = 0.0;              // (set by the driver once the first chunk is on its way)
         }
         rc = qlb_dgeqlf_dev(h, m, n, dA, ldd, dtau);
         h->d2h.host = nullptr;
@@ -782,6 +824,7 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
         QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
         QLB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+        if (stream_in) note_upload_rate(h);
     } else {
         rc = f(h, m, n, dA, ldd, dtau);
         if (rc) return rc;

@@ -29,11 +29,15 @@ struct qlb200_ctx {
     // being factored; a chunk joins the trailing update when it has arrived and caught up with the finished panels
     cudaStream_t h2d_stream = nullptr;
     cudaEvent_t ev_chunk[32] = {nullptr};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};   // timing events around the first upload of a host-pointer ql! (host_split = 2 policy)
+    double up_bytes = 0.0, h2d_gbps = 0.0;      // bytes between ev_up[0..1] of the call in flight; upload rate the last call saw (0: none yet)
     struct {
         const double *host = nullptr;      // source (column-major, ld = host_ld); null = the matrix is already on the device
         int64_t host_ld = 0;
     } h2d;
-    int64_t opt_host_split = 1;            // host-pointer ql!, large tall/square matrices: split schedule (capi.cu fact_host)
+    int64_t opt_host_split = 2;            // host-pointer ql!, large tall/square matrices: split schedule (capi.cu fact_host); 2: by upload rate
+    int64_t opt_host_split_gbps = 40;      // host_split = 2: split schedule only while the last upload ran at least this fast (GB/s)
+    int64_t opt_host_split_chunk = 0;      // ... left part uploaded and multiplied in chunks of this many columns (0: one piece)
     int64_t opt_host_split_min = 8192;     // ... from this number of columns on
     int64_t opt_stream_in = 1;
     int64_t opt_chunk_cols = 1024;         // columns per H2D chunk

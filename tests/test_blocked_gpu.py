@@ -333,6 +333,7 @@ def test_host_pointer_ql_split_schedule(q, h, shape, split_min):
     buf[:m, :] = rng.standard_normal((m, n))
     A = buf[:m, :]
     h.set_option("host_split_min", split_min)
+    h.set_option("host_split", 1)
     try:
         F = q.ql_(np.asfortranarray(A.copy()), handle=h)
         Fv = buf.copy(order="F")
@@ -350,8 +351,38 @@ def test_host_pointer_ql_split_schedule(q, h, shape, split_min):
     try:
         F0 = q.ql(np.asfortranarray(A.copy()), handle=h)
     finally:
-        h.set_option("host_split", 1)
+        h.set_option("host_split", 2)
     assert np.abs(F.factors - F0.factors).max() <= tol and np.abs(F.tau - F0.tau).max() <= 50 * max(m, n) * EPS
+
+
+def test_host_pointer_ql_schedule_follows_upload_rate(q, h):
+    """host_split = 2 (the default): the first large host-pointer ql! runs the split schedule and times its first upload piece;
+    the next call runs the split schedule only if that rate reached "host_split_gbps", else the chunk-joining schedule (which
+    hides a slow upload better).  Both schedules are deterministic, so which one ran is visible bit for bit."""
+    n = 2304
+    A = np.asfortranarray(np.random.default_rng(77).standard_normal((n, n)))
+    h.set_option("host_split_min", 1024)
+    try:
+        h.set_option("host_split", 1)
+        F_split = q.ql(A, handle=h)
+        h.set_option("host_split", 0)
+        F_chunk = q.ql(A, handle=h)
+        assert not np.array_equal(F_split.factors, F_chunk.factors)        # (different blockings: rounding differs)
+        h.set_option("host_split", 2)                                      # resets the measured rate
+        assert h.upload_rate() == 0.0
+        h.set_option("host_split_gbps", 10 ** 6)                           # no PCIe link is this fast
+        F1 = q.ql(A, handle=h)
+        assert h.upload_rate() > 0.5
+        F2 = q.ql(A, handle=h)
+        assert np.array_equal(F1.factors, F_split.factors) and np.array_equal(F2.factors, F_chunk.factors)
+        assert h.upload_rate() > 0.5                                       # the chunk-joining schedule measures too
+        h.set_option("host_split_gbps", 0)
+        F3 = q.ql(A, handle=h)
+        assert np.array_equal(F3.factors, F_split.factors) and np.array_equal(F3.tau, F_split.tau)
+    finally:
+        h.set_option("host_split_min", 8192)
+        h.set_option("host_split_gbps", 40)
+        h.set_option("host_split", 2)
 
 
 def _scaled_cmp(F, tau, Fo, tauo, A, k_rows_are_reflectors=False):
