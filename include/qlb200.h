@@ -60,8 +60,8 @@ int qlb200_sync(qlb200_handle h);
 const char *qlb200_last_error(qlb200_handle h);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t qlb200_launch_count(qlb200_handle h);
-/* Upload rate (GB/s) the first piece of the last large host-pointer ql! saw; 0 before the first such call.  The "host_split" = 2
- * policy reads it to choose the host schedule of the next call. */
+/* Upload rate (GB/s) the first chunk of the last large host-pointer ql! saw (plain launches only: a graph replay does not
+ * measure); 0 before the first such call.  Diagnostic: ~53 GB/s on an idle host, 17-19 GB/s with 8 GPUs uploading at once. */
 double qlb200_upload_rate(qlb200_handle h);
 /* With option "profile" = 1 the trailing-update / Q-apply DMMA GEMM launches are bracketed by CUDA
  * event pairs on the launching stream.  This call synchronizes, returns the summed device time (ms),
@@ -69,10 +69,11 @@ double qlb200_upload_rate(qlb200_handle h);
 int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_total, int64_t *launches);
 /* Tunables: "nb" (panel width, multiple of 16 in [16,256]; 0 = auto: 192 for look-ahead ql! with min(m,n) >= 14336, else 128),
  * "lookahead" (2 = default: ql!/ul!/complex ql! factor the next panel on a 16-SM green-context partition while the other SMs apply
- * the previous one, for large matrices; 1 = always; 0 = sequential schedule), "la_min", "host_split" / "host_split_min" / "host_split_gbps" /
- * "host_split_chunk" (host-pointer ql! of large tall/square matrices: split schedule; host_split 1 = always, 0 = the
- * chunk-joining schedule, 2 = default: split while the previous call's first upload ran at >= host_split_gbps (40) GB/s -- several
- * GPUs uploading at once share the host's memory system, and the chunk-joining schedule hides a slow upload better), "fuse_chunk" (fused batched factor + apply: matrices per
+ * the previous one, for large matrices; 1 = always; 0 = sequential schedule), "la_min", "host_split" / "host_split_min" (host-pointer ql! of large
+ * tall/square matrices, see DESIGN.md 6: 2 = default, the uploaded column chunks join the look-ahead factorization itself -- and a
+ * repeated call on the same PINNED host matrix replays the whole upload | factor | download schedule as one CUDA graph; 1 = split
+ * schedule; 0 = chunk-joining without look-ahead; "chunk_cols", "la_join_ramp", "la_join_chunks" tune the default schedule),
+ * "fuse_chunk" (fused batched factor + apply: matrices per
  * chunk, 0 = whole batch), "gemm_cfg"
  * (-1 auto, 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V), "strip_rpt"
  * (1/2/4 minimum rows per thread in the panel kernel), "profile" (0/1, see above), "graph" (1: repeated ql! calls with

@@ -351,7 +351,7 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     const int m = (int)m64, n = (int)n64;
     const int k = m < n ? m : n;
     if (k == 0) return 0;
-    const bool seq_host = h->h2d.host || (h->d2h.host && !h->d2h.la);      // the chunk-joining host schedule (no look-ahead)
+    const bool seq_host = (h->h2d.host && !h->h2d.la) || (h->d2h.host && !h->d2h.la);      // the chunk-joining host schedule without look-ahead
     const int nb = seq_host ? (h->opt_nb > 0 ? (int)h->opt_nb : 128) : qlb_effective_nb(h, m64, n64);
     cudaStream_t st = h->stream;
     const int npanels = (k + nb - 1) / nb;
@@ -540,6 +540,57 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
                                       (size_t)rows * 8, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, h->copy_stream));
         return 0;
     };
+    // Host source (h->h2d.host with h->h2d.la; tall/square, T cache on): the matrix is uploaded in chunks of CW columns, right to
+    // left, all queued on the H2D stream now.  Columns [joined_lo, n) take part in the factorization; a chunk JOINS on the
+    // update stream at a fixed iteration (one chunk per panel, and never later than the panel that needs its columns -- a
+    // deterministic schedule, so the result does not depend on transfer timing): G waits for its arrival, applies the panels
+    // factored AND applied so far to it (clean V extracted from the packed factors, T from the cache), and from then on the
+    // chunk is part of the ordinary trailing update.  Same arithmetic per column as the device-resident ql!.
+    const double *hsrc = (h->h2d.host && h->h2d.la && tcache && m >= n) ? h->h2d.host : nullptr;
+    int CW = (int)h->opt_chunk_cols;
+    while ((n + CW - 1) / CW > 32) CW *= 2;
+    const int nch = hsrc ? (n + CW - 1) / CW : 0;
+    int joined_lo = hsrc ? n : 0, next_join = nch - 1;
+    double *Vj = nullptr;
+    if (hsrc) {
+        rc = qlb_reserve(h, &h->joinV, &h->joinV_bytes, (size_t)ws.ldv * nb * sizeof(double));
+        if (rc) return rc;
+        Vj = (double *)h->joinV;
+        QLB_CUDA(h, cudaStreamWaitEvent(h->h2d_stream, gc ? h->ev_gc[0] : h->ev_a, 0));      // after the caller's work on the device buffer
+        for (int c = nch - 1; c >= 0; --c) {
+            const int lo = c * CW, hi = (lo + CW < n) ? lo + CW : n;
+            if (c == nch - 1) QLB_CUDA(h, cudaEventRecord(h->ev_up[0], h->h2d_stream));
+            QLB_CUDA(h, cudaMemcpy2DAsync(A + (int64_t)lo * lda, (size_t)lda * 8, hsrc + (int64_t)lo * h->h2d.host_ld, (size_t)h->h2d.host_ld * 8,
+                                          (size_t)m * 8, (size_t)(hi - lo), cudaMemcpyHostToDevice, h->h2d_stream));
+            QLB_CUDA(h, cudaEventRecord(h->ev_chunk[c], h->h2d_stream));
+            if (c == nch - 1) {
+                QLB_CUDA(h, cudaEventRecord(h->ev_up[1], h->h2d_stream));
+                h->up_bytes = (double)m * 8.0 * (double)(hi - lo);
+            }
+        }
+    }
+    // chunks down to column need_lo join; nfact = panels already applied to every joined column
+    auto join_until = [&](int need_lo, int nfact) -> int {
+        while (joined_lo > need_lo && next_join >= 0) {
+            const int c = next_join--, lo = c * CW, hi = joined_lo;
+            QLB_CUDA(h, cudaStreamWaitEvent(G, h->ev_chunk[c], 0));
+            for (int i = 0; i < nfact; ++i) {
+                const int c1i = panel_c1(i), c0i = panel_c0(i), ibi = c1i - c0i, pi = m - n + c1i;
+                int r = qlb_extract_v(h, G, A + (int64_t)c0i * lda, lda, pi, ibi, pi - ibi, Vj, ws.ldv);
+                if (r) return r;
+                r = apply_block(h, G, ws, true, false, Vj, ws.ldv, Tslot(i), nb, pi, ibi, A + (int64_t)lo * lda, lda, hi - lo, nullptr, smsG);
+                if (r) return r;
+            }
+            joined_lo = lo;
+        }
+        return 0;
+    };
+    if (hsrc) {      // the first panel's columns: P waits for their chunks (G's waits are queued by join_until)
+        const int cfirst = panel_c0(0) / CW;
+        rc = join_until(cfirst * CW, 0);
+        if (rc) return rc;
+        for (int c = nch - 1; c >= cfirst; --c) QLB_CUDA(h, cudaStreamWaitEvent(P, h->ev_chunk[c], 0));
+    }
     rc = factor_panel(h, P, ws2, A, lda, m, n, k, panel_c0(0), panel_c1(0), tau, Vb[0], ws.ldv, Tslot(0), nb, panel_c0(0) > 0 || tcache != nullptr, smsP);
     if (rc) return rc;
     QLB_CUDA(h, cudaEventRecord(evP, P));
@@ -548,6 +599,20 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     for (int j = 0; j < npanels; ++j) {
         const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
         double *V = Vb[j & 1], *T = Tslot(j);
+        if (hsrc) {      // panels 0 .. j-1 have been applied to [joined_lo, .): late chunks catch up with exactly those
+            // schedule: one chunk per panel while the upload is the limit (the first JRAMP panels), then JSTEP per panel -- the
+            // update stream is the limit from there on, and fewer, wider catch-up GEMMs run closer to the big ones' rate
+            const int JRAMP = (int)h->opt_la_join_ramp, JS = (int)h->opt_la_join_chunks;
+            const int nj = (j < JRAMP) ? j + 2 : JRAMP + 2 + (j - JRAMP) * JS + (JS - 1);
+            int need = n - nj * CW;
+            const int dnext = (j + 1 < npanels) ? panel_c0(j + 1) : 0;
+            if (need > dnext) need = dnext;                                    // ... and always the next panel's columns
+            if (j + 1 == npanels) need = 0;
+            if (need < 0) need = 0;
+            rc = join_until((need / CW) * CW, j);
+            if (rc) return rc;
+        }
+        const int lo_all = joined_lo;               // columns [lo_all, c0) are updated by panel j
         QLB_CUDA(h, cudaStreamWaitEvent(G, evP, 0));            // panel j (V, T) is complete
         if (j + 1 < npanels) {
             const int d0 = panel_c0(j + 1);          // next panel = columns [d0, c0)
@@ -560,12 +625,12 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             QLB_CUDA(h, cudaEventRecord(evP, P));
             rc = send_home(j + 1);
             if (rc) return rc;
-            if (d0 > 0) {
-                rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, d0, nullptr, smsG);
+            if (d0 > lo_all) {
+                rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)lo_all * lda, lda, d0 - lo_all, nullptr, smsG);
                 if (rc) return rc;
             }
-        } else if (c0 > 0) {
-            rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A, lda, c0, nullptr, smsG);
+        } else if (c0 > lo_all) {
+            rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)lo_all * lda, lda, c0 - lo_all, nullptr, smsG);
             if (rc) return rc;
         }
     }

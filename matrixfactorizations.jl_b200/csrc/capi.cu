@@ -107,6 +107,7 @@ int qlb200_create(qlb200_handle *out, int device) {
     QLB_CUDA(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 32; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) QLB_CUDA(h, cudaEventCreate(&h->ev_up[i]));
+    QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_home, cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_panel[i], cudaEventDisableTiming));
     QLB_CUDA(h, cudaMalloc(&h->dinfo, 64 + 256 * sizeof(unsigned)));      // status word + per-SM tickets
     QLB_CUDA(h, cudaMemset(h->dinfo, 0, 64 + 256 * sizeof(unsigned)));
@@ -136,6 +137,9 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->zws) cudaFree(h->zws);
     if (h->tall) cudaFree(h->tall);
     if (h->tcache) cudaFree(h->tcache);
+    if (h->joinV) cudaFree(h->joinV);
+    if (h->hgraph_exec) cudaGraphExecDestroy(h->hgraph_exec);
+    if (h->ev_home) cudaEventDestroy(h->ev_home);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->prof_ev) {
         for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
@@ -237,6 +241,12 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->opt_overlap_t = value ? 1 : 0;
     } else if (!strcmp(name, "ul_cluster")) {
         h->opt_ul_cluster = value ? 1 : 0;
+    } else if (!strcmp(name, "la_join_ramp")) {
+        if (value < 0 || value > 64) return qlb_fail(h, -3, "la_join_ramp must be in [0,64]%s");
+        h->opt_la_join_ramp = value;
+    } else if (!strcmp(name, "la_join_chunks")) {
+        if (value < 1 || value > 32) return qlb_fail(h, -3, "la_join_chunks must be in [1,32]%s");
+        h->opt_la_join_chunks = value;
     } else if (!strcmp(name, "join_step")) {
         if (value < 1 || value > 64) return qlb_fail(h, -3, "join_step must be in [1,64]%s");
         h->opt_join_step = value;
@@ -271,9 +281,6 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         if (value < 0 || value > 2) return qlb_fail(h, -3, "host_split must be 0, 1 or 2%s");
         h->opt_host_split = (int)value;
         h->h2d_gbps = 0.0;
-    } else if (!strcmp(name, "host_split_gbps")) {
-        if (value < 0) return qlb_fail(h, -3, "host_split_gbps must be >= 0%s");
-        h->opt_host_split_gbps = value;
     } else if (!strcmp(name, "host_split_min")) {
         if (value < 512) return qlb_fail(h, -3, "host_split_min must be >= 512%s");
         h->opt_host_split_min = value;
@@ -720,19 +727,125 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
     const int64_t k = m < n ? m : n;
     if (k == 0) return 0;
     QLB_CUDA(h, cudaSetDevice(h->device));
-    // ql! of a large matrix: plain launches (no graph); the matrix streams IN chunk by chunk while the right-hand panels
-    // are already being factored, and the finished panels stream OUT while the rest is still being factored -- both PCIe
-    // transfers disappear behind the computation (except the first chunk and the last panel)
-    // Large tall/square ql! with the SM partitions available: SPLIT schedule.  The right quarter of the columns is uploaded and
-    // factored first (look-ahead ql! of the m x wR block) while the rest is still on its way; then Q_R' is applied to the left
-    // part (blocked ormql with the cached T factors, all SMs), then the leading (m - wR) x wL block is factored (look-ahead
-    // again).  Same arithmetic as one ql! (LAPACK's right-to-left order restricted to column blocks); finished panels stream
-    // home behind the computation in both factorizations.  Option "host_split" = 0 falls back to the chunk-joining schedule.
-    // "host_split" = 2 (default) picks per call: the split schedule while the previous call's first upload ran at PCIe speed,
-    // the chunk-joining schedule (which hides a slow upload better: 8 GPUs uploading at once share the host's memory system)
-    // while it did not.  Both schedules time their first upload piece, so the choice follows the load.
-    const bool split_now = h->opt_host_split == 1 ||
-                           (h->opt_host_split == 2 && (h->h2d_gbps == 0.0 || h->h2d_gbps >= (double)h->opt_host_split_gbps));
+    // ql! of a large matrix: the matrix streams IN chunk by chunk while the right-hand panels are already being factored,
+    // and the finished panels stream OUT while the rest is still being factored -- both PCIe transfers disappear behind the
+    // computation (except the first chunk and the last panel).  Three schedules, option "host_split":
+    // "host_split" = 2 (default): the chunks join the LOOK-AHEAD factorization itself (blocked.cu): one ql! with the
+    // device-resident schedule, the upload hidden behind it except for the first chunk, finished panels streaming home.
+    // (1 = the split schedule below, 0 = the chunk-joining schedule without look-ahead: both kept for comparison;
+    // n = 16384 from pinned memory: 251 / 274 / 284 ms on an idle host, 325-330 / 382 / 348 ms with 8 GPUs uploading at once)
+    if (f == geqlf_dev_graph && h->opt_host_split == 2 && h->gc_ok && h->opt_lookahead == 2 && m >= n && n >= h->opt_host_split_min &&
+        h->opt_tcache && qlb_lookahead_active(h, m, n)) {
+        const int64_t ldd = (m + 1) & ~(int64_t)1;
+        rc = qlb_reserve(h, &h->stage, &h->stage_bytes, (size_t)ldd * n * sizeof(double));
+        if (!rc) rc = qlb_reserve(h, &h->stage2, &h->stage2_bytes, (size_t)k * sizeof(double));
+        if (rc) return rc;
+        double *dA = (double *)h->stage, *dtau = (double *)h->stage2;
+        // everything up to "all panels are home" on the handle's streams (the copy stream joins the main stream at the end)
+        auto enqueue = [&]() -> int {
+            h->h2d.host = A; h->h2d.host_ld = lda; h->h2d.la = true;
+            h->d2h.host = A; h->d2h.host_ld = lda; h->d2h.la = true; h->d2h.rows = m;
+            h->up_bytes = 0.0;
+            int r = qlb_dgeqlf_dev(h, m, n, dA, ldd, dtau);
+            h->h2d.host = nullptr; h->h2d.la = false;
+            h->d2h.host = nullptr; h->d2h.la = false; h->d2h.rows = 0;
+            if (r) return r;
+            QLB_CUDA(h, cudaEventRecord(h->ev_home, h->copy_stream));
+            QLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_home, 0));
+            return 0;
+        };
+        auto finish = [&]() -> int {
+            QLB_CUDA(h, cudaMemcpyAsync(tau, dtau, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            QLB_CUDA(h, cudaStreamSynchronize(h->stream));
+            return 0;
+        };
+        auto plain = [&]() -> int {
+            int r = enqueue();
+            if (r) {
+                cudaStreamSynchronize(h->h2d_stream);
+                cudaStreamSynchronize(h->copy_stream);
+                return r;
+            }
+            r = finish();
+            if (!r) note_upload_rate(h);
+            return r;
+        };
+        // The same call again (same pinned host matrix, same options): the whole schedule -- uploads, both partitions' kernels,
+        // downloads -- is replayed as ONE CUDA graph; ~1000 launches on two streams otherwise cost ~11 ms of a 262 ms call.
+        cudaPointerAttributes pa;
+        bool pinned = cudaPointerGetAttributes(&pa, A) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        (void)cudaGetLastError();
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        bool usable = pinned && h->opt_graph && h->opt_la_graph && !h->opt_profile && h->stream != nullptr;
+        if (usable && (cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)) {
+            (void)cudaGetLastError();
+            usable = false;
+        }
+        if (!usable) return plain();
+        auto make_key = [&](int64_t *key) {
+            const int64_t v[14] = {m, n, (int64_t)(uintptr_t)A, lda, (int64_t)(uintptr_t)dA, (int64_t)(uintptr_t)dtau, (int64_t)qlb_effective_nb(h, m, n),
+                                   h->opt_strip_rpt * 16 + h->opt_lookahead, h->opt_gemm_cfg * 16 + h->opt_trail_splits, (int64_t)(uintptr_t)h->stream,
+                                   1 + 2 * h->opt_overlap_t + 4 * h->opt_tcache + 32 * h->opt_la_gemm_all, h->opt_chunk_cols,
+                                   h->opt_la_join_ramp * 64 + h->opt_la_join_chunks, (int64_t)(uintptr_t)h->tcache};
+            memcpy(key, v, sizeof(v));
+        };
+        int64_t key[14];
+        make_key(key);
+        auto mark_cache = [&]() -> int {       // the replay refills the T cache of exactly this factorization
+            if (h->opt_tcache && h->tcache) {
+                h->tc_key[0] = (int64_t)(uintptr_t)dA; h->tc_key[1] = ldd; h->tc_key[2] = (int64_t)(uintptr_t)dtau;
+                h->tc_key[3] = m; h->tc_key[4] = k; h->tc_key[5] = qlb_effective_nb(h, m, n);
+                h->tc_valid = true;
+                QLB_CUDA(h, cudaEventRecord(h->ev_tc, h->stream));
+            }
+            return 0;
+        };
+        if (h->hgraph_exec && !memcmp(key, h->hgraph_key, sizeof(key))) {
+            QLB_CUDA(h, cudaGraphLaunch(h->hgraph_exec, h->stream));
+            h->launches += h->hgraph_nodes;
+            rc = mark_cache();
+            return rc ? rc : finish();
+        }
+        if (memcmp(key, h->hgraph_seen_key, sizeof(key))) {          // first sight: plain launches (allocations, attributes, upload rate)
+            rc = plain();
+            if (!rc) make_key(h->hgraph_seen_key);                  // (the T cache may have been allocated by this very call)
+            return rc;
+        }
+        if (h->hgraph_exec) {
+            cudaGraphExecDestroy(h->hgraph_exec);
+            h->hgraph_exec = nullptr;
+        }
+        const int64_t l0 = h->launches;
+        QLB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc || e != cudaSuccess || !graph) {
+            (void)cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            h->launches = l0;
+            if (rc) return rc;
+            return plain();                                          // capture refused
+        }
+        e = cudaGraphInstantiate(&h->hgraph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            h->hgraph_exec = nullptr;
+            h->launches = l0;
+            return plain();
+        }
+        h->hgraph_nodes = h->launches - l0;
+        memcpy(h->hgraph_key, key, sizeof(key));
+        QLB_CUDA(h, cudaGraphLaunch(h->hgraph_exec, h->stream));
+        rc = mark_cache();
+        return rc ? rc : finish();
+    }
+    // "host_split" = 1, SPLIT schedule.  The right quarter of the columns is uploaded and factored first (look-ahead ql! of the
+    // m x wR block) while the rest is still on its way; then Q_R' is applied to the left part (blocked ormql with the cached T
+    // factors, all SMs), then the leading (m - wR) x wL block is factored (look-ahead again).  Same arithmetic as one ql!
+    // (LAPACK's right-to-left order restricted to column blocks); finished panels stream home in both factorizations.
+    const bool split_now = h->opt_host_split == 1;
     if (f == geqlf_dev_graph && split_now && h->gc_ok && h->opt_lookahead == 2 && m >= n && n >= h->opt_host_split_min && h->opt_tcache &&
         (h->opt_host_split_chunk == 0 || n <= 31 * h->opt_host_split_chunk)) {      // (one event per chunk)
         const int64_t ldd = (m + 1) & ~(int64_t)1;
@@ -775,6 +888,7 @@ static int fact_host(qlb200_ctx *h, fact_fn f, int64_t m, int64_t n, double *A, 
             rc = qlb_dgeqlf_dev(h, m - wR, wL, dA, ldd, dtau);
             h->d2h.host = nullptr;
         }
+
         h->d2h.la = false;
         h->d2h.rows = 0;
         h->tc_valid = false;                 // the cache now holds the T factors of the leading block only

@@ -34,14 +34,20 @@ struct qlb200_ctx {
     struct {
         const double *host = nullptr;      // source (column-major, ld = host_ld); null = the matrix is already on the device
         int64_t host_ld = 0;
+        bool la = false;                   // chunks join the LOOK-AHEAD schedule (tall/square, SM partitions, T cache)
     } h2d;
-    int64_t opt_host_split = 2;            // host-pointer ql!, large tall/square matrices: split schedule (capi.cu fact_host); 2: by upload rate
-    int64_t opt_host_split_gbps = 40;      // host_split = 2: split schedule only while the last upload ran at least this fast (GB/s)
+    cudaGraphExec_t hgraph_exec = nullptr;  // host-pointer ql! (look-ahead joining schedule, pinned host memory) as a CUDA graph
+    int64_t hgraph_key[14] = {0}, hgraph_seen_key[14] = {0}, hgraph_nodes = 0;
+    cudaEvent_t ev_home = nullptr;         // copy stream -> main stream join at the end of a host-pointer ql!
+    void *joinV = nullptr;                 // clean reflectors of an already factored panel while a late chunk catches up
+    size_t joinV_bytes = 0;
+    int64_t opt_host_split = 2;            // host-pointer ql!, large tall/square matrices: 2 chunks join the look-ahead ql!, 1 split schedule, 0 chunk-joining without look-ahead (capi.cu fact_host)
     int64_t opt_host_split_chunk = 0;      // ... left part uploaded and multiplied in chunks of this many columns (0: one piece)
     int64_t opt_host_split_min = 8192;     // ... from this number of columns on
     int64_t opt_stream_in = 1;
     int64_t opt_chunk_cols = 1024;         // columns per H2D chunk
     int64_t opt_batch_chunk_mb = 32;       // host-pointer batched calls: operand megabytes per pipeline chunk (0: no chunking)
+    int64_t opt_la_join_ramp = 4, opt_la_join_chunks = 2;   // look-ahead host schedule: one chunk per panel for the first .. panels, then .. per panel
     int64_t opt_join_step = 1;             // panels factored per arriving chunk before the next chunk joins
     void *ws = nullptr;                    // device workspace (grown on demand)
     size_t ws_bytes = 0;

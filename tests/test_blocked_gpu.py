@@ -355,34 +355,81 @@ def test_host_pointer_ql_split_schedule(q, h, shape, split_min):
     assert np.abs(F.factors - F0.factors).max() <= tol and np.abs(F.tau - F0.tau).max() <= 50 * max(m, n) * EPS
 
 
-def test_host_pointer_ql_schedule_follows_upload_rate(q, h):
-    """host_split = 2 (the default): the first large host-pointer ql! runs the split schedule and times its first upload piece;
-    the next call runs the split schedule only if that rate reached "host_split_gbps", else the chunk-joining schedule (which
-    hides a slow upload better).  Both schedules are deterministic, so which one ran is visible bit for bit."""
-    n = 2304
-    A = np.asfortranarray(np.random.default_rng(77).standard_normal((n, n)))
-    h.set_option("host_split_min", 1024)
+@pytest.mark.parametrize("shape,cw,ramp,jc", [((2500, 2500), 512, 4, 2), ((3000, 2100), 1024, 4, 2), ((5000, 4600), 512, 2, 3),
+                                              ((4096, 4096), 1024, 64, 1), ((8192, 8192), 1024, 4, 2)])
+def test_host_pointer_ql_chunks_join_the_lookahead(q, h, shape, cw, ramp, jc):
+    """Default host-pointer schedule for large tall/square matrices (host_split = 2): column chunks are uploaded right to left
+    and JOIN the look-ahead factorization (blocked.cu) -- a late chunk first catches up with the panels factored so far (clean V
+    from the packed factors, cached T) and then takes part in the trailing updates; finished panels stream home.  Per column the
+    same sequence of block reflectors as LAPACK dgeqlf, so: the parity bar against dgeqlf, agreement with the schedule without
+    look-ahead, lda > m respected, and lmul! right after (validated T cache of the streamed factorization)."""
+    m, n = shape
+    rng = np.random.default_rng(m + 3 * n)
+    lda = m + 5
+    buf = np.zeros((lda, n), order="F")
+    buf[:m, :] = rng.standard_normal((m, n))
+    A = buf[:m, :]
+    for name, v in (("host_split_min", 1024), ("la_min", 1024), ("chunk_cols", cw), ("la_join_ramp", ramp), ("la_join_chunks", jc),
+                    ("host_split", 2)):
+        h.set_option(name, v)
     try:
-        h.set_option("host_split", 1)
-        F_split = q.ql(A, handle=h)
+        F = q.ql_(np.asfortranarray(A.copy()), handle=h)
+        assert h.upload_rate() > 0.1
+        B = np.asfortranarray(rng.standard_normal((m, 3)))
+        QtB = q.lmul_(F.Q.T, B.copy(order="F"))
+        Fv = buf.copy(order="F")
+        Av = Fv[:m, :]
+        q.ql_(Av, handle=h)                                   # a view with lda > m
         h.set_option("host_split", 0)
-        F_chunk = q.ql(A, handle=h)
-        assert not np.array_equal(F_split.factors, F_chunk.factors)        # (different blockings: rounding differs)
-        h.set_option("host_split", 2)                                      # resets the measured rate
-        assert h.upload_rate() == 0.0
-        h.set_option("host_split_gbps", 10 ** 6)                           # no PCIe link is this fast
-        F1 = q.ql(A, handle=h)
-        assert h.upload_rate() > 0.5
-        F2 = q.ql(A, handle=h)
-        assert np.array_equal(F1.factors, F_split.factors) and np.array_equal(F2.factors, F_chunk.factors)
-        assert h.upload_rate() > 0.5                                       # the chunk-joining schedule measures too
-        h.set_option("host_split_gbps", 0)
-        F3 = q.ql(A, handle=h)
-        assert np.array_equal(F3.factors, F_split.factors) and np.array_equal(F3.tau, F_split.tau)
+        F0 = q.ql(np.asfortranarray(A.copy()), handle=h)
     finally:
-        h.set_option("host_split_min", 8192)
-        h.set_option("host_split_gbps", 40)
-        h.set_option("host_split", 2)
+        for name, v in (("host_split_min", 8192), ("la_min", 4096), ("chunk_cols", 1024), ("la_join_ramp", 4), ("la_join_chunks", 2),
+                        ("host_split", 2)):
+            h.set_option(name, v)
+    lapack.set_num_threads(16)
+    Fo, tauo = lapack.geqlf(np.asfortranarray(A.copy()))
+    tol = 50 * max(m, n) * EPS * np.linalg.norm(A)
+    assert np.abs(F.tau - tauo).max() <= 50 * max(m, n) * EPS
+    assert np.abs(F.factors - Fo).max() <= tol
+    assert np.array_equal(Av, F.factors) and np.all(Fv[m:, :] == 0.0)
+    assert np.abs(F.factors - F0.factors).max() <= tol and np.abs(F.tau - F0.tau).max() <= 50 * max(m, n) * EPS
+    ref = lapack.ormql("L", "T", Fo, tauo, B.copy(order="F"))
+    assert np.abs(QtB - ref).max() <= 50 * max(m, n) * EPS * np.linalg.norm(B)
+
+
+def test_host_pointer_ql_pinned_matrix_replays_as_a_graph(q, h):
+    """The same large host-pointer ql! again on the same PINNED matrix: first call plain launches, second call captured
+    (uploads, both SM partitions' kernels, downloads) and launched as one CUDA graph, then replays.  Every call must leave the
+    same bits (the joining schedule is fixed, not timing-driven) and follow new CONTENT in the same buffer; a pageable matrix
+    never takes the graph and gives the same bits too."""
+    import torch
+    n = 2304
+    rng = np.random.default_rng(5)
+    hp = torch.empty((n, n), dtype=torch.float64, pin_memory=True)          # column-major n x n through the transpose view
+    Ah = hp.numpy().T
+    A1, A2 = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    for name, v in (("host_split_min", 1024), ("la_min", 1024), ("chunk_cols", 512)):
+        h.set_option(name, v)
+    try:
+        outs = []
+        for A in (A1, A1, A1, A2, A1):
+            Ah[...] = A
+            l0 = h.launches
+            F = q.ql_(Ah, handle=h)
+            assert h.launches > l0
+            outs.append((F.factors.copy(), F.tau.copy()))
+        Fp = q.ql(np.asfortranarray(A1), handle=h)                          # pageable copy: plain launches, same schedule
+    finally:
+        for name, v in (("host_split_min", 8192), ("la_min", 4096), ("chunk_cols", 1024)):
+            h.set_option(name, v)
+    for k in (1, 2, 4):
+        assert np.array_equal(outs[0][0], outs[k][0]) and np.array_equal(outs[0][1], outs[k][1])
+    assert np.array_equal(outs[0][0], Fp.factors) and np.array_equal(outs[0][1], Fp.tau)
+    lapack.set_num_threads(16)
+    for A, (Fa, ta) in ((A1, outs[0]), (A2, outs[3])):
+        Fo, tauo = lapack.geqlf(np.asfortranarray(A.copy()))
+        assert np.abs(ta - tauo).max() <= 50 * n * EPS
+        assert np.abs(Fa - Fo).max() <= 50 * n * EPS * np.linalg.norm(A)
 
 
 def _scaled_cmp(F, tau, Fo, tauo, A, k_rows_are_reflectors=False):

@@ -1,4 +1,4 @@
-"""e2e (host pointers, pinned memory) timing of ql! n=16384: split schedule vs the chunk-joining schedule (run under gpurun)."""
+"""e2e (host pointers, pinned memory) timing of ql! n=16384: the three host schedules of capi.cu fact_host (run under gpurun)."""
 import os, sys, time, json
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,11 +9,15 @@ q = load_package(); h = q.Handle(0)
 hp = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
 src = torch.randn((n, n), dtype=torch.float64)
 Ah = hp.numpy().T
-for split, cw in ((1, 0), (0, 0), (1, 6144), (1, 4096), (1, 2048), (1, 0)):
-    h.set_option("host_split", split); h.set_option("host_split_chunk", cw)
+for split, cw, ramp, jc in ((2, 1024, 4, 2), (1, 1024, 4, 2), (0, 1024, 4, 2)):
+    h.set_option("host_split", split); h.set_option("chunk_cols", cw); h.set_option("la_join_ramp", ramp); h.set_option("la_join_chunks", jc)
     ts = []
-    for i in range(3):
+    first = None
+    for i in range(5):
         hp.copy_(src); torch.cuda.synchronize()
-        t0 = time.perf_counter(); q.ql_(Ah, handle=h); ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); F = q.ql_(Ah, handle=h); ts.append(time.perf_counter() - t0)
+        if i == 0: first = (hp[:64].clone(), hp[-64:].clone(), F.tau.copy())
+        else: assert torch.equal(first[0], hp[:64]) and torch.equal(first[1], hp[-64:]) and (first[2] == F.tau).all(), "replay differs"
+    print([round(x * 1e3, 1) for x in ts], h.launches)
     t = min(ts[1:])
-    print(json.dumps({"n": n, "host_split": split, "chunk": cw, "ms": t * 1e3, "tflops": 4 / 3 * n ** 3 / t / 1e12}), flush=True)
+    print(json.dumps({"n": n, "host_split": split, "chunk": cw, "ramp": ramp, "jc": jc, "ms": t * 1e3, "tflops": 4 / 3 * n ** 3 / t / 1e12}), flush=True)

@@ -14,7 +14,7 @@ hp = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
 src = torch.randn((n, n), dtype=torch.float64)
 Ah = hp.numpy().T
 flag = torch.zeros(1, device="cuda")
-for split, cw in [tuple(int(x) for x in a.split(":")) for a in sys.argv[1:]] or ((1, 0), (0, 0), (2, 0)):
+for split, cw in [tuple(int(x) for x in a.split(":")) for a in sys.argv[1:]] or ((2, 0), (1, 0), (0, 0)):
     h.set_option("host_split", split); h.set_option("host_split_chunk", cw)
     ts = []
     for i in range(4):
