@@ -13,6 +13,7 @@
 //                     forward substitution with L = tril(factors).
 //   qlb_dgerqf_dev    rq!(A) (reference src/rq.jl:401) through gerqf(A) = geqlf(A')' (SURVEY.md A.4).
 #include "common.cuh"
+#include <vector>
 #include "internal.h"
 
 namespace qlb {
@@ -596,6 +597,9 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
     QLB_CUDA(h, cudaEventRecord(evP, P));
     rc = send_home(0);
     if (rc) return rc;
+    const bool trace = getenv("QLB_LA_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e_; cudaEventCreate(&e_); cudaEventRecord(e_, s_); tev.push_back(e_); } };
     for (int j = 0; j < npanels; ++j) {
         const int c1 = panel_c1(j), c0 = panel_c0(j), ib = c1 - c0, p = m - n + c1;
         double *V = Vb[j & 1], *T = Tslot(j);
@@ -613,15 +617,20 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             if (rc) return rc;
         }
         const int lo_all = joined_lo;               // columns [lo_all, c0) are updated by panel j
+        mark(G);                                                // [5j+0] G free (previous rest update done)
         QLB_CUDA(h, cudaStreamWaitEvent(G, evP, 0));            // panel j (V, T) is complete
         if (j + 1 < npanels) {
             const int d0 = panel_c0(j + 1);          // next panel = columns [d0, c0)
+            mark(G);                                            // [5j+1] G starts (panel j arrived)
             rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)d0 * lda, lda, c0 - d0, nullptr, smsG);
             if (rc) return rc;
             QLB_CUDA(h, cudaEventRecord(evN, G));
+            mark(G);                                            // [5j+2] next-panel update done
             QLB_CUDA(h, cudaStreamWaitEvent(P, evN, 0));
+            mark(P);                                            // [5j+3] P starts panel j+1
             rc = factor_panel(h, P, ws2, A, lda, m, n, k, d0, c0, tau, Vb[(j + 1) & 1], ws.ldv, Tslot(j + 1), nb, d0 > 0 || tcache != nullptr, smsP);
             if (rc) return rc;
+            mark(P);                                            // [5j+4] P done
             QLB_CUDA(h, cudaEventRecord(evP, P));
             rc = send_home(j + 1);
             if (rc) return rc;
@@ -633,6 +642,22 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)lo_all * lda, lda, c0 - lo_all, nullptr, smsG);
             if (rc) return rc;
         }
+    }
+    if (trace) {
+        mark(G);
+        cudaDeviceSynchronize();
+        double gwait = 0, small = 0, ptime = 0, rest = 0;
+        for (int j = 0; j + 1 < npanels; ++j) {
+            float a_, b_, c_, d_;
+            cudaEventElapsedTime(&a_, tev[5 * j], tev[5 * j + 1]);          // G waiting for panel j
+            cudaEventElapsedTime(&b_, tev[5 * j + 1], tev[5 * j + 2]);      // next-panel update
+            cudaEventElapsedTime(&c_, tev[5 * j + 3], tev[5 * j + 4]);      // panel j+1 on P
+            cudaEventElapsedTime(&d_, tev[5 * j + 2], tev[5 * (j + 1)]);    // rest update
+            gwait += a_; small += b_; ptime += c_; rest += d_;
+            if (j % 8 == 0 || j + 2 >= npanels) fprintf(stderr, "it %3d  Gwait %.3f  next-panel upd %.3f  panel(P) %.3f  rest upd %.3f ms\n", j, a_, b_, c_, d_);
+        }
+        fprintf(stderr, "sum: Gwait %.2f  next-panel upd %.2f  panels %.2f  rest upd %.2f ms\n", gwait, small, ptime, rest);
+        for (auto e_ : tev) cudaEventDestroy(e_);
     }
     // the caller's stream continues after both partitions (P's last event was already waited for by G)
     if (G != st) {
