@@ -69,7 +69,9 @@ double qlb200_upload_rate(qlb200_handle h);
 int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_total, int64_t *launches);
 /* Tunables: "nb" (panel width, multiple of 16 in [16,256]; 0 = auto: 192 for look-ahead ql! with min(m,n) >= 14336, else 128),
  * "lookahead" (2 = default: ql!/ul!/complex ql! factor the next panel on a 16-SM green-context partition while the other SMs apply
- * the previous one, for large matrices; 1 = always; 0 = sequential schedule), "la_min", "host_split" / "host_split_min" (host-pointer ql! of large
+ * the previous one, for large matrices; 1 = always; 0 = sequential schedule), "la_min", "la_pnarrow_min" (8192: while the next panel
+ * starts at or right of this column the panel partition also applies the finished panel to the next panel's columns, so the update
+ * partition runs nothing but the big GEMMs; 0 = never), "host_split" / "host_split_min" (host-pointer ql! of large
  * tall/square matrices, see DESIGN.md 6: 2 = default, the uploaded column chunks join the look-ahead factorization itself -- and a
  * repeated call on the same PINNED host matrix replays the whole upload | factor | download schedule as one CUDA graph; 1 = split
  * schedule; 0 = chunk-joining without look-ahead; "chunk_cols", "la_join_ramp", "la_join_chunks" tune the default schedule),

@@ -617,16 +617,29 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
             if (rc) return rc;
         }
         const int lo_all = joined_lo;               // columns [lo_all, c0) are updated by panel j
+        // While the trailing update is long (many columns left), the panel partition is far ahead of the update partition:
+        // it then also applies panel j to the columns of panel j+1 itself (16 SMs: slower, but off the update partition's
+        // critical path -- that one runs nothing but the big GEMMs, back to back, with no G -> P -> G round trip per panel).
+        // It must see panel j-1 applied to those columns first (event evR of the previous rest update).
+        const bool pnarrow = gc && j + 1 < npanels && h->opt_la_pnarrow_min > 0 && panel_c0(j + 1) >= h->opt_la_pnarrow_min;
+        if (hsrc && pnarrow) QLB_CUDA(h, cudaEventRecord(h->ev_join, G));      // (late chunks have caught up on G)
         mark(G);                                                // [5j+0] G free (previous rest update done)
         QLB_CUDA(h, cudaStreamWaitEvent(G, evP, 0));            // panel j (V, T) is complete
         if (j + 1 < npanels) {
             const int d0 = panel_c0(j + 1);          // next panel = columns [d0, c0)
             mark(G);                                            // [5j+1] G starts (panel j arrived)
-            rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)d0 * lda, lda, c0 - d0, nullptr, smsG);
-            if (rc) return rc;
-            QLB_CUDA(h, cudaEventRecord(evN, G));
+            if (pnarrow) {
+                if (j > 0) QLB_CUDA(h, cudaStreamWaitEvent(P, h->ev_rest[(j - 1) & 1], 0));
+                if (hsrc) QLB_CUDA(h, cudaStreamWaitEvent(P, h->ev_join, 0));
+                rc = apply_block(h, P, ws2, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)d0 * lda, lda, c0 - d0, nullptr, smsP);
+                if (rc) return rc;
+            } else {
+                rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)d0 * lda, lda, c0 - d0, nullptr, smsG);
+                if (rc) return rc;
+                QLB_CUDA(h, cudaEventRecord(evN, G));
+                QLB_CUDA(h, cudaStreamWaitEvent(P, evN, 0));
+            }
             mark(G);                                            // [5j+2] next-panel update done
-            QLB_CUDA(h, cudaStreamWaitEvent(P, evN, 0));
             mark(P);                                            // [5j+3] P starts panel j+1
             rc = factor_panel(h, P, ws2, A, lda, m, n, k, d0, c0, tau, Vb[(j + 1) & 1], ws.ldv, Tslot(j + 1), nb, d0 > 0 || tcache != nullptr, smsP);
             if (rc) return rc;
@@ -638,6 +651,7 @@ int qlb_dgeqlf_dev(qlb200_ctx *h, int64_t m64, int64_t n64, double *A, int64_t l
                 rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)lo_all * lda, lda, d0 - lo_all, nullptr, smsG);
                 if (rc) return rc;
             }
+            QLB_CUDA(h, cudaEventRecord(h->ev_rest[j & 1], G));
         } else if (c0 > lo_all) {
             rc = apply_block(h, G, ws, true, false, V, ws.ldv, T, nb, p, ib, A + (int64_t)lo_all * lda, lda, c0 - lo_all, nullptr, smsG);
             if (rc) return rc;

@@ -108,6 +108,8 @@ int qlb200_create(qlb200_handle *out, int device) {
     for (int i = 0; i < 32; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) QLB_CUDA(h, cudaEventCreate(&h->ev_up[i]));
     QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_home, cudaEventDisableTiming));
+    QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_rest[i], cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) QLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_panel[i], cudaEventDisableTiming));
     QLB_CUDA(h, cudaMalloc(&h->dinfo, 64 + 256 * sizeof(unsigned)));      // status word + per-SM tickets
     QLB_CUDA(h, cudaMemset(h->dinfo, 0, 64 + 256 * sizeof(unsigned)));
@@ -140,6 +142,9 @@ int qlb200_destroy(qlb200_handle h) {
     if (h->joinV) cudaFree(h->joinV);
     if (h->hgraph_exec) cudaGraphExecDestroy(h->hgraph_exec);
     if (h->ev_home) cudaEventDestroy(h->ev_home);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (int i = 0; i < 2; ++i)
+        if (h->ev_rest[i]) cudaEventDestroy(h->ev_rest[i]);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->prof_ev) {
         for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
@@ -241,6 +246,10 @@ int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
         h->opt_overlap_t = value ? 1 : 0;
     } else if (!strcmp(name, "ul_cluster")) {
         h->opt_ul_cluster = value ? 1 : 0;
+    } else if (!strcmp(name, "la_pnarrow_min")) {
+        if (value < 0) return qlb_fail(h, -3, "la_pnarrow_min must be >= 0%s");
+        h->opt_la_pnarrow_min = value;
+        h->graph_key[0] = 0; h->graph_seen_key[0] = 0; h->hgraph_key[0] = 0; h->hgraph_seen_key[0] = 0;
     } else if (!strcmp(name, "la_join_ramp")) {
         if (value < 0 || value > 64) return qlb_fail(h, -3, "la_join_ramp must be in [0,64]%s");
         h->opt_la_join_ramp = value;

@@ -38,6 +38,8 @@ struct qlb200_ctx {
     } h2d;
     cudaGraphExec_t hgraph_exec = nullptr;  // host-pointer ql! (look-ahead joining schedule, pinned host memory) as a CUDA graph
     int64_t hgraph_key[14] = {0}, hgraph_seen_key[14] = {0}, hgraph_nodes = 0;
+    cudaEvent_t ev_rest[2] = {nullptr, nullptr}, ev_join = nullptr;   // look-ahead: "rest update j done" (ring of 2), "late chunks joined"
+    int64_t opt_la_pnarrow_min = 8192;     // look-ahead: the panel partition updates the next panel's columns itself while that panel starts at or right of this column
     cudaEvent_t ev_home = nullptr;         // copy stream -> main stream join at the end of a host-pointer ql!
     void *joinV = nullptr;                 // clean reflectors of an already factored panel while a late chunk catches up
     size_t joinV_bytes = 0;
