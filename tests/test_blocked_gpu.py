@@ -355,14 +355,16 @@ def test_host_pointer_ql_split_schedule(q, h, shape, split_min):
     assert np.abs(F.factors - F0.factors).max() <= tol and np.abs(F.tau - F0.tau).max() <= 50 * max(m, n) * EPS
 
 
-@pytest.mark.parametrize("shape,cw,ramp,jc", [((2500, 2500), 512, 4, 2), ((3000, 2100), 1024, 4, 2), ((5000, 4600), 512, 2, 3),
-                                              ((4096, 4096), 1024, 64, 1), ((8192, 8192), 1024, 4, 2)])
-def test_host_pointer_ql_chunks_join_the_lookahead(q, h, shape, cw, ramp, jc):
+@pytest.mark.parametrize("shape,cw,ramp,jc,pn", [((2500, 2500), 512, 4, 2, 8192), ((3000, 2100), 1024, 4, 2, 8192), ((5000, 4600), 512, 2, 3, 8192),
+                                                 ((4096, 4096), 1024, 64, 1, 8192), ((8192, 8192), 1024, 4, 2, 8192),
+                                                 ((2500, 2500), 512, 4, 2, 1), ((5000, 4600), 512, 2, 3, 2048), ((4096, 4096), 1024, 4, 2, 1024)])
+def test_host_pointer_ql_chunks_join_the_lookahead(q, h, shape, cw, ramp, jc, pn):
     """Default host-pointer schedule for large tall/square matrices (host_split = 2): column chunks are uploaded right to left
     and JOIN the look-ahead factorization (blocked.cu) -- a late chunk first catches up with the panels factored so far (clean V
     from the packed factors, cached T) and then takes part in the trailing updates; finished panels stream home.  Per column the
     same sequence of block reflectors as LAPACK dgeqlf, so: the parity bar against dgeqlf, agreement with the schedule without
-    look-ahead, lda > m respected, and lmul! right after (validated T cache of the streamed factorization)."""
+    look-ahead, lda > m respected, and lmul! right after (validated T cache of the streamed factorization).  pn =
+    "la_pnarrow_min": with the next-panel update on the panel partition, that partition also has to wait for the joins."""
     m, n = shape
     rng = np.random.default_rng(m + 3 * n)
     lda = m + 5
@@ -370,7 +372,7 @@ def test_host_pointer_ql_chunks_join_the_lookahead(q, h, shape, cw, ramp, jc):
     buf[:m, :] = rng.standard_normal((m, n))
     A = buf[:m, :]
     for name, v in (("host_split_min", 1024), ("la_min", 1024), ("chunk_cols", cw), ("la_join_ramp", ramp), ("la_join_chunks", jc),
-                    ("host_split", 2)):
+                    ("host_split", 2), ("la_pnarrow_min", pn)):
         h.set_option(name, v)
     try:
         F = q.ql_(np.asfortranarray(A.copy()), handle=h)
@@ -384,7 +386,7 @@ def test_host_pointer_ql_chunks_join_the_lookahead(q, h, shape, cw, ramp, jc):
         F0 = q.ql(np.asfortranarray(A.copy()), handle=h)
     finally:
         for name, v in (("host_split_min", 8192), ("la_min", 4096), ("chunk_cols", 1024), ("la_join_ramp", 4), ("la_join_chunks", 2),
-                        ("host_split", 2)):
+                        ("host_split", 2), ("la_pnarrow_min", 8192)):
             h.set_option(name, v)
     lapack.set_num_threads(16)
     Fo, tauo = lapack.geqlf(np.asfortranarray(A.copy()))
@@ -586,11 +588,13 @@ def test_t_cache_is_validated_by_content(q, h):
     assert np.abs(got - ref).max() <= 50 * n * EPS * np.abs(Bh).max() * np.sqrt(n)
 
 
-@pytest.mark.parametrize("n,la", [(2304, 1), (700, 1), (4608, 2)])
-def test_lookahead_ql_plain_captured_and_replayed_agree(q, h, n, la):
+@pytest.mark.parametrize("n,la,pn", [(2304, 1, 8192), (700, 1, 8192), (4608, 2, 8192), (2304, 1, 1), (4608, 2, 2048), (1100, 1, 512)])
+def test_lookahead_ql_plain_captured_and_replayed_agree(q, h, n, la, pn):
     """The look-ahead ql! (panel j+1 factored on the panel SM partition while the GEMM partition applies panel j) called three
     times on the same buffers: plain launches, graph capture, graph replay -- bitwise the same factors, LAPACK parity, and
-    the same bits as a fresh handle (the schedule is fixed: no run-to-run variation)."""
+    the same bits as a fresh handle (the schedule is fixed: no run-to-run variation).  pn = "la_pnarrow_min": while the next
+    panel starts at or right of that column the PANEL partition applies the finished panel to the next panel's columns itself
+    (1: for every panel; 8192: never at these sizes; in between: the hand-over inside one factorization)."""
     import torch
 
     g = torch.Generator(device="cuda").manual_seed(n)
@@ -598,6 +602,7 @@ def test_lookahead_ql_plain_captured_and_replayed_agree(q, h, n, la):
     buf = torch.empty((n, n), dtype=torch.float64, device="cuda").T
     outs = []
     h.set_option("lookahead", la)
+    h.set_option("la_pnarrow_min", pn)
     try:
         for _ in range(3):
             buf.T.copy_(A.T)
@@ -606,6 +611,7 @@ def test_lookahead_ql_plain_captured_and_replayed_agree(q, h, n, la):
             outs.append((F.factors.clone(), F.tau.clone()))
     finally:
         h.set_option("lookahead", 2)
+        h.set_option("la_pnarrow_min", 8192)
     for f, t in outs[1:]:
         assert torch.equal(f, outs[0][0]) and torch.equal(t, outs[0][1])
     Ah = np.asfortranarray(A.cpu().numpy())
