@@ -130,6 +130,9 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     // in-panel strip update: many thin partials, fused reduce*T (that kernel reads only the lower triangle of T: not for the
     // real block form of a complex T, whose 2x2 diagonal blocks reach above the diagonal)
     const bool small = ib <= 16 && other <= 256 && !dense_T;
+    // "profile" option: the big block updates on the update partition (or the whole GPU) are the timed kernel; the panel
+    // partition's GEMMs run concurrently with them and are not part of that roofline
+    const bool timed = ib > 16 && 2 * sms >= h->sm_count;
     const int cfg_w = ib <= 16 ? 2 : -1;
     // 1. W partials: M = other, N = ib, K = p
     const int64_t tiles = (int64_t)((other + 127) / 128) * ((ib + 63) / 64);      // 128x64 tiles, 2 CTAs per SM
@@ -151,7 +154,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
     double *Wdst = to_part ? ws.part : ws.Wsum;
     int rc;
     {
-        QlbProfScope prof(h, st, ib > 16 ? 2.0 * other * ib * p : 0.0);
+        QlbProfScope prof(h, st, timed ? 2.0 * other * ib * p : 0.0);
         rc = qlb_gemm(h, st, cfg_w, /*akc=*/left, /*bkc=*/true, other, ib, p, 1.0, C, ldc, V, ldv, 0.0, Wdst, ldp, S, stride);
     }
     if (rc) return rc;
@@ -169,7 +172,7 @@ static int apply_block(qlb200_ctx *h, cudaStream_t st, const Workspace &ws, bool
         if (rc) return rc;
     }
     // 3. C += V W2' (left)  or  C += W2 V' (right), W2 already negated
-    QlbProfScope prof(h, st, ib > 16 ? 2.0 * other * ib * p : 0.0);
+    QlbProfScope prof(h, st, timed ? 2.0 * other * ib * p : 0.0);
     if (left) return qlb_gemm(h, st, -1, false, false, p, other, ib, 1.0, V, ldv, ws.W2, ws.ldw, 1.0, C, ldc, 1, 0);
     return qlb_gemm(h, st, -1, false, false, other, p, ib, 1.0, ws.W2, ws.ldw, V, ldv, 1.0, C, ldc, 1, 0);
 }

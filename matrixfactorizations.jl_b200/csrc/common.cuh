@@ -184,6 +184,12 @@ static inline int qlb_reserve(qlb200_ctx *h, void **buf, size_t *have, size_t ne
     }
     memset(h->graph_key, 0, sizeof(h->graph_key));
     memset(h->graph_seen_key, 0, sizeof(h->graph_seen_key));
+    if (h->hgraph_exec) {                  // ... and so does the host-pointer schedule's graph
+        cudaGraphExecDestroy(h->hgraph_exec);
+        h->hgraph_exec = nullptr;
+    }
+    memset(h->hgraph_key, 0, sizeof(h->hgraph_key));
+    memset(h->hgraph_seen_key, 0, sizeof(h->hgraph_seen_key));
     if (buf == &h->tcache) h->tc_valid = false;
     if (*buf) {
         QLB_CUDA(h, cudaStreamSynchronize(h->stream));
