@@ -63,6 +63,12 @@ int64_t qlb200_launch_count(qlb200_handle h);
 /* Upload rate (GB/s) the first chunk of the last large host-pointer ql! saw (plain launches only: a graph replay does not
  * measure); 0 before the first such call.  Diagnostic: ~53 GB/s on an idle host, 17-19 GB/s with 8 GPUs uploading at once. */
 double qlb200_upload_rate(qlb200_handle h);
+/* Page-lock (cudaHostRegister) / release a caller's host array.  Host-pointer entry points accept any host memory, but a
+ * registered array is copied at full PCIe speed (about 5x the pageable rate) and a repeated large ql! on it is replayed as one
+ * CUDA graph.  Registering twice / releasing an unregistered array is not an error.  The Julia shim calls these from
+ * `QLB200.pin!(A)` / `QLB200.unpin!(A)`. */
+int qlb200_host_register(qlb200_handle h, void *ptr, int64_t bytes);
+int qlb200_host_unregister(qlb200_handle h, void *ptr);
 /* With option "profile" = 1 the trailing-update / Q-apply DMMA GEMM launches are bracketed by CUDA
  * event pairs on the launching stream.  This call synchronizes, returns the summed device time (ms),
  * the summed algorithmic flops and the number of launches since the last collect, and resets. */

@@ -84,6 +84,8 @@ for _t in "ds":
     MG_SIGNATURES[f"qlb200_{_t}geqlf_batched_mg"] = _FACT_B
     MG_SIGNATURES[f"qlb200_{_t}ormql_batched_mg"] = _ORM_B
     MG_SIGNATURES[f"qlb200_{_t}qlsolve_batched_mg"] = _SOLVE_B
+SIGNATURES["qlb200_host_register"] = [_P, _I]
+SIGNATURES["qlb200_host_unregister"] = [_P]
 SIGNATURES["qlb200_dgemm_dev"] = [c_char, c_char, _I, _I, _I, ctypes.c_double, _P, _I, _P, _I, ctypes.c_double, _P, _I]
 HANDLE_FUNCS = ["qlb200_version", "qlb200_create", "qlb200_destroy", "qlb200_set_stream", "qlb200_sync",
                 "qlb200_last_error", "qlb200_launch_count", "qlb200_set_option", "qlb200_reset_stream",
@@ -198,6 +200,14 @@ class Handle:
     def upload_rate(self) -> float:
         """GB/s the first upload piece of the last large host-pointer ql! saw (0.0: none yet)."""
         return float(lib().qlb200_upload_rate(self._h))
+
+    def pin(self, a) -> None:
+        """Page-lock the NumPy array `a` (cudaHostRegister): host-pointer calls on it copy at PCIe speed and a repeated
+        large ql_ replays as one CUDA graph.  Undo with unpin(a) before the array is freed."""
+        self.call("qlb200_host_register", a.ctypes.data, a.nbytes)
+
+    def unpin(self, a) -> None:
+        self.call("qlb200_host_unregister", a.ctypes.data)
 
     def last_error(self) -> str:
         return lib().qlb200_last_error(self._h).decode(errors="replace")

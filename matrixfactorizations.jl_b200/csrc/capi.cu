@@ -212,6 +212,40 @@ int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_tota
 
 int64_t qlb200_launch_count(qlb200_handle h) { return h ? h->launches : -1; }
 double qlb200_upload_rate(qlb200_handle h) { return h ? h->h2d_gbps : -1.0; }
+// Page-lock / release a caller's host array (cudaHostRegister, portable): host-pointer calls then copy at PCIe speed
+// (pageable: ~10 GB/s here, pinned: ~53 GB/s) and the large ql! may replay its whole schedule as a CUDA graph.
+int qlb200_host_register(qlb200_handle h, void *ptr, int64_t bytes) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, ptr != nullptr, 2, "ptr is null");
+    QLB_REQUIRE(h, bytes > 0, 3, "bytes must be positive");
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    QLB_CUDA(h, e);
+    return 0;
+}
+int qlb200_host_unregister(qlb200_handle h, void *ptr) {
+    if (!h) return -1;
+    QLB_REQUIRE(h, ptr != nullptr, 2, "ptr is null");
+    QLB_CUDA(h, cudaSetDevice(h->device));
+    QLB_CUDA(h, cudaDeviceSynchronize());          // nothing of this handle may still be copying from / to the array
+    if (h->hgraph_exec) {                          // the cached host schedule holds this array's address
+        cudaGraphExecDestroy(h->hgraph_exec);
+        h->hgraph_exec = nullptr;
+    }
+    memset(h->hgraph_key, 0, sizeof(h->hgraph_key));
+    memset(h->hgraph_seen_key, 0, sizeof(h->hgraph_seen_key));
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    QLB_CUDA(h, e);
+    return 0;
+}
 
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value) {
     if (!h) return -1;

@@ -55,6 +55,14 @@ function chk(h::Handle, info::Integer; dims = ())
     throw(ArgumentError("libqlb200: invalid argument #$(-info): $msg"))
 end
 
+# Page-lock a Julia array for the host-pointer entry points (cudaHostRegister inside the library): copies then run at full PCIe
+# speed (about 5x the pageable rate) and a repeated large `ql!` on the same array replays its whole upload | factor | download
+# schedule as one CUDA graph.  `unpin!` before the array can be garbage-collected.
+pin!(A::StridedArray{<:LinearAlgebra.BlasFloat}; h::Handle = handle()) =
+    (chk(h, ccall((:qlb200_host_register, libqlb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), h.ptr, pointer(A), sizeof(eltype(A)) * (stride(A, ndims(A)) * size(A, ndims(A))))); A)
+unpin!(A::StridedArray{<:LinearAlgebra.BlasFloat}; h::Handle = handle()) =
+    (chk(h, ccall((:qlb200_host_unregister, libqlb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, pointer(A))); A)
+
 # ---- ql!, lmul!/rmul!, ldiv! for every BlasFloat element type ------------------------------------------------------
 # replaces `QL(LAPACK.geqlf!(A)...)` (src/ql.jl:72); ql!/ql/ql_layout! reach it unchanged (src/ql.jl:114-117,179-191).
 # Float64: native; ComplexF64: native complex panel + the same DMMA GEMMs (csrc/complex.cu); Float32 / ComplexF32: widened

@@ -434,6 +434,41 @@ def test_host_pointer_ql_pinned_matrix_replays_as_a_graph(q, h):
         assert np.abs(Fa - Fo).max() <= 50 * n * EPS * np.linalg.norm(A)
 
 
+def test_host_register_pins_a_numpy_matrix(q, h):
+    """qlb200_host_register / _unregister (Handle.pin / unpin, QLB200.pin!): a pageable NumPy matrix page-locked in place
+    uploads at PCIe speed and takes the graph replay of the large host-pointer ql!; same bits as the pageable call."""
+    n = 2304
+    A0 = np.asfortranarray(np.random.default_rng(11).standard_normal((n, n)))
+    for name, v in (("host_split_min", 1024), ("la_min", 1024), ("chunk_cols", 512)):
+        h.set_option(name, v)
+    try:
+        Fp = q.ql(A0, handle=h)                         # pageable
+        rate_pageable = h.upload_rate()
+        A = A0.copy(order="F")
+        h.pin(A)
+        h.pin(A)                                        # registering twice is not an error
+        try:
+            outs = []
+            for _ in range(3):
+                A[...] = A0
+                F = q.ql_(A, handle=h)
+                outs.append((F.factors.copy(), F.tau.copy()))
+        finally:
+            h.unpin(A)
+            h.unpin(A)                                  # neither is releasing twice
+        A[...] = A0
+        Fu = q.ql_(A, handle=h)                         # pageable again: plain launches, the cached graph is gone
+    finally:
+        for name, v in (("host_split_min", 8192), ("la_min", 4096), ("chunk_cols", 1024)):
+            h.set_option(name, v)
+    assert rate_pageable > 0.1
+    for f, t in outs:
+        assert np.array_equal(f, Fp.factors) and np.array_equal(t, Fp.tau)
+    assert np.array_equal(Fu.factors, Fp.factors) and np.array_equal(Fu.tau, Fp.tau)
+    with pytest.raises(Exception):
+        h.call("qlb200_host_register", 0, 8)
+
+
 def _scaled_cmp(F, tau, Fo, tauo, A, k_rows_are_reflectors=False):
     """Elementwise comparison that stays meaningful when columns of A live at very different scales: every entry of the
     packed factors is compared relative to max(1, ...) of ITS column -- reflector entries are O(1), L entries carry the
