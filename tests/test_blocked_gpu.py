@@ -420,6 +420,8 @@ def test_host_pointer_ql_pinned_matrix_replays_as_a_graph(q, h):
             F = q.ql_(Ah, handle=h)
             assert h.launches > l0
             outs.append((F.factors.copy(), F.tau.copy()))
+        Bq = np.asfortranarray(rng.standard_normal((n, 4)))
+        QtB = q.lmul_(F.Q.T, Bq.copy(order="F"))                            # T cache refilled by the replay (validated by content)
         Fp = q.ql(np.asfortranarray(A1), handle=h)                          # pageable copy: plain launches, same schedule
     finally:
         for name, v in (("host_split_min", 8192), ("la_min", 4096), ("chunk_cols", 1024)):
@@ -432,6 +434,8 @@ def test_host_pointer_ql_pinned_matrix_replays_as_a_graph(q, h):
         Fo, tauo = lapack.geqlf(np.asfortranarray(A.copy()))
         assert np.abs(ta - tauo).max() <= 50 * n * EPS
         assert np.abs(Fa - Fo).max() <= 50 * n * EPS * np.linalg.norm(A)
+    ref = lapack.ormql("L", "T", outs[4][0], outs[4][1], Bq.copy(order="F"))
+    assert np.abs(QtB - ref).max() <= 50 * n * EPS * np.linalg.norm(Bq)
 
 
 def test_host_register_pins_a_numpy_matrix(q, h):
