@@ -84,7 +84,7 @@ int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_tota
  * "fuse_chunk" (fused batched factor + apply: matrices per
  * chunk, 0 = whole batch), "gemm_cfg"
  * (-1 auto, 0..3 force a DMMA tile configuration), "trail_splits" (0 auto, 1..8 split-K of W = C'V), "strip_rpt"
- * (1/2/4 minimum rows per thread in the panel kernel), "profile" (0/1, see above), "graph" (1: repeated ql! calls with
+ * (1/2/4 minimum rows per thread in the panel kernel; default 1 = as many CTAs of the cluster as the rows fill), "profile" (0/1, see above), "graph" (1: repeated ql! calls with
  * the same arguments are replayed as a CUDA graph), "tcache" (1: ql! keeps the panels' T factors for the following
  * lmul!/rmul!/ldiv! on the same factors -- device-pointer callers must not modify the factors in between),
  * "overlap_t" (1: the panel's T is built on a side stream while W = C'V runs), "ul_cluster" (1: cluster strip kernel

@@ -85,7 +85,7 @@ struct qlb200_ctx {
     int gc_panel_sms = 0, gc_gemm_sms = 0;
     cudaEvent_t ev_gc[4] = {nullptr};
     int64_t opt_gemm_cfg = -1;             // -1 auto, else forces a tile configuration (benchmarking)
-    int64_t opt_strip_rpt = 4;             // minimum rows per thread in the strip kernel (1, 2 or 4)
+    int64_t opt_strip_rpt = 1;             // minimum rows per thread in the strip kernel (1, 2 or 4); 1 = as many CTAs of the cluster as the rows fill (measured best at every n, tools/sweep_geqlf.py: 2048: 6.9 vs 8.1 ms with 4; 8192: 44.3 vs 47.4; 16384: 232 vs 235)
     // ql! replayed as a CUDA graph: the launch sequence of one (m, n, A, lda, tau, options, stream) call is captured the
     // second time it is seen and replayed afterwards (same kernels, same order: bitwise identical results)
     int64_t opt_graph = 1;
