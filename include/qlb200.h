@@ -92,7 +92,9 @@ int qlb200_profile_collect(qlb200_handle h, double *ms_total, double *flops_tota
  * being factored; "chunk_cols", "join_step" tune it), "bvar" (batched kernel variants: 0 auto; n = 32: 2 always one kernel, 3 always the two-phase split; 32 < n <= 64: 6 warp-pair kernel, 7 one warp per matrix, 9 the literal ?geql2 kernels),
  * "pair_sync" (default 8; GEMMs with exactly two column tiles run each pair as a 2-CTA cluster that meets every this
  * many k-tiles so that the shared operand is read from DRAM once, 0 = off), "batch_chunk_mb" (default 32; host-pointer batched calls run as an upload | compute | download pipeline over chunks of
- * about this many megabytes, 0 = one chunk). */
+ * about this many megabytes, 0 = one chunk).
+ * Diagnostic: with the environment variable QLB_LA_TRACE set, a look-ahead ql! brackets its phases with CUDA events, synchronizes at
+ * the end and prints the per-iteration timeline (update partition idle / next-panel update / panel / trailing update) to stderr. */
 int qlb200_set_option(qlb200_handle h, const char *name, int64_t value);
 
 /* ---- single matrix: ql! -------------------------------------------------------------------
